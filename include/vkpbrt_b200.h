@@ -1,0 +1,295 @@
+/*
+ * vkpbrt_b200.h -- C ABI of the B200-native denoising modules (libvkpbrt_b200.so).
+ *
+ * Drop-in boundary for VulkanPBRT's data-parallel denoising path.  The reference has no FFI
+ * layer: its callers use C++ render-module classes directly.  This
+ * header is what those classes bind to in the replacement; the C++ headers under include/vkpbrt/ rebuild the
+ * reference's class surface (same names, constructor argument order, method names) on top of
+ * it.  Every entry point cites the reference interface it replaces (paths relative to the
+ * reference root).
+ *
+ * Model:
+ *   - plain C, opaque handles, int status returns (0 == VKPBRT_OK), no exceptions cross the
+ *     ABI; vkpbrt_last_error() returns the message of the calling thread's last failure.
+ *   - all image memory is pitch-linear device memory (cudaMalloc, or imported Vulkan
+ *     external memory, see vkpbrt_import_external_memory_fd).  TILING_OPTIMAL images are not
+ *     importable as linear pointers; the Vulkan side must allocate exportable linear images
+ *     or buffers.
+ *   - "record" == enqueue on the context's CUDA stream, in call order.  Stream order replaces
+ *     the reference's COMPUTE->COMPUTE pipeline barriers (denoisers/BMFR.cpp:203-230).  The
+ *     C++ layer keeps the reference's record-once / replay-per-frame command list on top.
+ *   - there is no CPU fallback: every *_record call launches sm_100a kernels or fails.
+ */
+#ifndef VKPBRT_B200_H
+#define VKPBRT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define VKPBRT_API
+#else
+#define VKPBRT_API __attribute__((visibility("default")))
+#endif
+
+/* ---------------------------------------------------------------------------------------- */
+/* status                                                                                    */
+/* ---------------------------------------------------------------------------------------- */
+enum {
+    VKPBRT_OK = 0,
+    VKPBRT_ERR_INVALID_ARGUMENT = 1,
+    VKPBRT_ERR_CUDA = 2,              /* a CUDA runtime call failed; message has cudaGetErrorString */
+    VKPBRT_ERR_UNSUPPORTED = 3,       /* e.g. block size / fitting kernel combination            */
+    VKPBRT_ERR_WRONG_BUFFER_TYPE = 4, /* denoisers/BMFR.cpp:17-22, BFR.cpp:15-20: reference prints and
+                                         half-constructs; the replacement rejects               */
+    VKPBRT_ERR_NOT_COMPILED = 5,      /* record() before compile()                               */
+    VKPBRT_ERR_MISSING_MATRICES = 6,  /* Accumulator.cpp:89-94 (separate matrices requested, absent) */
+    VKPBRT_ERR_NO_DEVICE = 7          /* no CUDA device / not sm_100: the library never falls back */
+};
+
+VKPBRT_API const char* vkpbrt_last_error(void);
+VKPBRT_API const char* vkpbrt_version(void);
+
+/* ---------------------------------------------------------------------------------------- */
+/* context  ~ vsg::Context& handed to compile()/update_image_layouts()                       */
+/* ---------------------------------------------------------------------------------------- */
+typedef struct vkpbrt_context_s* vkpbrt_context_t;
+
+/* stream: a cudaStream_t owned by the caller, or NULL to let the context create its own.     */
+VKPBRT_API int vkpbrt_context_create(int device, void* cuda_stream, vkpbrt_context_t* out);
+VKPBRT_API int vkpbrt_context_destroy(vkpbrt_context_t ctx);
+VKPBRT_API int vkpbrt_context_synchronize(vkpbrt_context_t ctx);
+VKPBRT_API int vkpbrt_context_stream(vkpbrt_context_t ctx, void** cuda_stream);
+/* number of kernels this context has launched so far (bench.py's gpu_launches)               */
+VKPBRT_API int vkpbrt_context_launch_count(vkpbrt_context_t ctx, uint64_t* out);
+
+/* ---------------------------------------------------------------------------------------- */
+/* images  ~ vsg::ref_ptr<vsg::DescriptorImage>                                              */
+/* ---------------------------------------------------------------------------------------- */
+typedef enum {
+    VKPBRT_FORMAT_UNDEFINED = 0,
+    VKPBRT_FORMAT_R32_SFLOAT = 1,          /* GBuffer.cpp:60  depth, AccumulationBuffer.cpp:277 prev_depth */
+    VKPBRT_FORMAT_R32G32_SFLOAT = 2,       /* GBuffer.cpp:77  normal (theta, phi)                       */
+    VKPBRT_FORMAT_R8G8B8A8_UNORM = 3,      /* GBuffer.cpp:94,111 material/albedo; Taa.cpp:24 history       */
+    VKPBRT_FORMAT_B8G8R8A8_UNORM = 4,      /* BMFR.cpp:81, BFR.cpp, BFRBlender.cpp, Taa.cpp:42 finals       */
+    VKPBRT_FORMAT_R16G16_SFLOAT = 5,       /* AccumulationBuffer.cpp:303 motion (normalised uv)           */
+    VKPBRT_FORMAT_R8_UNORM = 6,            /* AccumulationBuffer.cpp:251,264 spp / prev_spp                */
+    VKPBRT_FORMAT_R16G16B16A16_SFLOAT = 7, /* IlluminationBuffer.cpp:235, BMFR.cpp:59-64 denoised x2 layers */
+    VKPBRT_FORMAT_R32G32B32A32_SFLOAT = 8, /* IlluminationBuffer.cpp:260-282 raw 1-spp illumination        */
+    VKPBRT_FORMAT_R16_SFLOAT = 9,          /* BMFR.cpp:99-104 feature buffer, 13 layers                    */
+} vkpbrt_format;
+
+typedef struct vkpbrt_image_s* vkpbrt_image_t;
+
+typedef struct {
+    void* data;          /* CURRENT device pointer (ping-pong images flip it per frame)        */
+    uint32_t format;     /* vkpbrt_format                                                      */
+    uint32_t width, height, layers;
+    uint64_t row_pitch;  /* bytes; always width * texel size (tightly packed)                  */
+    uint64_t layer_pitch;
+    uint64_t size_bytes; /* layers * layer_pitch                                               */
+    int32_t owned;       /* 1: allocated by compile(); 0: wraps caller memory                   */
+} vkpbrt_image_info;
+
+VKPBRT_API uint32_t vkpbrt_format_texel_size(uint32_t format);
+/* describes an image; memory is allocated (and zeroed) by vkpbrt_image_compile, mirroring
+ * vsg::DescriptorImage::compile(context) (BMFR.cpp:172-178) */
+VKPBRT_API int vkpbrt_image_create(vkpbrt_context_t ctx, uint32_t format, uint32_t width, uint32_t height,
+                                   uint32_t layers, vkpbrt_image_t* out);
+/* wraps caller-owned device memory (Vulkan-imported or another allocator); tightly packed */
+VKPBRT_API int vkpbrt_image_wrap(vkpbrt_context_t ctx, uint32_t format, uint32_t width, uint32_t height,
+                                 uint32_t layers, void* device_ptr, vkpbrt_image_t* out);
+VKPBRT_API int vkpbrt_image_set_data(vkpbrt_image_t img, void* device_ptr); /* wrapped images only */
+VKPBRT_API int vkpbrt_image_compile(vkpbrt_image_t img);
+VKPBRT_API int vkpbrt_image_info_get(vkpbrt_image_t img, vkpbrt_image_info* out);
+/* async copies on the context stream (pin the host buffer for overlap) */
+VKPBRT_API int vkpbrt_image_upload(vkpbrt_image_t img, const void* host, uint64_t bytes);
+VKPBRT_API int vkpbrt_image_download(vkpbrt_image_t img, void* host, uint64_t bytes);
+VKPBRT_API int vkpbrt_image_clear(vkpbrt_image_t img);
+VKPBRT_API int vkpbrt_image_retain(vkpbrt_image_t img);
+VKPBRT_API int vkpbrt_image_release(vkpbrt_image_t img);
+
+/* ---------------------------------------------------------------------------------------- */
+/* buffer bundles                                                                            */
+/* ---------------------------------------------------------------------------------------- */
+/* GBuffer (source/buffers/GBuffer.hpp:12-21): public members depth, normal, material, albedo */
+typedef struct vkpbrt_gbuffer_s* vkpbrt_gbuffer_t;
+typedef enum { VKPBRT_GBUFFER_DEPTH = 0, VKPBRT_GBUFFER_NORMAL = 1, VKPBRT_GBUFFER_MATERIAL = 2, VKPBRT_GBUFFER_ALBEDO = 3 } vkpbrt_gbuffer_member;
+VKPBRT_API int vkpbrt_gbuffer_create(vkpbrt_context_t ctx, uint32_t width, uint32_t height, vkpbrt_gbuffer_t* out);
+VKPBRT_API int vkpbrt_gbuffer_create_from_images(vkpbrt_context_t ctx, vkpbrt_image_t depth, vkpbrt_image_t normal,
+                                                 vkpbrt_image_t material, vkpbrt_image_t albedo, vkpbrt_gbuffer_t* out);
+VKPBRT_API int vkpbrt_gbuffer_compile(vkpbrt_gbuffer_t g);
+VKPBRT_API int vkpbrt_gbuffer_image(vkpbrt_gbuffer_t g, uint32_t member, vkpbrt_image_t* out); /* borrowed */
+VKPBRT_API int vkpbrt_gbuffer_destroy(vkpbrt_gbuffer_t g);
+
+/* IlluminationBuffer family (source/buffers/IlluminationBuffer.hpp:14-78) */
+typedef struct vkpbrt_illumination_buffer_s* vkpbrt_illumination_buffer_t;
+typedef enum {
+    VKPBRT_ILLUMINATION_FINAL = 0,             /* IlluminationBufferFinal: rejected by the denoisers     */
+    VKPBRT_ILLUMINATION_DEMODULATED = 1,       /* 2 x rgba16f: illumination, illuminationSquared          */
+    VKPBRT_ILLUMINATION_DEMODULATED_FLOAT = 2, /* 1 x rgba32f: raw 1-spp demodulated illumination         */
+    VKPBRT_ILLUMINATION_FINAL_DEMODULATED = 3, /* rejected by the denoisers                               */
+} vkpbrt_illumination_type;
+VKPBRT_API int vkpbrt_illumination_buffer_create(vkpbrt_context_t ctx, uint32_t type, uint32_t width,
+                                                 uint32_t height, vkpbrt_illumination_buffer_t* out);
+VKPBRT_API int vkpbrt_illumination_buffer_compile(vkpbrt_illumination_buffer_t b);
+VKPBRT_API int vkpbrt_illumination_buffer_type(vkpbrt_illumination_buffer_t b, uint32_t* type, uint32_t* image_count);
+VKPBRT_API int vkpbrt_illumination_buffer_image(vkpbrt_illumination_buffer_t b, uint32_t index, vkpbrt_image_t* out);
+VKPBRT_API int vkpbrt_illumination_buffer_destroy(vkpbrt_illumination_buffer_t b);
+
+/* AccumulationBuffer (source/buffers/AccumulationBuffer.hpp:13-24) */
+typedef struct vkpbrt_accumulation_buffer_s* vkpbrt_accumulation_buffer_t;
+typedef enum {
+    VKPBRT_ACC_PREV_ILLU = 0, VKPBRT_ACC_PREV_ILLU_SQUARED = 1, VKPBRT_ACC_PREV_DEPTH = 2,
+    VKPBRT_ACC_PREV_NORMAL = 3, VKPBRT_ACC_SPP = 4, VKPBRT_ACC_PREV_SPP = 5, VKPBRT_ACC_MOTION = 6
+} vkpbrt_accumulation_member;
+VKPBRT_API int vkpbrt_accumulation_buffer_create(vkpbrt_context_t ctx, uint32_t width, uint32_t height,
+                                                 vkpbrt_accumulation_buffer_t* out);
+VKPBRT_API int vkpbrt_accumulation_buffer_compile(vkpbrt_accumulation_buffer_t b);
+VKPBRT_API int vkpbrt_accumulation_buffer_image(vkpbrt_accumulation_buffer_t b, uint32_t member, vkpbrt_image_t* out);
+/* AccumulationBuffer::copy_to_back_images (AccumulationBuffer.cpp:72-244): end-of-frame history
+ * rotation depth->prev_depth, spp->prev_spp, illumination[0]->prev_illu.  The five image copies of
+ * the reference (58 B/pixel) become pointer swaps: spp/prev_spp and illumination/prev_illu are
+ * exchanged when both sides are library-owned (device copy otherwise); prev_depth is produced by
+ * the accumulate kernel itself (it already reads depth) into a ping-pong pair that is flipped
+ * here.  prev_normal / prev_illu_squared are not maintained: no shader on the path reads them
+ * (accumulator.comp:82-83 is commented out, :104 never writes illuminationSquared). */
+VKPBRT_API int vkpbrt_accumulation_buffer_copy_to_back_images(vkpbrt_accumulation_buffer_t b, vkpbrt_gbuffer_t g,
+                                                              vkpbrt_illumination_buffer_t illumination);
+VKPBRT_API int vkpbrt_accumulation_buffer_destroy(vkpbrt_accumulation_buffer_t b);
+
+/* ---------------------------------------------------------------------------------------- */
+/* per-frame constants                                                                       */
+/* ---------------------------------------------------------------------------------------- */
+/* RayTracingPushConstants (source/renderModules/PipelineStructs.hpp:6-13), column-major mat4s */
+typedef struct {
+    float view_inverse[16];
+    float proj_inverse[16];
+    float prev_view[16];
+    uint32_t frame_number;
+    uint32_t sample_number;
+} vkpbrt_push_constants;
+
+/* CameraMatrices (source/io/RenderIO.hpp:28-34) */
+typedef struct {
+    float view[16];     /* combined view-projection when has_proj == 0 */
+    float inv_view[16];
+    int32_t has_proj;   /* std::optional<mat4> proj, inv_proj */
+    float proj[16];
+    float inv_proj[16];
+} vkpbrt_camera_matrices;
+
+/* ---------------------------------------------------------------------------------------- */
+/* Accumulator  (source/renderModules/Accumulator.hpp:15-25, Accumulator.cpp:4-117;          */
+/*               kernel: shaders/accumulator.comp:33-104)                                    */
+/* ---------------------------------------------------------------------------------------- */
+typedef struct vkpbrt_accumulator_s* vkpbrt_accumulator_t;
+/* Accumulator(g_buffer, illumination_buffer, separate_matrices, work_width = 16, work_height = 16):
+ * creates and owns an AccumulationBuffer and an IlluminationBufferDemodulated. */
+VKPBRT_API int vkpbrt_accumulator_create(vkpbrt_context_t ctx, vkpbrt_gbuffer_t g, vkpbrt_illumination_buffer_t illumination,
+                                         int separate_matrices, int work_width, int work_height,
+                                         vkpbrt_accumulator_t* out);
+VKPBRT_API int vkpbrt_accumulator_compile_images(vkpbrt_accumulator_t a);              /* compile_images()          */
+VKPBRT_API int vkpbrt_accumulator_accumulated_illumination(vkpbrt_accumulator_t a, vkpbrt_illumination_buffer_t* out);
+VKPBRT_API int vkpbrt_accumulator_accumulation_buffer(vkpbrt_accumulator_t a, vkpbrt_accumulation_buffer_t* out);
+VKPBRT_API int vkpbrt_accumulator_set_camera_matrices(vkpbrt_accumulator_t a, int frame_index,
+                                                      const vkpbrt_camera_matrices* cur, const vkpbrt_camera_matrices* prev);
+/* add_dispatch_to_command_graph(): one launch of the accumulate kernel */
+VKPBRT_API int vkpbrt_accumulator_record(vkpbrt_accumulator_t a);
+/* restrict the dispatch to image rows [row_begin, row_end) (multi-GPU band sharding) */
+VKPBRT_API int vkpbrt_accumulator_set_row_range(vkpbrt_accumulator_t a, int row_begin, int row_end);
+VKPBRT_API int vkpbrt_accumulator_destroy(vkpbrt_accumulator_t a);
+
+/* ---------------------------------------------------------------------------------------- */
+/* BMFR  (source/renderModules/denoisers/BMFR.hpp:17-25, BMFR.cpp:5-234;                     */
+/*        kernels: shaders/bmfrPre.comp, bmfrFit.comp, bmfrPost.comp)                        */
+/* ---------------------------------------------------------------------------------------- */
+typedef struct vkpbrt_bmfr_s* vkpbrt_bmfr_t;
+/* BMFR(width, height, work_width, work_height, g_buffer, illu_buffer, acc_buffer, fitting_kernel = 256).
+ * Supported (work, fitting_kernel): (32,256) (16,256) (8,64) -- the combinations
+ * util/DenoiserUtils.cpp:78-124 instantiates. */
+VKPBRT_API int vkpbrt_bmfr_create(vkpbrt_context_t ctx, uint32_t width, uint32_t height, uint32_t work_width,
+                                  uint32_t work_height, vkpbrt_gbuffer_t g, vkpbrt_illumination_buffer_t illumination,
+                                  vkpbrt_accumulation_buffer_t acc, uint32_t fitting_kernel, vkpbrt_bmfr_t* out);
+/* the fused kernel keeps the feature matrix and the weights on chip; enable to also materialise
+ * the reference's featureBuffer (r16f x13, padded) and weights (r32f x30) images for parity tests */
+VKPBRT_API int vkpbrt_bmfr_set_debug_outputs(vkpbrt_bmfr_t b, int enable);
+VKPBRT_API int vkpbrt_bmfr_compile(vkpbrt_bmfr_t b);
+VKPBRT_API int vkpbrt_bmfr_record(vkpbrt_bmfr_t b, const vkpbrt_push_constants* pc); /* pre+fit+post, one launch */
+VKPBRT_API int vkpbrt_bmfr_set_block_row_range(vkpbrt_bmfr_t b, int block_row_begin, int block_row_end);
+VKPBRT_API int vkpbrt_bmfr_final_image(vkpbrt_bmfr_t b, vkpbrt_image_t* out);        /* get_final_descriptor_image() */
+typedef enum { VKPBRT_BMFR_IMAGE_DENOISED = 0, VKPBRT_BMFR_IMAGE_FEATURES = 1, VKPBRT_BMFR_IMAGE_WEIGHTS = 2 } vkpbrt_bmfr_image;
+VKPBRT_API int vkpbrt_bmfr_image_get(vkpbrt_bmfr_t b, uint32_t which, vkpbrt_image_t* out);
+VKPBRT_API int vkpbrt_bmfr_destroy(vkpbrt_bmfr_t b);
+
+/* ---------------------------------------------------------------------------------------- */
+/* BFR  (denoisers/BFR.hpp:11-18, BFR.cpp:6-142; kernel: shaders/bfr.comp:202-309)           */
+/* ---------------------------------------------------------------------------------------- */
+typedef struct vkpbrt_bfr_s* vkpbrt_bfr_t;
+VKPBRT_API int vkpbrt_bfr_create(vkpbrt_context_t ctx, uint32_t width, uint32_t height, uint32_t work_width,
+                                 uint32_t work_height, vkpbrt_gbuffer_t g, vkpbrt_illumination_buffer_t illumination,
+                                 vkpbrt_accumulation_buffer_t acc, vkpbrt_bfr_t* out);
+VKPBRT_API int vkpbrt_bfr_compile(vkpbrt_bfr_t b);
+VKPBRT_API int vkpbrt_bfr_record(vkpbrt_bfr_t b, const vkpbrt_push_constants* pc);
+VKPBRT_API int vkpbrt_bfr_final_image(vkpbrt_bfr_t b, vkpbrt_image_t* out);
+VKPBRT_API int vkpbrt_bfr_denoised_image(vkpbrt_bfr_t b, vkpbrt_image_t* out);
+VKPBRT_API int vkpbrt_bfr_destroy(vkpbrt_bfr_t b);
+
+/* ---------------------------------------------------------------------------------------- */
+/* BFRBlender  (denoisers/BFRBlender.hpp:9-18, BFRBlender.cpp:5-130;                         */
+/*              kernel: shaders/bfrBlender.comp:22-68)                                       */
+/* ---------------------------------------------------------------------------------------- */
+typedef struct vkpbrt_bfr_blender_s* vkpbrt_bfr_blender_t;
+/* BFRBlender(width, height, average_image, average_squared_image, denoised0, denoised1, denoised2,
+ *            work_width = 16, work_height = 16, filter_radius = 2) */
+VKPBRT_API int vkpbrt_bfr_blender_create(vkpbrt_context_t ctx, uint32_t width, uint32_t height, vkpbrt_image_t average,
+                                         vkpbrt_image_t average_squared, vkpbrt_image_t denoised0,
+                                         vkpbrt_image_t denoised1, vkpbrt_image_t denoised2, uint32_t work_width,
+                                         uint32_t work_height, uint32_t filter_radius, vkpbrt_bfr_blender_t* out);
+VKPBRT_API int vkpbrt_bfr_blender_compile(vkpbrt_bfr_blender_t b);
+VKPBRT_API int vkpbrt_bfr_blender_record(vkpbrt_bfr_blender_t b);
+VKPBRT_API int vkpbrt_bfr_blender_final_image(vkpbrt_bfr_blender_t b, vkpbrt_image_t* out);
+VKPBRT_API int vkpbrt_bfr_blender_destroy(vkpbrt_bfr_blender_t b);
+
+/* ---------------------------------------------------------------------------------------- */
+/* Taa  (source/renderModules/Taa.hpp:14-20, Taa.cpp:4-147; kernel: shaders/taa.comp:48-104) */
+/* ---------------------------------------------------------------------------------------- */
+typedef struct vkpbrt_taa_s* vkpbrt_taa_t;
+/* Taa(width, height, work_width, work_height, g_buffer, acc_buffer, denoised) */
+VKPBRT_API int vkpbrt_taa_create(vkpbrt_context_t ctx, uint32_t width, uint32_t height, uint32_t work_width,
+                                 uint32_t work_height, vkpbrt_gbuffer_t g, vkpbrt_accumulation_buffer_t acc,
+                                 vkpbrt_image_t denoised, vkpbrt_taa_t* out);
+/* 0 (default): reproduce the reference's R/B-swapped history; 1: fix it */
+VKPBRT_API int vkpbrt_taa_set_fix_swizzle(vkpbrt_taa_t t, int fix);
+VKPBRT_API int vkpbrt_taa_compile(vkpbrt_taa_t t);
+/* dispatch + final->history hand-over (Taa.cpp:99-107).  The reference never pushes constants for
+ * TAA and inherits the denoiser's (App. C-10); here they are passed explicitly. */
+VKPBRT_API int vkpbrt_taa_record(vkpbrt_taa_t t, const vkpbrt_push_constants* pc);
+VKPBRT_API int vkpbrt_taa_set_row_range(vkpbrt_taa_t t, int row_begin, int row_end);
+VKPBRT_API int vkpbrt_taa_final_image(vkpbrt_taa_t t, vkpbrt_image_t* out);
+VKPBRT_API int vkpbrt_taa_history_image(vkpbrt_taa_t t, vkpbrt_image_t* out);
+VKPBRT_API int vkpbrt_taa_destroy(vkpbrt_taa_t t);
+
+/* ---------------------------------------------------------------------------------------- */
+/* Vulkan interop (north star: VK_KHR_external_memory_fd / VK_KHR_external_semaphore_fd)      */
+/* ---------------------------------------------------------------------------------------- */
+typedef struct vkpbrt_external_memory_s* vkpbrt_external_memory_t;
+typedef struct vkpbrt_external_semaphore_s* vkpbrt_external_semaphore_t;
+/* imports an opaque fd exported from a VkDeviceMemory (ownership of fd passes to CUDA) and maps
+ * [offset, offset+size) as a linear device pointer usable with vkpbrt_image_wrap */
+VKPBRT_API int vkpbrt_import_external_memory_fd(vkpbrt_context_t ctx, int fd, uint64_t allocation_size, uint64_t offset,
+                                                uint64_t size, vkpbrt_external_memory_t* out, void** device_ptr);
+VKPBRT_API int vkpbrt_external_memory_destroy(vkpbrt_external_memory_t m);
+VKPBRT_API int vkpbrt_import_external_semaphore_fd(vkpbrt_context_t ctx, int fd, int timeline, vkpbrt_external_semaphore_t* out);
+VKPBRT_API int vkpbrt_external_semaphore_wait(vkpbrt_external_semaphore_t s, uint64_t value);   /* on ctx stream */
+VKPBRT_API int vkpbrt_external_semaphore_signal(vkpbrt_external_semaphore_t s, uint64_t value); /* on ctx stream */
+VKPBRT_API int vkpbrt_external_semaphore_destroy(vkpbrt_external_semaphore_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VKPBRT_B200_H */

@@ -1,0 +1,1004 @@
+/*
+ * vkpbrt_oracle.c -- CPU restatement of VulkanPBRT's denoising compute shaders.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This file is the parity oracle for the CUDA path in
+ * vulkanpbrt_b200/csrc.  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may load it.  The product library
+ * (libvkpbrt_b200.so) never links, loads or calls anything in oracle/.
+ *
+ * PARITY STATUS: the reference ships no tests, golden vectors or fixtures for this path
+ *  and its shaders are GLSL, which cannot be compiled by any tool in
+ * this image (no glslc / glslang / Vulkan ICD).  The restatement is therefore pinned
+ * against oracle/_ref: the reference's own shader SOURCE TEXT compiled as C++ through the
+ * GLSL-compatibility shim in oracle/glsl_shim (see oracle/Makefile and
+ * tests/test_oracle_vs_ref.py).  Where oracle/_ref is not built the status is
+ * "parity unpinned".
+ *
+ * Every function cites the reference file:line it follows (paths relative to
+ * /root/reference).  All arithmetic is IEEE binary32, compiled with -ffp-contract=off so
+ * no FMA contraction takes place; the evaluation order written here IS the definition
+ * the CUDA kernels are compared against.
+ *
+ * Conventions fixed here where the reference leaves them to the Vulkan implementation
+ * (SURVEY.md App. C):
+ *   - fp32 -> fp16 image stores round to nearest even (C-3).
+ *   - fp32 -> unorm8 image stores: NaN -> 0, clamp to [0,1], (uint8)(c*255 + 0.5).
+ *   - texture(): bilinear, REPEAT, exact fp32 weights (App. A.1, C-6):
+ *       ((w00*t00 + w10*t10) + w01*t01) + w11*t11
+ *   - subgroup size 32; subgroupAdd is the xor-butterfly tree (lane^16, ^8, ^4, ^2, ^1) that a
+ *     shuffle-based implementation produces; subgroups are then folded serially by invocation
+ *     0 exactly as the shaders do (C-1, C-2).  The fit is ill-conditioned by construction
+ *     (noise-level residual columns), so this order is part of the definition: a different
+ *     IEEE-correct order moves ~2% of the pixels by more than 1e-3.
+ *   - sin / cos / pow have implementation-defined precision in GLSL; the oracle defines them
+ *     as the fixed plain-IEEE algorithms vk_sincos / vk_pow below (Cephes-style, ~1e-7
+ *     relative), which the CUDA kernels restate operation for operation.
+ *   - BGRA8 "final" images keep memory order B,G,R,A; the TAA history is a raw byte copy
+ *     of the BGRA8 final read back as RGBA8 (C-4), i.e. R/B swapped, unless
+ *     fix_taa_swizzle is set.
+ *   - out-of-bounds imageLoad returns 0 (robust access; bfrBlender, App. A.8).
+ *   - images never written keep their previous contents (App. A.2).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define ORACLE_API __attribute__((visibility("default")))
+
+/* ------------------------------------------------------------------------------------ */
+/* storage formats                                                                      */
+/* ------------------------------------------------------------------------------------ */
+
+static inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+static inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+
+/* fp32 -> fp16, round to nearest even (VK_FORMAT_R16*_SFLOAT stores) */
+static inline uint16_t f32_to_f16(float f)
+{
+    uint32_t x = f2u(f);
+    uint32_t sign = (x >> 16) & 0x8000u;
+    uint32_t ax = x & 0x7fffffffu;
+    if (ax > 0x7f800000u) return (uint16_t)(sign | 0x7fffu);          /* NaN */
+    if (ax >= 0x477ff000u) return (uint16_t)(sign | 0x7c00u);         /* >= 65520 -> inf */
+    if (ax < 0x38800000u) {                                           /* < 2^-14: subnormal half */
+        if (ax <= 0x33000000u) return (uint16_t)sign;                 /* <= 2^-25 -> 0 (tie to even) */
+        uint32_t e = ax >> 23;
+        uint32_t m = (ax & 0x7fffffu) | 0x800000u;
+        uint32_t s = 126u - e;                                        /* 14..24 */
+        uint32_t h = m >> s;
+        uint32_t rem = m & ((1u << s) - 1u);
+        uint32_t half = 1u << (s - 1u);
+        if (rem > half || (rem == half && (h & 1u))) h++;
+        return (uint16_t)(sign | h);
+    }
+    uint32_t e = (ax >> 23) - 112u;
+    uint32_t m = ax & 0x7fffffu;
+    uint32_t h = (e << 10) | (m >> 13);
+    uint32_t rem = m & 0x1fffu;
+    if (rem > 0x1000u || (rem == 0x1000u && (h & 1u))) h++;           /* carries into exponent correctly */
+    return (uint16_t)(sign | h);
+}
+
+static inline float f16_to_f32(uint16_t h)
+{
+    uint32_t sign = ((uint32_t)h & 0x8000u) << 16;
+    uint32_t e = (h >> 10) & 0x1fu;
+    uint32_t m = h & 0x3ffu;
+    if (e == 0) {
+        if (m == 0) return u2f(sign);
+        float v = (float)m * 5.9604644775390625e-08f;                 /* m * 2^-24, exact */
+        return sign ? -v : v;
+    }
+    if (e == 31) return u2f(sign | 0x7f800000u | (m << 13));
+    return u2f(sign | ((e + 112u) << 23) | (m << 13));
+}
+
+static inline uint8_t f32_to_unorm8(float c)
+{
+    if (!(c == c)) return 0;
+    if (c < 0.0f) c = 0.0f;
+    if (c > 1.0f) c = 1.0f;
+    return (uint8_t)(c * 255.0f + 0.5f);
+}
+static inline float unorm8_to_f32(uint8_t c) { return (float)c / 255.0f; }
+
+ORACLE_API uint16_t vkpbrt_oracle_f32_to_f16(float f) { return f32_to_f16(f); }
+ORACLE_API float vkpbrt_oracle_f16_to_f32(uint16_t h) { return f16_to_f32(h); }
+ORACLE_API uint8_t vkpbrt_oracle_f32_to_unorm8(float f) { return f32_to_unorm8(f); }
+
+/* GLSL min/max/clamp semantics (NaN behaviour follows the ternary definitions) */
+static inline float gl_min(float x, float y) { return (y < x) ? y : x; }
+static inline float gl_max(float x, float y) { return (x < y) ? y : x; }
+static inline float gl_clamp(float x, float lo, float hi) { return gl_min(gl_max(x, lo), hi); }
+static inline float gl_mix(float x, float y, float a) { return x * (1.0f - a) + y * a; }
+
+
+/* ------------------------------------------------------------------------------------ */
+/* deterministic transcendental functions (plain IEEE mul/add/div only, no FMA)         */
+/* ------------------------------------------------------------------------------------ */
+/* sin and cos of x, |x| < 8192 (NaN outside): Cody-Waite reduction by pi/4 in three parts
+ * and the Cephes single-precision minimax polynomials. */
+static inline void vk_sincos(float x, float* sn, float* cs)
+{
+    float ax = fabsf(x);
+    if (!(ax < 8192.0f)) { *sn = *cs = (x - x) / (x - x); return; }
+    uint32_t j = (uint32_t)(ax * 1.27323954473516f);      /* ax / (pi/4) */
+    float y = (float)j;
+    if (j & 1u) { j += 1u; y += 1.0f; }
+    float r = ((ax - y * 0.78515625f) - y * 2.4187564849853515625e-4f) - y * 3.77489497744594108e-8f;
+    float z = r * r;
+    float ps = ((-1.9515295891e-4f * z + 8.3321608736e-3f) * z + -1.6666654611e-1f) * z * r + r;
+    float pc = ((2.443315711809948e-5f * z + -1.388731625493765e-3f) * z + 4.166664568298827e-2f) * z * z;
+    pc = pc - 0.5f * z;
+    pc = pc + 1.0f;
+    uint32_t q = (j >> 1) & 3u;                             /* angle = q*pi/2 + r */
+    float s = (q == 0u) ? ps : ((q == 1u) ? pc : ((q == 2u) ? -ps : -pc));
+    float c = (q == 0u) ? pc : ((q == 1u) ? -ps : ((q == 2u) ? -pc : ps));
+    *sn = (x < 0.0f) ? -s : s;
+    *cs = c;
+}
+
+/* pow(x, y) for x >= 0 as exp2(y * log2(x)) */
+static inline float vk_pow(float x, float y)
+{
+    if (!(x > 0.0f)) return (x == 0.0f) ? 0.0f : (x - x) / (x - x);
+    if (x > 3.0e38f) return x;
+    int e = 0;
+    if (x < 1.17549435e-38f) { x = x * 8388608.0f; e = -23; }
+    uint32_t bits = f2u(x);
+    e += (int)((bits >> 23) & 255u) - 127;
+    float m = u2f((bits & 0x007fffffu) | 0x3f800000u);      /* [1, 2) */
+    if (m > 1.41421356f) { m = m * 0.5f; e += 1; }
+    float z = (m - 1.0f) / (m + 1.0f);
+    float z2 = z * z;
+    float p = ((((0.0909090909f * z2 + 0.1111111111f) * z2 + 0.1428571429f) * z2 + 0.2f) * z2 + 0.3333333333f) * z2;
+    float lnm = 2.0f * (z + z * p);
+    float lg = (float)e + lnm * 1.44269504089f;
+    float t = y * lg;
+    if (t > 127.99f) return u2f(0x7f800000u);
+    if (t < -150.0f) return 0.0f;
+    float n = rintf(t);
+    float f = t - n;
+    float px = ((((1.535336188319500e-4f * f + 1.339887440266574e-3f) * f + 9.618437357674640e-3f) * f +
+                 5.550332471162809e-2f) * f + 2.402264791363012e-1f) * f + 6.931472028550421e-1f;
+    float r = 1.0f + f * px;
+    int ni = (int)n, n1 = ni / 2, n2 = ni - n1;
+    return (r * u2f((uint32_t)(n1 + 127) << 23)) * u2f((uint32_t)(n2 + 127) << 23);
+}
+
+ORACLE_API void vkpbrt_oracle_sincos(float x, float* s, float* c) { vk_sincos(x, s, c); }
+ORACLE_API float vkpbrt_oracle_pow(float x, float y) { return vk_pow(x, y); }
+
+/* ------------------------------------------------------------------------------------ */
+/* sampler: default vsg::Sampler (external/vsg/include/vsg/state/Sampler.h:29-43):      */
+/* LINEAR / REPEAT / normalised coordinates.  SURVEY.md App. A.1                        */
+/* ------------------------------------------------------------------------------------ */
+
+typedef struct {
+    int x0, x1, y0, y1;
+    float w00, w10, w01, w11;
+} bilin_t;
+
+static inline int wrapi(int i, int n) { i %= n; return i < 0 ? i + n : i; }
+
+static inline bilin_t bilin_setup(float u, float v, int W, int H)
+{
+    bilin_t b;
+    float x = u * (float)W - 0.5f;
+    float y = v * (float)H - 0.5f;
+    float fx0 = floorf(x), fy0 = floorf(y);
+    float a = x - fx0, bt = y - fy0;
+    int ix = (int)fx0, iy = (int)fy0;
+    b.x0 = wrapi(ix, W); b.x1 = wrapi(ix + 1, W);
+    b.y0 = wrapi(iy, H); b.y1 = wrapi(iy + 1, H);
+    float oma = 1.0f - a, omb = 1.0f - bt;
+    b.w00 = oma * omb; b.w10 = a * omb; b.w01 = oma * bt; b.w11 = a * bt;
+    return b;
+}
+static inline float bilin_mix(const bilin_t* b, float t00, float t10, float t01, float t11)
+{
+    return ((b->w00 * t00 + b->w10 * t10) + b->w01 * t01) + b->w11 * t11;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* small column-major mat4 helpers (vsg::mat4 / GLSL mat4: m[col*4 + row])              */
+/* ------------------------------------------------------------------------------------ */
+
+static inline void mat_vec(const float* m, const float* v, float* r)
+{
+    for (int i = 0; i < 4; ++i)
+        r[i] = ((m[0 + i] * v[0] + m[4 + i] * v[1]) + m[8 + i] * v[2]) + m[12 + i] * v[3];
+}
+/* r = a * b */
+static void mat_mul(const float* a, const float* b, float* r)
+{
+    for (int c = 0; c < 4; ++c) mat_vec(a, b + 4 * c, r + 4 * c);
+}
+/* cofactor inverse, fp32.  GLSL inverse() precision is implementation-defined; this order
+ * is the definition shared with the host side of the CUDA path. */
+static void mat_inverse(const float* m, float* inv)
+{
+    float a00 = m[0], a01 = m[1], a02 = m[2], a03 = m[3];
+    float a10 = m[4], a11 = m[5], a12 = m[6], a13 = m[7];
+    float a20 = m[8], a21 = m[9], a22 = m[10], a23 = m[11];
+    float a30 = m[12], a31 = m[13], a32 = m[14], a33 = m[15];
+    float b00 = a00 * a11 - a01 * a10;
+    float b01 = a00 * a12 - a02 * a10;
+    float b02 = a00 * a13 - a03 * a10;
+    float b03 = a01 * a12 - a02 * a11;
+    float b04 = a01 * a13 - a03 * a11;
+    float b05 = a02 * a13 - a03 * a12;
+    float b06 = a20 * a31 - a21 * a30;
+    float b07 = a20 * a32 - a22 * a30;
+    float b08 = a20 * a33 - a23 * a30;
+    float b09 = a21 * a32 - a22 * a31;
+    float b10 = a21 * a33 - a23 * a31;
+    float b11 = a22 * a33 - a23 * a32;
+    float det = ((((b00 * b11 - b01 * b10) + b02 * b09) + b03 * b08) - b04 * b07) + b05 * b06;
+    float id = 1.0f / det;
+    inv[0] = ((a11 * b11 - a12 * b10) + a13 * b09) * id;
+    inv[1] = ((a02 * b10 - a01 * b11) - a03 * b09) * id;
+    inv[2] = ((a31 * b05 - a32 * b04) + a33 * b03) * id;
+    inv[3] = ((a22 * b04 - a21 * b05) - a23 * b03) * id;
+    inv[4] = ((a12 * b08 - a10 * b11) - a13 * b07) * id;
+    inv[5] = ((a00 * b11 - a02 * b08) + a03 * b07) * id;
+    inv[6] = ((a32 * b02 - a30 * b05) - a33 * b01) * id;
+    inv[7] = ((a20 * b05 - a22 * b02) + a23 * b01) * id;
+    inv[8] = ((a10 * b10 - a11 * b08) + a13 * b06) * id;
+    inv[9] = ((a01 * b08 - a00 * b10) - a03 * b06) * id;
+    inv[10] = ((a30 * b04 - a31 * b02) + a33 * b00) * id;
+    inv[11] = ((a21 * b02 - a20 * b04) - a23 * b00) * id;
+    inv[12] = ((a11 * b07 - a10 * b09) - a12 * b06) * id;
+    inv[13] = ((a00 * b09 - a01 * b07) + a02 * b06) * id;
+    inv[14] = ((a31 * b01 - a30 * b03) - a32 * b00) * id;
+    inv[15] = ((a20 * b03 - a21 * b01) + a22 * b00) * id;
+}
+
+ORACLE_API void vkpbrt_oracle_mat_inverse(const float* m, float* inv) { mat_inverse(m, inv); }
+ORACLE_API void vkpbrt_oracle_mat_mul(const float* a, const float* b, float* r) { mat_mul(a, b, r); }
+
+/* ------------------------------------------------------------------------------------ */
+/* accumulator.comp  (shaders/accumulator.comp:33-104)              */
+/* push constants (accumulator.comp:20-27): view, inverseView, prevView, prevOrigin,    */
+/* frameNumber -- filled by Accumulator::set_camera_matrices                            */
+/* (source/renderModules/Accumulator.cpp:85-117).                                       */
+/* ------------------------------------------------------------------------------------ */
+
+typedef struct {
+    float view[16];       /* SEPARATE_MATRICES: inverse projection; else combined VP        */
+    float inv_view[16];   /* inverse view (separate) / inverse VP (combined)                */
+    float prev_view[16];  /* previous view (separate) / previous VP (combined)              */
+    float prev_origin[4];
+    uint32_t frame_number;
+} oracle_acc_push_t;
+
+ORACLE_API void vkpbrt_oracle_accumulator(
+    int W, int H, int separate_matrices, const oracle_acc_push_t* pc,
+    const void* src, int src_is_f16,            /* srcImage: rgba32f or rgba16f [H][W][4]       */
+    const float* depth,                         /* r32f [H][W]                                   */
+    const float* prev_depth,                    /* r32f [H][W]        (sampled, bilinear)        */
+    const uint16_t* prev_illum,                 /* rgba16f [H][W][4]  (sampled, bilinear)        */
+    const uint8_t* prev_spp,                    /* r8 [H][W]          (sampled, bilinear)        */
+    uint16_t* motion,                           /* rg16f [H][W][2]                               */
+    uint8_t* spp,                               /* r8 [H][W]                                     */
+    uint16_t* illum)                            /* rgba16f [H][W][4]                             */
+{
+    float proj_prev[16];
+    if (separate_matrices) {
+        /* accumulator.comp:46 "mat4 proj = inverse(camParams.view)" and :54
+         * "proj * camParams.prevView * p" == (proj * prevView) * p; both are uniform over
+         * the dispatch so they are evaluated once. */
+        float proj[16];
+        mat_inverse(pc->view, proj);
+        mat_mul(proj, pc->prev_view, proj_prev);
+    }
+    const float sizex = (float)W, sizey = (float)H;
+#pragma omp parallel for schedule(static)
+    for (int gy = 0; gy < H; ++gy) {
+        for (int gx = 0; gx < W; ++gx) {
+            const size_t pix = (size_t)gy * W + gx;
+            int reprojected = 0;
+            float pixel_spp = 1.0f / 256.0f;                            /* :43 */
+            const float d = depth[pix];                                  /* :44 */
+            float p[4], prev_pos[4];
+            if (separate_matrices) {
+                /* :46-54 */
+                float pos[4] = {pc->inv_view[12], pc->inv_view[13], pc->inv_view[14], 1.0f};
+                float cx = (((float)gx + 0.5f) / sizex) * 2.0f - 1.0f;
+                float cy = (((float)gy + 0.5f) / sizey) * 2.0f - 1.0f;
+                float cv[4] = {cx, cy, 1.0f, 1.0f}, dir[4];
+                mat_vec(pc->view, cv, dir);
+                float inv_len = 1.0f / sqrtf((dir[0] * dir[0] + dir[1] * dir[1]) + dir[2] * dir[2]);
+                float nd[4] = {dir[0] * inv_len, dir[1] * inv_len, dir[2] * inv_len, 0.0f};
+                mat_vec(pc->inv_view, nd, dir);
+                for (int i = 0; i < 4; ++i) p[i] = pos[i] + d * dir[i];
+                mat_vec(proj_prev, p, prev_pos);
+            } else {
+                /* :56-64 */
+                float co[4];
+                float cw = pc->inv_view[11];
+                for (int i = 0; i < 4; ++i) co[i] = pc->inv_view[8 + i] / cw;
+                float cx = (((float)gx + 0.5f) / sizex) * 2.0f - 1.0f;
+                float cy = (((float)gy + 0.5f) / sizey) * 2.0f - 1.0f;
+                float cv[4] = {cx, cy, 1.0f, 1.0f}, cd[4];
+                mat_vec(pc->inv_view, cv, cd);
+                float dw = cd[3] + 1e-9f;
+                for (int i = 0; i < 4; ++i) cd[i] = cd[i] / dw;
+                float df[4];
+                for (int i = 0; i < 4; ++i) df[i] = cd[i] - co[i];
+                float inv_len = 1.0f / sqrtf(((df[0] * df[0] + df[1] * df[1]) + df[2] * df[2]) + df[3] * df[3]);
+                for (int i = 0; i < 4; ++i) cd[i] = -(df[i] * inv_len);
+                for (int i = 0; i < 4; ++i) p[i] = co[i] + d * cd[i];
+                mat_vec(pc->prev_view, p, prev_pos);
+            }
+            /* :66-70 */
+            float dx = p[0] - pc->prev_origin[0], dy = p[1] - pc->prev_origin[1], dz = p[2] - pc->prev_origin[2];
+            float pre_depth = sqrtf((dx * dx + dy * dy) + dz * dz);
+            float u = prev_pos[0] / prev_pos[3], v = prev_pos[1] / prev_pos[3];
+            u = (u + 1.0f) * 0.5f;
+            v = (v + 1.0f) * 0.5f;
+            u = u * (sizex / (sizex - 0.5f));
+            v = v * (sizey / (sizey - 0.5f));
+            float prev_color[3] = {0, 0, 0};
+            if (pc->frame_number > 0) {                                  /* :72 */
+                /* the depth texture is fetched before the bounds test in the shader, but the
+                 * value is only consumed when the test passes (:74-76) */
+                if (u >= 0.0f && v >= 0.0f && u <= 1.0f && v <= 1.0f) {
+                    bilin_t b = bilin_setup(u, v, W, H);
+                    float t00 = prev_depth[(size_t)b.y0 * W + b.x0], t10 = prev_depth[(size_t)b.y0 * W + b.x1];
+                    float t01 = prev_depth[(size_t)b.y1 * W + b.x0], t11 = prev_depth[(size_t)b.y1 * W + b.x1];
+                    float true_prev_depth = bilin_mix(&b, t00, t10, t01, t11);
+                    float dissim = (true_prev_depth / pre_depth) - 1.0f;
+                    if (fabsf(dissim) <= 0.01f) {
+                        reprojected = 1;                                 /* :85 */
+                        const uint16_t* q00 = prev_illum + 4 * ((size_t)b.y0 * W + b.x0);
+                        const uint16_t* q10 = prev_illum + 4 * ((size_t)b.y0 * W + b.x1);
+                        const uint16_t* q01 = prev_illum + 4 * ((size_t)b.y1 * W + b.x0);
+                        const uint16_t* q11 = prev_illum + 4 * ((size_t)b.y1 * W + b.x1);
+                        for (int c = 0; c < 3; ++c)
+                            prev_color[c] = bilin_mix(&b, f16_to_f32(q00[c]), f16_to_f32(q10[c]),
+                                                      f16_to_f32(q01[c]), f16_to_f32(q11[c]));   /* :86 */
+                        pixel_spp += bilin_mix(&b, unorm8_to_f32(prev_spp[(size_t)b.y0 * W + b.x0]),
+                                               unorm8_to_f32(prev_spp[(size_t)b.y0 * W + b.x1]),
+                                               unorm8_to_f32(prev_spp[(size_t)b.y1 * W + b.x0]),
+                                               unorm8_to_f32(prev_spp[(size_t)b.y1 * W + b.x1]));  /* :87 */
+                    }
+                }
+            }
+            /* :91-97 */
+            if (reprojected) {
+                motion[2 * pix + 0] = f32_to_f16(u);
+                motion[2 * pix + 1] = f32_to_f16(v);
+            } else {
+                motion[2 * pix + 0] = f32_to_f16(-1.0f);
+                motion[2 * pix + 1] = f32_to_f16(-1.0f);
+            }
+            spp[pix] = f32_to_unorm8(pixel_spp);
+            /* :99-104 */
+            float c[3];
+            if (src_is_f16) {
+                const uint16_t* s = (const uint16_t*)src + 4 * pix;
+                for (int k = 0; k < 3; ++k) c[k] = f16_to_f32(s[k]);
+            } else {
+                const float* s = (const float*)src + 4 * pix;
+                for (int k = 0; k < 3; ++k) c[k] = s[k];
+            }
+            if (reprojected) {
+                float blend = gl_max(1.0f / (pixel_spp * 256.0f), 0.1f);
+                for (int k = 0; k < 3; ++k) c[k] = gl_mix(prev_color[k], c[k], blend);
+            }
+            for (int k = 0; k < 3; ++k) illum[4 * pix + k] = f32_to_f16(c[k]);
+            illum[4 * pix + 3] = f32_to_f16(1.0f);
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* BMFR common (shaders/bmfrGeneral.comp)                                               */
+/* ------------------------------------------------------------------------------------ */
+
+/* bmfrGeneral.comp:36 */
+static const float bmfr_pixel_offsets[16][2] = {
+    {.7f, .85f}, {.95f, .5f}, {.43f, .76f}, {.97f, .03f}, {.37f, .58f}, {.03f, .36f}, {.81f, .46f}, {0.f, .78f},
+    {.36f, -.08f}, {-.06f, 0.f}, {.95f, .1f}, {.85f, .61f}, {.06f, .1f}, {.43f, .16f}, {0.f, .5f}, {.73f, .38f}};
+
+/* bmfrGeneral.comp:93-97 */
+static inline int mirror(int x, int s)
+{
+    if (x < 0) return abs(x) - 1;
+    if (x >= s) return 2 * s - x - 1;
+    return x;
+}
+
+/* ivec2(vec2(BLOCK_WIDTH, BLOCK_HEIGHT) * pixelOffsets[frame % 16])  (bmfrPre.comp:16) */
+ORACLE_API void vkpbrt_oracle_bmfr_block_offset(int bw, int bh, uint32_t frame, int* ox, int* oy)
+{
+    *ox = (int)((float)bw * bmfr_pixel_offsets[frame % 16][0]);
+    *oy = (int)((float)bh * bmfr_pixel_offsets[frame % 16][1]);
+}
+
+/* bmfrGeneral.comp:103-113 */
+static inline float bmfr_random(uint32_t a)
+{
+    a = (a + 0x7ed55d16u) + (a << 12);
+    a = (a ^ 0xc761c23cu) ^ (a >> 19);
+    a = (a + 0x165667b1u) + (a << 5);
+    a = (a + 0xd3a2646cu) ^ (a << 9);
+    a = (a + 0xfd7046c5u) + (a << 3);
+    a = (a ^ 0xb55a4f09u) ^ (a >> 16);
+    return (float)a / (float)0xffffffffu;
+}
+ORACLE_API float vkpbrt_oracle_bmfr_random(uint32_t a) { return bmfr_random(a); }
+
+/* bmfrGeneral.comp:115-116 -- BLOCK_WIDTH is the fit kernel's local size (fitting_kernel),
+ * PIXEL_BLOCK = PIXEL_BLOCK_WIDTH^2; int arithmetic wraps. */
+static inline float bmfr_add_random(float value, int id, int sub, int feature, int frame, int T, int pixel_block)
+{
+    uint32_t pb2 = (uint32_t)pixel_block * (uint32_t)pixel_block;
+    uint32_t seed = (uint32_t)id + (uint32_t)sub * (uint32_t)T + (uint32_t)feature * pb2 + (uint32_t)frame * 13u * pb2;
+    return value + (1e-4f * 2.f) * (bmfr_random(seed) - .5f);
+}
+
+/* block reductions (bmfrGeneral.comp:79-91, bfr.comp:100-125): subgroupAdd over 32 lanes as the
+ * xor-butterfly tree, then invocation 0 folds reduction[1..n) onto its own subgroup's value. */
+static float block_sum(const float* v, int n)
+{
+    float total = 0.0f;
+    for (int sg = 0; sg * 32 < n; ++sg) {
+        float a[32];
+        for (int l = 0; l < 32; ++l) a[l] = v[sg * 32 + l];
+        for (int off = 16; off >= 1; off >>= 1)
+            for (int l = 0; l < off; ++l) a[l] = a[l] + a[l + off];
+        total = (sg == 0) ? a[0] : total + a[0];
+    }
+    return total;
+}
+
+/* shared feature computation of bmfrPre.comp:18-42 / bmfrPost.comp:15-38 for one b x b block.
+ * out: img index per thread (or -1 never), noisy rgb, normal xyz, pos xyz (POSITION_DEPTH). */
+typedef struct {
+    int img_x, img_y, abs_x, abs_y;
+    float noisy[3];
+    float n[3];
+    float pos[3];
+} bmfr_px_t;
+
+static void bmfr_block_features(int W, int H, int b, int ox, int oy, int bx, int by,
+                                const uint16_t* noisy_acc, const float* depth, const float* normal, bmfr_px_t* px)
+{
+    float zmin = 0, zmax = 0;
+    /* invocation order inside the workgroup: local index = ly*b + lx */
+    for (int ly = 0; ly < b; ++ly)
+        for (int lx = 0; lx < b; ++lx) {
+            bmfr_px_t* q = &px[ly * b + lx];
+            q->abs_x = bx * b + lx - ox;
+            q->abs_y = by * b + ly - oy;
+            q->img_x = mirror(q->abs_x, W);
+            q->img_y = mirror(q->abs_y, H);
+            size_t pix = (size_t)q->img_y * W + q->img_x;
+            for (int c = 0; c < 3; ++c) q->noisy[c] = f16_to_f32(noisy_acc[4 * pix + c]);
+            q->pos[2] = depth[pix];
+            float th = normal[2 * pix + 0], ph = normal[2 * pix + 1];
+            float sth, cth, sph, cph;
+            vk_sincos(th, &sth, &cth);
+            vk_sincos(ph, &sph, &cph);
+            q->n[0] = cph * sth;
+            q->n[1] = sph * sth;
+            q->n[2] = cth;
+        }
+    /* parallel_reduction_min / max: exact, order-independent */
+    zmin = zmax = px[0].pos[2];
+    for (int i = 1; i < b * b; ++i) {
+        zmin = gl_min(px[i].pos[2], zmin);
+        zmax = gl_max(px[i].pos[2], zmax);
+    }
+    for (int ly = 0; ly < b; ++ly)
+        for (int lx = 0; lx < b; ++lx) {
+            bmfr_px_t* q = &px[ly * b + lx];
+            float z = q->pos[2];
+            z -= zmin;
+            z /= zmax - zmin + 1e-6f;
+            q->pos[2] = z;
+            q->pos[0] = (float)lx / ((float)b - 1.0f);
+            q->pos[1] = (float)ly / ((float)b - 1.0f);
+        }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* bmfrPre.comp:5-97 (POSITION_DEPTH), SURVEY.md App. A.4                               */
+/* feature: r16f [13][Hp][Wp], Hp = (H/b+2)*b, Wp = (W/b+2)*b  (BMFR.cpp:12-13, 99-104) */
+/* ------------------------------------------------------------------------------------ */
+ORACLE_API void vkpbrt_oracle_bmfr_pre(int W, int H, int b, uint32_t frame, const uint16_t* noisy_acc,
+                                       const float* depth, const float* normal, uint16_t* feature)
+{
+    const int Wb = W / b + 2, Hb = H / b + 2, Wp = Wb * b, Hp = Hb * b;
+    int ox, oy;
+    vkpbrt_oracle_bmfr_block_offset(b, b, frame, &ox, &oy);
+#pragma omp parallel
+    {
+        bmfr_px_t* px = (bmfr_px_t*)malloc(sizeof(bmfr_px_t) * (size_t)b * b);
+#pragma omp for schedule(static) collapse(2)
+        for (int by = 0; by < Hb; ++by)
+            for (int bx = 0; bx < Wb; ++bx) {
+                bmfr_block_features(W, H, b, ox, oy, bx, by, noisy_acc, depth, normal, px);
+                for (int ly = 0; ly < b; ++ly)
+                    for (int lx = 0; lx < b; ++lx) {
+                        const bmfr_px_t* q = &px[ly * b + lx];
+                        float f[13] = {1.f, q->n[0], q->n[1], q->n[2], q->pos[0], q->pos[1], q->pos[2],
+                                       q->pos[0] * q->pos[0], q->pos[1] * q->pos[1], q->pos[2] * q->pos[2],
+                                       q->noisy[0], q->noisy[1], q->noisy[2]};
+                        size_t g = (size_t)(by * b + ly) * Wp + (size_t)(bx * b + lx);
+                        for (int i = 0; i < 13; ++i) feature[(size_t)i * Hp * Wp + g] = f32_to_f16(f[i]);
+                    }
+            }
+        free(px);
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* bmfrFit.comp:7-92, SURVEY.md App. A.5.  T = fitting_kernel, S = b*b / T.             */
+/* weights: r32f [30][Hb][Wb], layer = feature*3 + channel (bmfrFit.comp:88-90)         */
+/* ------------------------------------------------------------------------------------ */
+ORACLE_API void vkpbrt_oracle_bmfr_fit(int W, int H, int b, int T, uint32_t frame, const uint16_t* feature,
+                                       float* weights)
+{
+    const int Wb = W / b + 2, Hb = H / b + 2, Wp = Wb * b, Hp = Hb * b;
+    const int PB = b * b, S = PB / T;
+#pragma omp parallel
+    {
+        /* features[id][sub][col] */
+        float* A = (float*)malloc(sizeof(float) * (size_t)T * S * 13);
+        float* u = (float*)malloc(sizeof(float) * (size_t)T * S);
+        float* part = (float*)malloc(sizeof(float) * (size_t)T);
+#define FA(id, sub, col) A[((size_t)(id) * S + (sub)) * 13 + (col)]
+#define FU(id, sub) u[(size_t)(id) * S + (sub)]
+#pragma omp for schedule(static) collapse(2)
+        for (int by = 0; by < Hb; ++by)
+            for (int bx = 0; bx < Wb; ++bx) {
+                /* :16-23 load features and add noise */
+                for (int col = 0; col < 13; ++col)
+                    for (int sub = 0; sub < S; ++sub)
+                        for (int id = 0; id < T; ++id) {
+                            int index = id + sub * T;
+                            int pxx = index / b + bx * b, pyy = index % b + by * b;      /* x = index / b (!) */
+                            float tmp = f16_to_f32(feature[(size_t)col * Hp * Wp + (size_t)pyy * Wp + pxx]);
+                            if (col < 10) tmp = bmfr_add_random(tmp, id, sub, col, (int)frame, T, PB);
+                            FA(id, sub, col) = tmp;
+                        }
+                float u_length_squared = 0.0f;
+                /* :27-69 */
+                for (int col = 0; col < 10; ++col) {
+                    for (int id = 0; id < T; ++id) {
+                        float val2 = 0;
+                        for (int sub = 0; sub < S; ++sub) {
+                            int index = id + sub * T;
+                            FU(id, sub) = FA(id, sub, col);
+                            if (index > col) val2 += FU(id, sub) * FU(id, sub);
+                        }
+                        part[id] = val2;
+                    }
+                    float vec_len_squ = block_sum(part, T);
+                    for (int id = 0; id < T; ++id) {
+                        if (id < col) FU(id, 0) = 0;
+                        else if (id == col) {
+                            float u0 = FU(id, 0);
+                            float vec_len = sqrtf(vec_len_squ + u0 * u0);
+                            u0 -= vec_len;
+                            FU(id, 0) = u0;
+                            u_length_squared = vec_len_squ + u0 * u0;
+                            FA(id, 0, col) = vec_len;
+                        } else {
+                            FA(id, 0, col) = 0;
+                        }
+                    }
+                    for (int f = col + 1; f < 13; ++f) {
+                        for (int id = 0; id < T; ++id) {
+                            float v = 0;
+                            for (int sub = 0; sub < S; ++sub) {
+                                int index = id + sub * T;
+                                if (index >= col) v += FA(id, sub, f) * FU(id, sub);
+                            }
+                            part[id] = v;
+                        }
+                        float v = block_sum(part, T);
+                        for (int id = 0; id < T; ++id)
+                            for (int sub = 0; sub < S; ++sub) {
+                                int index = id + sub * T;
+                                if (index >= col) FA(id, sub, f) -= 2 * FU(id, sub) * v / u_length_squared;
+                            }
+                    }
+                }
+                /* :72-81 back substitution: invocation i holds row i in features[0][*] */
+                float ws[10][3];
+                for (int i = 9; i >= 0; --i) {
+                    for (int k = 0; k < 3; ++k) ws[i][k] = FA(i, 0, 10 + k);
+                    for (int x = i + 1; x < 10; ++x)
+                        for (int k = 0; k < 3; ++k) ws[i][k] -= ws[x][k] * FA(i, 0, x);
+                    for (int k = 0; k < 3; ++k) ws[i][k] /= FA(i, 0, i);
+                }
+                /* :84-90 */
+                for (int id = 0; id < 10; ++id)
+                    for (int k = 0; k < 3; ++k) {
+                        float w = ws[id][k];
+                        if (u_length_squared == 0) w = .2f;
+                        weights[(size_t)(id * 3 + k) * Hb * Wb + (size_t)by * Wb + bx] = w;
+                    }
+            }
+#undef FA
+#undef FU
+        free(A); free(u); free(part);
+    }
+}
+
+/* shared epilogue of bmfrPost.comp:105-123 and bfr.comp:293-308 */
+static inline void denoise_epilogue(int W, int H, uint32_t frame, size_t pix, float color[3], const uint16_t* motion,
+                                    const uint8_t* spp, const uint8_t* albedo, uint16_t* denoised /* [2][H][W][4] */,
+                                    uint8_t* final_bgra)
+{
+    float uvx = f16_to_f32(motion[2 * pix + 0]), uvy = f16_to_f32(motion[2 * pix + 1]);
+    int accept = uvx >= 0;
+    float pixel_spp = unorm8_to_f32(spp[pix]) * 256.0f;
+    float prev[3] = {0, 0, 0};
+    float blend = 1.0f;
+    if (frame > 0 && accept) {
+        const uint16_t* layer = denoised + (size_t)(frame & 1u) * H * W * 4;
+        bilin_t bl = bilin_setup(uvx, uvy, W, H);
+        const uint16_t* q00 = layer + 4 * ((size_t)bl.y0 * W + bl.x0);
+        const uint16_t* q10 = layer + 4 * ((size_t)bl.y0 * W + bl.x1);
+        const uint16_t* q01 = layer + 4 * ((size_t)bl.y1 * W + bl.x0);
+        const uint16_t* q11 = layer + 4 * ((size_t)bl.y1 * W + bl.x1);
+        for (int c = 0; c < 3; ++c)
+            prev[c] += bilin_mix(&bl, f16_to_f32(q00[c]), f16_to_f32(q10[c]), f16_to_f32(q01[c]), f16_to_f32(q11[c]));
+        blend = gl_max(1.f / pixel_spp, 0.1f);
+    }
+    uint16_t* out = denoised + (size_t)((frame & 1u) ^ 1u) * H * W * 4 + 4 * pix;
+    for (int c = 0; c < 3; ++c) {
+        color[c] = blend * color[c] + (1 - blend) * prev[c];
+        out[c] = f32_to_f16(color[c]);
+    }
+    out[3] = f32_to_f16(1.0f);
+    /* remodulate + tone map; BGRA8 memory order */
+    float tm[3];
+    for (int c = 0; c < 3; ++c) {
+        float a = unorm8_to_f32(albedo[4 * pix + c]) + 1e-6f;
+        tm[c] = gl_clamp(vk_pow(gl_max(0.0f, a * color[c]), .454545f), 0.0f, 1.0f);
+    }
+    final_bgra[4 * pix + 0] = f32_to_unorm8(tm[2]);
+    final_bgra[4 * pix + 1] = f32_to_unorm8(tm[1]);
+    final_bgra[4 * pix + 2] = f32_to_unorm8(tm[0]);
+    final_bgra[4 * pix + 3] = f32_to_unorm8(1.0f);
+}
+
+static inline float sane(float w) { return (isinf(w) || isnan(w)) ? 0.0f : w; }
+
+/* ------------------------------------------------------------------------------------ */
+/* bmfrPost.comp:5-124, SURVEY.md App. A.6                                              */
+/* ------------------------------------------------------------------------------------ */
+ORACLE_API void vkpbrt_oracle_bmfr_post(int W, int H, int b, uint32_t frame, const uint16_t* noisy_acc,
+                                        const float* depth, const float* normal, const uint8_t* albedo,
+                                        const uint16_t* motion, const uint8_t* spp, const float* weights,
+                                        uint16_t* denoised, uint8_t* final_bgra)
+{
+    const int Wb = W / b + 2, Hb = H / b + 2;
+    int ox, oy;
+    vkpbrt_oracle_bmfr_block_offset(b, b, frame, &ox, &oy);
+#pragma omp parallel
+    {
+        bmfr_px_t* px = (bmfr_px_t*)malloc(sizeof(bmfr_px_t) * (size_t)b * b);
+#pragma omp for schedule(static) collapse(2)
+        for (int by = 0; by < Hb; ++by)
+            for (int bx = 0; bx < Wb; ++bx) {
+                bmfr_block_features(W, H, b, ox, oy, bx, by, noisy_acc, depth, normal, px);
+                float w[10][3];
+                for (int f = 0; f < 10; ++f)
+                    for (int k = 0; k < 3; ++k)
+                        w[f][k] = sane(weights[(size_t)(f * 3 + k) * Hb * Wb + (size_t)by * Wb + bx]);
+                for (int i = 0; i < b * b; ++i) {
+                    const bmfr_px_t* q = &px[i];
+                    if (q->abs_x != q->img_x || q->abs_y != q->img_y) continue;      /* :74 */
+                    float f[10] = {1.f, q->n[0], q->n[1], q->n[2], q->pos[0], q->pos[1], q->pos[2],
+                                   q->pos[0] * q->pos[0], q->pos[1] * q->pos[1], q->pos[2] * q->pos[2]};
+                    float c[3] = {0, 0, 0};
+                    for (int k = 0; k < 10; ++k)
+                        for (int ch = 0; ch < 3; ++ch) c[ch] += w[k][ch] * f[k];       /* :91-101 */
+                    for (int ch = 0; ch < 3; ++ch) c[ch] = gl_clamp(c[ch], 0.0f, 10.0f);
+                    denoise_epilogue(W, H, frame, (size_t)q->img_y * W + q->img_x, c, motion, spp, albedo, denoised,
+                                     final_bgra);
+                }
+            }
+        free(px);
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* bfr.comp:202-309 + parallel_reduction_alpha :100-142, SURVEY.md App. A.7             */
+/* ------------------------------------------------------------------------------------ */
+/* bfr.comp:92 */
+static const int bfr_pixel_offsets[16][2] = {{-7, -11}, {-14, -8}, {-5, -12}, {-15, -1}, {-5, -9}, {-1, -4},
+                                             {-14, -7}, {0, -13},  {-5, -1},  {-1, 0},   {-15, -2}, {-14, -10},
+                                             {-1, -1},  {-6, -3},  {0, -8},   {-10, -4}};
+
+ORACLE_API void vkpbrt_oracle_bfr_block_offset(uint32_t frame, int* ox, int* oy)
+{
+    *ox = bfr_pixel_offsets[frame % 16][0];
+    *oy = bfr_pixel_offsets[frame % 16][1];
+}
+
+/* step-size factor of bfr.comp:134 without the l1-dependent alpha:
+ * exp(-K*t) * sqrt(1 - pow(BETA2, t)) / (1 - pow(BETA1, t)) */
+/* exp / pow of the step-size schedule: evaluated in double and rounded once so the value does
+ * not depend on libm's float variants or on compile-time folding */
+static inline float lr_exp(int t) { return (float)exp((double)(-.116f * (float)t)); }
+static inline float lr_pow(float b, int t) { return (float)pow((double)b, (double)t); }
+ORACLE_API float vkpbrt_oracle_bfr_lr(int t)
+{
+    return lr_exp(t) * sqrtf(1 - lr_pow(.7314f, t)) / (1 - lr_pow(.3f, t));
+}
+
+typedef struct {
+    int img_x, img_y, save;
+    float noisy[3];
+    float feat[7];
+    int l1;
+} bfr_px_t;
+
+ORACLE_API void vkpbrt_oracle_bfr(int W, int H, int b, uint32_t frame, const uint16_t* noisy_acc, const float* depth,
+                                  const float* normal, const uint8_t* albedo, const uint16_t* motion,
+                                  const uint8_t* spp, uint16_t* denoised, uint8_t* final_bgra)
+{
+    const int Wb = W / b + 2, Hb = H / b + 2, N = b * b;
+    const int ox = bfr_pixel_offsets[frame % 16][0], oy = bfr_pixel_offsets[frame % 16][1];
+#pragma omp parallel
+    {
+        bfr_px_t* px = (bfr_px_t*)malloc(sizeof(bfr_px_t) * (size_t)N);
+        float* part = (float*)malloc(sizeof(float) * (size_t)N);
+        float* resid = (float*)malloc(sizeof(float) * (size_t)N * 3);
+#pragma omp for schedule(dynamic, 4) collapse(2)
+        for (int by = 0; by < Hb; ++by)
+            for (int bx = 0; bx < Wb; ++bx) {
+                /* subgroup layout follows gl_LocalInvocationIndex = ly*b + lx */
+                float zmin = 0, zmax = 0;
+                for (int ly = 0; ly < b; ++ly)
+                    for (int lx = 0; lx < b; ++lx) {
+                        bfr_px_t* q = &px[ly * b + lx];
+                        int ax = bx * b + lx + ox, ay = by * b + ly + oy;                 /* :209 */
+                        q->img_x = mirror(ax, W);
+                        q->img_y = mirror(ay, H);
+                        q->save = (ax == q->img_x) && (ay == q->img_y);
+                        size_t pix = (size_t)q->img_y * W + q->img_x;
+                        for (int c = 0; c < 3; ++c) q->noisy[c] = f16_to_f32(noisy_acc[4 * pix + c]);
+                        float z = depth[pix];
+                        float th = normal[2 * pix + 0], ph = normal[2 * pix + 1];
+                        q->feat[0] = 1.f;
+                        q->feat[3] = z;
+                        float sth, cth, sph, cph;
+                        vk_sincos(th, &sth, &cth);
+                        vk_sincos(ph, &sph, &cph);
+                        q->feat[4] = cph * sth;
+                        q->feat[5] = sph * sth;
+                        q->feat[6] = cth;
+                        float pixel_spp = unorm8_to_f32(spp[pix]) * 256.0f;
+                        q->l1 = pixel_spp >= 10.0f;
+                        if (ly == 0 && lx == 0) zmin = zmax = z;
+                        zmin = gl_min(z, zmin);
+                        zmax = gl_max(z, zmax);
+                    }
+                for (int ly = 0; ly < b; ++ly)
+                    for (int lx = 0; lx < b; ++lx) {
+                        bfr_px_t* q = &px[ly * b + lx];
+                        float z = q->feat[3];
+                        z -= zmin;
+                        z /= zmax - zmin + 1e-8f;                                          /* :244, EPS 1e-8 */
+                        q->feat[3] = z * 2 - 1;
+                        q->feat[1] = (float)lx / ((float)b - 1.0f) - 0.5f;                  /* :247 */
+                        q->feat[2] = (float)ly / ((float)b - 1.0f) - 0.5f;
+                    }
+                float alpha[7][3], m[7][3], v[7][3];
+                memset(alpha, 0, sizeof alpha);
+                memset(m, 0, sizeof m);
+                memset(v, 0, sizeof v);
+                /* :260-278; GRADIENT_THRESH == 0 so the loop runs all 40 iterations unless the
+                 * gradient sum turns NaN (NaN >= 0 is false) */
+                float gradient_rest = 0.0f;
+                for (int it = 0; gradient_rest >= 0.0f && it < 40; ++it) {
+                    const int t = it + 1;
+                    float delta[7][3];
+                    int l1 = 0;
+                    for (int i = 0; i < N; ++i) l1 += px[i].l1;
+                    /* :261-268 residual (sign of it for pixels with spp >= SPP_THRESH) */
+                    for (int i = 0; i < N; ++i) {
+                        const bfr_px_t* q = &px[i];
+                        for (int c = 0; c < 3; ++c) {
+                            float pred = 0.0f;
+                            for (int jj = 0; jj < 7; ++jj) pred += q->feat[jj] * alpha[jj][c];
+                            float r = q->noisy[c] - pred;
+                            if (q->l1) r = (r > 0.0f) ? 1.0f : ((r < 0.0f) ? -1.0f : 0.0f);
+                            resid[3 * i + c] = r;
+                        }
+                    }
+                    /* :272-274, :100-125 per-feature gradient, block-reduced */
+                    for (int j = 0; j < 7; ++j)
+                        for (int c = 0; c < 3; ++c) {
+                            for (int i = 0; i < N; ++i) part[i] = px[i].feat[j] * resid[3 * i + c];
+                            delta[j][c] = block_sum(part, N);
+                        }
+                    /* :127-134 */
+                    float l1_ratio = (float)l1 * 1.0f / (float)N;
+                    float a = l1_ratio * 1.1f + (1 - l1_ratio) * .863f;
+                    float beta1 = l1_ratio * .45f + (1 - l1_ratio) * .3f;
+                    float beta2 = l1_ratio * .75f + (1 - l1_ratio) * .7314f;
+                    float lr = a * lr_exp(t) * sqrtf(1 - lr_pow(.7314f, t)) / (1 - lr_pow(.3f, t));
+                    float gsum[3] = {0, 0, 0};
+                    for (int j = 0; j < 7; ++j)
+                        for (int c = 0; c < 3; ++c) {
+                            float d = delta[j][c];
+                            m[j][c] = beta1 * m[j][c] + (1 - .3f) * d;
+                            v[j][c] = beta2 * v[j][c] + (1 - .7314f) * (fabsf(d) * fabsf(d));
+                            alpha[j][c] += lr * (m[j][c] / (sqrtf(v[j][c]) + 1e-8f));
+                            gsum[c] += fabsf(d);
+                        }
+                    gradient_rest = gsum[0] + gsum[1] + gsum[2];
+                }
+                /* :282-308 */
+                for (int i = 0; i < N; ++i) {
+                    const bfr_px_t* q = &px[i];
+                    if (!q->save) continue;
+                    float c[3] = {0, 0, 0};
+                    for (int f = 0; f < 7; ++f)
+                        for (int ch = 0; ch < 3; ++ch) c[ch] += q->feat[f] * alpha[f][ch];
+                    for (int ch = 0; ch < 3; ++ch) c[ch] = gl_clamp(c[ch], 0.0f, 10.0f);
+                    denoise_epilogue(W, H, frame, (size_t)q->img_y * W + q->img_x, c, motion, spp, albedo, denoised,
+                                     final_bgra);
+                }
+            }
+        free(px); free(part); free(resid);
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* bfrBlender.comp:22-68, SURVEY.md App. A.8.  den0/1/2 are the BINDINGS denoised0/1/2  */
+/* (b = 8, 16, 32 finals, BGRA8); the shader swaps them (:50-52).                       */
+/* ------------------------------------------------------------------------------------ */
+static inline float mix3(float a, float b, float c, float t, float mid, float max_dev)
+{
+    t /= max_dev;
+    t = gl_min(t, 1.0f);
+    float a_fac = gl_max(1.0f - (t / mid), 0.0f);
+    float b_fac = (t < mid) ? t / mid : 1 - (t - mid) / (1.0f - mid);
+    float c_fac = 1.0f - a_fac - b_fac;
+    return a_fac * a + b_fac * b + c_fac * c;
+}
+
+ORACLE_API void vkpbrt_oracle_bfr_blender(int W, int H, int radius, const uint16_t* average,
+                                          const uint16_t* average_squared, const uint8_t* denoised0,
+                                          const uint8_t* denoised1, const uint8_t* denoised2, uint8_t* final_bgra)
+{
+    const float third = (float)(1.0 / 3.0);
+#pragma omp parallel for schedule(static)
+    for (int gy = 0; gy < H; ++gy)
+        for (int gx = 0; gx < W; ++gx) {
+            float sq = 0, av = 0;
+            int count = 0;
+            for (int y = -radius; y <= radius; ++y)
+                for (int x = -radius; x <= radius; ++x) {
+                    int sx = gx + x, sy = gy + y;
+                    float a3[3] = {0, 0, 0};
+                    if (sx >= 0 && sy >= 0 && sx < W && sy < H)
+                        for (int c = 0; c < 3; ++c) a3[c] = f16_to_f32(average[4 * ((size_t)sy * W + sx) + c]);
+                    float cur = (a3[0] * third + a3[1] * third) + a3[2] * third;     /* dot(aver, vec3(1/3)) */
+                    ++count;
+                    float w = 1.0f / (float)count;
+                    sq = gl_mix(sq, cur * cur, w);
+                    av = gl_mix(av, cur, w);
+                }
+            size_t pix = (size_t)gy * W + gx;
+            float ave[3], avs[3];
+            for (int c = 0; c < 3; ++c) {
+                ave[c] = f16_to_f32(average[4 * pix + c]);
+                avs[c] = f16_to_f32(average_squared[4 * pix + c]);
+            }
+            av = gl_mix(av, (ave[0] * third + ave[1] * third) + ave[2] * third, .5f);
+            sq = gl_mix(sq, (avs[0] * third + avs[1] * third) + avs[2] * third, .5f);
+            float std_dev = sqrtf(sq - (av * av));
+            uint8_t out[4];
+            for (int c = 0; c < 3; ++c) {      /* c = logical r,g,b ; memory index 2-c */
+                float den2 = unorm8_to_f32(denoised0[4 * pix + (2 - c)]);
+                float den1 = unorm8_to_f32(denoised1[4 * pix + (2 - c)]);
+                float den0 = unorm8_to_f32(denoised2[4 * pix + (2 - c)]);
+                out[2 - c] = f32_to_unorm8(mix3(den0, den1, den2, std_dev, .5f, 1.0f));
+            }
+            out[3] = 255;
+            memcpy(final_bgra + 4 * pix, out, 4);
+        }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* taa.comp:48-104 + Taa.cpp:99-143 (final -> history raw copy), SURVEY.md App. A.9     */
+/* denoised: BGRA8 final of the denoiser (texelFetch); history: bytes of the previous   */
+/* TAA final (BGRA8) viewed as RGBA8; out_final: BGRA8.  The caller copies out_final    */
+/* to history afterwards (Taa.cpp:106).                                                 */
+/* ------------------------------------------------------------------------------------ */
+static inline void ycocg(const float* rgb, float* o)
+{
+    o[0] = (rgb[0] * 1.f + rgb[1] * 2.f) + rgb[2] * 1.f;
+    o[1] = (rgb[0] * 2.f + rgb[1] * 0.f) + rgb[2] * -2.f;
+    o[2] = (rgb[0] * -1.f + rgb[1] * 2.f) + rgb[2] * -1.f;
+}
+
+ORACLE_API void vkpbrt_oracle_taa(int W, int H, uint32_t frame, int fix_taa_swizzle, const uint16_t* motion,
+                                  const uint8_t* denoised_bgra, const uint8_t* history, uint8_t* out_final_bgra)
+{
+#pragma omp parallel for schedule(static)
+    for (int gy = 0; gy < H; ++gy)
+        for (int gx = 0; gx < W; ++gx) {
+            size_t pix = (size_t)gy * W + gx;
+            float cur[3];
+            for (int c = 0; c < 3; ++c) cur[c] = unorm8_to_f32(denoised_bgra[4 * pix + (2 - c)]);
+            float u = f16_to_f32(motion[2 * pix + 0]), v = f16_to_f32(motion[2 * pix + 1]);
+            float res[3];
+            if (frame == 0 || u < 0 || v < 0 || u > 1 || v > 1) {
+                for (int c = 0; c < 3; ++c) res[c] = cur[c];
+            } else {
+                /* vec3(1/0): glslang folds the integer division by zero to INT_MAX; the centre
+                 * texel is always in range so the value never survives. */
+                float mnb[3], mnc[3], mxb[3], mxc[3];
+                for (int c = 0; c < 3; ++c) {
+                    mnb[c] = mnc[c] = 2147483647.0f;
+                    mxb[c] = mxc[c] = -2147483647.0f;
+                }
+                for (int y = -1; y <= 1; ++y)
+                    for (int x = -1; x <= 1; ++x) {
+                        int sx = gx + x, sy = gy + y;
+                        if (sx >= 0 && sy >= 0 && sx < W && sy < H) {
+                            float s[3], yc[3];
+                            for (int c = 0; c < 3; ++c) s[c] = unorm8_to_f32(denoised_bgra[4 * ((size_t)sy * W + sx) + (2 - c)]);
+                            ycocg(s, yc);
+                            for (int c = 0; c < 3; ++c) {
+                                if (x == 0 || y == 0) {
+                                    mnc[c] = gl_min(mnc[c], yc[c]);
+                                    mxc[c] = gl_max(mxc[c], yc[c]);
+                                }
+                                mnb[c] = gl_min(mnb[c], yc[c]);
+                                mxb[c] = gl_max(mxb[c], yc[c]);
+                            }
+                        }
+                    }
+                bilin_t bl = bilin_setup(u, v, W, H);
+                float prev[3], pyc[3];
+                for (int c = 0; c < 3; ++c) {
+                    /* history bytes are B,G,R,A of the previous final; as RGBA8 the sampler's
+                     * .x reads byte 0 (=B).  With the fix, .x reads R (byte 2). */
+                    int byte = fix_taa_swizzle ? (2 - c) : c;
+                    prev[c] = bilin_mix(&bl, unorm8_to_f32(history[4 * ((size_t)bl.y0 * W + bl.x0) + byte]),
+                                        unorm8_to_f32(history[4 * ((size_t)bl.y0 * W + bl.x1) + byte]),
+                                        unorm8_to_f32(history[4 * ((size_t)bl.y1 * W + bl.x0) + byte]),
+                                        unorm8_to_f32(history[4 * ((size_t)bl.y1 * W + bl.x1) + byte]));
+                }
+                ycocg(prev, pyc);
+                int inside = 1;
+                for (int c = 0; c < 3; ++c) {
+                    float mn = (mnb[c] + mnc[c]) * .5f, mx = (mxb[c] + mxc[c]) * .5f;
+                    if (!(pyc[c] >= mn) || !(pyc[c] <= mx)) inside = 0;
+                }
+                for (int c = 0; c < 3; ++c) res[c] = inside ? (.4f * cur[c] + (1 - .4f) * prev[c]) : cur[c];
+            }
+            out_final_bgra[4 * pix + 0] = f32_to_unorm8(res[2]);
+            out_final_bgra[4 * pix + 1] = f32_to_unorm8(res[1]);
+            out_final_bgra[4 * pix + 2] = f32_to_unorm8(res[0]);
+            out_final_bgra[4 * pix + 3] = 255;
+        }
+}
+
+ORACLE_API int vkpbrt_oracle_num_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}

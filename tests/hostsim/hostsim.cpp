@@ -1,0 +1,152 @@
+// hostsim.cpp -- TEST-ONLY: builds the whole C ABI (api.cpp + the kernel sources) against the SIMT
+// emulator in hostsim.h.  See the header for what this is and is not.
+#include "hostsim.h"
+
+#include <sys/mman.h>
+
+asm(R"(
+.text
+.globl hostsim_switch
+.type hostsim_switch,@function
+hostsim_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+.size hostsim_switch, .-hostsim_switch
+)");
+
+namespace hostsim {
+
+static const size_t kStack = 96 * 1024;
+static const int kMaxThreads = 1024;
+
+struct ThreadState {
+    Block* blk = nullptr;
+    char* stacks = nullptr;
+    Fiber fibers[kMaxThreads];
+};
+static thread_local ThreadState tls;
+
+Block*& blk() { return tls.blk; }
+
+void yield(int new_state)
+{
+    Block* b = tls.blk;
+    Fiber* f = b->cur;
+    f->state = new_state;
+    hostsim_switch(&f->sp, b->sched_sp);
+}
+
+static void fiber_entry()
+{
+    Block* b = tls.blk;
+    (*b->body)();
+    b = tls.blk;
+    b->cur->state = DONE;
+    hostsim_switch(&b->cur->sp, b->sched_sp);
+    abort();   // never resumed
+}
+
+static void run_fiber(Block* b, Fiber* f)
+{
+    b->cur = f;
+    f->state = RUN;
+    hostsim_switch(&b->sched_sp, f->sp);
+}
+
+static void run_block(Block* b)
+{
+    const int n = b->n;
+    const int nwarps = (n + 31) / 32;
+    for (;;) {
+        bool any_live = false;
+        for (int w = 0; w < nwarps; ++w) {
+            const int lo = w * 32, hi = lo + 32 < n ? lo + 32 : n;
+            for (;;) {
+                for (int i = lo; i < hi; ++i)
+                    if (b->fibers[i].state == RUN) run_fiber(b, &b->fibers[i]);
+                bool waiting = false;
+                for (int i = lo; i < hi; ++i) waiting |= b->fibers[i].state == WARP_WAIT;
+                if (!waiting) break;
+                // every lane of this warp is now parked: resolve the exchange among the waiting lanes
+                for (int i = lo; i < hi; ++i) {
+                    Fiber& f = b->fibers[i];
+                    if (f.state != WARP_WAIT) continue;
+                    const int src = lo + f.xsrc;
+                    f.xout = (src < hi && b->fibers[src].state == WARP_WAIT) ? b->fibers[src].xin : f.xin;
+                }
+                for (int i = lo; i < hi; ++i)
+                    if (b->fibers[i].state == WARP_WAIT) b->fibers[i].state = RUN;
+            }
+        }
+        for (int i = 0; i < n; ++i)
+            if (b->fibers[i].state == BLOCK_WAIT) {
+                b->fibers[i].state = RUN;
+                any_live = true;
+            }
+        if (!any_live) break;
+    }
+}
+
+void launch(dim3 grid, dim3 block, const std::function<void()>& body)
+{
+    const int n = (int)(block.x * block.y * block.z);
+    if (n > kMaxThreads) { fprintf(stderr, "hostsim: block too large\n"); abort(); }
+    const long nblocks = (long)grid.x * grid.y * grid.z;
+#pragma omp parallel
+    {
+        ThreadState& ts = tls;
+        if (!ts.stacks) {
+            ts.stacks = (char*)mmap(nullptr, kStack * kMaxThreads, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+            if (ts.stacks == MAP_FAILED) { perror("hostsim mmap"); abort(); }
+        }
+        Block b;
+        b.grid = grid; b.block = block; b.fibers = ts.fibers; b.n = n; b.body = &body; b.cur = nullptr; b.sched_sp = nullptr;
+        ts.blk = &b;
+#pragma omp for schedule(dynamic, 1)
+        for (long bi = 0; bi < nblocks; ++bi) {
+            b.bid.x = (unsigned)(bi % grid.x);
+            b.bid.y = (unsigned)((bi / grid.x) % grid.y);
+            b.bid.z = (unsigned)(bi / ((long)grid.x * grid.y));
+            for (int i = 0; i < n; ++i) {
+                Fiber& f = ts.fibers[i];
+                f.tid.x = i % block.x;
+                f.tid.y = (i / block.x) % block.y;
+                f.tid.z = i / (block.x * block.y);
+                f.lane = i & 31;
+                f.state = RUN;
+                // initial frame: 6 callee-saved registers, then the entry address, then a pad slot so
+                // that rsp is 8 mod 16 when fiber_entry starts (as after a call)
+                uintptr_t top = ((uintptr_t)(ts.stacks + (size_t)(i + 1) * kStack)) & ~(uintptr_t)15;
+                uint64_t* sp = (uint64_t*)top;
+                *--sp = 0;                               // pad / fake return address
+                *--sp = (uint64_t)(uintptr_t)&fiber_entry;
+                for (int r = 0; r < 6; ++r) *--sp = 0;
+                f.sp = sp;
+            }
+            run_block(&b);
+        }
+        ts.blk = nullptr;
+    }
+}
+
+}  // namespace hostsim
+
+// ---- the library under test -------------------------------------------------------------------------
+#include "../../vulkanpbrt_b200/csrc/accumulate.cu"
+#include "../../vulkanpbrt_b200/csrc/bmfr.cu"
+#include "../../vulkanpbrt_b200/csrc/bfr.cu"
+#include "../../vulkanpbrt_b200/csrc/taa.cu"
+#include "../../vulkanpbrt_b200/csrc/api.cpp"

@@ -1,0 +1,186 @@
+"""ctypes binding of the C ABI in include/vkpbrt_b200.h (libvkpbrt_b200.so).
+
+This is the only way the Python host layer reaches the kernels.  There is no fallback: if the
+shared library is missing the import raises, and on a machine without an sm_100 GPU
+``vkpbrt_context_create`` fails with VKPBRT_ERR_NO_DEVICE.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libvkpbrt_b200.so"
+
+
+class VkpbrtError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"[vkpbrt error {code}] {message}")
+        self.code = code
+
+
+OK = 0
+ERR_INVALID_ARGUMENT = 1
+ERR_CUDA = 2
+ERR_UNSUPPORTED = 3
+ERR_WRONG_BUFFER_TYPE = 4
+ERR_NOT_COMPILED = 5
+ERR_MISSING_MATRICES = 6
+ERR_NO_DEVICE = 7
+
+FORMAT_R32_SFLOAT = 1
+FORMAT_R32G32_SFLOAT = 2
+FORMAT_R8G8B8A8_UNORM = 3
+FORMAT_B8G8R8A8_UNORM = 4
+FORMAT_R16G16_SFLOAT = 5
+FORMAT_R8_UNORM = 6
+FORMAT_R16G16B16A16_SFLOAT = 7
+FORMAT_R32G32B32A32_SFLOAT = 8
+FORMAT_R16_SFLOAT = 9
+
+GBUFFER_DEPTH, GBUFFER_NORMAL, GBUFFER_MATERIAL, GBUFFER_ALBEDO = range(4)
+ILLUMINATION_FINAL, ILLUMINATION_DEMODULATED, ILLUMINATION_DEMODULATED_FLOAT, ILLUMINATION_FINAL_DEMODULATED = range(4)
+(ACC_PREV_ILLU, ACC_PREV_ILLU_SQUARED, ACC_PREV_DEPTH, ACC_PREV_NORMAL, ACC_SPP, ACC_PREV_SPP, ACC_MOTION) = range(7)
+BMFR_IMAGE_DENOISED, BMFR_IMAGE_FEATURES, BMFR_IMAGE_WEIGHTS = range(3)
+
+
+class ImageInfo(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("format", C.c_uint32), ("width", C.c_uint32), ("height", C.c_uint32),
+                ("layers", C.c_uint32), ("row_pitch", C.c_uint64), ("layer_pitch", C.c_uint64),
+                ("size_bytes", C.c_uint64), ("owned", C.c_int32)]
+
+
+class PushConstants(C.Structure):
+    """RayTracingPushConstants (source/renderModules/PipelineStructs.hpp:6-13)."""
+    _fields_ = [("view_inverse", C.c_float * 16), ("proj_inverse", C.c_float * 16), ("prev_view", C.c_float * 16),
+                ("frame_number", C.c_uint32), ("sample_number", C.c_uint32)]
+
+
+class CameraMatrices(C.Structure):
+    """CameraMatrices (source/io/RenderIO.hpp:28-34)."""
+    _fields_ = [("view", C.c_float * 16), ("inv_view", C.c_float * 16), ("has_proj", C.c_int32),
+                ("proj", C.c_float * 16), ("inv_proj", C.c_float * 16)]
+
+
+H = C.c_void_p          # every opaque handle
+PH = C.POINTER(C.c_void_p)
+u32, u64, i32 = C.c_uint32, C.c_uint64, C.c_int
+
+# name -> argtypes (restype is int unless listed in _RESTYPES)
+_PROTOS = {
+    "vkpbrt_context_create": [i32, C.c_void_p, PH],
+    "vkpbrt_context_destroy": [H],
+    "vkpbrt_context_synchronize": [H],
+    "vkpbrt_context_stream": [H, PH],
+    "vkpbrt_context_launch_count": [H, C.POINTER(u64)],
+    "vkpbrt_image_create": [H, u32, u32, u32, u32, PH],
+    "vkpbrt_image_wrap": [H, u32, u32, u32, u32, C.c_void_p, PH],
+    "vkpbrt_image_set_data": [H, C.c_void_p],
+    "vkpbrt_image_compile": [H],
+    "vkpbrt_image_info_get": [H, C.POINTER(ImageInfo)],
+    "vkpbrt_image_upload": [H, C.c_void_p, u64],
+    "vkpbrt_image_download": [H, C.c_void_p, u64],
+    "vkpbrt_image_clear": [H],
+    "vkpbrt_image_retain": [H],
+    "vkpbrt_image_release": [H],
+    "vkpbrt_gbuffer_create": [H, u32, u32, PH],
+    "vkpbrt_gbuffer_create_from_images": [H, H, H, H, H, PH],
+    "vkpbrt_gbuffer_compile": [H],
+    "vkpbrt_gbuffer_image": [H, u32, PH],
+    "vkpbrt_gbuffer_destroy": [H],
+    "vkpbrt_illumination_buffer_create": [H, u32, u32, u32, PH],
+    "vkpbrt_illumination_buffer_compile": [H],
+    "vkpbrt_illumination_buffer_type": [H, C.POINTER(u32), C.POINTER(u32)],
+    "vkpbrt_illumination_buffer_image": [H, u32, PH],
+    "vkpbrt_illumination_buffer_destroy": [H],
+    "vkpbrt_accumulation_buffer_create": [H, u32, u32, PH],
+    "vkpbrt_accumulation_buffer_compile": [H],
+    "vkpbrt_accumulation_buffer_image": [H, u32, PH],
+    "vkpbrt_accumulation_buffer_copy_to_back_images": [H, H, H],
+    "vkpbrt_accumulation_buffer_destroy": [H],
+    "vkpbrt_accumulator_create": [H, H, H, i32, i32, i32, PH],
+    "vkpbrt_accumulator_compile_images": [H],
+    "vkpbrt_accumulator_accumulated_illumination": [H, PH],
+    "vkpbrt_accumulator_accumulation_buffer": [H, PH],
+    "vkpbrt_accumulator_set_camera_matrices": [H, i32, C.POINTER(CameraMatrices), C.POINTER(CameraMatrices)],
+    "vkpbrt_accumulator_record": [H],
+    "vkpbrt_accumulator_set_row_range": [H, i32, i32],
+    "vkpbrt_accumulator_destroy": [H],
+    "vkpbrt_bmfr_create": [H, u32, u32, u32, u32, H, H, H, u32, PH],
+    "vkpbrt_bmfr_set_debug_outputs": [H, i32],
+    "vkpbrt_bmfr_compile": [H],
+    "vkpbrt_bmfr_record": [H, C.POINTER(PushConstants)],
+    "vkpbrt_bmfr_set_block_row_range": [H, i32, i32],
+    "vkpbrt_bmfr_final_image": [H, PH],
+    "vkpbrt_bmfr_image_get": [H, u32, PH],
+    "vkpbrt_bmfr_destroy": [H],
+    "vkpbrt_bfr_create": [H, u32, u32, u32, u32, H, H, H, PH],
+    "vkpbrt_bfr_compile": [H],
+    "vkpbrt_bfr_record": [H, C.POINTER(PushConstants)],
+    "vkpbrt_bfr_final_image": [H, PH],
+    "vkpbrt_bfr_denoised_image": [H, PH],
+    "vkpbrt_bfr_destroy": [H],
+    "vkpbrt_bfr_blender_create": [H, u32, u32, H, H, H, H, H, u32, u32, u32, PH],
+    "vkpbrt_bfr_blender_compile": [H],
+    "vkpbrt_bfr_blender_record": [H],
+    "vkpbrt_bfr_blender_final_image": [H, PH],
+    "vkpbrt_bfr_blender_destroy": [H],
+    "vkpbrt_taa_create": [H, u32, u32, u32, u32, H, H, H, PH],
+    "vkpbrt_taa_set_fix_swizzle": [H, i32],
+    "vkpbrt_taa_compile": [H],
+    "vkpbrt_taa_record": [H, C.POINTER(PushConstants)],
+    "vkpbrt_taa_set_row_range": [H, i32, i32],
+    "vkpbrt_taa_final_image": [H, PH],
+    "vkpbrt_taa_history_image": [H, PH],
+    "vkpbrt_taa_destroy": [H],
+    "vkpbrt_import_external_memory_fd": [H, i32, u64, u64, u64, PH, PH],
+    "vkpbrt_external_memory_destroy": [H],
+    "vkpbrt_import_external_semaphore_fd": [H, i32, i32, PH],
+    "vkpbrt_external_semaphore_wait": [H, u64],
+    "vkpbrt_external_semaphore_signal": [H, u64],
+    "vkpbrt_external_semaphore_destroy": [H],
+}
+_RESTYPES = {"vkpbrt_last_error": C.c_char_p, "vkpbrt_version": C.c_char_p, "vkpbrt_format_texel_size": u32}
+EXPORTS = sorted(list(_PROTOS) + list(_RESTYPES))
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Loads libvkpbrt_b200.so (built in-tree by vulkanpbrt_b200.build).  Raises if it is missing."""
+    global _lib
+    if _lib is None:
+        if not _LIB_PATH.exists():
+            raise ImportError(f"{_LIB_PATH} is missing: run `python -m vulkanpbrt_b200.build` "
+                              "(the package has no fallback path without its CUDA library)")
+        l = C.CDLL(str(_LIB_PATH))
+        for name, args in _PROTOS.items():
+            fn = getattr(l, name)
+            fn.argtypes = args
+            fn.restype = C.c_int
+        l.vkpbrt_last_error.restype = C.c_char_p
+        l.vkpbrt_last_error.argtypes = []
+        l.vkpbrt_version.restype = C.c_char_p
+        l.vkpbrt_version.argtypes = []
+        l.vkpbrt_format_texel_size.restype = u32
+        l.vkpbrt_format_texel_size.argtypes = [u32]
+        _lib = l
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != OK:
+        msg = lib().vkpbrt_last_error()
+        raise VkpbrtError(rc, msg.decode() if msg else "")
+
+
+def call(name: str, *args) -> None:
+    check(getattr(lib(), name)(*args))
+
+
+def mat16(values) -> "C.Array":
+    arr = (C.c_float * 16)()
+    flat = [float(v) for v in values]
+    assert len(flat) == 16
+    for i, v in enumerate(flat):
+        arr[i] = v
+    return arr

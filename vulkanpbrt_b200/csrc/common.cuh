@@ -1,0 +1,219 @@
+// common.cuh -- device helpers shared by the sm_100a denoising kernels.
+//
+// Storage conventions (DESIGN.md "Data layout in HBM"): every plane is pitch-linear and tightly
+// packed in the reference's own texel formats, so fusing stages does not move any rounding point
+// (SURVEY.md section 0 item 5 / App. C):
+//   fp32 -> fp16 stores   round-to-nearest-even (cvt.rn.f16.f32)
+//   fp32 -> unorm8 stores NaN -> 0, clamp, (uint8)(c*255 + 0.5)
+//   texture()             bilinear, REPEAT, exact fp32 weights (App. A.1)
+// The *_rn helpers below use __fmul_rn/__fadd_rn so the compiler cannot contract them into
+// FMAs: they feed integer decisions (validity masks, unorm8 codes) that must be bit-exact.
+#pragma once
+
+#ifdef VKPBRT_HOSTSIM
+#include "hostsim.h"   // tests/hostsim: CPU emulator used by the GPU-less debug tests only
+#else
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#endif
+#include <stdint.h>
+
+#ifndef VKPBRT_HOSTSIM
+#define VK_DEVICE __device__ __forceinline__
+#define VKPBRT_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#else
+#define VK_DEVICE inline
+#endif
+
+namespace vkpbrt {
+
+// GLSL min/max/clamp: NaN behaviour follows the ternary definitions of the GLSL spec, which is
+// what the reference shaders get (fminf/fmaxf would drop NaNs).
+VK_DEVICE float gl_min(float x, float y) { return (y < x) ? y : x; }
+VK_DEVICE float gl_max(float x, float y) { return (x < y) ? y : x; }
+VK_DEVICE float gl_clamp(float x, float lo, float hi) { return gl_min(gl_max(x, lo), hi); }
+
+VK_DEVICE float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+VK_DEVICE float add_rn(float a, float b) { return __fadd_rn(a, b); }
+VK_DEVICE float sub_rn(float a, float b) { return __fadd_rn(a, -b); }
+
+VK_DEVICE float div_rn(float a, float b) { return __fdiv_rn(a, b); }
+VK_DEVICE float sqrt_rn(float a) { return __fsqrt_rn(a); }
+
+// ---- deterministic sin / cos / pow ------------------------------------------------------------
+// GLSL leaves their precision to the implementation; the oracle (oracle/vkpbrt_oracle.c: vk_sincos,
+// vk_pow) fixes them as plain-IEEE Cephes-style algorithms and these are the same operations in the
+// same order, so normals, features and tone-mapped texels are bit-identical on CPU and GPU.
+VK_DEVICE void vk_sincos(float x, float& sn, float& cs)
+{
+    const float ax = fabsf(x);
+    if (!(ax < 8192.0f)) { sn = cs = div_rn(sub_rn(x, x), sub_rn(x, x)); return; }
+    uint32_t j = (uint32_t)mul_rn(ax, 1.27323954473516f);
+    float y = (float)j;
+    if (j & 1u) { j += 1u; y = add_rn(y, 1.0f); }
+    const float r = sub_rn(sub_rn(sub_rn(ax, mul_rn(y, 0.78515625f)), mul_rn(y, 2.4187564849853515625e-4f)), mul_rn(y, 3.77489497744594108e-8f));
+    const float z = mul_rn(r, r);
+    const float ps = add_rn(mul_rn(mul_rn(add_rn(mul_rn(add_rn(mul_rn(-1.9515295891e-4f, z), 8.3321608736e-3f), z), -1.6666654611e-1f), z), r), r);
+    float pc = mul_rn(mul_rn(add_rn(mul_rn(add_rn(mul_rn(2.443315711809948e-5f, z), -1.388731625493765e-3f), z), 4.166664568298827e-2f), z), z);
+    pc = sub_rn(pc, mul_rn(0.5f, z));
+    pc = add_rn(pc, 1.0f);
+    const uint32_t q = (j >> 1) & 3u;
+    const float s = (q == 0u) ? ps : ((q == 1u) ? pc : ((q == 2u) ? -ps : -pc));
+    const float c = (q == 0u) ? pc : ((q == 1u) ? -ps : ((q == 2u) ? -pc : ps));
+    sn = (x < 0.0f) ? -s : s;
+    cs = c;
+}
+
+VK_DEVICE float vk_pow(float x, float y)
+{
+    if (!(x > 0.0f)) return (x == 0.0f) ? 0.0f : div_rn(sub_rn(x, x), sub_rn(x, x));
+    if (x > 3.0e38f) return x;
+    int e = 0;
+    if (x < 1.17549435e-38f) { x = mul_rn(x, 8388608.0f); e = -23; }
+    const uint32_t bits = __float_as_uint(x);
+    e += (int)((bits >> 23) & 255u) - 127;
+    float m = __uint_as_float((bits & 0x007fffffu) | 0x3f800000u);
+    if (m > 1.41421356f) { m = mul_rn(m, 0.5f); e += 1; }
+    const float z = div_rn(sub_rn(m, 1.0f), add_rn(m, 1.0f));
+    const float z2 = mul_rn(z, z);
+    const float p = mul_rn(add_rn(mul_rn(add_rn(mul_rn(add_rn(mul_rn(add_rn(mul_rn(0.0909090909f, z2), 0.1111111111f), z2), 0.1428571429f), z2), 0.2f), z2), 0.3333333333f), z2);
+    const float lnm = mul_rn(2.0f, add_rn(z, mul_rn(z, p)));
+    const float lg = add_rn((float)e, mul_rn(lnm, 1.44269504089f));
+    const float t = mul_rn(y, lg);
+    if (t > 127.99f) return __uint_as_float(0x7f800000u);
+    if (t < -150.0f) return 0.0f;
+    const float n = rintf(t);
+    const float f = sub_rn(t, n);
+    const float px = add_rn(mul_rn(add_rn(mul_rn(add_rn(mul_rn(add_rn(mul_rn(add_rn(mul_rn(1.535336188319500e-4f, f), 1.339887440266574e-3f), f),
+                                                                    9.618437357674640e-3f), f), 5.550332471162809e-2f), f), 2.402264791363012e-1f), f), 6.931472028550421e-1f);
+    const float r = add_rn(1.0f, mul_rn(f, px));
+    const int ni = (int)n, n1 = ni / 2, n2 = ni - n1;
+    return mul_rn(mul_rn(r, __uint_as_float((uint32_t)(n1 + 127) << 23)), __uint_as_float((uint32_t)(n2 + 127) << 23));
+}
+
+// mix(x, y, a) = x*(1-a) + y*a, no contraction
+VK_DEVICE float gl_mix_exact(float x, float y, float a) { return add_rn(mul_rn(x, sub_rn(1.0f, a)), mul_rn(y, a)); }
+
+VK_DEVICE uint16_t f32_to_f16_bits(float f) { return __half_as_ushort(__float2half_rn(f)); }
+VK_DEVICE float f16_bits_to_f32(uint16_t h) { return __half2float(__ushort_as_half(h)); }
+
+VK_DEVICE uint8_t f32_to_unorm8(float c)
+{
+    if (!(c == c)) return 0;
+    c = c < 0.0f ? 0.0f : c;
+    c = c > 1.0f ? 1.0f : c;
+    return (uint8_t)add_rn(mul_rn(c, 255.0f), 0.5f);
+}
+VK_DEVICE float unorm8_to_f32(uint32_t c) { return __fdiv_rn((float)c, 255.0f); }
+
+// bmfrGeneral.comp:93-97 / bfr.comp:192-196
+VK_DEVICE int mirror(int x, int s)
+{
+    if (x < 0) return -x - 1;
+    if (x >= s) return 2 * s - x - 1;
+    return x;
+}
+
+// ---- bilinear sampler, REPEAT addressing, normalised coordinates ----
+struct Bilin {
+    int x0, x1, y0, y1;
+    float w00, w10, w01, w11;
+};
+
+VK_DEVICE int wrapi(int i, int n)
+{
+    i %= n;
+    return i < 0 ? i + n : i;
+}
+
+VK_DEVICE Bilin bilin_setup(float u, float v, int W, int H)
+{
+    Bilin b;
+    float x = sub_rn(mul_rn(u, (float)W), 0.5f);
+    float y = sub_rn(mul_rn(v, (float)H), 0.5f);
+    float fx0 = floorf(x), fy0 = floorf(y);
+    float a = sub_rn(x, fx0), bt = sub_rn(y, fy0);
+    int ix = (int)fx0, iy = (int)fy0;
+    // callers guarantee uv in [0,1] so ix in [-1, W-1]: cheap wrap
+    b.x0 = ix < 0 ? ix + W : ix;
+    b.x1 = ix + 1 >= W ? ix + 1 - W : ix + 1;
+    b.y0 = iy < 0 ? iy + H : iy;
+    b.y1 = iy + 1 >= H ? iy + 1 - H : iy + 1;
+    float oma = sub_rn(1.0f, a), omb = sub_rn(1.0f, bt);
+    b.w00 = mul_rn(oma, omb);
+    b.w10 = mul_rn(a, omb);
+    b.w01 = mul_rn(oma, bt);
+    b.w11 = mul_rn(a, bt);
+    return b;
+}
+
+VK_DEVICE float bilin_mix(const Bilin& b, float t00, float t10, float t01, float t11)
+{
+    return add_rn(add_rn(add_rn(mul_rn(b.w00, t00), mul_rn(b.w10, t10)), mul_rn(b.w01, t01)), mul_rn(b.w11, t11));
+}
+
+// rgba16f texel = 8 bytes
+struct Half4 {
+    uint16_t x, y, z, w;
+};
+
+VK_DEVICE void load_rgb16f(const uint2* __restrict__ plane, size_t idx, float& r, float& g, float& b)
+{
+    uint2 t = __ldg(plane + idx);
+    r = f16_bits_to_f32((uint16_t)(t.x & 0xffffu));
+    g = f16_bits_to_f32((uint16_t)(t.x >> 16));
+    b = f16_bits_to_f32((uint16_t)(t.y & 0xffffu));
+}
+
+VK_DEVICE uint2 pack_rgba16f(float r, float g, float b, float a)
+{
+    uint2 t;
+    t.x = (uint32_t)f32_to_f16_bits(r) | ((uint32_t)f32_to_f16_bits(g) << 16);
+    t.y = (uint32_t)f32_to_f16_bits(b) | ((uint32_t)f32_to_f16_bits(a) << 16);
+    return t;
+}
+
+// bilinear fetch of the rgb channels of an rgba16f plane
+VK_DEVICE void sample_rgb16f(const uint2* __restrict__ plane, const Bilin& bl, int W, float& r, float& g, float& b)
+{
+    float r00, g00, b00, r10, g10, b10, r01, g01, b01, r11, g11, b11;
+    load_rgb16f(plane, (size_t)bl.y0 * W + bl.x0, r00, g00, b00);
+    load_rgb16f(plane, (size_t)bl.y0 * W + bl.x1, r10, g10, b10);
+    load_rgb16f(plane, (size_t)bl.y1 * W + bl.x0, r01, g01, b01);
+    load_rgb16f(plane, (size_t)bl.y1 * W + bl.x1, r11, g11, b11);
+    r = bilin_mix(bl, r00, r10, r01, r11);
+    g = bilin_mix(bl, g00, g10, g01, g11);
+    b = bilin_mix(bl, b00, b10, b01, b11);
+}
+
+// ---- epilogue shared by bmfrPost.comp:105-123 and bfr.comp:293-308 ----
+// color: clamped regression output.  Writes the rgba16f history texel and the BGRA8 tone-mapped
+// texel for image pixel `pix`.
+VK_DEVICE void denoise_epilogue(float cr, float cg, float cb, uint32_t frame, size_t pix, int W, int H, uint32_t motion_bits,
+                                uint32_t spp_code, uchar4 alb, const uint2* __restrict__ denoised_prev,
+                                uint2* __restrict__ denoised_next, uint32_t* __restrict__ final_bgra)
+{
+    float uvx = f16_bits_to_f32((uint16_t)(motion_bits & 0xffffu));
+    float uvy = f16_bits_to_f32((uint16_t)(motion_bits >> 16));
+    bool accept = uvx >= 0.0f;
+    float pixel_spp = mul_rn(unorm8_to_f32(spp_code), 256.0f);
+    float pr = 0.0f, pg = 0.0f, pb = 0.0f, blend = 1.0f;
+    if (frame > 0 && accept) {
+        Bilin bl = bilin_setup(uvx, uvy, W, H);
+        sample_rgb16f(denoised_prev, bl, W, pr, pg, pb);
+        blend = gl_max(__fdiv_rn(1.0f, pixel_spp), 0.1f);
+    }
+    float omb = sub_rn(1.0f, blend);
+    cr = add_rn(mul_rn(blend, cr), mul_rn(omb, pr));
+    cg = add_rn(mul_rn(blend, cg), mul_rn(omb, pg));
+    cb = add_rn(mul_rn(blend, cb), mul_rn(omb, pb));
+    denoised_next[pix] = pack_rgba16f(cr, cg, cb, 1.0f);
+    float ar = add_rn(unorm8_to_f32(alb.x), 1e-6f), ag = add_rn(unorm8_to_f32(alb.y), 1e-6f), ab = add_rn(unorm8_to_f32(alb.z), 1e-6f);
+    float tr = gl_clamp(vk_pow(gl_max(0.0f, mul_rn(ar, cr)), .454545f), 0.0f, 1.0f);
+    float tg = gl_clamp(vk_pow(gl_max(0.0f, mul_rn(ag, cg)), .454545f), 0.0f, 1.0f);
+    float tb = gl_clamp(vk_pow(gl_max(0.0f, mul_rn(ab, cb)), .454545f), 0.0f, 1.0f);
+    // B8G8R8A8_UNORM memory order
+    final_bgra[pix] = (uint32_t)f32_to_unorm8(tb) | ((uint32_t)f32_to_unorm8(tg) << 8) | ((uint32_t)f32_to_unorm8(tr) << 16) | 0xff000000u;
+}
+
+}  // namespace vkpbrt

@@ -1,0 +1,106 @@
+// kernels.h -- parameter blocks and launchers of the sm_100a kernels (host-visible part).
+#pragma once
+#ifdef VKPBRT_HOSTSIM
+#include "hostsim.h"
+#else
+#include <cuda_runtime.h>
+#endif
+#include <stdint.h>
+
+namespace vkpbrt {
+
+// ---- k_accumulate : shaders/accumulator.comp:33-104 -------------------------------------
+struct AccumulateParams {
+    int W, H;
+    int row_begin, row_end;   // image rows processed (band sharding); full frame = [0, H)
+    int separate_matrices;
+    int src_is_f16;           // srcImage rgba16f (IlluminationBufferDemodulated) or rgba32f (...Float)
+    uint32_t frame;
+    // uniform matrices, column-major.  m_dir: "view" push constant (inverse projection in separate
+    // mode, unused otherwise); inv_view; m_prev: proj*prevView (separate) or prevView (combined VP)
+    float m_dir[16];
+    float inv_view[16];
+    float m_prev[16];
+    float prev_origin[4];
+    const void* src;              // raw 1-spp illumination
+    const float* depth;           // r32f
+    const float* prev_depth;      // r32f   (bilinear)
+    const uint2* prev_illum;      // rgba16f (bilinear)
+    const uint8_t* prev_spp;      // r8     (bilinear)
+    uint32_t* motion;             // rg16f  (packed half2)
+    uint8_t* spp;                 // r8
+    uint2* illum;                 // rgba16f
+    float* depth_history;         // r32f: next frame's prev_depth (fused copy_to_back), may be null
+};
+cudaError_t launch_accumulate(const AccumulateParams& p, cudaStream_t stream);
+
+// ---- k_bmfr_block : bmfrPre.comp + bmfrFit.comp + bmfrPost.comp, one launch ---------------
+struct BmfrParams {
+    int W, H;
+    int block;                    // work_width == work_height: 8, 16 or 32
+    int fitting_kernel;           // threads per block row-group: 64 (b=8) or 256
+    int blocks_x, blocks_y;       // W/b+2, H/b+2
+    int block_row_begin, block_row_end;  // block rows processed (band sharding)
+    uint32_t frame;
+    const float* depth;
+    const float2* normal;
+    const uchar4* albedo;
+    const uint32_t* motion;
+    const uint8_t* spp;
+    const uint2* noisy;           // accumulated illumination rgba16f
+    const uint2* denoised_prev;   // layer (frame & 1)
+    uint2* denoised_next;         // layer (frame & 1) ^ 1
+    uint32_t* final_bgra;
+    uint16_t* dbg_features;       // optional r16f [13][Hp][Wp]
+    float* dbg_weights;           // optional r32f [30][blocks_y][blocks_x]
+};
+cudaError_t launch_bmfr(const BmfrParams& p, cudaStream_t stream);
+
+// ---- k_bfr_block : shaders/bfr.comp ------------------------------------------------------
+struct BfrParams {
+    int W, H;
+    int block;                    // 8, 16, 32
+    int blocks_x, blocks_y;
+    uint32_t frame;
+    // bfr.comp:134 step size factors for t = 1..40, evaluated once on the host:
+    float lr_exp[40];             // exp(-K * t)
+    float lr_sqrt[40];            // sqrt(1 - pow(BETA2, t))
+    float lr_den[40];             // 1 - pow(BETA1, t)
+    const float* depth;
+    const float2* normal;
+    const uchar4* albedo;
+    const uint32_t* motion;
+    const uint8_t* spp;
+    const uint2* noisy;
+    const uint2* denoised_prev;
+    uint2* denoised_next;
+    uint32_t* final_bgra;
+};
+cudaError_t launch_bfr(const BfrParams& p, cudaStream_t stream);
+
+// ---- k_bfr_blend : shaders/bfrBlender.comp -----------------------------------------------
+struct BlendParams {
+    int W, H, radius;
+    const uint2* average;         // rgba16f
+    const uint2* average_squared; // rgba16f
+    const uint32_t* denoised0;    // BGRA8 (b = 8)
+    const uint32_t* denoised1;    // BGRA8 (b = 16)
+    const uint32_t* denoised2;    // BGRA8 (b = 32)
+    uint32_t* final_bgra;
+};
+cudaError_t launch_bfr_blend(const BlendParams& p, cudaStream_t stream);
+
+// ---- k_taa : shaders/taa.comp + Taa.cpp:106 hand-over -------------------------------------
+struct TaaParams {
+    int W, H;
+    int row_begin, row_end;
+    uint32_t frame;
+    int fix_swizzle;
+    const uint32_t* motion;
+    const uint32_t* denoised;     // BGRA8 final of the denoiser
+    const uint32_t* history;      // previous TAA final, bytes as written (BGRA8) viewed as RGBA8
+    uint32_t* final_bgra;         // this frame's TAA final == next frame's history (ping-pong)
+};
+cudaError_t launch_taa(const TaaParams& p, cudaStream_t stream);
+
+}  // namespace vkpbrt
