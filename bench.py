@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py -- BMFR denoised MPix/s and ms/frame on the synthetic G-buffer sequence (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+
+A "step" is one frame through the hot path: accumulate -> fused BMFR (pre + fit + post) [-> TAA].
+N = 1 runs BASELINE.json configs[1]: BMFR 1920x1080, 1 spp, camera motion.  For N > 1 (torchrun, one
+rank per GPU) the frame is partitioned into horizontal block bands, one 1920x1080 band per GPU
+(weak scaling: the frame is 1920 x 1080*N), with the history halo rows exchanged over NCCL/NVLink
+every frame (vulkanpbrt_b200/multigpu.py).
+
+value   whole-job MPix/s with the input sequence already resident in HBM (each frame's planes are
+        distinct buffers, read once: inputs larger than L2)
+e2e     the same metric through the public API with HOST buffers: per frame the G-buffer + raw
+        illumination are copied from pinned host memory and the BGRA8 result is read back, inside the
+        timed region (2-deep copy/compute overlap)
+roofline  the dominant kernel's algorithmic bytes / its CUDA-event time, against MEASURED_PEAKS.json
+cpu_baseline  the oracle (CPU restatement of the reference shaders) on the host cores, bounded sample
+--impl reference  times the reference's CPU path (oracle/_ref when built, else the oracle port) alone
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (W, H, taa, description)
+    "bmfr_1080p": (1920, 1080, False, "BMFR 1920x1080 1-spp synthetic sequence with camera motion (BASELINE configs[1])"),
+    "bmfr_taa_4k": (3840, 2160, True, "accumulator + BMFR + TAA 3840x2160 1-spp (BASELINE configs[3])"),
+    "bmfr_8k": (7680, 4320, False, "BMFR 7680x4320 (BASELINE configs[4])"),
+    "bmfr_256": (256, 256, False, "BMFR 256x256 (BASELINE configs[0], plumbing)"),
+}
+# algorithmic (compulsory) HBM bytes per image pixel, reference storage formats (DESIGN.md / SURVEY.md 8d)
+BYTES_ACCUMULATE = 33 + 17     # reads depth 4 + raw 16 + prev_depth 4 + prev_illum 8 + prev_spp 1; writes motion 4 + spp 1 + illum 8 + depth history 4
+BYTES_BMFR = 37 + 12           # reads depth 4 + normal 8 + noisyAcc 8 + albedo 4 + motion 4 + spp 1 + history 8; writes denoised 8 + final 4
+BYTES_TAA = 12 + 4             # reads denoised 4 + motion 4 + history 4; writes final 4
+BYTES_CHAIN_FUSED = 78         # ideal fully fused chain, the figure BASELINE.md quotes
+INPUT_BYTES = 4 + 8 + 4 + 16   # depth + normal + albedo + raw rgba32f per pixel (host -> device per frame)
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """samples SM clock / throttle reasons during the timed region (nvml, falling back to nvidia-smi)"""
+
+    def __init__(self, device):
+        super().__init__(daemon=True)
+        self.device, self.samples, self.reasons, self.max_mhz, self._stop = device, [], set(), None, threading.Event()
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.device)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown",
+                     0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown"}
+            while not self._stop.is_set():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, n in names.items():
+                    if r & bit:
+                        self.reasons.add(n)
+                time.sleep(0.02)
+        except Exception as e:  # pragma: no cover
+            self.reasons.add(f"sampler_error:{type(e).__name__}")
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def render_sequence(W, H, n, rows=None, pinned=True, first=0):
+    """n frames of the synthetic sequence in (pinned) host memory: dict of torch tensors + cameras"""
+    import torch
+
+    from vulkanpbrt_b200 import synth
+    mk = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=pinned)
+    seq = {"depth": mk((n, H, W), torch.float32), "normal": mk((n, H, W, 2), torch.float32),
+           "albedo": mk((n, H, W, 4), torch.uint8), "illum": mk((n, H, W, 4), torch.float32), "cams": []}
+    material = np.zeros((H, W, 4), np.uint8)
+    for i in range(n):
+        fr = synth.Frame(first + i, seq["depth"][i].numpy(), seq["normal"][i].numpy(), seq["albedo"][i].numpy(), material,
+                         seq["illum"][i].numpy(), None)
+        synth.render_frame(W, H, first + i, rows=rows, out=fr)
+        seq["cams"].append(fr.camera)
+    return seq
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's CPU path
+# ---------------------------------------------------------------------------------------------------
+def cpu_chain(W, H, taa):
+    from oracle import oracle as O
+    return O, O.OracleChain(W, H, "bmfr", 32, use_taa=taa)
+
+
+def run_cpu(W, H, taa, frames, budget_s=None, warmup=0):
+    """times the oracle chain on `frames` synthetic frames (stops early once budget_s is spent)"""
+    from vulkanpbrt_b200 import synth
+    O, chain = cpu_chain(W, H, taa)
+    fs = [synth.render_frame(W, H, f) for f in range(min(frames + warmup, 8))]
+    for f in range(warmup):
+        chain.run_frame(f, fs[f % len(fs)])
+    t0 = time.perf_counter()
+    done = 0
+    for f in range(warmup, warmup + frames):
+        chain.run_frame(f, fs[f % len(fs)])
+        done += 1
+        if budget_s is not None and time.perf_counter() - t0 > budget_s and done >= 2:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": W * H * done / dt / 1e6, "unit": "MPix/s", "cores": int(O.lib().vkpbrt_oracle_num_threads()),
+            "kind": "port", "sample": f"{done} frames of {W}x{H} (oracle/vkpbrt_oracle.c, OpenMP), {dt:.1f} s",
+            "ms_per_frame": dt / done * 1e3}
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    W, H, taa, desc = WORKLOADS[args.workload or "bmfr_1080p"]
+    r = run_cpu(W, H, taa, args.steps, warmup=min(args.warmup, 3))
+    line = {"impl": "reference", "metric": "BMFR denoised MPix/s", "value": r["value"], "unit": "MPix/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_frame"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload or "bmfr_1080p", "description": desc, "width": W, "height": H,
+                       "note": "reference CPU path: GLSL shaders restated in C (the SPIR-V cannot run here: no Vulkan ICD)"},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "MPix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
+def main_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        from vulkanpbrt_b200.multigpu import bench_multi
+        return bench_multi(args, rank, world, local)
+
+    from vulkanpbrt_b200 import Context, DenoisePipeline, DenoisingBlockSize, DenoisingType
+
+    name = args.workload or "bmfr_1080p"
+    W, H, taa, desc = WORKLOADS[name]
+    K, Wm = args.steps, args.warmup
+    R = min(K + Wm, args.resident_frames)        # frames kept resident; longer runs cycle through them
+    dev = torch.device("cuda", local)
+    stream = torch.cuda.current_stream()
+    ctx = Context(local, stream.cuda_stream)
+    t_gen = time.perf_counter()
+    seq = render_sequence(W, H, R)
+    t_gen = time.perf_counter() - t_gen
+    dseq = {k: seq[k].to(dev, non_blocking=True) for k in ("depth", "normal", "albedo", "illum")}
+    torch.cuda.synchronize()
+
+    def make_pipe():
+        return DenoisePipeline(W, H, DenoisingType.BMFR, DenoisingBlockSize.X32, use_taa=taa, ctx=ctx, external_inputs=True)
+
+    def bind(pipe, bufs, i):
+        pipe.bind_inputs(bufs["depth"][i].data_ptr(), bufs["normal"][i].data_ptr(), bufs["albedo"][i].data_ptr(),
+                         bufs["illum"][i].data_ptr())
+
+    # ---- value: inputs resident in HBM -----------------------------------------------------------------
+    pipe = make_pipe()
+
+    def frame_resident(f):
+        i = f % R
+        bind(pipe, dseq, i)
+        pipe.set_frame_constants(f, seq["cams"][i])
+        pipe.record()
+        pipe.end_frame(seq["cams"][i])
+
+    for f in range(Wm):
+        frame_resident(f)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for f in range(Wm, Wm + K):
+        frame_resident(f)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count - launches0
+    value = W * H * K / (ms * 1e-3) / 1e6
+
+    # ---- per-kernel times (CUDA events around each recorded command), same steady state ---------------------
+    ncmd = len(pipe.commands.children)
+    names = ["k_accumulate", "k_bmfr_block<32,256>"] + (["k_taa"] if taa else []) + ["copy_to_back(host swap)"]
+    acc_ms = [0.0] * ncmd
+    nprobe = min(20, K)
+    for f in range(Wm + K, Wm + K + nprobe):
+        i = f % R
+        bind(pipe, dseq, i)
+        pipe.set_frame_constants(f, seq["cams"][i])
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(ncmd + 1)]
+        evs[0].record(stream)
+        for c in range(ncmd):
+            pipe.commands.children[c](pipe.commands)
+            evs[c + 1].record(stream)
+        pipe.end_frame(seq["cams"][i])
+        torch.cuda.synchronize()
+        for c in range(ncmd):
+            acc_ms[c] += evs[c].elapsed_time(evs[c + 1]) / nprobe
+    hbm_peak, peak_src = peaks()
+    per_kernel_bytes = {"k_accumulate": BYTES_ACCUMULATE, "k_bmfr_block<32,256>": BYTES_BMFR, "k_taa": BYTES_TAA}
+    kernels = {}
+    for n, t in zip(names, acc_ms):
+        if n in per_kernel_bytes and t > 0:
+            gbs = per_kernel_bytes[n] * W * H / (t * 1e-3) / 1e9
+            kernels[n] = {"ms": round(t, 4), "share": round(t / sum(acc_ms), 3), "algorithmic_bytes_per_pixel": per_kernel_bytes[n],
+                          "achieved_gbs": round(gbs, 1), "frac_of_hbm_peak": round(gbs / hbm_peak, 3)}
+    dom = max(kernels, key=lambda n: kernels[n]["ms"])
+    traffic = None
+    tp = ROOT / "profiles" / "roofline_traffic.json"
+    if tp.exists():
+        traffic = json.loads(tp.read_text()).get(name, {}).get(dom)
+    # FP32 work of the fit (4.05e5 FLOP per 32x32 block as FMAs; executed as separate mul/add)
+    nblocks = (W // 32 + 2) * (H // 32 + 2)
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
+                "frac": round(kernels[dom]["achieved_gbs"] / hbm_peak, 4), "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": per_kernel_bytes[dom] * W * H,
+                "note": "k_bmfr_block is FP32-pipe/latency bound (batched Householder QR), see fit_gflops; the streaming "
+                        "kernels' HBM fractions are under 'kernels'",
+                "fit_gflops": round(nblocks * 4.05e5 / (kernels[dom]["ms"] * 1e-3) / 1e9, 1) if "bmfr" in dom else None,
+                "chain_fused_bytes_per_pixel": BYTES_CHAIN_FUSED,
+                "chain_achieved_gbs": round(BYTES_CHAIN_FUSED * W * H / (ms / K * 1e-3) / 1e9, 1)}
+
+    # ---- e2e: host buffers, H2D + D2H inside the timed region ------------------------------------------------
+    del pipe
+    pipe = make_pipe()
+    copy_stream = torch.cuda.Stream()
+    dbuf = [{k: torch.empty_like(dseq[k][0]) for k in ("depth", "normal", "albedo", "illum")} for _ in range(2)]
+    out_host = [torch.empty((H, W, 4), dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+    copied = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    final_view = lambda: torch.as_tensor(pipe.final, device=dev)
+
+    def issue_copy(f):
+        s = f % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[s])
+            for k in ("depth", "normal", "albedo", "illum"):
+                dbuf[s][k].copy_(seq[k][f % R], non_blocking=True)
+            copied[s].record(copy_stream)
+
+    def frame_e2e(f):
+        s = f % 2
+        stream.wait_event(copied[s])
+        pipe.bind_inputs(dbuf[s]["depth"].data_ptr(), dbuf[s]["normal"].data_ptr(), dbuf[s]["albedo"].data_ptr(),
+                         dbuf[s]["illum"].data_ptr())
+        pipe.set_frame_constants(f, seq["cams"][f % R])
+        pipe.record()
+        pipe.end_frame(seq["cams"][f % R])
+        consumed[s].record(stream)
+        out_host[s].copy_(final_view(), non_blocking=True)       # the step's result, read back every frame
+
+    for s in range(2):
+        consumed[s].record(stream)
+    issue_copy(0)
+    for f in range(Wm):
+        issue_copy(f + 1)
+        frame_e2e(f)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for f in range(Wm, Wm + K):
+        issue_copy(f + 1)
+        frame_e2e(f)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max(e0.elapsed_time(e1), 0.0)
+    e2e_value = W * H * K / (e2e_ms * 1e-3) / 1e6
+
+    cpu = run_cpu(W, H, taa, frames=64, budget_s=args.cpu_budget, warmup=1) if args.cpu_budget > 0 else None
+
+    line = {"metric": "BMFR denoised MPix/s", "value": round(value, 1), "unit": "MPix/s", "n_gpus": 1, "steps": K, "warmup": Wm,
+            "ms_per_step": round(ms / K, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": name, "description": desc, "width": W, "height": H, "block": 32, "taa": taa,
+                       "l2": f"inputs larger than L2: {R} resident frames x {INPUT_BYTES * W * H / 1e6:.0f} MB, each read once per step",
+                       "resident_frames": R, "sequence_generation_s": round(t_gen, 1)},
+            "e2e": {"value": round(e2e_value, 1), "unit": "MPix/s", "h2d_bytes_per_step": INPUT_BYTES * W * H,
+                    "d2h_bytes_per_step": 4 * W * H, "ms_per_step": round(e2e_ms / K, 5), "wall_ms_per_step": round(wall_ms / K, 5)},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
+    ap.add_argument("--resident-frames", type=int, default=70)
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for cpu_baseline (0 = skip)")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return main_reference(args)
+    return main_ours(args)
+
+
+if __name__ == "__main__":
+    main()

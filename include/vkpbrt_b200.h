@@ -136,6 +136,9 @@ typedef enum {
 } vkpbrt_illumination_type;
 VKPBRT_API int vkpbrt_illumination_buffer_create(vkpbrt_context_t ctx, uint32_t type, uint32_t width,
                                                  uint32_t height, vkpbrt_illumination_buffer_t* out);
+/* wraps caller-provided images (e.g. Vulkan-imported raw illumination) in a buffer of the given type */
+VKPBRT_API int vkpbrt_illumination_buffer_create_from_images(vkpbrt_context_t ctx, uint32_t type, const vkpbrt_image_t* images,
+                                                             uint32_t count, vkpbrt_illumination_buffer_t* out);
 VKPBRT_API int vkpbrt_illumination_buffer_compile(vkpbrt_illumination_buffer_t b);
 VKPBRT_API int vkpbrt_illumination_buffer_type(vkpbrt_illumination_buffer_t b, uint32_t* type, uint32_t* image_count);
 VKPBRT_API int vkpbrt_illumination_buffer_image(vkpbrt_illumination_buffer_t b, uint32_t index, vkpbrt_image_t* out);

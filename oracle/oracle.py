@@ -29,7 +29,9 @@ class AccPush(C.Structure):
 def build(force: bool = False) -> Path:
     src = _DIR / "vkpbrt_oracle.c"
     if force or not _LIB_PATH.exists() or _LIB_PATH.stat().st_mtime < src.stat().st_mtime:
-        subprocess.run(["make", "-C", str(_DIR), "-B", "liboracle.so"], check=True, capture_output=True)
+        r = subprocess.run(["make", "-C", str(_DIR), "-B", "liboracle.so"], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("building the oracle failed:\n" + r.stdout + r.stderr)
     return _LIB_PATH
 
 
@@ -39,8 +41,7 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        if not _LIB_PATH.exists():
-            build()
+        build()   # no-op when liboracle.so is newer than its source
         l = C.CDLL(str(_LIB_PATH))
         vp, i32, u32 = C.c_void_p, C.c_int, C.c_uint32
         l.vkpbrt_oracle_f32_to_f16.argtypes = [C.c_float]; l.vkpbrt_oracle_f32_to_f16.restype = C.c_uint16

@@ -1,0 +1,78 @@
+"""pytest configuration.
+
+Markers
+  gpu      needs a real B200: runs the product library (vulkanpbrt_b200/lib/libvkpbrt_b200.so)
+           through the C ABI and compares with the oracle.  These are the parity tests proper.
+  (none)   CPU-only: oracle vs golden vectors / known answers, host logic, C-ABI export check, and the
+           SAME parity scenarios executed on tests/hostsim (a SIMT emulator that runs the CUDA kernel
+           sources on the CPU) so kernel logic is covered in the GPU-less container as well.
+
+The `backend` fixture is the only place that can point vulkanpbrt_b200._capi at the emulator; the
+package itself has no such switch and no fallback.
+"""
+import ctypes
+import gc
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+HOSTSIM_DIR = ROOT / "tests" / "hostsim"
+HOSTSIM_LIB = HOSTSIM_DIR / "libvkpbrt_hostsim.so"
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (sm_100a); run with -m gpu on the B200 box")
+    config.addinivalue_line("markers", "slow: longer CPU test")
+
+
+def _build_native():
+    from vulkanpbrt_b200 import build
+    build.build_all()
+
+
+def _build_hostsim():
+    r = subprocess.run(["make", "-C", str(HOSTSIM_DIR)], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("hostsim build failed:\n" + r.stdout + r.stderr)
+
+
+@pytest.fixture(scope="session", autouse=True)
+def native_libs():
+    _build_native()
+
+
+def backend_params():
+    return [pytest.param("hostsim", id="hostsim"), pytest.param("cuda", id="cuda", marks=pytest.mark.gpu)]
+
+
+@pytest.fixture
+def backend(request):
+    """'cuda': the product library on a real GPU.  'hostsim': the test emulator (CPU)."""
+    from vulkanpbrt_b200 import _capi
+    kind = request.param
+    gc.collect()
+    saved = _capi._lib
+    if kind == "hostsim":
+        _build_hostsim()
+        _capi._lib = _capi.configure(ctypes.CDLL(str(HOSTSIM_LIB)))
+        assert b"HOSTSIM" in _capi._lib.vkpbrt_version()
+    else:
+        _capi._lib = None
+        lib = _capi.lib()
+        assert b"HOSTSIM" not in lib.vkpbrt_version()
+    yield kind
+    gc.collect()      # every handle created by the test dies before the library is swapped back
+    _capi._lib = saved
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle import oracle as O
+    O.lib()
+    return O

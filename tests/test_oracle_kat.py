@@ -1,0 +1,166 @@
+"""CPU tests of the oracle itself: known answers derived independently from the reference's constants
+and formulas (the reference ships no test vectors), plus the committed golden
+hashes that pin the oracle's outputs across machines and revisions (tests/golden/make_golden.py)."""
+import ctypes as C
+import hashlib
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from vulkanpbrt_b200 import synth
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+
+
+def test_f16_roundtrip_all_halves(oracle):
+    L = oracle.lib()
+    bits = np.arange(65536, dtype=np.uint16)
+    ref = bits.view(np.float16).astype(np.float32)
+    for b in range(0, 65536, 7):
+        got = L.vkpbrt_oracle_f16_to_f32(int(b))
+        if np.isnan(ref[b]):
+            assert np.isnan(got)
+        else:
+            assert got == ref[b]
+            assert L.vkpbrt_oracle_f32_to_f16(float(ref[b])) == b
+
+
+def test_f32_to_f16_rounds_to_nearest_even(oracle):
+    L = oracle.lib()
+    rng = np.random.default_rng(1)
+    vals = np.concatenate([
+        rng.standard_normal(4000).astype(np.float32) * np.float32(10.0) ** rng.integers(-9, 5, 4000).astype(np.float32),
+        np.array([0.0, -0.0, 65504.0, 65519.9, 65520.0, 1e-8, 5.96e-8, 2.98e-8, 2.9802322e-8, 6.1e-5, 6.1035156e-5,
+                  1.0009765, 1.00048828125, 1.0014648], np.float32)])
+    with np.errstate(over="ignore"):
+        want = vals.astype(np.float16).view(np.uint16)
+    for v, w in zip(vals, want):
+        assert L.vkpbrt_oracle_f32_to_f16(float(v)) == int(w), float(v)
+
+
+def test_unorm8(oracle):
+    L = oracle.lib()
+    assert L.vkpbrt_oracle_f32_to_unorm8(float("nan")) == 0
+    assert L.vkpbrt_oracle_f32_to_unorm8(-3.0) == 0
+    assert L.vkpbrt_oracle_f32_to_unorm8(7.0) == 255
+    assert L.vkpbrt_oracle_f32_to_unorm8(1.0 / 256.0) == 1       # first-frame sample count (accumulator.comp:43)
+    for c in range(256):
+        assert L.vkpbrt_oracle_f32_to_unorm8(c / 255.0) == c
+
+
+# ivec2(vec2(b, b) * pixelOffsets[f % 16]) for the table of bmfrGeneral.comp:36
+BMFR_OFFSETS = {
+    32: [(22, 27), (30, 16), (13, 24), (31, 0), (11, 18), (0, 11), (25, 14), (0, 24), (11, -2), (-1, 0), (30, 3), (27, 19),
+         (1, 3), (13, 5), (0, 16), (23, 12)],
+    16: [(11, 13), (15, 8), (6, 12), (15, 0), (5, 9), (0, 5), (12, 7), (0, 12), (5, -1), (0, 0), (15, 1), (13, 9), (0, 1),
+         (6, 2), (0, 8), (11, 6)],
+    8: [(5, 6), (7, 4), (3, 6), (7, 0), (2, 4), (0, 2), (6, 3), (0, 6), (2, 0), (0, 0), (7, 0), (6, 4), (0, 0), (3, 1),
+        (0, 4), (5, 3)],
+}
+BFR_OFFSETS = [(-7, -11), (-14, -8), (-5, -12), (-15, -1), (-5, -9), (-1, -4), (-14, -7), (0, -13), (-5, -1), (-1, 0),
+               (-15, -2), (-14, -10), (-1, -1), (-6, -3), (0, -8), (-10, -4)]
+
+
+@pytest.mark.parametrize("b", [8, 16, 32])
+def test_bmfr_block_jitter_table(oracle, b):
+    for f in range(48):
+        assert oracle.bmfr_block_offset(b, f) == BMFR_OFFSETS[b][f % 16]
+
+
+def test_bfr_block_jitter_table(oracle):
+    for f in range(40):
+        assert oracle.bfr_block_offset(f) == BFR_OFFSETS[f % 16]
+
+
+def _ref_hash(a):
+    """bmfrGeneral.comp:103-113, restated independently with Python integers"""
+    M = 0xFFFFFFFF
+    a = ((a + 0x7ed55d16) + (a << 12)) & M
+    a = ((a ^ 0xc761c23c) ^ (a >> 19)) & M
+    a = ((a + 0x165667b1) + (a << 5)) & M
+    a = ((a + 0xd3a2646c) ^ (a << 9)) & M
+    a = ((a + 0xfd7046c5) + (a << 3)) & M
+    a = ((a ^ 0xb55a4f09) ^ (a >> 16)) & M
+    return np.float32(a) / np.float32(4294967295.0)      # float(0xffffffff) rounds to 2^32
+
+
+def test_noise_hash_known_answers(oracle):
+    L = oracle.lib()
+    rng = np.random.default_rng(7)
+    seeds = [0, 1, 255, 1023, 1 << 20, 13 * (1 << 20) * 157 & 0xFFFFFFFF, 0xFFFFFFFF] + [int(s) for s in rng.integers(0, 2**32, 500)]
+    for s in seeds:
+        assert L.vkpbrt_oracle_bmfr_random(s) == _ref_hash(s)
+
+
+def test_mat_inverse_matches_numpy(oracle):
+    cam = synth.camera(640, 360, 5)
+    for m in (cam.view, cam.proj, cam.inv_view):
+        inv = oracle.mat_inverse(m).reshape(4, 4).T
+        want = np.linalg.inv(np.asarray(m, np.float64).reshape(4, 4).T)
+        np.testing.assert_allclose(inv, want, rtol=2e-5, atol=2e-6)
+
+
+def test_deterministic_transcendentals(oracle):
+    L = oracle.lib()
+    L.vkpbrt_oracle_sincos.argtypes = [C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.vkpbrt_oracle_pow.argtypes = [C.c_float, C.c_float]
+    L.vkpbrt_oracle_pow.restype = C.c_float
+    for x in np.linspace(-7.0, 7.0, 4001).astype(np.float32):
+        s, c = C.c_float(), C.c_float()
+        L.vkpbrt_oracle_sincos(float(x), C.byref(s), C.byref(c))
+        assert abs(s.value - np.sin(np.float64(x))) < 2e-7 and abs(c.value - np.cos(np.float64(x))) < 2e-7
+    s, c = C.c_float(), C.c_float()
+    L.vkpbrt_oracle_sincos(0.0, C.byref(s), C.byref(c))
+    assert (s.value, c.value) == (0.0, 1.0)               # flat ground: theta = 0 -> n = (0, 0, 1) exactly
+    for x in np.logspace(-6, 1.1, 2001).astype(np.float32):
+        v = L.vkpbrt_oracle_pow(float(x), 0.454545)
+        t = np.float64(x) ** np.float64(np.float32(0.454545))
+        assert abs(v - t) / t < 2e-6
+    assert L.vkpbrt_oracle_pow(0.0, 0.454545) == 0.0 and L.vkpbrt_oracle_pow(1.0, 0.454545) == 1.0
+
+
+def test_fit_solves_the_least_squares_problem(oracle):
+    """bmfrFit's Householder QR + back substitution must reproduce a float64 least-squares fit of the same
+    (noisy, fp16) system on the block's own features (checks the algorithm, not the rounding)."""
+    W = H = 128
+    orc = oracle.OracleChain(W, H, "bmfr", 32)
+    fr = synth.render_frame(W, H, 0)
+    orc.run_frame(0, fr, keep_debug=True)
+    L = oracle.lib()
+    feat, wts = orc.features, orc.weights
+    checked = 0
+    for by in range(1, 4):
+        for bx in range(1, 4):
+            i = np.arange(1024)
+            px, py = i // 32 + bx * 32, i % 32 + by * 32          # bmfrFit.comp:18-19: x = i / 32
+            A = np.zeros((1024, 13))
+            for c in range(13):
+                v = oracle.f16_bits_to_f32(feat[c, py, px])
+                if c < 10:
+                    r = np.array([L.vkpbrt_oracle_bmfr_random(int(s)) for s in (i + c * (1 << 20))], np.float32)
+                    v = v + np.float32(2e-4) * (r - np.float32(0.5))
+                A[:, c] = v
+            if np.abs(A[:, 10:]).max() == 0:
+                continue
+            sol = np.linalg.lstsq(A[:, :10], A[:, 10:], rcond=None)[0]
+            w = wts[:, by, bx].reshape(10, 3).astype(np.float64)
+            # compare the FITS (predictions on the fitted system): the weights themselves are ill-conditioned
+            np.testing.assert_allclose(A[:, :10] @ w, A[:, :10] @ sol, atol=2e-3)
+            checked += 1
+    assert checked >= 4
+
+
+def _sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.mark.parametrize("name", ["bmfr32_taa_256x256_8f", "bfrx3_taa_160x128_3f"])
+def test_oracle_matches_committed_golden_hashes(oracle, name):
+    """tests/golden/*.json were produced by tests/golden/make_golden.py from this oracle; they pin its
+    outputs bit for bit (any change to the restatement, the compiler flags or the host libm shows up here)."""
+    from tests.golden.make_golden import CASES, run_case
+    spec = json.loads((GOLDEN / f"{name}.json").read_text())
+    got = run_case(oracle, CASES[name])
+    assert got["frames"] == spec["frames"]

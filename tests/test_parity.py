@@ -1,0 +1,125 @@
+"""Parity of the CUDA path against the oracle, through the C ABI.
+
+Every scenario runs twice: on the real GPU (marker gpu, the parity result that counts) and on the
+tests/hostsim emulator (CPU, same kernel sources) so the GPU-less container also exercises the kernels.
+The bar is BIT-EXACT equality of every plane of every frame: motion / sample counts / masks (integer
+work), the rgba16f radiance planes and the BGRA8 finals.  The north-star tolerance (relative error
+<= 1e-3 on >= 99.9 % of pixels, PSNR >= 60 dB) is asserted as well, on top, at the BASELINE sizes."""
+import numpy as np
+import pytest
+
+from tests.conftest import backend_params
+from tests.util import assert_frame_equal, make_pair, step_both, tolerance_report
+
+pytestmark = pytest.mark.parametrize("backend", backend_params(), indirect=True)
+
+
+def run_sequence(oracle, W, H, frames, first=0, **kw):
+    pipe, orc = make_pair(oracle, W, H, **kw)
+    for f in range(first, first + frames):
+        step_both(oracle, pipe, orc, W, H, f, keep_debug=kw.get("debug", False))
+        assert_frame_equal(pipe, orc, f)
+        if kw.get("debug", False):
+            # integer work of the fit: row <-> pixel map, mirror, jitter and the noise hash all feed these
+            np.testing.assert_array_equal(pipe.modules[0].feature_buffer.download(), orc.features)
+            np.testing.assert_array_equal(pipe.modules[0].weights.download().view(np.uint32), orc.weights.view(np.uint32))
+    return pipe, orc
+
+
+def test_bmfr_chain_256x256_8_frames(backend, oracle):
+    """BASELINE.json configs[0]: BMFR chain on the synthetic 256x256 G-buffer sequence, 8 frames, + TAA"""
+    run_sequence(oracle, 256, 256, 8, denoiser="bmfr", block=32, use_taa=True, debug=True)
+
+
+def test_bmfr_negative_jitter_frames_leave_pixels_unwritten(backend, oracle):
+    """frames 8, 9 (mod 16): offsets (11,-2) and (-1,0) leave rows 0-1 / column 0 untouched
+    (SURVEY.md App. A.2); ragged size so the last block row/column is mirrored"""
+    run_sequence(oracle, 250, 130, 5, first=6, denoiser="bmfr", block=32, use_taa=True)
+
+
+@pytest.mark.parametrize("block,W,H", [(16, 208, 144), (8, 200, 136)])
+def test_bmfr_other_block_sizes(backend, oracle, block, W, H):
+    """BMFR::create(w, h, 16, 16, ...) and (8, 8, ..., fitting_kernel = 64) (DenoiserUtils.cpp:78-95)"""
+    run_sequence(oracle, W, H, 3, first=7, denoiser="bmfr", block=block, debug=True)
+
+
+def test_bmfr_combined_matrices_mode(backend, oracle):
+    """accumulator.comp without SEPARATE_MATRICES (offline mode, :56-64)"""
+    run_sequence(oracle, 256, 128, 3, denoiser="bmfr", block=32, use_taa=True, separate_matrices=False)
+
+
+def test_bmfr_rgba16f_input(backend, oracle):
+    """offline input as IlluminationBufferDemodulated (rgba16f), VulkanPBRT.cpp:375-388"""
+    run_sequence(oracle, 256, 128, 3, denoiser="bmfr", block=32, raw_f16=True)
+
+
+def test_taa_fixed_swizzle(backend, oracle):
+    run_sequence(oracle, 192, 128, 3, denoiser="bmfr", block=32, use_taa=True, fix_taa_swizzle=True)
+
+
+@pytest.mark.parametrize("block,W,H", [(32, 160, 128), (16, 168, 104), (8, 128, 96)])
+def test_bfr_block_sizes(backend, oracle, block, W, H):
+    """BFR::create(w, h, b, b, ...) for b = 32 / 16 / 8 (DenoiserUtils.cpp:22-47); frames 8.. exercise the
+    L1 (sign) branch only once spp >= 10, so start late enough for both branches"""
+    run_sequence(oracle, W, H, 2, denoiser="bfr", block=block)
+
+
+def test_bfr_x8x16x32_blender_taa(backend, oracle):
+    """BASELINE.json configs[2] structure: three BFRs + BFRBlender (+ TAA), DenoiserUtils.cpp:48-70"""
+    run_sequence(oracle, 160, 128, 3, denoiser="bfrx3", block=32, use_taa=True)
+
+
+def test_bfr_l1_branch_after_ten_samples(backend, oracle):
+    """after ~10 accumulated frames pixel_spp >= SPP_THRESH switches residuals to sign() (bfr.comp:267-268)"""
+    W, H = 96, 64
+    pipe, orc = make_pair(oracle, W, H, denoiser="bfr", block=16)
+    for f in range(13):
+        step_both(oracle, pipe, orc, W, H, f)
+    assert (orc.spp.astype(np.float32) / 255.0 * 256.0 >= 10.0).mean() > 0.3
+    assert_frame_equal(pipe, orc, 12)
+
+
+# ---- BASELINE sizes: only on the GPU (the emulator would take minutes) -----------------------------
+def _gpu_only(backend):
+    if backend != "cuda":
+        pytest.skip("full-size configuration: GPU only")
+
+
+def test_bmfr_1080p_chain(backend, oracle):
+    """BASELINE.json configs[1]: BMFR 1920x1080 1-spp with camera motion (first frames of the sequence)"""
+    _gpu_only(backend)
+    pipe, orc = run_sequence(oracle, 1920, 1080, 4, denoiser="bmfr", block=32, use_taa=True)
+    frac, p = tolerance_report(oracle, pipe.modules[0].denoised.download(), orc.denoised[32])
+    assert frac >= 0.999 and p >= 60.0
+
+
+def test_bmfr_4k_two_frames(backend, oracle):
+    """BASELINE.json configs[3] at full size: accumulator + BMFR + TAA, 3840x2160"""
+    _gpu_only(backend)
+    pipe, orc = run_sequence(oracle, 3840, 2160, 2, first=8, denoiser="bmfr", block=32, use_taa=True)
+    frac, p = tolerance_report(oracle, pipe.modules[0].denoised.download(), orc.denoised[32])
+    assert frac >= 0.999 and p >= 60.0
+
+
+def test_bfr_blender_1080p(backend, oracle):
+    """BASELINE.json configs[2] at full size"""
+    _gpu_only(backend)
+    run_sequence(oracle, 1920, 1080, 2, denoiser="bfrx3", block=32, use_taa=False)
+
+
+def test_replay_is_deterministic_8k(backend, oracle):
+    """size-independent property at the largest BASELINE size: two independent pipelines fed the same
+    7680x4320 frames produce identical bytes (no atomics / scheduling dependence in any kernel)"""
+    _gpu_only(backend)
+    from vulkanpbrt_b200 import DenoisePipeline, synth
+    W, H = 7680, 4320
+    outs = []
+    for _ in range(2):
+        pipe = DenoisePipeline(W, H, use_taa=True)
+        for f in range(2):
+            pipe.run_frame(f, synth.render_frame(W, H, f))
+        pipe.ctx.synchronize()
+        outs.append((pipe.final.download(), pipe.modules[0].denoised.download()))
+        del pipe
+    np.testing.assert_array_equal(outs[0][0], outs[1][0])
+    np.testing.assert_array_equal(outs[0][1], outs[1][1])

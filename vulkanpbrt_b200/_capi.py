@@ -88,6 +88,7 @@ _PROTOS = {
     "vkpbrt_gbuffer_image": [H, u32, PH],
     "vkpbrt_gbuffer_destroy": [H],
     "vkpbrt_illumination_buffer_create": [H, u32, u32, u32, PH],
+    "vkpbrt_illumination_buffer_create_from_images": [H, u32, PH, u32, PH],
     "vkpbrt_illumination_buffer_compile": [H],
     "vkpbrt_illumination_buffer_type": [H, C.POINTER(u32), C.POINTER(u32)],
     "vkpbrt_illumination_buffer_image": [H, u32, PH],
@@ -152,19 +153,23 @@ def lib() -> C.CDLL:
         if not _LIB_PATH.exists():
             raise ImportError(f"{_LIB_PATH} is missing: run `python -m vulkanpbrt_b200.build` "
                               "(the package has no fallback path without its CUDA library)")
-        l = C.CDLL(str(_LIB_PATH))
-        for name, args in _PROTOS.items():
-            fn = getattr(l, name)
-            fn.argtypes = args
-            fn.restype = C.c_int
-        l.vkpbrt_last_error.restype = C.c_char_p
-        l.vkpbrt_last_error.argtypes = []
-        l.vkpbrt_version.restype = C.c_char_p
-        l.vkpbrt_version.argtypes = []
-        l.vkpbrt_format_texel_size.restype = u32
-        l.vkpbrt_format_texel_size.argtypes = [u32]
-        _lib = l
+        _lib = configure(C.CDLL(str(_LIB_PATH)))
     return _lib
+
+
+def configure(l: C.CDLL) -> C.CDLL:
+    """declares the prototypes of include/vkpbrt_b200.h on a loaded library"""
+    for name, args in _PROTOS.items():
+        fn = getattr(l, name)
+        fn.argtypes = args
+        fn.restype = C.c_int
+    l.vkpbrt_last_error.restype = C.c_char_p
+    l.vkpbrt_last_error.argtypes = []
+    l.vkpbrt_version.restype = C.c_char_p
+    l.vkpbrt_version.argtypes = []
+    l.vkpbrt_format_texel_size.restype = u32
+    l.vkpbrt_format_texel_size.argtypes = [u32]
+    return l
 
 
 def check(rc: int) -> None:

@@ -481,6 +481,21 @@ int vkpbrt_illumination_buffer_create(vkpbrt_context_t ctx, uint32_t type, uint3
     return VKPBRT_OK;
 }
 
+int vkpbrt_illumination_buffer_create_from_images(vkpbrt_context_t ctx, uint32_t type, const vkpbrt_image_t* images,
+                                                  uint32_t count, vkpbrt_illumination_buffer_t* out)
+{
+    VK_REQUIRE(ctx && images && out && count > 0, "vkpbrt_illumination_buffer_create_from_images: bad argument");
+    VK_REQUIRE(type <= VKPBRT_ILLUMINATION_FINAL_DEMODULATED, "unknown illumination buffer type");
+    for (uint32_t i = 0; i < count; ++i) VK_REQUIRE(images[i], "null image");
+    auto* b = new vkpbrt_illumination_buffer_s{ctx, type, images[0]->width, images[0]->height, {}};
+    for (uint32_t i = 0; i < count; ++i) {
+        vkpbrt_image_retain(images[i]);
+        b->images.push_back(images[i]);
+    }
+    *out = b;
+    return VKPBRT_OK;
+}
+
 int vkpbrt_illumination_buffer_compile(vkpbrt_illumination_buffer_t b)
 {
     VK_REQUIRE(b, "null illumination buffer");

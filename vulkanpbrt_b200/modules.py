@@ -243,6 +243,18 @@ class IlluminationBuffer:
     def create(cls, ctx: Context, width: int, height: int):
         return cls(ctx, width, height)
 
+    @classmethod
+    def from_images(cls, ctx: Context, images: List[DescriptorImage]):
+        """wraps caller-provided images (imported / externally allocated memory)"""
+        arr = (C.c_void_p * len(images))(*[i.handle for i in images])
+        h = C.c_void_p()
+        capi.call("vkpbrt_illumination_buffer_create_from_images", ctx.handle, cls.TYPE, arr, len(images), C.byref(h))
+        i0 = images[0].info()
+        self = cls(ctx, i0.width, i0.height, _handle=h)
+        self._owner = True
+        self._keep = list(images)
+        return self
+
     @property
     def handle(self):
         return self._h

@@ -21,16 +21,27 @@ class DenoisePipeline:
                  block_size: DenoisingBlockSize = DenoisingBlockSize.X32, use_taa: bool = False, device: int = 0,
                  stream: Optional[int] = None, separate_matrices: bool = True, raw_f16: bool = False,
                  fix_taa_swizzle: bool = False, bmfr_debug_outputs: bool = False, average_squared: bool = False,
-                 ctx: Optional[Context] = None):
+                 ctx: Optional[Context] = None, external_inputs: bool = False):
         self.width, self.height = width, height
         self.ctx = ctx if ctx is not None else Context(device, stream)
         self.separate_matrices = separate_matrices
         ctx = self.ctx
         # VulkanPBRT.cpp:337-339 (live) / :375-388 (offline rgba16f input)
-        self.g_buffer = GBuffer.create(ctx, width, height)
-        self.raw_illumination = (IlluminationBufferDemodulated if raw_f16 else IlluminationBufferDemodulatedFloat).create(ctx, width, height)
-        self.g_buffer.compile(ctx)
-        self.raw_illumination.compile(ctx)
+        raw_cls = IlluminationBufferDemodulated if raw_f16 else IlluminationBufferDemodulatedFloat
+        if external_inputs:
+            # the producer owns the input planes (Vulkan-imported memory, a resident sequence, ...): wrap them and
+            # re-point the handles per frame with bind_inputs()
+            F = capi
+            wrap = lambda fmt: DescriptorImage.wrap(ctx, fmt, width, height, 0)
+            self._ext = [wrap(F.FORMAT_R32_SFLOAT), wrap(F.FORMAT_R32G32_SFLOAT), wrap(F.FORMAT_R8G8B8A8_UNORM),
+                         wrap(F.FORMAT_R16G16B16A16_SFLOAT if raw_f16 else F.FORMAT_R32G32B32A32_SFLOAT)]
+            self.g_buffer = GBuffer.from_images(ctx, self._ext[0], self._ext[1], None, self._ext[2])
+            self.raw_illumination = raw_cls.from_images(ctx, [self._ext[3]])
+        else:
+            self.g_buffer = GBuffer.create(ctx, width, height)
+            self.raw_illumination = raw_cls.create(ctx, width, height)
+            self.g_buffer.compile(ctx)
+            self.raw_illumination.compile(ctx)
         self.commands = Commands.create()
         self.push_constants = PushConstants.create()
         self.push_constants.value.prev_view = capi.mat16(IDENTITY)
@@ -113,6 +124,11 @@ class DenoisePipeline:
         else:
             img.upload(frame.illumination, sync=False)
         self.ctx.synchronize()
+
+    def bind_inputs(self, depth_ptr: int, normal_ptr: int, albedo_ptr: int, illumination_ptr: int) -> None:
+        """external_inputs mode: point the G-buffer / raw illumination handles at this frame's device planes"""
+        for img, ptr in zip(self._ext, (depth_ptr, normal_ptr, albedo_ptr, illumination_ptr)):
+            img.set_data(ptr)
 
     def record(self) -> None:
         self.commands.record()     # viewer->recordAndSubmit() (:588)
