@@ -38,6 +38,7 @@ WORKLOADS = {
     "bmfr_taa_4k": (3840, 2160, True, "accumulator + BMFR + TAA 3840x2160 1-spp (BASELINE configs[3])"),
     "bmfr_8k": (7680, 4320, False, "BMFR 7680x4320 (BASELINE configs[4])"),
     "bmfr_256": (256, 256, False, "BMFR 256x256 (BASELINE configs[0], plumbing)"),
+    "bfr_blend_1080p": (1920, 1080, False, "BFR b=8/16/32 + BFRBlender 1920x1080 1-spp (BASELINE configs[2])"),
 }
 # algorithmic (compulsory) HBM bytes per image pixel, reference storage formats (DESIGN.md / SURVEY.md 8d)
 BYTES_ACCUMULATE = 33 + 17     # reads depth 4 + raw 16 + prev_depth 4 + prev_illum 8 + prev_spp 1; writes motion 4 + spp 1 + illum 8 + depth history 4
@@ -60,7 +61,7 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, device):
         super().__init__(daemon=True)
-        self.device, self.samples, self.reasons, self.max_mhz, self._stop = device, [], set(), None, threading.Event()
+        self.device, self.samples, self.reasons, self.max_mhz, self._halt = device, [], set(), None, threading.Event()
 
     def run(self):
         try:
@@ -70,7 +71,7 @@ class ClockSampler(threading.Thread):
             self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
             names = {0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown",
                      0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown"}
-            while not self._stop.is_set():
+            while not self._halt.is_set():
                 self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
                 try:
                     r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
@@ -84,7 +85,7 @@ class ClockSampler(threading.Thread):
             self.reasons.add(f"sampler_error:{type(e).__name__}")
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=2)
         s = sorted(self.samples)
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
@@ -185,7 +186,12 @@ def main_ours(args):
     dseq = {k: seq[k].to(dev, non_blocking=True) for k in ("depth", "normal", "albedo", "illum")}
     torch.cuda.synchronize()
 
+    bfr = name.startswith("bfr")
+
     def make_pipe():
+        if bfr:
+            return DenoisePipeline(W, H, DenoisingType.BFR, DenoisingBlockSize.X8X16X32, use_taa=taa, ctx=ctx, external_inputs=True,
+                                   average_squared=True)
         return DenoisePipeline(W, H, DenoisingType.BMFR, DenoisingBlockSize.X32, use_taa=taa, ctx=ctx, external_inputs=True)
 
     def bind(pipe, bufs, i):
@@ -221,7 +227,7 @@ def main_ours(args):
 
     # ---- per-kernel times (CUDA events around each recorded command), same steady state ---------------------
     ncmd = len(pipe.commands.children)
-    names = ["k_accumulate", "k_bmfr_block<32,256>"] + (["k_taa"] if taa else []) + ["copy_to_back(host swap)"]
+    names = pipe.command_labels
     acc_ms = [0.0] * ncmd
     nprobe = min(20, K)
     for f in range(Wm + K, Wm + K + nprobe):
@@ -238,7 +244,9 @@ def main_ours(args):
         for c in range(ncmd):
             acc_ms[c] += evs[c].elapsed_time(evs[c + 1]) / nprobe
     hbm_peak, peak_src = peaks()
-    per_kernel_bytes = {"k_accumulate": BYTES_ACCUMULATE, "k_bmfr_block<32,256>": BYTES_BMFR, "k_taa": BYTES_TAA}
+    per_kernel_bytes = {"k_accumulate": BYTES_ACCUMULATE, "k_bmfr_block<32,256>": BYTES_BMFR, "k_taa": BYTES_TAA,
+                        "k_bfr_block<8>": BYTES_BMFR - 8, "k_bfr_block<16>": BYTES_BMFR - 8, "k_bfr_block<32>": BYTES_BMFR - 8,
+                        "k_bfr_blend": 8 + 8 + 12 + 4}
     kernels = {}
     for n, t in zip(names, acc_ms):
         if n in per_kernel_bytes and t > 0:
@@ -308,9 +316,9 @@ def main_ours(args):
     e2e_ms = max(e0.elapsed_time(e1), 0.0)
     e2e_value = W * H * K / (e2e_ms * 1e-3) / 1e6
 
-    cpu = run_cpu(W, H, taa, frames=64, budget_s=args.cpu_budget, warmup=1) if args.cpu_budget > 0 else None
+    cpu = run_cpu(W, H, taa, frames=64, budget_s=args.cpu_budget, warmup=1) if (args.cpu_budget > 0 and not bfr) else None
 
-    line = {"metric": "BMFR denoised MPix/s", "value": round(value, 1), "unit": "MPix/s", "n_gpus": 1, "steps": K, "warmup": Wm,
+    line = {"metric": ("BFR+blend" if bfr else "BMFR") + " denoised MPix/s", "value": round(value, 1), "unit": "MPix/s", "n_gpus": 1, "steps": K, "warmup": Wm,
             "ms_per_step": round(ms / K, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": name, "description": desc, "width": W, "height": H, "block": 32, "taa": taa,

@@ -152,6 +152,7 @@ inline float __fmul_rn(float a, float b) { return a * b; }
 inline float __fadd_rn(float a, float b) { return a + b; }
 inline float __fdiv_rn(float a, float b) { return a / b; }
 inline float __fsqrt_rn(float a) { return sqrtf(a); }
+inline float __frcp_rn(float a) { return 1.0f / a; }
 template <typename T>
 inline T __ldg(const T* p) { return *p; }
 inline uint32_t __float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }

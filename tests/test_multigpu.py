@@ -1,0 +1,124 @@
+"""Band sharding: integer geometry on the CPU, and a 2-rank gloo run of the
+whole banded chain (through the tests/hostsim emulator) that must reproduce the single-rank result
+bit for bit -- i.e. the halo plan delivers every history row a rank reads."""
+import ctypes
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+@pytest.mark.parametrize("W,H,N", [(1920, 1080, 2), (1920, 1080, 4), (3840, 2160, 8), (1920, 8640, 8), (7680, 4320, 8), (256, 256, 2)])
+def test_band_plan_partitions_the_frame(W, H, N):
+    from vulkanpbrt_b200.multigpu import BandPlan, block_offset
+    plan = BandPlan(W, H, N, taa=True)
+    assert plan.block_rows(0)[0] == 0 and plan.block_rows(N - 1)[1] == H // 32 + 2
+    for f in range(34):
+        oy = block_offset(32, f)[1]
+        rows = [plan.owned_rows(g, f) for g in range(N)]
+        assert rows[0][0] == 0 and rows[-1][1] == H
+        for g in range(N - 1):
+            assert rows[g][1] == rows[g + 1][0]                      # contiguous partition of [0, H)
+        for g in range(N):
+            b0, b1 = plan.block_rows(g)
+            # rows written by the rank's BMFR blocks (non-mirrored pixels, bmfrPost.comp:74) lie in its owned rows
+            wlo, whi = max(0, 32 * b0 - oy), min(H, 32 * b1 - oy)
+            assert rows[g][0] <= wlo and whi <= rows[g][1]
+            a = plan.accumulate_rows(g, f)
+            assert a[0] <= rows[g][0] and rows[g][1] <= a[1]
+            # every image row a block of the rank reads through jitter + mirror is accumulated locally
+            for ay in (32 * b0 - oy, 32 * b1 - oy - 1):
+                m = -ay - 1 if ay < 0 else (2 * H - ay - 1 if ay >= H else ay)
+                assert a[0] <= m < a[1]
+
+
+def test_history_transfers_cover_every_needed_row():
+    from vulkanpbrt_b200.multigpu import BandPlan
+    for (W, H, N) in [(1920, 1080, 4), (640, 2160, 8), (256, 256, 2)]:
+        plan = BandPlan(W, H, N, taa=True)
+        for f in range(1, 34):
+            ts = plan.history_transfers(f)
+            for dst in range(N):
+                for plane, have, need in (("acc", plan.accumulate_rows(dst, f - 1), plan.accumulate_rows(dst, f)),
+                                          ("denoised", plan.owned_rows(dst, f - 1), plan.owned_rows(dst, f)),
+                                          ("taa", plan.owned_rows(dst, f - 1), plan.owned_rows(dst, f))):
+                    got = np.zeros(H, bool)
+                    got[have[0]:have[1]] = True
+                    for t in ts:
+                        if t.dst == dst and t.plane == plane:
+                            o = plan.owned_rows(t.src, f - 1)
+                            assert o[0] <= t.rows[0] and t.rows[1] <= o[1]          # sent by the canonical owner
+                            got[t.rows[0]:t.rows[1]] = True
+                    lo, hi = max(0, need[0] - plan.D - 1), min(H, need[1] + plan.D + 1)
+                    assert got[lo:hi].all()
+                    if lo == 0:
+                        assert got[H - 1]                                          # REPEAT wrap rows
+                    if hi == H:
+                        assert got[0]
+
+
+def _worker(rank, world, W, H, frames, use_taa, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, str(ROOT))
+    import torch
+    import torch.distributed as dist
+    from vulkanpbrt_b200 import Context, _capi, synth
+    from vulkanpbrt_b200.multigpu import BandedPipeline
+    _capi._lib = _capi.configure(ctypes.CDLL(str(ROOT / "tests" / "hostsim" / "libvkpbrt_hostsim.so")))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    def view(img):     # emulator "device" memory is host memory
+        bv = img.byte_view()
+        n = int(np.prod(bv.shape))
+        return torch.from_numpy(np.ctypeslib.as_array((ctypes.c_uint8 * n).from_address(bv.ptr)).reshape(bv.shape))
+
+    bp = BandedPipeline(W, H, rank, world, use_taa, Context(0), view, max_disp_rows=12, external_inputs=False, dist=dist)
+    lo, hi = bp.plan.input_rows(rank)
+    finals, denoised = [], []
+    for f in range(frames):
+        fr = synth.render_frame(W, H, f, rows=(lo, hi))      # the rank only ever sees its band + apron of the inputs
+        bp.pipe.upload_frame(fr)
+        bp.run_frame(f, fr.camera)
+        o = bp.owned_rows(f)
+        finals.append((o, bp.pipe.final.download()[o[0]:o[1]].copy()))
+        denoised.append((o, bp.bmfr.denoised.download()[(f & 1) ^ 1, o[0]:o[1]].copy()))
+    np.save(os.path.join(out_dir, f"final_{rank}.npy"), np.array([(o, a) for o, a in finals], dtype=object), allow_pickle=True)
+    np.save(os.path.join(out_dir, f"den_{rank}.npy"), np.array([(o, a) for o, a in denoised], dtype=object), allow_pickle=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("use_taa", [False, True])
+def test_two_rank_banded_chain_equals_single_rank(tmp_path, use_taa):
+    import subprocess
+    import torch.multiprocessing as mp
+    subprocess.run(["make", "-C", str(ROOT / "tests" / "hostsim")], check=True, capture_output=True)
+    W, H, frames, world = 128, 192, 10, 2
+    port = 29500 + (os.getpid() % 2000)
+    mp.start_processes(_worker, args=(world, W, H, frames, use_taa, port, str(tmp_path)), nprocs=world, join=True, start_method="spawn")
+    # single-rank run of the same sequence (emulator, this process)
+    from vulkanpbrt_b200 import DenoisePipeline, _capi, synth
+    saved = _capi._lib
+    _capi._lib = _capi.configure(ctypes.CDLL(str(ROOT / "tests" / "hostsim" / "libvkpbrt_hostsim.so")))
+    try:
+        pipe = DenoisePipeline(W, H, use_taa=use_taa)
+        per_rank_f = [np.load(tmp_path / f"final_{r}.npy", allow_pickle=True) for r in range(world)]
+        per_rank_d = [np.load(tmp_path / f"den_{r}.npy", allow_pickle=True) for r in range(world)]
+        for f in range(frames):
+            pipe.run_frame(f, synth.render_frame(W, H, f))
+            full_final = pipe.final.download()
+            full_den = pipe.modules[0].denoised.download()[(f & 1) ^ 1]
+            for r in range(world):
+                (lo, hi), band = per_rank_f[r][f]
+                np.testing.assert_array_equal(band, full_final[lo:hi], err_msg=f"final, frame {f}, rank {r}")
+                (lo, hi), band = per_rank_d[r][f]
+                np.testing.assert_array_equal(band, full_den[lo:hi], err_msg=f"denoised, frame {f}, rank {r}")
+        del pipe
+    finally:
+        import gc
+        gc.collect()
+        _capi._lib = saved

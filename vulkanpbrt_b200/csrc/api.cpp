@@ -725,6 +725,12 @@ int vkpbrt_accumulator_record(vkpbrt_accumulator_t a)
         std::memcpy(p.m_prev, a->pc_prev_view, 64);
     }
     std::memcpy(p.prev_origin, a->pc_prev_pos, 16);
+    const float sz[2] = {(float)a->width, (float)a->height};
+    for (int i = 0; i < 2; ++i) {
+        p.uv_scale[i] = sz[i] / (sz[i] - 0.5f);
+        p.rcp_size[i] = 1.0f / sz[i];
+    }
+    for (int i = 0; i < 4; ++i) p.cur_origin[i] = a->pc_inv_view[8 + i] / a->pc_inv_view[11];
     p.src = src->data;
     p.depth = (const float*)depth->data;
     p.prev_depth = (const float*)a->acc->img[VKPBRT_ACC_PREV_DEPTH]->data;

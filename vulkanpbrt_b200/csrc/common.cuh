@@ -40,6 +40,44 @@ VK_DEVICE float sub_rn(float a, float b) { return __fadd_rn(a, -b); }
 VK_DEVICE float div_rn(float a, float b) { return __fdiv_rn(a, b); }
 VK_DEVICE float sqrt_rn(float a) { return __fsqrt_rn(a); }
 
+// a / b == RN(a / b) from a correctly rounded reciprocal rb = RN(1 / b) (Markstein): q0 = RN(a*rb),
+// e = a - b*q0 (exact in one FMA), q = RN(q0 + e*rb).  Bit-identical to IEEE division whenever no
+// intermediate leaves the normal range; callers guarantee that with the range predicates below
+// (2^-40 <= |b| <= 2^40, |a| == 0 or 2^-60 <= |a| <= 2^60; validated against a / b on 4e8 random and
+// adversarial operand pairs, tools/markstein_check.c).  3 instructions instead of the ~12 + branch of
+// the generic IEEE sequence.
+VK_DEVICE float div_by_rcp(float a, float b, float rb)
+{
+    const float q0 = mul_rn(a, rb);
+    const float e = fmaf(-q0, b, a);
+    return fmaf(e, rb, q0);
+}
+// out-of-line generic division for the rare operands outside div_by_rcp's range (keeps the ~12-instruction
+// IEEE sequence and its slow-path call out of the unrolled hot loops)
+#ifndef VKPBRT_HOSTSIM
+static __device__ __noinline__ float div_rn_cold(float a, float b) { return __fdiv_rn(a, b); }
+#else
+inline float div_rn_cold(float a, float b) { return a / b; }
+#endif
+
+VK_DEVICE bool in_pow2_range(float x, uint32_t lo_bits, uint32_t hi_bits)   // lo <= |x| <= hi (normal numbers)
+{
+    return ((__float_as_uint(x) & 0x7fffffffu) - lo_bits) <= (hi_bits - lo_bits);
+}
+VK_DEVICE bool safe_divisor(float b) { return in_pow2_range(b, 0x2b800000u, 0x53800000u); }        // 2^-40 .. 2^40
+VK_DEVICE bool safe_factor(float x)                                                               // 0 or 2^-30 .. 2^30
+{
+    return (__float_as_uint(x) & 0x7fffffffu) == 0u || in_pow2_range(x, 0x30800000u, 0x4e800000u);
+}
+// a / b for a divisor whose reciprocal is reused: exact fast path when both operands are in range
+VK_DEVICE float div_guarded(float a, float b, float rb, bool b_safe)
+{
+    const uint32_t ia = __float_as_uint(a) & 0x7fffffffu;
+    if (b_safe && (ia == 0u || (ia - 0x21800000u) <= (0x5d800000u - 0x21800000u)))     // 0 or 2^-60 .. 2^60
+        return div_by_rcp(a, b, rb);
+    return div_rn_cold(a, b);
+}
+
 // ---- deterministic sin / cos / pow ------------------------------------------------------------
 // GLSL leaves their precision to the implementation; the oracle (oracle/vkpbrt_oracle.c: vk_sincos,
 // vk_pow) fixes them as plain-IEEE Cephes-style algorithms and these are the same operations in the
@@ -104,7 +142,8 @@ VK_DEVICE uint8_t f32_to_unorm8(float c)
     c = c > 1.0f ? 1.0f : c;
     return (uint8_t)add_rn(mul_rn(c, 255.0f), 0.5f);
 }
-VK_DEVICE float unorm8_to_f32(uint32_t c) { return __fdiv_rn((float)c, 255.0f); }
+// c / 255.0f, exactly rounded (checked for all 256 codes by tests/test_oracle_kat.py against the oracle)
+VK_DEVICE float unorm8_to_f32(uint32_t c) { return div_by_rcp((float)c, 255.0f, 0.0039215688593685627f); }
 
 // bmfrGeneral.comp:93-97 / bfr.comp:192-196
 VK_DEVICE int mirror(int x, int s)
@@ -201,7 +240,7 @@ VK_DEVICE void denoise_epilogue(float cr, float cg, float cb, uint32_t frame, si
     if (frame > 0 && accept) {
         Bilin bl = bilin_setup(uvx, uvy, W, H);
         sample_rgb16f(denoised_prev, bl, W, pr, pg, pb);
-        blend = gl_max(__fdiv_rn(1.0f, pixel_spp), 0.1f);
+        blend = gl_max(__frcp_rn(pixel_spp), 0.1f);
     }
     float omb = sub_rn(1.0f, blend);
     cr = add_rn(mul_rn(blend, cr), mul_rn(omb, pr));

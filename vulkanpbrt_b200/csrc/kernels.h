@@ -22,6 +22,10 @@ struct AccumulateParams {
     float inv_view[16];
     float m_prev[16];
     float prev_origin[4];
+    // uniform sub-expressions of the shader, evaluated once on the host with the same IEEE operations
+    float uv_scale[2];        // size / (size - 0.5)                         (accumulator.comp:70)
+    float rcp_size[2];        // RN(1 / size): exact (gid + .5) / size through div_by_rcp
+    float cur_origin[4];      // inverseView[2] / inverseView[2].w, combined-matrix mode (:56-57)
     const void* src;              // raw 1-spp illumination
     const float* depth;           // r32f
     const float* prev_depth;      // r32f   (bilinear)

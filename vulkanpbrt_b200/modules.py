@@ -158,12 +158,27 @@ class DescriptorImage:
         shape, dt = self.shape_dtype()
         return {"shape": shape, "typestr": np.dtype(dt).str, "data": (self.device_ptr, False), "version": 2}
 
+    def byte_view(self) -> "_ByteView":
+        """the CURRENT device buffer as raw bytes, shape [layers?][H][row_pitch] uint8 (any NCCL-friendly dtype)"""
+        i = self.info()
+        shape = (i.height, int(i.row_pitch)) if i.layers == 1 else (i.layers, i.height, int(i.row_pitch))
+        return _ByteView(i.data or 0, shape)
+
     def __del__(self):
         try:
             if self._owner and self._h:
                 capi.lib().vkpbrt_image_release(self._h)
         except Exception:
             pass
+
+
+class _ByteView:
+    def __init__(self, ptr: int, shape):
+        self.ptr, self.shape = ptr, tuple(shape)
+
+    @property
+    def __cuda_array_interface__(self):
+        return {"shape": self.shape, "typestr": "|u1", "data": (self.ptr, False), "version": 2}
 
 
 def _borrow(ctx: Context, getter: str, owner_handle, *args) -> DescriptorImage:
@@ -498,6 +513,7 @@ class BMFR(_BlockDenoiser):
                   illu_buffer.handle, acc_buffer.handle, fitting_kernel, C.byref(self._h))
         if debug_outputs:
             capi.call("vkpbrt_bmfr_set_debug_outputs", self._h, 1)
+        self.kernel_name = f"k_bmfr_block<{work_width},{fitting_kernel}>"
         self._final = _borrow(self.ctx, "vkpbrt_bmfr_final_image", self._h)
 
     @classmethod
@@ -534,6 +550,7 @@ class BFR(_BlockDenoiser):
         self._h = C.c_void_p()
         capi.call("vkpbrt_bfr_create", self.ctx.handle, width, height, work_width, work_height, g_buffer.handle,
                   illu_buffer.handle, acc_buffer.handle, C.byref(self._h))
+        self.kernel_name = f"k_bfr_block<{work_width}>"
         self._final = _borrow(self.ctx, "vkpbrt_bfr_final_image", self._h)
 
     @classmethod
@@ -557,6 +574,7 @@ class BFRBlender:
         capi.call("vkpbrt_bfr_blender_create", self.ctx.handle, width, height, average_image.handle,
                   average_squared_image.handle, denoised0.handle, denoised1.handle, denoised2.handle, work_width,
                   work_height, filter_radius, C.byref(self._h))
+        self.kernel_name = "k_bfr_blend"
         self._final = _borrow(self.ctx, "vkpbrt_bfr_blender_final_image", self._h)
 
     @classmethod

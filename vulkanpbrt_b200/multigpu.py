@@ -1,0 +1,399 @@
+"""Band-sharded multi-GPU execution of the denoising chain.
+
+The reference is single-device; this is new work.  One process per GPU (torch.distributed, NCCL over
+NVLink).  The frame is partitioned by horizontal bands of whole BLOCK ROWS of the jittered BMFR grid:
+rank g owns block rows [b_g, b_{g+1}).  Blocks are independent, so the only inter-GPU traffic is
+
+  * the HISTORY HALO: rows of prev_depth / accumulated illumination / sample counts / denoised
+    history / TAA history that the next frame's reprojection (bilinear, displacement <= D rows, REPEAT
+    wrap at the image edge) reads outside the rank's own rows, sent by their canonical owner; and
+  * one row of the tone-mapped denoiser output on each side for TAA's 3x3 neighbourhood.
+
+Both are neighbour exchanges of a few rows (tens of KB .. a few MB): latency- not bandwidth-bound, so
+they are batched into one NCCL group per exchange point.  Accumulate runs redundantly on the apron
+rows a rank's blocks read through the jitter/mirror footprint instead of exchanging current-frame
+planes.  Every rank keeps full-frame planes (the whole 8K working set is 3.5 GB) and only computes its
+band; the producer's input planes are band-local buffers addressed through a virtual full-frame base.
+
+BandPlan is pure integer geometry (tested on CPU); BandedPipeline drives one rank.
+"""
+from __future__ import annotations
+
+import json
+import time
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Tuple
+
+import numpy as np
+
+from . import _capi as capi
+from .modules import DenoisingBlockSize, DenoisingType
+from .pipeline import DenoisePipeline
+
+# bmfrGeneral.comp:36 -- the y component of ivec2(vec2(b, b) * pixelOffsets[f % 16])
+_OFFSETS = [(.7, .85), (.95, .5), (.43, .76), (.97, .03), (.37, .58), (.03, .36), (.81, .46), (0, .78), (.36, -.08),
+            (-.06, 0), (.95, .1), (.85, .61), (.06, .1), (.43, .16), (0, .5), (.73, .38)]
+
+
+def block_offset(block: int, frame: int) -> Tuple[int, int]:
+    ox, oy = _OFFSETS[frame % 16]
+    return int(np.float32(block) * np.float32(ox)), int(np.float32(block) * np.float32(oy))
+
+
+def _mirror(x: int, s: int) -> int:
+    if x < 0:
+        return -x - 1
+    if x >= s:
+        return 2 * s - x - 1
+    return x
+
+
+Rows = Tuple[int, int]   # [lo, hi)
+
+
+def _clip(r: Rows, H: int) -> Rows:
+    lo, hi = max(0, r[0]), min(H, r[1])
+    return (lo, max(lo, hi))
+
+
+def _intersect(a: Rows, b: Rows) -> Rows:
+    lo, hi = max(a[0], b[0]), min(a[1], b[1])
+    return (lo, max(lo, hi))
+
+
+@dataclass
+class Transfer:
+    src: int
+    dst: int
+    plane: str
+    rows: Rows
+
+
+class BandPlan:
+    """Integer geometry of the band partition for a W x H frame on `world` ranks."""
+
+    def __init__(self, width: int, height: int, world: int, block: int = 32, max_disp_rows: int = 24, taa: bool = False):
+        self.W, self.H, self.N, self.b, self.D, self.taa = width, height, world, block, max_disp_rows, taa
+        self.nby = height // block + 2
+        self.brow = [round(g * self.nby / world) for g in range(world + 1)]
+        if any(self.brow[g + 1] - self.brow[g] < 2 for g in range(world)):
+            raise ValueError("bands must be at least two block rows high")
+
+    def block_rows(self, g: int) -> Rows:
+        return (self.brow[g], self.brow[g + 1])
+
+    def boundary(self, g: int, frame: int) -> int:
+        """first image row of rank g's canonical band at `frame` (rows written by its BMFR blocks)"""
+        if g <= 0:
+            return 0
+        if g >= self.N:
+            return self.H
+        _, oy = block_offset(self.b, frame)
+        return min(self.H, max(0, self.b * self.brow[g] - oy))
+
+    def owned_rows(self, g: int, frame: int) -> Rows:
+        return (self.boundary(g, frame), self.boundary(g + 1, frame))
+
+    def accumulate_rows(self, g: int, frame: int) -> Rows:
+        """image rows the rank's blocks read through the jitter + mirror footprint (+1 for TAA's stencil is
+        not needed: TAA reads the denoiser output, not accumulate planes, outside its own rows)"""
+        _, oy = block_offset(self.b, frame)
+        lo_abs, hi_abs = self.b * self.brow[g] - oy, self.b * self.brow[g + 1] - oy - 1
+        rows = [_mirror(lo_abs, self.H), _mirror(hi_abs, self.H), _mirror(max(lo_abs, 0), self.H), _mirror(min(hi_abs, self.H - 1), self.H)]
+        lo, hi = min(rows), max(rows) + 1
+        # TAA on the owned rows reads motion there: owned rows are inside [lo, hi) by construction
+        o = self.owned_rows(g, frame)
+        return _clip((min(lo, o[0]), max(hi, o[1])), self.H)
+
+    def input_rows(self, g: int) -> Rows:
+        """rows of the producer's planes the rank ever touches (all 16 jitter phases)"""
+        lo = min(self.accumulate_rows(g, f)[0] for f in range(16))
+        hi = max(self.accumulate_rows(g, f)[1] for f in range(16))
+        return (lo, hi)
+
+    # ---- halo requirements of frame `frame` (reads of the history written at frame - 1) -----------------
+    def _with_disp(self, r: Rows) -> List[Rows]:
+        lo, hi = max(0, r[0] - self.D - 1), min(self.H, r[1] + self.D + 1)
+        out = [(lo, hi)]
+        # REPEAT addressing: a tap at row -1 / H wraps to the opposite image edge
+        if lo == 0 and hi < self.H:
+            out.append((self.H - 1, self.H))
+        if hi == self.H and lo > 0:
+            out.append((0, 1))
+        return out
+
+    def history_transfers(self, frame_next: int) -> List[Transfer]:
+        """rows every rank must receive before running `frame_next`, sent by the canonical owner of the row
+        at frame_next - 1.  Planes: acc (prev_depth, prev_illu, prev_spp), denoised, taa."""
+        f0 = frame_next - 1
+        out: List[Transfer] = []
+        for dst in range(self.N):
+            have_acc = self.accumulate_rows(dst, f0)
+            have_own = self.owned_rows(dst, f0)
+            need = {"acc": self._with_disp(self.accumulate_rows(dst, frame_next)),
+                    "denoised": self._with_disp(self.owned_rows(dst, frame_next))}
+            if self.taa:
+                need["taa"] = self._with_disp(self.owned_rows(dst, frame_next))
+            for plane, ranges in need.items():
+                have = have_acc if plane == "acc" else have_own
+                for r in ranges:
+                    for src in range(self.N):
+                        if src == dst:
+                            continue
+                        part = _intersect(r, self.owned_rows(src, f0))
+                        # drop what the receiver computed itself (identical values)
+                        for piece in _subtract(part, have):
+                            if piece[1] > piece[0]:
+                                out.append(Transfer(src, dst, plane, piece))
+        return out
+
+    def final_transfers(self, frame: int) -> List[Transfer]:
+        """one row of the denoiser's tone-mapped output on each side of the owned rows, for TAA (taa.comp:66-83)"""
+        out: List[Transfer] = []
+        if not self.taa:
+            return out
+        for dst in range(self.N):
+            lo, hi = self.owned_rows(dst, frame)
+            for row in (lo - 1, hi):
+                if 0 <= row < self.H:
+                    for src in range(self.N):
+                        o = self.owned_rows(src, frame)
+                        if src != dst and o[0] <= row < o[1]:
+                            out.append(Transfer(src, dst, "final", (row, row + 1)))
+        return out
+
+
+def _subtract(a: Rows, b: Rows) -> List[Rows]:
+    """a \\ b for half-open row ranges"""
+    if a[1] <= a[0]:
+        return []
+    lo, hi = max(a[0], b[0]), min(a[1], b[1])
+    if hi <= lo:
+        return [a]
+    out = []
+    if a[0] < lo:
+        out.append((a[0], lo))
+    if hi < a[1]:
+        out.append((hi, a[1]))
+    return out
+
+
+class BandedPipeline:
+    """One rank of the band-sharded chain.  `view(image)` must return a uint8 torch tensor aliasing the image's
+    CURRENT device buffer as raw bytes, shaped [layers?][H][row bytes] (cuda_view() below on a GPU)."""
+
+    def __init__(self, width: int, height: int, rank: int, world: int, use_taa: bool, ctx, view: Callable,
+                 max_disp_rows: int = 24, external_inputs: bool = True, dist=None):
+        self.rank, self.world, self.view = rank, world, view
+        self.plan = BandPlan(width, height, world, 32, max_disp_rows, use_taa)
+        self.pipe = DenoisePipeline(width, height, DenoisingType.BMFR, DenoisingBlockSize.X32, use_taa=use_taa, ctx=ctx,
+                                    external_inputs=external_inputs)
+        self.dist = dist
+        self.bmfr = self.pipe.modules[0]
+        self.bmfr.set_block_row_range(*self.plan.block_rows(rank))
+        c = self.pipe.commands.children
+        self._acc_cmd, self._bmfr_cmd = c[0], c[1]
+        self._taa_cmd = c[2] if use_taa else None
+        self._back_cmd = c[-1]
+        self.bytes_exchanged = 0
+
+    # planes by name, AFTER copy_to_back_images (the frame's outputs live in the prev_* handles)
+    def _history_planes(self, frame_done: int) -> Dict[str, list]:
+        acc = self.pipe.accumulation_buffer
+        den = self.view(self.bmfr.denoised)
+        planes = {"acc": [self.view(acc.prev_depth), self.view(acc.prev_illu), self.view(acc.prev_spp)],
+                  "denoised": [den[(frame_done & 1) ^ 1]]}
+        if self.pipe.taa is not None:
+            planes["taa"] = [self.view(self.pipe.taa.history)]
+        return planes
+
+    def _exchange(self, transfers: List[Transfer], planes: Dict[str, list]) -> None:
+        if self.world == 1 or not transfers:
+            return
+        dist = self.dist
+        ops = []
+        for t in transfers:     # identical order on every rank
+            if t.src != self.rank and t.dst != self.rank:
+                continue
+            for p in planes[t.plane]:
+                sl = p[t.rows[0]:t.rows[1]]
+                if t.src == self.rank:
+                    ops.append(dist.P2POp(dist.isend, sl, t.dst))
+                else:
+                    ops.append(dist.P2POp(dist.irecv, sl, t.src))
+                    self.bytes_exchanged += sl.numel() * sl.element_size()
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+
+    def run_frame(self, frame: int, cam) -> None:
+        """inputs must already be bound / uploaded for this frame"""
+        p, plan, g = self.pipe, self.plan, self.rank
+        p.set_frame_constants(frame, cam)
+        p.accumulator.set_row_range(*plan.accumulate_rows(g, frame))
+        self._acc_cmd(p.commands)
+        self._bmfr_cmd(p.commands)
+        if p.taa is not None:
+            self._exchange(plan.final_transfers(frame), {"final": [self.view(p.denoiser_final)]})
+            p.taa.set_row_range(*plan.owned_rows(g, frame))
+            self._taa_cmd(p.commands)
+        self._back_cmd(p.commands)
+        p.end_frame(cam)
+        self._exchange(plan.history_transfers(frame + 1), self._history_planes(frame))
+
+    def owned_rows(self, frame: int) -> Rows:
+        return self.plan.owned_rows(self.rank, frame)
+
+
+def cuda_view(device):
+    """view(image) for CUDA ranks: zero-copy uint8 tensor over the image's current device buffer"""
+    import torch
+
+    def view(img):
+        return torch.as_tensor(img.byte_view(), device=device)
+    return view
+
+
+# ---------------------------------------------------------------------------------------------------
+# bench.py --gpus N (N > 1): weak scaling, one 1920x1080 band per GPU
+# ---------------------------------------------------------------------------------------------------
+def bench_multi(args, rank: int, world: int, local: int):
+    import torch
+    import torch.distributed as dist
+
+    from . import synth
+    from .modules import Context
+    import bench as B     # the repo-root bench.py (constants, sampler, cpu baseline)
+
+    name = args.workload or "bmfr_1080p"
+    W, Hband, taa, desc = B.WORKLOADS[name]
+    strong = name != "bmfr_1080p"
+    H = Hband if strong else Hband * world
+    K, Wm = args.steps, args.warmup
+    R = min(K + Wm, args.resident_frames)
+    dev = torch.device("cuda", local)
+    stream = torch.cuda.current_stream()
+    ctx = Context(local, stream.cuda_stream)
+    view = cuda_view(dev)
+    bp = BandedPipeline(W, H, rank, world, taa, ctx, view, dist=dist)
+    lo, hi = bp.plan.input_rows(rank)
+    rows = hi - lo
+    # band-local resident sequence; the kernels index absolute rows through a virtual full-frame base pointer
+    mk = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True)
+    host = {"depth": mk((R, rows, W), torch.float32), "normal": mk((R, rows, W, 2), torch.float32),
+            "albedo": mk((R, rows, W, 4), torch.uint8), "illum": mk((R, rows, W, 4), torch.float32)}
+    cams = []
+    full = synth.Frame(0, np.zeros((H, W), np.float32), np.zeros((H, W, 2), np.float32), np.zeros((H, W, 4), np.uint8),
+                       np.zeros((H, W, 4), np.uint8), np.zeros((H, W, 4), np.float32), None)
+    t_gen = time.perf_counter()
+    for i in range(R):
+        synth.render_frame(W, H, i, rows=(lo, hi), out=full)
+        host["depth"][i].numpy()[...] = full.depth[lo:hi]
+        host["normal"][i].numpy()[...] = full.normal[lo:hi]
+        host["albedo"][i].numpy()[...] = full.albedo[lo:hi]
+        host["illum"][i].numpy()[...] = full.illumination[lo:hi]
+        cams.append(full.camera)
+    t_gen = time.perf_counter() - t_gen
+    dseq = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+    torch.cuda.synchronize()
+    pitch = {"depth": 4 * W, "normal": 8 * W, "albedo": 4 * W, "illum": 16 * W}
+
+    def bind(bufs, i):
+        bp.pipe.bind_inputs(*[bufs[k][i].data_ptr() - lo * pitch[k] for k in ("depth", "normal", "albedo", "illum")])
+
+    def frame(f):
+        i = f % R
+        bind(dseq, i)
+        bp.run_frame(f, cams[i])
+
+    for f in range(Wm):
+        frame(f)
+    torch.cuda.synchronize()
+    dist.barrier()
+    sampler = B.ClockSampler(local)
+    sampler.start()
+    launches0 = ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for f in range(Wm, Wm + K):
+        frame(f)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    dist.barrier()
+    clocks = sampler.stop()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    launches = ctx.launch_count - launches0
+    value = W * H * K / (ms * 1e-3) / 1e6
+
+    # ---- e2e: per-rank band uploaded from pinned host memory every frame, owned rows of the result read back ----
+    copy_stream = torch.cuda.Stream()
+    dbuf = [{k: torch.empty_like(dseq[k][0]) for k in host} for _ in range(2)]
+    out_host = torch.empty((H, W * 4), dtype=torch.uint8, pin_memory=True)
+    copied = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def issue_copy(f):
+        s = f % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[s])
+            for k in host:
+                dbuf[s][k].copy_(host[k][f % R], non_blocking=True)
+            copied[s].record(copy_stream)
+
+    def frame_e2e(f):
+        s = f % 2
+        stream.wait_event(copied[s])
+        bp.pipe.bind_inputs(*[dbuf[s][k].data_ptr() - lo * pitch[k] for k in ("depth", "normal", "albedo", "illum")])
+        bp.run_frame(f, cams[f % R])
+        consumed[s].record(stream)
+        o = bp.owned_rows(f)
+        out_host[o[0]:o[1]].copy_(view(bp.pipe.final)[o[0]:o[1]], non_blocking=True)     # [H][W*4] bytes
+
+    for s in range(2):
+        consumed[s].record(stream)
+    f0 = Wm + K
+    issue_copy(f0)
+    for f in range(f0, f0 + 3):
+        issue_copy(f + 1)
+        frame_e2e(f)
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0.record(stream)
+    for f in range(f0 + 3, f0 + 3 + K):
+        issue_copy(f + 1)
+        frame_e2e(f)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    dist.barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    halo = torch.tensor([bp.bytes_exchanged], device=dev, dtype=torch.float64)
+    dist.all_reduce(halo)
+    if rank == 0:
+        hbm_peak, peak_src = B.peaks()
+        chain = (B.BYTES_ACCUMULATE + B.BYTES_BMFR + (B.BYTES_TAA if taa else 0))
+        gbs = chain * W * H / (ms / K * 1e-3) / 1e9
+        line = {"metric": "BMFR denoised MPix/s", "value": round(value, 1), "unit": "MPix/s", "n_gpus": world, "steps": K, "warmup": Wm,
+                "ms_per_step": round(ms / K, 5), "higher_is_better": True, "scaling": "strong" if strong else "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": name + ("" if strong else "_bands"), "description": desc + f"; band-sharded over {world} GPUs"
+                           + ("" if strong else f" (weak scaling: one {W}x{Hband} band per GPU, frame {W}x{H})"),
+                           "width": W, "height": H, "block": 32, "taa": taa, "band_block_rows": bp.plan.brow,
+                           "halo": f"history rows +-{bp.plan.D + 1} (+ REPEAT wrap row) per boundary, NCCL send/recv per frame",
+                           "l2": f"inputs larger than L2: {R} resident band frames, each read once per step",
+                           "sequence_generation_s": round(t_gen, 1)},
+                "e2e": {"value": round(W * H * K / (e2e_ms * 1e-3) / 1e6, 1), "unit": "MPix/s",
+                        "h2d_bytes_per_step": B.INPUT_BYTES * W * rows * world, "d2h_bytes_per_step": 4 * W * H,
+                        "ms_per_step": round(e2e_ms / K, 5)},
+                "gpu_launches": int(launches) * world, "clocks": clocks,
+                "roofline": {"kernel": "chain (k_accumulate + k_bmfr_block" + (" + k_taa)" if taa else ")"), "bound": "hbm",
+                             "achieved": round(gbs, 1), "peak": hbm_peak * world, "unit": "GB/s",
+                             "frac": round(gbs / (hbm_peak * world), 4), "traffic": None, "peak_source": peak_src,
+                             "note": "aggregate over ranks; per-kernel fractions are reported by the N=1 run"},
+                "halo_bytes_per_step": float(halo.item()) / (2 * K + Wm + 3), "cpu_baseline": None}
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()

@@ -83,6 +83,10 @@ class DenoisePipeline:
             self.final = self.taa.get_final_descriptor_image()
         # :502-505
         self.accumulation_buffer.copy_to_back_images(self.commands, self.g_buffer, self.illumination_buffer)
+        # one label per recorded command, in replay order (bench.py's per-kernel timing)
+        self.command_labels = (["k_accumulate"] + [m.kernel_name for m in self.modules] + (["k_taa"] if self.taa else [])
+                               + ["copy_to_back_images (pointer swaps)"])
+        assert len(self.command_labels) == len(self.commands.children)
         self._prev_camera = None
         ctx.synchronize()
 
