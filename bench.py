@@ -80,7 +80,7 @@ class ClockSampler(threading.Thread):
                 for bit, n in names.items():
                     if r & bit:
                         self.reasons.add(n)
-                time.sleep(0.02)
+                time.sleep(0.004)
         except Exception as e:  # pragma: no cover
             self.reasons.add(f"sampler_error:{type(e).__name__}")
 
@@ -178,8 +178,11 @@ def main_ours(args):
     K, Wm = args.steps, args.warmup
     R = min(K + Wm, args.resident_frames)        # frames kept resident; longer runs cycle through them
     dev = torch.device("cuda", local)
-    stream = torch.cuda.current_stream()
+    # an explicit stream: the library records on the stream it is handed and the CUDA events below must sit on the same one
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     ctx = Context(local, stream.cuda_stream)
+    assert ctx.stream == stream.cuda_stream
     t_gen = time.perf_counter()
     seq = render_sequence(W, H, R)
     t_gen = time.perf_counter() - t_gen

@@ -148,7 +148,8 @@ VKPBRT_API int vkpbrt_illumination_buffer_destroy(vkpbrt_illumination_buffer_t b
 typedef struct vkpbrt_accumulation_buffer_s* vkpbrt_accumulation_buffer_t;
 typedef enum {
     VKPBRT_ACC_PREV_ILLU = 0, VKPBRT_ACC_PREV_ILLU_SQUARED = 1, VKPBRT_ACC_PREV_DEPTH = 2,
-    VKPBRT_ACC_PREV_NORMAL = 3, VKPBRT_ACC_SPP = 4, VKPBRT_ACC_PREV_SPP = 5, VKPBRT_ACC_MOTION = 6
+    VKPBRT_ACC_PREV_NORMAL = 3, VKPBRT_ACC_SPP = 4, VKPBRT_ACC_PREV_SPP = 5, VKPBRT_ACC_MOTION = 6,
+    VKPBRT_ACC_NEXT_DEPTH = 7 /* not in the reference: the depth history k_accumulate is writing (becomes prev_depth at copy_to_back) */
 } vkpbrt_accumulation_member;
 VKPBRT_API int vkpbrt_accumulation_buffer_create(vkpbrt_context_t ctx, uint32_t width, uint32_t height,
                                                  vkpbrt_accumulation_buffer_t* out);

@@ -41,6 +41,12 @@ static thread_local ThreadState tls;
 
 Block*& blk() { return tls.blk; }
 
+unsigned char* dyn_smem()
+{
+    alignas(16) static thread_local unsigned char buf[256 * 1024];
+    return buf;
+}
+
 void yield(int new_state)
 {
     Block* b = tls.blk;

@@ -54,6 +54,9 @@ inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
 inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { strcpy(p->name, "HOSTSIM (CPU test emulator)"); p->major = 10; p->minor = 0; return cudaSuccess; }
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+template <typename F>
+inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = nullptr; return cudaSuccess; }
 inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
@@ -105,6 +108,7 @@ struct Block {
 };
 
 Block*& blk();                       // per OS thread
+unsigned char* dyn_smem();           // per OS thread, 256 KB (dynamic shared memory of the running block)
 void launch(dim3 grid, dim3 block, const std::function<void()>& body);
 void yield(int new_state);
 

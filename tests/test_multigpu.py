@@ -86,18 +86,21 @@ def _worker(rank, world, W, H, frames, use_taa, port, out_dir):
         o = bp.owned_rows(f)
         finals.append((o, bp.pipe.final.download()[o[0]:o[1]].copy()))
         denoised.append((o, bp.bmfr.denoised.download()[(f & 1) ^ 1, o[0]:o[1]].copy()))
+    bp.flush()
     np.save(os.path.join(out_dir, f"final_{rank}.npy"), np.array([(o, a) for o, a in finals], dtype=object), allow_pickle=True)
     np.save(os.path.join(out_dir, f"den_{rank}.npy"), np.array([(o, a) for o, a in denoised], dtype=object), allow_pickle=True)
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("use_taa", [False, True])
-def test_two_rank_banded_chain_equals_single_rank(tmp_path, use_taa):
+@pytest.mark.parametrize("use_taa,W,H,frames", [(False, 128, 192, 10), (True, 128, 192, 10), (True, 64, 1080, 27)])
+def test_two_rank_banded_chain_equals_single_rank(tmp_path, use_taa, W, H, frames):
+    """the 1080-row case moves the band boundary over rows whose column 0 is left unwritten at frames 9 and 25
+    (negative x jitter): the stale pixels must come from whichever rank wrote them last"""
     import subprocess
     import torch.multiprocessing as mp
     subprocess.run(["make", "-C", str(ROOT / "tests" / "hostsim")], check=True, capture_output=True)
-    W, H, frames, world = 128, 192, 10, 2
+    world = 2
     port = 29500 + (os.getpid() % 2000)
     mp.start_processes(_worker, args=(world, W, H, frames, use_taa, port, str(tmp_path)), nprocs=world, join=True, start_method="spawn")
     # single-rank run of the same sequence (emulator, this process)
@@ -122,3 +125,56 @@ def test_two_rank_banded_chain_equals_single_rank(tmp_path, use_taa):
         import gc
         gc.collect()
         _capi._lib = saved
+
+
+# ---- real GPUs: NCCL halo exchange over NVLink ------------------------------------------------------
+def _gpu_worker(rank, world, W, H, frames, use_taa, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    sys.path.insert(0, str(ROOT))
+    import torch
+    import torch.distributed as dist
+    from vulkanpbrt_b200 import Context, synth
+    from vulkanpbrt_b200.multigpu import BandedPipeline, cuda_view
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    bp = BandedPipeline(W, H, rank, world, use_taa, Context(rank, stream.cuda_stream), cuda_view(dev), external_inputs=False, dist=dist)
+    lo, hi = bp.plan.input_rows(rank)
+    finals = []
+    for f in range(frames):
+        fr = synth.render_frame(W, H, f, rows=(lo, hi))
+        bp.pipe.upload_frame(fr)
+        bp.run_frame(f, fr.camera)
+        torch.cuda.synchronize()
+        o = bp.owned_rows(f)
+        finals.append((o, bp.pipe.final.download()[o[0]:o[1]].copy(), bp.bmfr.denoised.download()[(f & 1) ^ 1, o[0]:o[1]].copy()))
+    bp.flush()
+    torch.cuda.synchronize()
+    np.save(os.path.join(out_dir, f"gpu_{rank}.npy"), np.array(finals, dtype=object), allow_pickle=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_banded_chain_on_gpus_equals_single_gpu(tmp_path, world):
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import torch.multiprocessing as mp
+    W, H, frames = 1920, 1080, 12
+    port = 29500 + (os.getpid() % 2000)
+    mp.start_processes(_gpu_worker, args=(world, W, H, frames, True, port, str(tmp_path)), nprocs=world, join=True, start_method="spawn")
+    from vulkanpbrt_b200 import DenoisePipeline, synth
+    pipe = DenoisePipeline(W, H, use_taa=True)
+    per_rank = [np.load(tmp_path / f"gpu_{r}.npy", allow_pickle=True) for r in range(world)]
+    for f in range(frames):
+        pipe.run_frame(f, synth.render_frame(W, H, f))
+        full_final = pipe.final.download()
+        full_den = pipe.modules[0].denoised.download()[(f & 1) ^ 1]
+        for r in range(world):
+            (lo, hi), band_f, band_d = per_rank[r][f]
+            np.testing.assert_array_equal(band_f, full_final[lo:hi], err_msg=f"final, frame {f}, rank {r}")
+            np.testing.assert_array_equal(band_d, full_den[lo:hi], err_msg=f"denoised, frame {f}, rank {r}")

@@ -39,7 +39,7 @@ FORMAT_R16_SFLOAT = 9
 
 GBUFFER_DEPTH, GBUFFER_NORMAL, GBUFFER_MATERIAL, GBUFFER_ALBEDO = range(4)
 ILLUMINATION_FINAL, ILLUMINATION_DEMODULATED, ILLUMINATION_DEMODULATED_FLOAT, ILLUMINATION_FINAL_DEMODULATED = range(4)
-(ACC_PREV_ILLU, ACC_PREV_ILLU_SQUARED, ACC_PREV_DEPTH, ACC_PREV_NORMAL, ACC_SPP, ACC_PREV_SPP, ACC_MOTION) = range(7)
+(ACC_PREV_ILLU, ACC_PREV_ILLU_SQUARED, ACC_PREV_DEPTH, ACC_PREV_NORMAL, ACC_SPP, ACC_PREV_SPP, ACC_MOTION, ACC_NEXT_DEPTH) = range(8)
 BMFR_IMAGE_DENOISED, BMFR_IMAGE_FEATURES, BMFR_IMAGE_WEIGHTS = range(3)
 
 

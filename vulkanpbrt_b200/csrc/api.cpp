@@ -561,8 +561,8 @@ int vkpbrt_accumulation_buffer_compile(vkpbrt_accumulation_buffer_t b)
 
 int vkpbrt_accumulation_buffer_image(vkpbrt_accumulation_buffer_t b, uint32_t member, vkpbrt_image_t* out)
 {
-    VK_REQUIRE(b && out && member < 7, "vkpbrt_accumulation_buffer_image: bad argument");
-    *out = b->img[member];
+    VK_REQUIRE(b && out && member < 8, "vkpbrt_accumulation_buffer_image: bad argument");
+    *out = member == VKPBRT_ACC_NEXT_DEPTH ? b->depth_next : b->img[member];
     return VKPBRT_OK;
 }
 

@@ -21,7 +21,9 @@
 #ifndef VKPBRT_HOSTSIM
 #define VK_DEVICE __device__ __forceinline__
 #define VKPBRT_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define VKPBRT_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #else
+#define VKPBRT_DYN_SMEM(name) unsigned char* name = hostsim::dyn_smem()
 #define VK_DEVICE inline
 #endif
 

@@ -348,6 +348,7 @@ class AccumulationBuffer:
         self.spp = g(capi.ACC_SPP)
         self.prev_spp = g(capi.ACC_PREV_SPP)
         self.motion = g(capi.ACC_MOTION)
+        self.next_depth = g(capi.ACC_NEXT_DEPTH)     # extension: depth history being written this frame
 
     @classmethod
     def create(cls, ctx: Context, width: int, height: int):

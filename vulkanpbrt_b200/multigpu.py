@@ -147,6 +147,22 @@ class BandPlan:
                                 out.append(Transfer(src, dst, plane, piece))
         return out
 
+    def stale_column_transfers(self, frame: int) -> List[Transfer]:
+        """Frames with a negative x jitter (f = 9 mod 16: offset (-1, 0)) leave image column 0 UNWRITTEN: the
+        reference keeps whatever the previous frames stored there.  The band boundary
+        moves with the y jitter, so the rank that owns such a pixel may not be the one that wrote it last.
+        After every frame each rank therefore mirrors column 0 of the rows it wrote inside the window the
+        boundary can move in to its neighbour (planes: denoiser final, denoised layer just written)."""
+        out: List[Transfer] = []
+        for g in range(1, self.N):
+            win = _clip((self.b * self.brow[g] - self.b, self.b * self.brow[g] + 3), self.H)
+            for src, dst in ((g - 1, g), (g, g - 1)):
+                rows = _intersect(win, self.owned_rows(src, frame))
+                if rows[1] > rows[0]:
+                    out.append(Transfer(src, dst, "final_col0", rows))
+                    out.append(Transfer(src, dst, "denoised_col0", rows))
+        return out
+
     def final_transfers(self, frame: int) -> List[Transfer]:
         """one row of the denoiser's tone-mapped output on each side of the owned rows, for TAA (taa.comp:66-83)"""
         out: List[Transfer] = []
@@ -196,50 +212,85 @@ class BandedPipeline:
         self._taa_cmd = c[2] if use_taa else None
         self._back_cmd = c[-1]
         self.bytes_exchanged = 0
+        self._pending_a = self._pending_b = None
 
-    # planes by name, AFTER copy_to_back_images (the frame's outputs live in the prev_* handles)
-    def _history_planes(self, frame_done: int) -> Dict[str, list]:
-        acc = self.pipe.accumulation_buffer
-        den = self.view(self.bmfr.denoised)
-        planes = {"acc": [self.view(acc.prev_depth), self.view(acc.prev_illu), self.view(acc.prev_spp)],
-                  "denoised": [den[(frame_done & 1) ^ 1]]}
-        if self.pipe.taa is not None:
-            planes["taa"] = [self.view(self.pipe.taa.history)]
-        return planes
-
-    def _exchange(self, transfers: List[Transfer], planes: Dict[str, list]) -> None:
+    def _start(self, transfers: List[Transfer], planes: Dict[str, list]):
+        """enqueues one NCCL group with every send / recv of `transfers` that involves this rank and returns
+        the pending handle; nothing waits.  NCCL orders the group after the work already enqueued on the
+        current stream, so a group started right after a kernel overlaps whatever is enqueued next."""
         if self.world == 1 or not transfers:
-            return
+            return None
         dist = self.dist
-        ops = []
+        ops, scatter, keep = [], [], []
         for t in transfers:     # identical order on every rank
             if t.src != self.rank and t.dst != self.rank:
                 continue
-            for p in planes[t.plane]:
-                sl = p[t.rows[0]:t.rows[1]]
+            for p, ncol_bytes in planes[t.plane]:
+                sl = p[t.rows[0]:t.rows[1]] if ncol_bytes is None else p[t.rows[0]:t.rows[1], :ncol_bytes]
                 if t.src == self.rank:
-                    ops.append(dist.P2POp(dist.isend, sl, t.dst))
+                    buf = sl if ncol_bytes is None else sl.contiguous()     # column strips are staged
+                    keep.append(buf)
+                    ops.append(dist.P2POp(dist.isend, buf, t.dst))
                 else:
-                    ops.append(dist.P2POp(dist.irecv, sl, t.src))
+                    buf = sl if ncol_bytes is None else sl.new_empty(sl.shape)
+                    if ncol_bytes is not None:
+                        scatter.append((sl, buf))
+                    ops.append(dist.P2POp(dist.irecv, buf, t.src))
                     self.bytes_exchanged += sl.numel() * sl.element_size()
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
+        if not ops:
+            return None
+        return (dist.batch_isend_irecv(ops), scatter, keep)
+
+    @staticmethod
+    def _finish(pending) -> None:
+        """makes the current stream wait for a group started by _start (stream-side wait for NCCL)"""
+        if pending is None:
+            return
+        works, scatter, _keep = pending
+        for w in works:
+            w.wait()
+        for sl, buf in scatter:
+            sl.copy_(buf)
 
     def run_frame(self, frame: int, cam) -> None:
-        """inputs must already be bound / uploaded for this frame"""
+        """inputs must already be bound / uploaded for this frame.  Per frame and boundary:
+             A  accumulate-plane halos (depth history, accumulated illumination, sample counts): started right
+                after k_accumulate, overlaps k_bmfr_block, awaited before the next frame's k_accumulate;
+             F  one row of the denoiser output for TAA's stencil (TAA configurations only, not overlapped);
+             B  denoised / TAA history halos + the stale-column strip: started at the end of the frame,
+                overlaps the next frame's k_accumulate, awaited before its k_bmfr_block."""
         p, plan, g = self.pipe, self.plan, self.rank
+        acc = p.accumulation_buffer
         p.set_frame_constants(frame, cam)
         p.accumulator.set_row_range(*plan.accumulate_rows(g, frame))
+        self._finish(self._pending_a)
         self._acc_cmd(p.commands)
+        # pre-swap handles: what k_accumulate just wrote becomes prev_depth / prev_illu / prev_spp at copy_to_back
+        planes_a = {"acc": [(self.view(acc.next_depth), None), (self.view(p.illumination_buffer.illumination_images[0]), None),
+                            (self.view(acc.spp), None)]}
+        self._pending_a = self._start([t for t in plan.history_transfers(frame + 1) if t.plane == "acc"], planes_a)
+        self._finish(self._pending_b)
         self._bmfr_cmd(p.commands)
         if p.taa is not None:
-            self._exchange(plan.final_transfers(frame), {"final": [self.view(p.denoiser_final)]})
+            self._finish(self._start(plan.final_transfers(frame), {"final": [(self.view(p.denoiser_final), None)]}))
             p.taa.set_row_range(*plan.owned_rows(g, frame))
             self._taa_cmd(p.commands)
         self._back_cmd(p.commands)
         p.end_frame(cam)
-        self._exchange(plan.history_transfers(frame + 1), self._history_planes(frame))
+        written = self.view(self.bmfr.denoised)[(frame & 1) ^ 1]
+        planes_b = {"denoised": [(written, None)],
+                    "final_col0": [(self.view(p.denoiser_final), 4)],      # 1 BGRA8 texel
+                    "denoised_col0": [(written, 8)]}                        # 1 rgba16f texel
+        if p.taa is not None:
+            planes_b["taa"] = [(self.view(p.taa.history), None)]
+        self._pending_b = self._start([t for t in plan.history_transfers(frame + 1) if t.plane != "acc"]
+                                      + plan.stale_column_transfers(frame), planes_b)
+
+    def flush(self) -> None:
+        """waits (stream-side) for the halos in flight; call before reading planes outside the owned rows"""
+        self._finish(self._pending_a)
+        self._finish(self._pending_b)
+        self._pending_a = self._pending_b = None
 
     def owned_rows(self, frame: int) -> Rows:
         return self.plan.owned_rows(self.rank, frame)
@@ -272,8 +323,10 @@ def bench_multi(args, rank: int, world: int, local: int):
     K, Wm = args.steps, args.warmup
     R = min(K + Wm, args.resident_frames)
     dev = torch.device("cuda", local)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     ctx = Context(local, stream.cuda_stream)
+    assert ctx.stream == stream.cuda_stream
     view = cuda_view(dev)
     bp = BandedPipeline(W, H, rank, world, taa, ctx, view, dist=dist)
     lo, hi = bp.plan.input_rows(rank)
@@ -317,6 +370,7 @@ def bench_multi(args, rank: int, world: int, local: int):
     e0.record(stream)
     for f in range(Wm, Wm + K):
         frame(f)
+    bp.flush()
     e1.record(stream)
     torch.cuda.synchronize()
     dist.barrier()
@@ -364,6 +418,7 @@ def bench_multi(args, rank: int, world: int, local: int):
     for f in range(f0 + 3, f0 + 3 + K):
         issue_copy(f + 1)
         frame_e2e(f)
+    bp.flush()
     e1.record(stream)
     torch.cuda.synchronize()
     dist.barrier()
