@@ -167,9 +167,17 @@ def main_ours(args):
         args.gpus = world
     torch.cuda.set_device(local)
     if world > 1:
+        # exactly ONE line on stdout (the JSON): library chatter such as NCCL's version banner goes to stderr
+        real_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         from vulkanpbrt_b200.multigpu import bench_multi
-        return bench_multi(args, rank, world, local)
+        line = bench_multi(args, rank, world, local)
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        if line is not None:
+            print(json.dumps(line), flush=True)
+        return
 
     from vulkanpbrt_b200 import Context, DenoisePipeline, DenoisingBlockSize, DenoisingType
 

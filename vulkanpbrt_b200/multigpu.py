@@ -213,40 +213,82 @@ class BandedPipeline:
         self._back_cmd = c[-1]
         self.bytes_exchanged = 0
         self._pending_a = self._pending_b = None
+        self._views: Dict = {}
+        self._desc: Dict = {}
 
-    def _start(self, transfers: List[Transfer], planes: Dict[str, list]):
-        """enqueues one NCCL group with every send / recv of `transfers` that involves this rank and returns
-        the pending handle; nothing waits.  NCCL orders the group after the work already enqueued on the
-        current stream, so a group started right after a kernel overlaps whatever is enqueued next."""
-        if self.world == 1 or not transfers:
-            return None
+    # ---- cached exchange descriptors -------------------------------------------------------------------
+    # Row ranges repeat with the 16-frame jitter period and the ping-pong buffers with period 2, so the
+    # P2POp lists (and the tensor views they alias) are built once per (phase, buffer pointers) and reused:
+    # the per-frame host cost is one batch_isend_irecv per exchange point.
+    def _view(self, img):
+        i = img.info()
+        key = (i.data, i.size_bytes)
+        v = self._views.get(key)
+        if v is None:
+            v = self._views[key] = self.view(img)
+        return v
+
+    def _build(self, transfers: List[Transfer], planes: Dict[str, list]):
         dist = self.dist
-        ops, scatter, keep = [], [], []
+        ops, scatter, gather = [], [], []
+        nbytes = 0
         for t in transfers:     # identical order on every rank
             if t.src != self.rank and t.dst != self.rank:
                 continue
             for p, ncol_bytes in planes[t.plane]:
                 sl = p[t.rows[0]:t.rows[1]] if ncol_bytes is None else p[t.rows[0]:t.rows[1], :ncol_bytes]
                 if t.src == self.rank:
-                    buf = sl if ncol_bytes is None else sl.contiguous()     # column strips are staged
-                    keep.append(buf)
+                    buf = sl
+                    if ncol_bytes is not None:          # column strips are staged through a contiguous buffer
+                        buf = sl.new_empty(sl.shape)
+                        gather.append((buf, sl))
                     ops.append(dist.P2POp(dist.isend, buf, t.dst))
                 else:
-                    buf = sl if ncol_bytes is None else sl.new_empty(sl.shape)
+                    buf = sl
                     if ncol_bytes is not None:
+                        buf = sl.new_empty(sl.shape)
                         scatter.append((sl, buf))
                     ops.append(dist.P2POp(dist.irecv, buf, t.src))
-                    self.bytes_exchanged += sl.numel() * sl.element_size()
+                    nbytes += sl.numel() * sl.element_size()
+        return (ops, gather, scatter, nbytes)
+
+    def _exchange_desc(self, kind: str, frame: int, images: Dict[str, list], transfers_fn):
+        """images: plane name -> [(DescriptorImage or (DescriptorImage, layer), ncol_bytes)]"""
+        ptrs = tuple((img[0] if isinstance(img, tuple) else img).info().data for lst in images.values() for img, _ in lst)
+        key = (kind, frame % 16, ptrs)
+        d = self._desc.get(key)
+        if d is None:
+            planes = {}
+            for name, lst in images.items():
+                planes[name] = []
+                for img, ncol in lst:
+                    if isinstance(img, tuple):
+                        planes[name].append((self._view(img[0])[img[1]], ncol))
+                    else:
+                        planes[name].append((self._view(img), ncol))
+            d = self._desc[key] = self._build(transfers_fn(), planes)
+        return d
+
+    def _start(self, desc):
+        """enqueues one NCCL group with every send / recv of the descriptor and returns the pending handle;
+        nothing waits.  NCCL orders the group after the work already enqueued on the current stream, so a
+        group started right after a kernel overlaps whatever is enqueued next."""
+        if self.world == 1 or desc is None:
+            return None
+        ops, gather, scatter, nbytes = desc
         if not ops:
             return None
-        return (dist.batch_isend_irecv(ops), scatter, keep)
+        for buf, sl in gather:
+            buf.copy_(sl)
+        self.bytes_exchanged += nbytes
+        return (self.dist.batch_isend_irecv(ops), scatter)
 
     @staticmethod
     def _finish(pending) -> None:
         """makes the current stream wait for a group started by _start (stream-side wait for NCCL)"""
         if pending is None:
             return
-        works, scatter, _keep = pending
+        works, scatter = pending
         for w in works:
             w.wait()
         for sl, buf in scatter:
@@ -261,30 +303,39 @@ class BandedPipeline:
                 overlaps the next frame's k_accumulate, awaited before its k_bmfr_block."""
         p, plan, g = self.pipe, self.plan, self.rank
         acc = p.accumulation_buffer
+        multi = self.world > 1
         p.set_frame_constants(frame, cam)
         p.accumulator.set_row_range(*plan.accumulate_rows(g, frame))
         self._finish(self._pending_a)
         self._acc_cmd(p.commands)
-        # pre-swap handles: what k_accumulate just wrote becomes prev_depth / prev_illu / prev_spp at copy_to_back
-        planes_a = {"acc": [(self.view(acc.next_depth), None), (self.view(p.illumination_buffer.illumination_images[0]), None),
-                            (self.view(acc.spp), None)]}
-        self._pending_a = self._start([t for t in plan.history_transfers(frame + 1) if t.plane == "acc"], planes_a)
+        if multi:
+            # pre-swap handles: what k_accumulate just wrote becomes prev_depth / prev_illu / prev_spp at copy_to_back
+            da = self._exchange_desc("A", frame, {"acc": [(acc.next_depth, None), (p.illumination_buffer.illumination_images[0], None),
+                                                          (acc.spp, None)]},
+                                     lambda: [t for t in plan.history_transfers(frame + 1) if t.plane == "acc"])
+            self._pending_a = self._start(da)
         self._finish(self._pending_b)
+        self._pending_b = None
         self._bmfr_cmd(p.commands)
         if p.taa is not None:
-            self._finish(self._start(plan.final_transfers(frame), {"final": [(self.view(p.denoiser_final), None)]}))
+            if multi:
+                df = self._exchange_desc("F", frame, {"final": [(p.denoiser_final, None)]}, lambda: plan.final_transfers(frame))
+                self._finish(self._start(df))
             p.taa.set_row_range(*plan.owned_rows(g, frame))
             self._taa_cmd(p.commands)
         self._back_cmd(p.commands)
         p.end_frame(cam)
-        written = self.view(self.bmfr.denoised)[(frame & 1) ^ 1]
-        planes_b = {"denoised": [(written, None)],
-                    "final_col0": [(self.view(p.denoiser_final), 4)],      # 1 BGRA8 texel
-                    "denoised_col0": [(written, 8)]}                        # 1 rgba16f texel
-        if p.taa is not None:
-            planes_b["taa"] = [(self.view(p.taa.history), None)]
-        self._pending_b = self._start([t for t in plan.history_transfers(frame + 1) if t.plane != "acc"]
-                                      + plan.stale_column_transfers(frame), planes_b)
+        if multi:
+            layer = (frame & 1) ^ 1
+            images_b = {"denoised": [((self.bmfr.denoised, layer), None)],
+                        "final_col0": [(p.denoiser_final, 4)],                     # 1 BGRA8 texel
+                        "denoised_col0": [((self.bmfr.denoised, layer), 8)]}       # 1 rgba16f texel
+            if p.taa is not None:
+                images_b["taa"] = [(p.taa.history, None)]
+            db = self._exchange_desc("B", frame, images_b,
+                                     lambda: [t for t in plan.history_transfers(frame + 1) if t.plane != "acc"]
+                                     + plan.stale_column_transfers(frame))
+            self._pending_b = self._start(db)
 
     def flush(self) -> None:
         """waits (stream-side) for the halos in flight; call before reading planes outside the owned rows"""
@@ -449,6 +500,8 @@ def bench_multi(args, rank: int, world: int, local: int):
                              "frac": round(gbs / (hbm_peak * world), 4), "traffic": None, "peak_source": peak_src,
                              "note": "aggregate over ranks; per-kernel fractions are reported by the N=1 run"},
                 "halo_bytes_per_step": float(halo.item()) / (2 * K + Wm + 3), "cpu_baseline": None}
-        print(json.dumps(line), flush=True)
+    else:
+        line = None
     dist.barrier()
     dist.destroy_process_group()
+    return line
