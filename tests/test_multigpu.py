@@ -128,19 +128,20 @@ def test_two_rank_banded_chain_equals_single_rank(tmp_path, use_taa, W, H, frame
 
 
 # ---- real GPUs: NCCL halo exchange over NVLink ------------------------------------------------------
-def _gpu_worker(rank, world, W, H, frames, use_taa, port, out_dir):
+def _gpu_worker(rank, world, W, H, frames, use_taa, port, out_dir, direct):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
     sys.path.insert(0, str(ROOT))
     import torch
     import torch.distributed as dist
     from vulkanpbrt_b200 import Context, synth
-    from vulkanpbrt_b200.multigpu import BandedPipeline, cuda_view
+    from vulkanpbrt_b200.multigpu import BandedPipeline, NcclDirect, cuda_view
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
-    bp = BandedPipeline(W, H, rank, world, use_taa, Context(rank, stream.cuda_stream), cuda_view(dev), external_inputs=False, dist=dist)
+    bp = BandedPipeline(W, H, rank, world, use_taa, Context(rank, stream.cuda_stream), cuda_view(dev), external_inputs=False, dist=dist,
+                        nccl=NcclDirect(dist, rank, world, dev) if direct else None)
     lo, hi = bp.plan.input_rows(rank)
     finals = []
     for f in range(frames):
@@ -158,15 +159,17 @@ def _gpu_worker(rank, world, W, H, frames, use_taa, port, out_dir):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("world", [2, 4, 8])
-def test_banded_chain_on_gpus_equals_single_gpu(tmp_path, world):
+@pytest.mark.parametrize("world,direct", [(2, True), (2, False), (4, True), (8, True)])
+def test_banded_chain_on_gpus_equals_single_gpu(tmp_path, world, direct):
+    """direct: NCCL groups issued through ctypes on a communication stream (the bench path); otherwise
+    torch.distributed's own P2P ops"""
     import torch
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
     W, H, frames = 1920, 1080, 12
     port = 29500 + (os.getpid() % 2000)
-    mp.start_processes(_gpu_worker, args=(world, W, H, frames, True, port, str(tmp_path)), nprocs=world, join=True, start_method="spawn")
+    mp.start_processes(_gpu_worker, args=(world, W, H, frames, True, port, str(tmp_path), direct), nprocs=world, join=True, start_method="spawn")
     from vulkanpbrt_b200 import DenoisePipeline, synth
     pipe = DenoisePipeline(W, H, use_taa=True)
     per_rank = [np.load(tmp_path / f"gpu_{r}.npy", allow_pickle=True) for r in range(world)]

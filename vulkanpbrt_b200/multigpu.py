@@ -194,17 +194,72 @@ def _subtract(a: Rows, b: Rows) -> List[Rows]:
     return out
 
 
+class NcclDirect:
+    """Thin ctypes binding of the NCCL library torch already loaded: one ncclGroup of sends / receives per
+    exchange point, issued on a dedicated communication stream.  torch.distributed (backend nccl) stays the
+    plumbing -- rendezvous, the unique-id broadcast, barriers -- but its Python P2P path costs ~100 us of
+    host time per group, which is the whole budget of a 240 us frame."""
+
+    def __init__(self, dist, rank: int, world: int, device):
+        import ctypes as C
+
+        import torch
+        path = None
+        with open("/proc/self/maps") as f:
+            for line in f:
+                if "libnccl" in line:
+                    path = line.split()[-1]
+                    break
+        if path is None:
+            raise RuntimeError("libnccl is not loaded in this process (torch.distributed nccl backend required)")
+        self.C, self.lib = C, C.CDLL(path)
+
+        class UniqueId(C.Structure):
+            _fields_ = [("internal", C.c_char * 128)]
+        uid = UniqueId()
+        if rank == 0:
+            self._check(self.lib.ncclGetUniqueId(C.byref(uid)))
+        t = torch.frombuffer(bytearray(bytes(uid)), dtype=torch.uint8).to(device)
+        dist.broadcast(t, 0)
+        C.memmove(C.byref(uid), bytes(t.cpu().numpy().tobytes()), 128)
+        self.comm = C.c_void_p()
+        self.lib.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, UniqueId, C.c_int]
+        self._check(self.lib.ncclCommInitRank(C.byref(self.comm), world, uid, rank))
+        for fn in (self.lib.ncclSend, self.lib.ncclRecv):
+            fn.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        self.stream = torch.cuda.Stream(device=device)
+
+    def _check(self, rc: int) -> None:
+        if rc != 0:
+            raise RuntimeError(f"NCCL error {rc}")
+
+    def group(self, ops) -> None:
+        """ops: [(is_send, device_ptr, nbytes, peer)] issued as one group on the communication stream"""
+        lib, st = self.lib, self.stream.cuda_stream
+        self._check(lib.ncclGroupStart())
+        for is_send, ptr, n, peer in ops:
+            self._check((lib.ncclSend if is_send else lib.ncclRecv)(ptr, n, 1, peer, self.comm, st))    # 1 = ncclUint8
+        self._check(lib.ncclGroupEnd())
+
+    def close(self) -> None:
+        if self.comm:
+            self.lib.ncclCommDestroy.argtypes = [self.C.c_void_p]
+            self.lib.ncclCommDestroy(self.comm)
+            self.comm = None
+
+
 class BandedPipeline:
     """One rank of the band-sharded chain.  `view(image)` must return a uint8 torch tensor aliasing the image's
     CURRENT device buffer as raw bytes, shaped [layers?][H][row bytes] (cuda_view() below on a GPU)."""
 
     def __init__(self, width: int, height: int, rank: int, world: int, use_taa: bool, ctx, view: Callable,
-                 max_disp_rows: int = 24, external_inputs: bool = True, dist=None):
+                 max_disp_rows: int = 24, external_inputs: bool = True, dist=None, nccl: "NcclDirect" = None):
         self.rank, self.world, self.view = rank, world, view
         self.plan = BandPlan(width, height, world, 32, max_disp_rows, use_taa)
         self.pipe = DenoisePipeline(width, height, DenoisingType.BMFR, DenoisingBlockSize.X32, use_taa=use_taa, ctx=ctx,
                                     external_inputs=external_inputs)
         self.dist = dist
+        self.nccl = nccl                      # direct NCCL issue path (GPU); None: torch.distributed P2P ops (gloo tests)
         self.bmfr = self.pipe.modules[0]
         self.bmfr.set_block_row_range(*self.plan.block_rows(rank))
         c = self.pipe.commands.children
@@ -215,6 +270,9 @@ class BandedPipeline:
         self._pending_a = self._pending_b = None
         self._views: Dict = {}
         self._desc: Dict = {}
+        self._keep: list = []
+        self._events: list = []
+        self._ev_i = 0
 
     # ---- cached exchange descriptors -------------------------------------------------------------------
     # Row ranges repeat with the 16-frame jitter period and the ping-pong buffers with period 2, so the
@@ -230,7 +288,7 @@ class BandedPipeline:
 
     def _build(self, transfers: List[Transfer], planes: Dict[str, list]):
         dist = self.dist
-        ops, scatter, gather = [], [], []
+        ops, scatter, gather, raw = [], [], [], []
         nbytes = 0
         for t in transfers:     # identical order on every rank
             if t.src != self.rank and t.dst != self.rank:
@@ -242,15 +300,20 @@ class BandedPipeline:
                     if ncol_bytes is not None:          # column strips are staged through a contiguous buffer
                         buf = sl.new_empty(sl.shape)
                         gather.append((buf, sl))
-                    ops.append(dist.P2POp(dist.isend, buf, t.dst))
+                    raw.append((True, buf.data_ptr(), buf.numel(), t.dst))
+                    if self.nccl is None:
+                        ops.append(dist.P2POp(dist.isend, buf, t.dst))
                 else:
                     buf = sl
                     if ncol_bytes is not None:
                         buf = sl.new_empty(sl.shape)
                         scatter.append((sl, buf))
-                    ops.append(dist.P2POp(dist.irecv, buf, t.src))
+                    raw.append((False, buf.data_ptr(), buf.numel(), t.src))
+                    if self.nccl is None:
+                        ops.append(dist.P2POp(dist.irecv, buf, t.src))
                     nbytes += sl.numel() * sl.element_size()
-        return (ops, gather, scatter, nbytes)
+                    self._keep.append(buf)
+        return (ops, gather, scatter, nbytes, raw)
 
     def _exchange_desc(self, kind: str, frame: int, images: Dict[str, list], transfers_fn):
         """images: plane name -> [(DescriptorImage or (DescriptorImage, layer), ncol_bytes)]"""
@@ -269,18 +332,36 @@ class BandedPipeline:
             d = self._desc[key] = self._build(transfers_fn(), planes)
         return d
 
+    def _event(self):
+        import torch
+        self._ev_i = (self._ev_i + 1) % len(self._events) if self._events else 0
+        if len(self._events) < 16:
+            self._events.append(torch.cuda.Event())
+            return self._events[-1]
+        return self._events[self._ev_i]
+
     def _start(self, desc):
         """enqueues one NCCL group with every send / recv of the descriptor and returns the pending handle;
         nothing waits.  NCCL orders the group after the work already enqueued on the current stream, so a
         group started right after a kernel overlaps whatever is enqueued next."""
         if self.world == 1 or desc is None:
             return None
-        ops, gather, scatter, nbytes = desc
-        if not ops:
+        ops, gather, scatter, nbytes, raw = desc
+        if not raw:
             return None
         for buf, sl in gather:
             buf.copy_(sl)
         self.bytes_exchanged += nbytes
+        if self.nccl is not None:
+            import torch
+            cur = torch.cuda.current_stream()
+            ready = self._event()
+            ready.record(cur)
+            self.nccl.stream.wait_event(ready)
+            self.nccl.group(raw)
+            done = self._event()
+            done.record(self.nccl.stream)
+            return (done, scatter)
         return (self.dist.batch_isend_irecv(ops), scatter)
 
     @staticmethod
@@ -289,8 +370,12 @@ class BandedPipeline:
         if pending is None:
             return
         works, scatter = pending
-        for w in works:
-            w.wait()
+        if isinstance(works, list):
+            for w in works:
+                w.wait()
+        else:
+            import torch
+            torch.cuda.current_stream().wait_event(works)
         for sl, buf in scatter:
             sl.copy_(buf)
 
@@ -379,7 +464,7 @@ def bench_multi(args, rank: int, world: int, local: int):
     ctx = Context(local, stream.cuda_stream)
     assert ctx.stream == stream.cuda_stream
     view = cuda_view(dev)
-    bp = BandedPipeline(W, H, rank, world, taa, ctx, view, dist=dist)
+    bp = BandedPipeline(W, H, rank, world, taa, ctx, view, dist=dist, nccl=NcclDirect(dist, rank, world, dev))
     lo, hi = bp.plan.input_rows(rank)
     rows = hi - lo
     # band-local resident sequence; the kernels index absolute rows through a virtual full-frame base pointer
