@@ -227,9 +227,11 @@ def main_ours(args):
     launches0 = ctx.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
+    t_host = time.perf_counter()
     for f in range(Wm, Wm + K):
         frame_resident(f)
     e1.record(stream)
+    t_host = (time.perf_counter() - t_host) / K * 1e3          # host time to ENQUEUE one frame (no sync inside)
     torch.cuda.synchronize()
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
@@ -337,7 +339,7 @@ def main_ours(args):
                        "resident_frames": R, "sequence_generation_s": round(t_gen, 1)},
             "e2e": {"value": round(e2e_value, 1), "unit": "MPix/s", "h2d_bytes_per_step": INPUT_BYTES * W * H,
                     "d2h_bytes_per_step": 4 * W * H, "ms_per_step": round(e2e_ms / K, 5), "wall_ms_per_step": round(wall_ms / K, 5)},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu}
+            "gpu_launches": int(launches), "host_enqueue_ms_per_step": round(t_host, 4), "clocks": clocks, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
 
 

@@ -36,6 +36,29 @@ def test_band_plan_partitions_the_frame(W, H, N):
                 assert a[0] <= m < a[1]
 
 
+def test_everything_sent_after_bmfr_comes_from_the_edge_block_rows():
+    """exchange B starts after the edge block rows only: every row it sends must have been written by them"""
+    from vulkanpbrt_b200.multigpu import BandPlan, block_offset
+    for (W, H, N) in [(1920, 1080, 2), (1920, 2160, 2), (3840, 2160, 8), (1920, 8640, 8)]:
+        plan = BandPlan(W, H, N, taa=True)
+        ne = plan.edge_block_rows
+        for f in range(34):
+            oy = block_offset(32, f)[1]
+            ts = [t for t in plan.history_transfers(f + 1) if t.plane == "denoised"] + plan.stale_column_transfers(f) + plan.final_transfers(f)
+            for t in ts:
+                b0, b1 = plan.block_rows(t.src)
+                nt, nb = (ne if t.src > 0 else 1), (ne if t.src < N - 1 else 2)       # as BandedPipeline.run_frame
+                top = (max(0, 32 * b0 - oy), min(H, 32 * (b0 + nt) - oy))
+                bot = (max(0, 32 * (b1 - nb) - oy), min(H, 32 * b1 - oy))
+                # rows above -oy are written by nobody this frame (frame 8: rows 0..1 keep their old content)
+                r0, r1 = max(t.rows[0], -oy, 0), t.rows[1]
+                if r1 <= r0:
+                    continue
+                in_top = top[0] <= r0 and r1 <= top[1]
+                in_bot = bot[0] <= r0 and r1 <= bot[1]
+                assert in_top or in_bot, (W, H, N, f, t, top, bot)
+
+
 def test_history_transfers_cover_every_needed_row():
     from vulkanpbrt_b200.multigpu import BandPlan
     for (W, H, N) in [(1920, 1080, 4), (640, 2160, 8), (256, 256, 2)]:

@@ -76,8 +76,10 @@ class BandPlan:
         self.W, self.H, self.N, self.b, self.D, self.taa = width, height, world, block, max_disp_rows, taa
         self.nby = height // block + 2
         self.brow = [round(g * self.nby / world) for g in range(world + 1)]
-        if any(self.brow[g + 1] - self.brow[g] < 2 for g in range(world)):
-            raise ValueError("bands must be at least two block rows high")
+        # block rows at a band edge whose output a neighbour can ask for: displacement + jitter shift of the boundary
+        self.edge_block_rows = -(-(max_disp_rows + 1 + block) // block)
+        if any(self.brow[g + 1] - self.brow[g] < 2 * self.edge_block_rows for g in range(world)):
+            raise ValueError("bands must be at least two edge regions high")
 
     def block_rows(self, g: int) -> Rows:
         return (self.brow[g], self.brow[g + 1])
@@ -267,7 +269,7 @@ class BandedPipeline:
         self._taa_cmd = c[2] if use_taa else None
         self._back_cmd = c[-1]
         self.bytes_exchanged = 0
-        self._pending_a = self._pending_b = None
+        self._pending_a = self._pending_b = self._pending_c = None
         self._views: Dict = {}
         self._desc: Dict = {}
         self._keep: list = []
@@ -380,53 +382,79 @@ class BandedPipeline:
             sl.copy_(buf)
 
     def run_frame(self, frame: int, cam) -> None:
-        """inputs must already be bound / uploaded for this frame.  Per frame and boundary:
+        """inputs must already be bound / uploaded for this frame.  Exchange points (one NCCL group each), all
+        hidden under compute:
              A  accumulate-plane halos (depth history, accumulated illumination, sample counts): started right
                 after k_accumulate, overlaps k_bmfr_block, awaited before the next frame's k_accumulate;
-             F  one row of the denoiser output for TAA's stencil (TAA configurations only, not overlapped);
-             B  denoised / TAA history halos + the stale-column strip: started at the end of the frame,
-                overlaps the next frame's k_accumulate, awaited before its k_bmfr_block."""
+             B  what the neighbours need of this frame's BMFR output -- denoised history halo rows, the
+                stale-column strip, and (TAA) one row of the tone-mapped output for the 3x3 stencil.  The
+                band's EDGE block rows are launched first, B starts as soon as they finish and overlaps the
+                launch of the interior block rows; awaited before this frame's TAA / the next frame's BMFR;
+             C  TAA history halo rows: started after k_taa, awaited before the next frame's k_taa."""
         p, plan, g = self.pipe, self.plan, self.rank
         acc = p.accumulation_buffer
         multi = self.world > 1
+        b0, b1 = plan.block_rows(g)
         p.set_frame_constants(frame, cam)
         p.accumulator.set_row_range(*plan.accumulate_rows(g, frame))
         self._finish(self._pending_a)
+        self._pending_a = None
         self._acc_cmd(p.commands)
-        if multi:
-            # pre-swap handles: what k_accumulate just wrote becomes prev_depth / prev_illu / prev_spp at copy_to_back
-            da = self._exchange_desc("A", frame, {"acc": [(acc.next_depth, None), (p.illumination_buffer.illumination_images[0], None),
-                                                          (acc.spp, None)]},
-                                     lambda: [t for t in plan.history_transfers(frame + 1) if t.plane == "acc"])
-            self._pending_a = self._start(da)
-        self._finish(self._pending_b)
+        if not multi:
+            self._bmfr_cmd(p.commands)
+            if p.taa is not None:
+                p.taa.set_row_range(*plan.owned_rows(g, frame))
+                self._taa_cmd(p.commands)
+            self._back_cmd(p.commands)
+            p.end_frame(cam)
+            return
+        # pre-swap handles: what k_accumulate just wrote becomes prev_depth / prev_illu / prev_spp at copy_to_back
+        da = self._exchange_desc("A", frame, {"acc": [(acc.next_depth, None), (p.illumination_buffer.illumination_images[0], None),
+                                                      (acc.spp, None)]},
+                                 lambda: [t for t in plan.history_transfers(frame + 1) if t.plane == "acc"])
+        self._pending_a = self._start(da)
+        self._finish(self._pending_b)        # denoised halos of the previous frame (read by this frame's BMFR)
         self._pending_b = None
-        self._bmfr_cmd(p.commands)
+        # edge block rows first: everything a neighbour will ask for lies in the rows they write
+        ne = plan.edge_block_rows
+        # (the image-top / image-bottom ranks launch the block rows holding row 0 / row H-1 early as well: those
+        # rows travel to the opposite rank for the sampler's REPEAT wrap)
+        top = (b0, min(b0 + (ne if g > 0 else 1), b1))
+        bot = (max(b1 - (ne if g < self.world - 1 else 2), top[1]), b1)
+        for r in (top, bot):
+            if r[1] > r[0]:
+                self.bmfr.set_block_row_range(*r)
+                self._bmfr_cmd(p.commands)
+        layer = (frame & 1) ^ 1
+        images_b = {"denoised": [((self.bmfr.denoised, layer), None)],
+                    "final_col0": [(p.denoiser_final, 4)],                     # 1 BGRA8 texel
+                    "denoised_col0": [((self.bmfr.denoised, layer), 8)],       # 1 rgba16f texel
+                    "final": [(p.denoiser_final, None)]}
+        db = self._exchange_desc("B", frame, images_b,
+                                 lambda: [t for t in plan.history_transfers(frame + 1) if t.plane == "denoised"]
+                                 + plan.stale_column_transfers(frame) + plan.final_transfers(frame))
+        self._pending_b = self._start(db)
+        self.bmfr.set_block_row_range(top[1], bot[0])
+        self._bmfr_cmd(p.commands)                                          # interior block rows overlap exchange B
         if p.taa is not None:
-            if multi:
-                df = self._exchange_desc("F", frame, {"final": [(p.denoiser_final, None)]}, lambda: plan.final_transfers(frame))
-                self._finish(self._start(df))
+            self._finish(self._pending_b)                                   # stencil rows of the neighbours' output
+            self._pending_b = None
+            self._finish(self._pending_c)                                   # TAA history halos of the previous frame
             p.taa.set_row_range(*plan.owned_rows(g, frame))
             self._taa_cmd(p.commands)
         self._back_cmd(p.commands)
         p.end_frame(cam)
-        if multi:
-            layer = (frame & 1) ^ 1
-            images_b = {"denoised": [((self.bmfr.denoised, layer), None)],
-                        "final_col0": [(p.denoiser_final, 4)],                     # 1 BGRA8 texel
-                        "denoised_col0": [((self.bmfr.denoised, layer), 8)]}       # 1 rgba16f texel
-            if p.taa is not None:
-                images_b["taa"] = [(p.taa.history, None)]
-            db = self._exchange_desc("B", frame, images_b,
-                                     lambda: [t for t in plan.history_transfers(frame + 1) if t.plane != "acc"]
-                                     + plan.stale_column_transfers(frame))
-            self._pending_b = self._start(db)
+        if p.taa is not None:
+            dc = self._exchange_desc("C", frame, {"taa": [(p.taa.history, None)]},
+                                     lambda: [t for t in plan.history_transfers(frame + 1) if t.plane == "taa"])
+            self._pending_c = self._start(dc)
 
     def flush(self) -> None:
         """waits (stream-side) for the halos in flight; call before reading planes outside the owned rows"""
         self._finish(self._pending_a)
         self._finish(self._pending_b)
-        self._pending_a = self._pending_b = None
+        self._finish(self._pending_c)
+        self._pending_a = self._pending_b = self._pending_c = None
 
     def owned_rows(self, frame: int) -> Rows:
         return self.plan.owned_rows(self.rank, frame)
@@ -504,10 +532,12 @@ def bench_multi(args, rank: int, world: int, local: int):
     launches0 = ctx.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
+    t_host = time.perf_counter()
     for f in range(Wm, Wm + K):
         frame(f)
     bp.flush()
     e1.record(stream)
+    t_host = (time.perf_counter() - t_host) / K * 1e3      # host time to ENQUEUE one frame (no sync inside)
     torch.cuda.synchronize()
     dist.barrier()
     clocks = sampler.stop()
@@ -584,7 +614,8 @@ def bench_multi(args, rank: int, world: int, local: int):
                              "achieved": round(gbs, 1), "peak": hbm_peak * world, "unit": "GB/s",
                              "frac": round(gbs / (hbm_peak * world), 4), "traffic": None, "peak_source": peak_src,
                              "note": "aggregate over ranks; per-kernel fractions are reported by the N=1 run"},
-                "halo_bytes_per_step": float(halo.item()) / (2 * K + Wm + 3), "cpu_baseline": None}
+                "halo_bytes_per_step": float(halo.item()) / (2 * K + Wm + 3), "host_enqueue_ms_per_step": round(t_host, 4),
+                "cpu_baseline": None}
     else:
         line = None
     dist.barrier()
