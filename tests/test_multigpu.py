@@ -47,7 +47,7 @@ def test_everything_sent_after_bmfr_comes_from_the_edge_block_rows():
             ts = [t for t in plan.history_transfers(f + 1) if t.plane == "denoised"] + plan.stale_column_transfers(f) + plan.final_transfers(f)
             for t in ts:
                 b0, b1 = plan.block_rows(t.src)
-                nt, nb = (ne if t.src > 0 else 1), (ne if t.src < N - 1 else 2)       # as BandedPipeline.run_frame
+                nt, nb = (ne if t.src > 0 else 1), (ne if t.src < N - 1 else plan.bottom_wrap_block_rows)   # as BandedPipeline.run_frame
                 top = (max(0, 32 * b0 - oy), min(H, 32 * (b0 + nt) - oy))
                 bot = (max(0, 32 * (b1 - nb) - oy), min(H, 32 * b1 - oy))
                 # rows above -oy are written by nobody this frame (frame 8: rows 0..1 keep their old content)

@@ -78,6 +78,7 @@ class BandPlan:
         self.brow = [round(g * self.nby / world) for g in range(world + 1)]
         # block rows at a band edge whose output a neighbour can ask for: displacement + jitter shift of the boundary
         self.edge_block_rows = -(-(max_disp_rows + 1 + block) // block)
+        self.bottom_wrap_block_rows = self.nby - (height - 1) // block     # block rows that can hold image row H-1
         if any(self.brow[g + 1] - self.brow[g] < 2 * self.edge_block_rows for g in range(world)):
             raise ValueError("bands must be at least two edge regions high")
 
@@ -269,7 +270,7 @@ class BandedPipeline:
         self._taa_cmd = c[2] if use_taa else None
         self._back_cmd = c[-1]
         self.bytes_exchanged = 0
-        self._pending_a = self._pending_b = self._pending_c = None
+        self._pending = None
         self._views: Dict = {}
         self._desc: Dict = {}
         self._keep: list = []
@@ -382,25 +383,24 @@ class BandedPipeline:
             sl.copy_(buf)
 
     def run_frame(self, frame: int, cam) -> None:
-        """inputs must already be bound / uploaded for this frame.  Exchange points (one NCCL group each), all
-        hidden under compute:
-             A  accumulate-plane halos (depth history, accumulated illumination, sample counts): started right
-                after k_accumulate, overlaps k_bmfr_block, awaited before the next frame's k_accumulate;
-             B  what the neighbours need of this frame's BMFR output -- denoised history halo rows, the
-                stale-column strip, and (TAA) one row of the tone-mapped output for the 3x3 stencil.  The
-                band's EDGE block rows are launched first, B starts as soon as they finish and overlaps the
-                launch of the interior block rows; awaited before this frame's TAA / the next frame's BMFR;
-             C  TAA history halo rows: started after k_taa, awaited before the next frame's k_taa."""
+        """inputs must already be bound / uploaded for this frame.  ONE NCCL group per frame carries everything
+        the neighbours need:
+            - accumulate-plane halos of this frame (depth history, accumulated illumination, sample counts),
+            - this frame's BMFR output they will read: denoised history halo rows, the stale-column strip and
+              (TAA) one row of the tone-mapped output for the 3x3 stencil,
+            - (TAA) halo rows of the previous frame's TAA output, i.e. this frame's TAA history.
+        The band's EDGE block rows are launched first; the group starts as soon as they finish and is hidden
+        under the launch of the interior block rows.  It is awaited before this frame's k_taa, or (no TAA)
+        before the next frame's k_accumulate."""
         p, plan, g = self.pipe, self.plan, self.rank
         acc = p.accumulation_buffer
-        multi = self.world > 1
         b0, b1 = plan.block_rows(g)
         p.set_frame_constants(frame, cam)
         p.accumulator.set_row_range(*plan.accumulate_rows(g, frame))
-        self._finish(self._pending_a)
-        self._pending_a = None
+        self._finish(self._pending)
+        self._pending = None
         self._acc_cmd(p.commands)
-        if not multi:
+        if self.world == 1:
             self._bmfr_cmd(p.commands)
             if p.taa is not None:
                 p.taa.set_row_range(*plan.owned_rows(g, frame))
@@ -408,53 +408,47 @@ class BandedPipeline:
             self._back_cmd(p.commands)
             p.end_frame(cam)
             return
-        # pre-swap handles: what k_accumulate just wrote becomes prev_depth / prev_illu / prev_spp at copy_to_back
-        da = self._exchange_desc("A", frame, {"acc": [(acc.next_depth, None), (p.illumination_buffer.illumination_images[0], None),
-                                                      (acc.spp, None)]},
-                                 lambda: [t for t in plan.history_transfers(frame + 1) if t.plane == "acc"])
-        self._pending_a = self._start(da)
-        self._finish(self._pending_b)        # denoised halos of the previous frame (read by this frame's BMFR)
-        self._pending_b = None
         # edge block rows first: everything a neighbour will ask for lies in the rows they write
-        ne = plan.edge_block_rows
         # (the image-top / image-bottom ranks launch the block rows holding row 0 / row H-1 early as well: those
         # rows travel to the opposite rank for the sampler's REPEAT wrap)
+        ne = plan.edge_block_rows
         top = (b0, min(b0 + (ne if g > 0 else 1), b1))
-        bot = (max(b1 - (ne if g < self.world - 1 else 2), top[1]), b1)
+        bot = (max(b1 - (ne if g < self.world - 1 else plan.bottom_wrap_block_rows), top[1]), b1)
         for r in (top, bot):
             if r[1] > r[0]:
                 self.bmfr.set_block_row_range(*r)
                 self._bmfr_cmd(p.commands)
         layer = (frame & 1) ^ 1
-        images_b = {"denoised": [((self.bmfr.denoised, layer), None)],
-                    "final_col0": [(p.denoiser_final, 4)],                     # 1 BGRA8 texel
-                    "denoised_col0": [((self.bmfr.denoised, layer), 8)],       # 1 rgba16f texel
-                    "final": [(p.denoiser_final, None)]}
-        db = self._exchange_desc("B", frame, images_b,
-                                 lambda: [t for t in plan.history_transfers(frame + 1) if t.plane == "denoised"]
-                                 + plan.stale_column_transfers(frame) + plan.final_transfers(frame))
-        self._pending_b = self._start(db)
-        self.bmfr.set_block_row_range(top[1], bot[0])
-        self._bmfr_cmd(p.commands)                                          # interior block rows overlap exchange B
+        # pre-swap handles: what k_accumulate just wrote becomes prev_depth / prev_illu / prev_spp at copy_to_back
+        images = {"acc": [(acc.next_depth, None), (p.illumination_buffer.illumination_images[0], None), (acc.spp, None)],
+                  "denoised": [((self.bmfr.denoised, layer), None)],
+                  "final_col0": [(p.denoiser_final, 4)],                      # 1 BGRA8 texel
+                  "denoised_col0": [((self.bmfr.denoised, layer), 8)],        # 1 rgba16f texel
+                  "final": [(p.denoiser_final, None)]}
         if p.taa is not None:
-            self._finish(self._pending_b)                                   # stencil rows of the neighbours' output
-            self._pending_b = None
-            self._finish(self._pending_c)                                   # TAA history halos of the previous frame
+            images["taa"] = [(p.taa.history, None)]                            # output of the previous frame's k_taa
+
+        def transfers():
+            nxt = plan.history_transfers(frame + 1)
+            ts = [t for t in nxt if t.plane in ("acc", "denoised")] + plan.stale_column_transfers(frame) + plan.final_transfers(frame)
+            if p.taa is not None and frame > 0:
+                ts += [t for t in plan.history_transfers(frame) if t.plane == "taa"]
+            return ts
+        self._pending = self._start(self._exchange_desc("G" if frame > 0 else "G0", frame, images, transfers))
+        self.bmfr.set_block_row_range(top[1], bot[0])
+        self._bmfr_cmd(p.commands)                                          # interior block rows overlap the exchange
+        if p.taa is not None:
+            self._finish(self._pending)                                     # neighbours' stencil rows + TAA history halos
+            self._pending = None
             p.taa.set_row_range(*plan.owned_rows(g, frame))
             self._taa_cmd(p.commands)
         self._back_cmd(p.commands)
         p.end_frame(cam)
-        if p.taa is not None:
-            dc = self._exchange_desc("C", frame, {"taa": [(p.taa.history, None)]},
-                                     lambda: [t for t in plan.history_transfers(frame + 1) if t.plane == "taa"])
-            self._pending_c = self._start(dc)
 
     def flush(self) -> None:
         """waits (stream-side) for the halos in flight; call before reading planes outside the owned rows"""
-        self._finish(self._pending_a)
-        self._finish(self._pending_b)
-        self._finish(self._pending_c)
-        self._pending_a = self._pending_b = self._pending_c = None
+        self._finish(self._pending)
+        self._pending = None
 
     def owned_rows(self, frame: int) -> Rows:
         return self.plan.owned_rows(self.rank, frame)
