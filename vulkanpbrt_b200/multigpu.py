@@ -270,7 +270,7 @@ class BandedPipeline:
         self._taa_cmd = c[2] if use_taa else None
         self._back_cmd = c[-1]
         self.bytes_exchanged = 0
-        self._pending = None
+        self._pending_a = self._pending_b = None
         self._views: Dict = {}
         self._desc: Dict = {}
         self._keep: list = []
@@ -383,72 +383,53 @@ class BandedPipeline:
             sl.copy_(buf)
 
     def run_frame(self, frame: int, cam) -> None:
-        """inputs must already be bound / uploaded for this frame.  ONE NCCL group per frame carries everything
-        the neighbours need:
-            - accumulate-plane halos of this frame (depth history, accumulated illumination, sample counts),
-            - this frame's BMFR output they will read: denoised history halo rows, the stale-column strip and
-              (TAA) one row of the tone-mapped output for the 3x3 stencil,
-            - (TAA) halo rows of the previous frame's TAA output, i.e. this frame's TAA history.
-        The band's EDGE block rows are launched first; the group starts as soon as they finish and is hidden
-        under the launch of the interior block rows.  It is awaited before this frame's k_taa, or (no TAA)
-        before the next frame's k_accumulate."""
+        """inputs must already be bound / uploaded for this frame.  Per frame and boundary:
+             A  accumulate-plane halos (depth history, accumulated illumination, sample counts): started right
+                after k_accumulate, overlaps k_bmfr_block, awaited before the next frame's k_accumulate;
+             F  one row of the denoiser output for TAA's stencil (TAA configurations only, not overlapped);
+             B  denoised / TAA history halos + the stale-column strip: started at the end of the frame,
+                overlaps the next frame's k_accumulate, awaited before its k_bmfr_block."""
         p, plan, g = self.pipe, self.plan, self.rank
         acc = p.accumulation_buffer
-        b0, b1 = plan.block_rows(g)
+        multi = self.world > 1
         p.set_frame_constants(frame, cam)
         p.accumulator.set_row_range(*plan.accumulate_rows(g, frame))
-        self._finish(self._pending)
-        self._pending = None
+        self._finish(self._pending_a)
         self._acc_cmd(p.commands)
-        if self.world == 1:
-            self._bmfr_cmd(p.commands)
-            if p.taa is not None:
-                p.taa.set_row_range(*plan.owned_rows(g, frame))
-                self._taa_cmd(p.commands)
-            self._back_cmd(p.commands)
-            p.end_frame(cam)
-            return
-        # edge block rows first: everything a neighbour will ask for lies in the rows they write
-        # (the image-top / image-bottom ranks launch the block rows holding row 0 / row H-1 early as well: those
-        # rows travel to the opposite rank for the sampler's REPEAT wrap)
-        ne = plan.edge_block_rows
-        top = (b0, min(b0 + (ne if g > 0 else 1), b1))
-        bot = (max(b1 - (ne if g < self.world - 1 else plan.bottom_wrap_block_rows), top[1]), b1)
-        for r in (top, bot):
-            if r[1] > r[0]:
-                self.bmfr.set_block_row_range(*r)
-                self._bmfr_cmd(p.commands)
-        layer = (frame & 1) ^ 1
-        # pre-swap handles: what k_accumulate just wrote becomes prev_depth / prev_illu / prev_spp at copy_to_back
-        images = {"acc": [(acc.next_depth, None), (p.illumination_buffer.illumination_images[0], None), (acc.spp, None)],
-                  "denoised": [((self.bmfr.denoised, layer), None)],
-                  "final_col0": [(p.denoiser_final, 4)],                      # 1 BGRA8 texel
-                  "denoised_col0": [((self.bmfr.denoised, layer), 8)],        # 1 rgba16f texel
-                  "final": [(p.denoiser_final, None)]}
+        if multi:
+            # pre-swap handles: what k_accumulate just wrote becomes prev_depth / prev_illu / prev_spp at copy_to_back
+            da = self._exchange_desc("A", frame, {"acc": [(acc.next_depth, None), (p.illumination_buffer.illumination_images[0], None),
+                                                          (acc.spp, None)]},
+                                     lambda: [t for t in plan.history_transfers(frame + 1) if t.plane == "acc"])
+            self._pending_a = self._start(da)
+        self._finish(self._pending_b)
+        self._pending_b = None
+        self._bmfr_cmd(p.commands)
         if p.taa is not None:
-            images["taa"] = [(p.taa.history, None)]                            # output of the previous frame's k_taa
-
-        def transfers():
-            nxt = plan.history_transfers(frame + 1)
-            ts = [t for t in nxt if t.plane in ("acc", "denoised")] + plan.stale_column_transfers(frame) + plan.final_transfers(frame)
-            if p.taa is not None and frame > 0:
-                ts += [t for t in plan.history_transfers(frame) if t.plane == "taa"]
-            return ts
-        self._pending = self._start(self._exchange_desc("G" if frame > 0 else "G0", frame, images, transfers))
-        self.bmfr.set_block_row_range(top[1], bot[0])
-        self._bmfr_cmd(p.commands)                                          # interior block rows overlap the exchange
-        if p.taa is not None:
-            self._finish(self._pending)                                     # neighbours' stencil rows + TAA history halos
-            self._pending = None
+            if multi:
+                df = self._exchange_desc("F", frame, {"final": [(p.denoiser_final, None)]}, lambda: plan.final_transfers(frame))
+                self._finish(self._start(df))
             p.taa.set_row_range(*plan.owned_rows(g, frame))
             self._taa_cmd(p.commands)
         self._back_cmd(p.commands)
         p.end_frame(cam)
+        if multi:
+            layer = (frame & 1) ^ 1
+            images_b = {"denoised": [((self.bmfr.denoised, layer), None)],
+                        "final_col0": [(p.denoiser_final, 4)],                     # 1 BGRA8 texel
+                        "denoised_col0": [((self.bmfr.denoised, layer), 8)]}       # 1 rgba16f texel
+            if p.taa is not None:
+                images_b["taa"] = [(p.taa.history, None)]
+            db = self._exchange_desc("B", frame, images_b,
+                                     lambda: [t for t in plan.history_transfers(frame + 1) if t.plane != "acc"]
+                                     + plan.stale_column_transfers(frame))
+            self._pending_b = self._start(db)
 
     def flush(self) -> None:
         """waits (stream-side) for the halos in flight; call before reading planes outside the owned rows"""
-        self._finish(self._pending)
-        self._pending = None
+        self._finish(self._pending_a)
+        self._finish(self._pending_b)
+        self._pending_a = self._pending_b = None
 
     def owned_rows(self, frame: int) -> Rows:
         return self.plan.owned_rows(self.rank, frame)
