@@ -1,0 +1,394 @@
+// vkpbrt.hpp -- C++ render-module classes of the denoising path, rebuilt on the C ABI (vkpbrt_b200.h).
+//
+// Same class names, constructor parameter order and method names as the reference
+// (source/renderModules/{Accumulator,Taa}.hpp, source/renderModules/denoisers/{BMFR,BFR,BFRBlender}.hpp,
+// source/buffers/{GBuffer,IlluminationBuffer,AccumulationBuffer}.hpp, source/util/DenoiserUtils.hpp), so the
+// reference's wiring code (util/DenoiserUtils.cpp:8-130, VulkanPBRT.cpp:424-505, :551-618) compiles against these
+// with three substitutions:
+//     vsg::ref_ptr<T>                   -> vkpbrt::ref_ptr<T>          (std::shared_ptr; T::create(...) kept)
+//     vsg::Context&                     -> vkpbrt::Context&            (device + CUDA stream)
+//     vsg::Commands / vsg::PushConstants -> vkpbrt::Commands / vkpbrt::PushConstants
+// Header-only; link against libvkpbrt_b200.so.  Errors of the C ABI become std::runtime_error (the reference throws
+// vsg::Exception in the same places; wrong illumination buffer types are REJECTED instead of half-constructing,
+// denoisers/BMFR.cpp:17-22 -- documented deviation).
+#pragma once
+
+#include <cstdint>
+#include <functional>
+#include <memory>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../vkpbrt_b200.h"
+
+namespace vkpbrt {
+
+template <typename T>
+using ref_ptr = std::shared_ptr<T>;
+
+inline void check(int rc)
+{
+    if (rc != VKPBRT_OK) throw std::runtime_error(std::string("vkpbrt: ") + vkpbrt_last_error());
+}
+
+template <typename T>
+struct Inherit {
+    template <typename... Args>
+    static ref_ptr<T> create(Args&&... args) { return std::make_shared<T>(std::forward<Args>(args)...); }
+};
+
+struct mat4 {
+    float m[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};   // column-major, like vsg::mat4
+};
+
+// vsg::Context stand-in
+class Context : public Inherit<Context> {
+public:
+    explicit Context(int device = 0, void* cuda_stream = nullptr) { check(vkpbrt_context_create(device, cuda_stream, &handle)); }
+    ~Context() { vkpbrt_context_destroy(handle); }
+    Context(const Context&) = delete;
+    void waitForCompletion() { check(vkpbrt_context_synchronize(handle)); }
+    vkpbrt_context_t handle = nullptr;
+};
+
+// vsg::DescriptorImage stand-in: a device image handle
+class DescriptorImage : public Inherit<DescriptorImage> {
+public:
+    DescriptorImage(vkpbrt_image_t h, bool owner) : handle(h), _owner(owner) {}
+    DescriptorImage(Context& ctx, uint32_t format, uint32_t w, uint32_t h, uint32_t layers = 1) : _owner(true)
+    {
+        check(vkpbrt_image_create(ctx.handle, format, w, h, layers, &handle));
+    }
+    ~DescriptorImage() { if (_owner) vkpbrt_image_release(handle); }
+    void compile(Context&) { check(vkpbrt_image_compile(handle)); }
+    vkpbrt_image_info info() const { vkpbrt_image_info i; check(vkpbrt_image_info_get(handle, &i)); return i; }
+    vkpbrt_image_t handle = nullptr;
+private:
+    bool _owner;
+};
+
+// source/renderModules/PipelineStructs.hpp
+struct RayTracingPushConstants {
+    mat4 view_inverse, proj_inverse, prev_view;
+    uint32_t frame_number = 0, sample_number = 0;
+};
+static_assert(sizeof(RayTracingPushConstants) == sizeof(vkpbrt_push_constants), "layout must match the C ABI");
+enum class DenoisingType { NONE, BMFR, BFR, SVG };
+enum class DenoisingBlockSize { X8, X16, X32, X64, X8X16X32 };
+
+class PushConstants : public Inherit<PushConstants> {   // vsg::PushConstants holding RayTracingPushConstants
+public:
+    RayTracingPushConstants& value() { return _value; }
+    const vkpbrt_push_constants* c() const { return reinterpret_cast<const vkpbrt_push_constants*>(&_value); }
+private:
+    RayTracingPushConstants _value;
+};
+
+// vsg::Commands: filled once, replayed every frame (viewer->recordAndSubmit(), VulkanPBRT.cpp:588)
+class Commands : public Inherit<Commands> {
+public:
+    void addChild(std::function<void(Commands&)> c) { children.push_back(std::move(c)); }
+    void record() { for (auto& c : children) c(*this); }
+    std::vector<std::function<void(Commands&)>> children;
+    ref_ptr<PushConstants> bound_push_constants;   // what taa.comp inherits from the denoiser (Taa.cpp:99-107)
+};
+
+// source/io/RenderIO.hpp:28-34
+class CameraMatrices {
+public:
+    mat4 view, inv_view;
+    std::optional<mat4> proj, inv_proj;
+    vkpbrt_camera_matrices c() const
+    {
+        vkpbrt_camera_matrices r{};
+        for (int i = 0; i < 16; ++i) { r.view[i] = view.m[i]; r.inv_view[i] = inv_view.m[i]; }
+        r.has_proj = (proj && inv_proj) ? 1 : 0;
+        if (r.has_proj) for (int i = 0; i < 16; ++i) { r.proj[i] = proj->m[i]; r.inv_proj[i] = inv_proj->m[i]; }
+        return r;
+    }
+};
+
+// ---- buffers ----------------------------------------------------------------------------------------------------
+class GBuffer : public Inherit<GBuffer> {   // source/buffers/GBuffer.hpp:12-21
+public:
+    GBuffer(Context& ctx, uint32_t w, uint32_t h) : width(w), height(h)
+    {
+        check(vkpbrt_gbuffer_create(ctx.handle, w, h, &handle));
+        depth = member(VKPBRT_GBUFFER_DEPTH); normal = member(VKPBRT_GBUFFER_NORMAL);
+        material = member(VKPBRT_GBUFFER_MATERIAL); albedo = member(VKPBRT_GBUFFER_ALBEDO);
+    }
+    ~GBuffer() { vkpbrt_gbuffer_destroy(handle); }
+    void compile(Context&) const { check(vkpbrt_gbuffer_compile(handle)); }
+    void update_image_layouts(Context&) const {}   // no image layouts on linear device memory
+    uint32_t width, height;
+    ref_ptr<DescriptorImage> depth, normal, material, albedo;
+    vkpbrt_gbuffer_t handle = nullptr;
+private:
+    ref_ptr<DescriptorImage> member(uint32_t m) { vkpbrt_image_t i; check(vkpbrt_gbuffer_image(handle, m, &i)); return DescriptorImage::create(i, false); }
+};
+
+class IlluminationBuffer {   // source/buffers/IlluminationBuffer.hpp:14-29
+public:
+    virtual ~IlluminationBuffer() { if (_owner) vkpbrt_illumination_buffer_destroy(handle); }
+    void compile(Context&) { check(vkpbrt_illumination_buffer_compile(handle)); }
+    void update_image_layouts(Context&) {}
+    std::vector<ref_ptr<DescriptorImage>> illumination_images;
+    uint32_t width = 0, height = 0;
+    vkpbrt_illumination_buffer_t handle = nullptr;
+protected:
+    IlluminationBuffer(Context& ctx, uint32_t type, uint32_t w, uint32_t h) : width(w), height(h), _owner(true)
+    {
+        check(vkpbrt_illumination_buffer_create(ctx.handle, type, w, h, &handle));
+        fill();
+    }
+    IlluminationBuffer(vkpbrt_illumination_buffer_t borrowed, uint32_t w, uint32_t h) : width(w), height(h), handle(borrowed), _owner(false) { fill(); }
+private:
+    void fill()
+    {
+        uint32_t type, n;
+        check(vkpbrt_illumination_buffer_type(handle, &type, &n));
+        for (uint32_t i = 0; i < n; ++i) { vkpbrt_image_t im; check(vkpbrt_illumination_buffer_image(handle, i, &im)); illumination_images.push_back(DescriptorImage::create(im, false)); }
+    }
+    bool _owner;
+};
+class IlluminationBufferFinal : public IlluminationBuffer, public Inherit<IlluminationBufferFinal> {
+public: IlluminationBufferFinal(Context& c, uint32_t w, uint32_t h) : IlluminationBuffer(c, VKPBRT_ILLUMINATION_FINAL, w, h) {}
+};
+class IlluminationBufferDemodulated : public IlluminationBuffer, public Inherit<IlluminationBufferDemodulated> {
+public:
+    IlluminationBufferDemodulated(Context& c, uint32_t w, uint32_t h) : IlluminationBuffer(c, VKPBRT_ILLUMINATION_DEMODULATED, w, h) {}
+    IlluminationBufferDemodulated(vkpbrt_illumination_buffer_t borrowed, uint32_t w, uint32_t h) : IlluminationBuffer(borrowed, w, h) {}
+};
+class IlluminationBufferDemodulatedFloat : public IlluminationBuffer, public Inherit<IlluminationBufferDemodulatedFloat> {
+public: IlluminationBufferDemodulatedFloat(Context& c, uint32_t w, uint32_t h) : IlluminationBuffer(c, VKPBRT_ILLUMINATION_DEMODULATED_FLOAT, w, h) {}
+};
+
+class AccumulationBuffer : public Inherit<AccumulationBuffer> {   // source/buffers/AccumulationBuffer.hpp:13-24
+public:
+    AccumulationBuffer(Context& ctx, uint32_t w, uint32_t h) : _owner(true) { check(vkpbrt_accumulation_buffer_create(ctx.handle, w, h, &handle)); fill(); }
+    explicit AccumulationBuffer(vkpbrt_accumulation_buffer_t borrowed) : handle(borrowed), _owner(false) { fill(); }
+    ~AccumulationBuffer() { if (_owner) vkpbrt_accumulation_buffer_destroy(handle); }
+    void compile(Context&) const { check(vkpbrt_accumulation_buffer_compile(handle)); }
+    void update_image_layouts(Context&) const {}
+    // AccumulationBuffer.cpp:72-244: appended once, at the end of the command list
+    void copy_to_back_images(ref_ptr<Commands> commands, ref_ptr<GBuffer> g_buffer, ref_ptr<IlluminationBuffer> illumination_buffer)
+    {
+        auto h = handle;
+        commands->addChild([h, g_buffer, illumination_buffer](Commands&) {
+            check(vkpbrt_accumulation_buffer_copy_to_back_images(h, g_buffer->handle, illumination_buffer->handle));
+        });
+    }
+    ref_ptr<DescriptorImage> prev_illu, prev_illu_squared, prev_depth, prev_normal, spp, prev_spp, motion;
+    vkpbrt_accumulation_buffer_t handle = nullptr;
+private:
+    ref_ptr<DescriptorImage> member(uint32_t m) { vkpbrt_image_t i; check(vkpbrt_accumulation_buffer_image(handle, m, &i)); return DescriptorImage::create(i, false); }
+    void fill()
+    {
+        prev_illu = member(VKPBRT_ACC_PREV_ILLU); prev_illu_squared = member(VKPBRT_ACC_PREV_ILLU_SQUARED);
+        prev_depth = member(VKPBRT_ACC_PREV_DEPTH); prev_normal = member(VKPBRT_ACC_PREV_NORMAL);
+        spp = member(VKPBRT_ACC_SPP); prev_spp = member(VKPBRT_ACC_PREV_SPP); motion = member(VKPBRT_ACC_MOTION);
+    }
+    bool _owner;
+};
+
+// ---- render modules ---------------------------------------------------------------------------------------------
+class Accumulator : public Inherit<Accumulator> {   // source/renderModules/Accumulator.hpp:15-25
+public:
+    Accumulator(ref_ptr<GBuffer> g_buffer, ref_ptr<IlluminationBuffer> illumination_buffer, bool separate_matrices,
+                int work_width = 16, int work_height = 16)
+        : _g(g_buffer), _illum(illumination_buffer)
+    {
+        check(vkpbrt_accumulator_create(context_of(g_buffer), g_buffer->handle, illumination_buffer->handle, separate_matrices,
+                                        work_width, work_height, &handle));
+        vkpbrt_illumination_buffer_t ib; vkpbrt_accumulation_buffer_t ab;
+        check(vkpbrt_accumulator_accumulated_illumination(handle, &ib));
+        check(vkpbrt_accumulator_accumulation_buffer(handle, &ab));
+        accumulated_illumination = std::make_shared<IlluminationBufferDemodulated>(ib, g_buffer->width, g_buffer->height);
+        accumulation_buffer = std::make_shared<AccumulationBuffer>(ab);
+    }
+    ~Accumulator() { accumulated_illumination.reset(); accumulation_buffer.reset(); vkpbrt_accumulator_destroy(handle); }
+    void compile_images(Context&) const { check(vkpbrt_accumulator_compile_images(handle)); }
+    void update_image_layouts(Context&) const {}
+    void add_dispatch_to_command_graph(ref_ptr<Commands> command_graph)
+    {
+        auto h = handle;
+        command_graph->addChild([h](Commands&) { check(vkpbrt_accumulator_record(h)); });
+    }
+    void set_camera_matrices(int frame_index, const CameraMatrices& cur, const CameraMatrices& prev)
+    {
+        auto c = cur.c(), p = prev.c();
+        check(vkpbrt_accumulator_set_camera_matrices(handle, frame_index, &c, &p));
+    }
+    ref_ptr<IlluminationBuffer> accumulated_illumination;
+    ref_ptr<AccumulationBuffer> accumulation_buffer;
+    vkpbrt_accumulator_t handle = nullptr;
+private:
+    // every bundle remembers the context it was created in through its first image
+    static vkpbrt_context_t context_of(const ref_ptr<GBuffer>& g);
+    ref_ptr<GBuffer> _g;
+    ref_ptr<IlluminationBuffer> _illum;
+};
+
+// the C ABI needs the context explicitly; the reference passes it only to compile().  Modules therefore take it from a
+// process-wide "current context" set by the application before constructing modules (one per device / thread).
+inline vkpbrt_context_t& current_context() { static thread_local vkpbrt_context_t c = nullptr; return c; }
+inline void make_current(Context& ctx) { current_context() = ctx.handle; }
+inline vkpbrt_context_t Accumulator::context_of(const ref_ptr<GBuffer>&) { return current_context(); }
+
+class BMFR : public Inherit<BMFR> {   // source/renderModules/denoisers/BMFR.hpp:17-25
+public:
+    BMFR(uint32_t width, uint32_t height, uint32_t work_width, uint32_t work_height, ref_ptr<GBuffer> g_buffer,
+         ref_ptr<IlluminationBuffer> illu_buffer, ref_ptr<AccumulationBuffer> acc_buffer, uint32_t fitting_kernel = 256)
+        : _keep{g_buffer, illu_buffer, acc_buffer}
+    {
+        check(vkpbrt_bmfr_create(current_context(), width, height, work_width, work_height, g_buffer->handle, illu_buffer->handle,
+                                 acc_buffer->handle, fitting_kernel, &handle));
+        vkpbrt_image_t f; check(vkpbrt_bmfr_final_image(handle, &f));
+        _final = DescriptorImage::create(f, false);
+    }
+    ~BMFR() { vkpbrt_bmfr_destroy(handle); }
+    void compile(Context&) { check(vkpbrt_bmfr_compile(handle)); }
+    void update_image_layouts(Context&) {}
+    void add_dispatch_to_command_graph(ref_ptr<Commands> command_graph, ref_ptr<PushConstants> push_constants)
+    {
+        auto h = handle;
+        command_graph->addChild([h, push_constants](Commands& c) { c.bound_push_constants = push_constants; check(vkpbrt_bmfr_record(h, push_constants->c())); });
+    }
+    ref_ptr<DescriptorImage> get_final_descriptor_image() const { return _final; }
+    vkpbrt_bmfr_t handle = nullptr;
+private:
+    struct Keep { ref_ptr<GBuffer> g; ref_ptr<IlluminationBuffer> i; ref_ptr<AccumulationBuffer> a; } _keep;
+    ref_ptr<DescriptorImage> _final;
+};
+
+class BFR : public Inherit<BFR> {   // source/renderModules/denoisers/BFR.hpp:11-18
+public:
+    BFR(uint32_t width, uint32_t height, uint32_t work_width, uint32_t work_height, ref_ptr<GBuffer> g_buffer,
+        ref_ptr<IlluminationBuffer> illu_buffer, ref_ptr<AccumulationBuffer> acc_buffer)
+        : _keep{g_buffer, illu_buffer, acc_buffer}
+    {
+        check(vkpbrt_bfr_create(current_context(), width, height, work_width, work_height, g_buffer->handle, illu_buffer->handle,
+                                acc_buffer->handle, &handle));
+        vkpbrt_image_t f; check(vkpbrt_bfr_final_image(handle, &f));
+        _final = DescriptorImage::create(f, false);
+    }
+    ~BFR() { vkpbrt_bfr_destroy(handle); }
+    void compile(Context&) { check(vkpbrt_bfr_compile(handle)); }
+    void update_image_layouts(Context&) {}
+    void add_dispatch_to_command_graph(ref_ptr<Commands> command_graph, ref_ptr<PushConstants> push_constants)
+    {
+        auto h = handle;
+        command_graph->addChild([h, push_constants](Commands& c) { c.bound_push_constants = push_constants; check(vkpbrt_bfr_record(h, push_constants->c())); });
+    }
+    ref_ptr<DescriptorImage> get_final_descriptor_image() const { return _final; }
+    vkpbrt_bfr_t handle = nullptr;
+private:
+    struct Keep { ref_ptr<GBuffer> g; ref_ptr<IlluminationBuffer> i; ref_ptr<AccumulationBuffer> a; } _keep;
+    ref_ptr<DescriptorImage> _final;
+};
+
+class BFRBlender : public Inherit<BFRBlender> {   // source/renderModules/denoisers/BFRBlender.hpp:9-18
+public:
+    BFRBlender(uint32_t width, uint32_t height, ref_ptr<DescriptorImage> average_image, ref_ptr<DescriptorImage> average_squared_image,
+               ref_ptr<DescriptorImage> denoised0, ref_ptr<DescriptorImage> denoised1, ref_ptr<DescriptorImage> denoised2,
+               uint32_t work_width = 16, uint32_t work_height = 16, uint32_t filter_radius = 2)
+        : _keep{average_image, average_squared_image, denoised0, denoised1, denoised2}
+    {
+        check(vkpbrt_bfr_blender_create(current_context(), width, height, average_image->handle, average_squared_image->handle,
+                                        denoised0->handle, denoised1->handle, denoised2->handle, work_width, work_height,
+                                        filter_radius, &handle));
+        vkpbrt_image_t f; check(vkpbrt_bfr_blender_final_image(handle, &f));
+        _final = DescriptorImage::create(f, false);
+    }
+    ~BFRBlender() { vkpbrt_bfr_blender_destroy(handle); }
+    void compile(Context&) { check(vkpbrt_bfr_blender_compile(handle)); }
+    void update_image_layouts(Context&) {}
+    void add_dispatch_to_command_graph(ref_ptr<Commands> command_graph)
+    {
+        auto h = handle;
+        command_graph->addChild([h](Commands&) { check(vkpbrt_bfr_blender_record(h)); });
+    }
+    ref_ptr<DescriptorImage> get_final_descriptor_image() const { return _final; }
+    vkpbrt_bfr_blender_t handle = nullptr;
+private:
+    std::vector<ref_ptr<DescriptorImage>> _keep;
+    ref_ptr<DescriptorImage> _final;
+};
+
+class Taa : public Inherit<Taa> {   // source/renderModules/Taa.hpp:14-20
+public:
+    Taa(uint32_t width, uint32_t height, uint32_t work_width, uint32_t work_height, ref_ptr<GBuffer> g_buffer,
+        ref_ptr<AccumulationBuffer> acc_buffer, ref_ptr<DescriptorImage> denoised)
+        : _g(g_buffer), _acc(acc_buffer), _den(denoised)
+    {
+        check(vkpbrt_taa_create(current_context(), width, height, work_width, work_height, g_buffer->handle, acc_buffer->handle,
+                                denoised->handle, &handle));
+        vkpbrt_image_t f; check(vkpbrt_taa_final_image(handle, &f));
+        _final = DescriptorImage::create(f, false);
+    }
+    ~Taa() { vkpbrt_taa_destroy(handle); }
+    void compile(Context&) { check(vkpbrt_taa_compile(handle)); }
+    void update_image_layouts(Context&) {}
+    void add_dispatch_to_command_graph(ref_ptr<Commands> command_graph)
+    {
+        auto h = handle;
+        command_graph->addChild([h](Commands& c) {
+            if (!c.bound_push_constants) throw std::runtime_error("Taa: no push constants bound; record a denoiser first (Taa.cpp:99-107)");
+            check(vkpbrt_taa_record(h, c.bound_push_constants->c()));
+        });
+    }
+    ref_ptr<DescriptorImage> get_final_descriptor_image() const { return _final; }
+    vkpbrt_taa_t handle = nullptr;
+private:
+    ref_ptr<GBuffer> _g;
+    ref_ptr<AccumulationBuffer> _acc;
+    ref_ptr<DescriptorImage> _den, _final;
+};
+
+// source/util/DenoiserUtils.hpp:11-15.  `compile` is the context the reference reaches through
+// vsg::CompileTraversal::context; `modules` keeps the created modules alive (the reference leaks them into the graph).
+inline void add_denoiser_to_commands(DenoisingType denoising_type, DenoisingBlockSize denoising_size, ref_ptr<Commands>& commands,
+                                     Context& compile, int width, int height, ref_ptr<PushConstants> compute_constants,
+                                     ref_ptr<GBuffer>& g_buffer, ref_ptr<IlluminationBuffer>& illumination_buffer,
+                                     ref_ptr<AccumulationBuffer>& accumulation_buffer, ref_ptr<DescriptorImage>& final_descriptor_image,
+                                     std::vector<std::shared_ptr<void>>& modules)
+{
+    auto one = [&](auto mod) {
+        mod->compile(compile);
+        mod->update_image_layouts(compile);
+        mod->add_dispatch_to_command_graph(commands, compute_constants);
+        final_descriptor_image = mod->get_final_descriptor_image();
+        modules.push_back(mod);
+    };
+    auto size_of = [&]() { return denoising_size == DenoisingBlockSize::X8 ? 8u : denoising_size == DenoisingBlockSize::X16 ? 16u : 32u; };
+    switch (denoising_type) {
+    case DenoisingType::NONE: break;
+    case DenoisingType::SVG: break;   // "Not yet implemented" (DenoiserUtils.cpp:126)
+    case DenoisingType::BFR:
+    case DenoisingType::BMFR: {
+        const bool bmfr = denoising_type == DenoisingType::BMFR;
+        if (denoising_size == DenoisingBlockSize::X8X16X32) {
+            std::vector<ref_ptr<DescriptorImage>> finals;
+            for (uint32_t b : {8u, 16u, 32u}) {
+                if (bmfr) { auto m = BMFR::create(width, height, b, b, g_buffer, illumination_buffer, accumulation_buffer, b == 8 ? 64u : 256u); m->compile(compile); m->add_dispatch_to_command_graph(commands, compute_constants); finals.push_back(m->get_final_descriptor_image()); modules.push_back(m); }
+                else { auto m = BFR::create(width, height, b, b, g_buffer, illumination_buffer, accumulation_buffer); m->compile(compile); m->add_dispatch_to_command_graph(commands, compute_constants); finals.push_back(m->get_final_descriptor_image()); modules.push_back(m); }
+            }
+            auto blender = BFRBlender::create(width, height, illumination_buffer->illumination_images[0], illumination_buffer->illumination_images[1],
+                                              finals[0], finals[1], finals[2]);
+            blender->compile(compile);
+            blender->add_dispatch_to_command_graph(commands);
+            final_descriptor_image = blender->get_final_descriptor_image();
+            modules.push_back(blender);
+        } else if (bmfr) {
+            one(BMFR::create(width, height, size_of(), size_of(), g_buffer, illumination_buffer, accumulation_buffer, size_of() == 8 ? 64u : 256u));
+        } else {
+            one(BFR::create(width, height, size_of(), size_of(), g_buffer, illumination_buffer, accumulation_buffer));
+        }
+        break;
+    }
+    }
+}
+
+}  // namespace vkpbrt
