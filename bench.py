@@ -113,15 +113,22 @@ def render_sequence(W, H, n, rows=None, pinned=True, first=0):
 # reference arm / cpu baseline: the reference's CPU path
 # ---------------------------------------------------------------------------------------------------
 def cpu_chain(W, H, taa):
+    """the reference's CPU implementation of the path: oracle/_ref (the reference's shader source compiled through
+    oracle/glsl_shim) when it is built, else the oracle port"""
     from oracle import oracle as O
-    return O, O.OracleChain(W, H, "bmfr", 32, use_taa=taa)
+    from oracle import ref as R
+    if R.available():
+        return O, R.RefChain(W, H, "bmfr", 32, use_taa=taa), "reference"
+    return O, O.OracleChain(W, H, "bmfr", 32, use_taa=taa), "port"
 
 
-def run_cpu(W, H, taa, frames, budget_s=None, warmup=0):
-    """times the oracle chain on `frames` synthetic frames (stops early once budget_s is spent)"""
+def run_cpu(W, H, taa, frames, budget_s=None, warmup=0, sample_scale=1):
+    """times the CPU chain on `frames` synthetic frames of (W / sample_scale) x (H / sample_scale) -- MPix/s does not
+    depend on the frame size -- and stops early once budget_s is spent"""
     from vulkanpbrt_b200 import synth
-    O, chain = cpu_chain(W, H, taa)
-    fs = [synth.render_frame(W, H, f) for f in range(min(frames + warmup, 8))]
+    w, h = (W // sample_scale) // 32 * 32, (H // sample_scale) // 4 * 4
+    O, chain, kind = cpu_chain(w, h, taa)
+    fs = [synth.render_frame(w, h, f) for f in range(min(frames + warmup, 8))]
     for f in range(warmup):
         chain.run_frame(f, fs[f % len(fs)])
     t0 = time.perf_counter()
@@ -132,8 +139,10 @@ def run_cpu(W, H, taa, frames, budget_s=None, warmup=0):
         if budget_s is not None and time.perf_counter() - t0 > budget_s and done >= 2:
             break
     dt = time.perf_counter() - t0
-    return {"value": W * H * done / dt / 1e6, "unit": "MPix/s", "cores": int(O.lib().vkpbrt_oracle_num_threads()),
-            "kind": "port", "sample": f"{done} frames of {W}x{H} (oracle/vkpbrt_oracle.c, OpenMP), {dt:.1f} s",
+    what = ("reference shader source (shaders/*.comp) compiled for the CPU via oracle/glsl_shim" if kind == "reference"
+            else "oracle/vkpbrt_oracle.c")
+    return {"value": w * h * done / dt / 1e6, "unit": "MPix/s", "cores": int(O.lib().vkpbrt_oracle_num_threads()),
+            "kind": kind, "sample": f"{done} frames of {w}x{h} ({what}, OpenMP over workgroups), {dt:.1f} s",
             "ms_per_frame": dt / done * 1e3}
 
 
@@ -142,12 +151,12 @@ def main_reference(args):
     if rank != 0:
         return
     W, H, taa, desc = WORKLOADS[args.workload or "bmfr_1080p"]
-    r = run_cpu(W, H, taa, args.steps, warmup=min(args.warmup, 3))
+    r = run_cpu(W, H, taa, args.steps, warmup=min(args.warmup, 3), sample_scale=2)      # bounded sample: quarter-size frames
     line = {"impl": "reference", "metric": "BMFR denoised MPix/s", "value": r["value"], "unit": "MPix/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_frame"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload or "bmfr_1080p", "description": desc, "width": W, "height": H,
-                       "note": "reference CPU path: GLSL shaders restated in C (the SPIR-V cannot run here: no Vulkan ICD)"},
+                       "note": "reference CPU path (no Vulkan ICD / lavapipe on this machine): " + r["sample"]},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "MPix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -329,7 +338,7 @@ def main_ours(args):
     e2e_ms = max(e0.elapsed_time(e1), 0.0)
     e2e_value = W * H * K / (e2e_ms * 1e-3) / 1e6
 
-    cpu = run_cpu(W, H, taa, frames=64, budget_s=args.cpu_budget, warmup=1) if (args.cpu_budget > 0 and not bfr) else None
+    cpu = run_cpu(W, H, taa, frames=64, budget_s=args.cpu_budget, warmup=1, sample_scale=2) if (args.cpu_budget > 0 and not bfr) else None
 
     line = {"metric": ("BFR+blend" if bfr else "BMFR") + " denoised MPix/s", "value": round(value, 1), "unit": "MPix/s", "n_gpus": 1, "steps": K, "warmup": Wm,
             "ms_per_step": round(ms / K, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",

@@ -7,12 +7,14 @@
  * (libvkpbrt_b200.so) never links, loads or calls anything in oracle/.
  *
  * PARITY STATUS: the reference ships no tests, golden vectors or fixtures for this path
- *  and its shaders are GLSL, which cannot be compiled by any tool in
- * this image (no glslc / glslang / Vulkan ICD).  The restatement is therefore pinned
- * against oracle/_ref: the reference's own shader SOURCE TEXT compiled as C++ through the
- * GLSL-compatibility shim in oracle/glsl_shim (see oracle/Makefile and
- * tests/test_oracle_vs_ref.py).  Where oracle/_ref is not built the status is
- * "parity unpinned".
+ *  and its shaders are GLSL, which no tool in this image can compile to
+ * SPIR-V or execute (no glslc / glslang / Vulkan ICD).  The restatement is PINNED against
+ * oracle/_ref instead: the reference's own shader SOURCE TEXT, read where it lies under
+ * /root/reference, compiled as C++ through the GLSL-compatibility shim in oracle/glsl_shim and
+ * run with the reference's bindings / dispatch sizes / push constants (oracle/ref.py).
+ * tests/test_oracle_vs_ref.py requires every plane of every frame -- feature buffer and fitted
+ * weights included -- to be bit-identical between this file and oracle/_ref.  On a machine
+ * where oracle/_ref is neither built nor buildable that test skips and parity is unpinned.
  *
  * Every function cites the reference file:line it follows (paths relative to
  * /root/reference).  All arithmetic is IEEE binary32, compiled with -ffp-contract=off so

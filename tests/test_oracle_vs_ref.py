@@ -1,0 +1,60 @@
+"""Pins the oracle: oracle/vkpbrt_oracle.c (the hand-written restatement every parity test compares the CUDA path
+with) against oracle/_ref -- the reference's OWN shader source text (shaders/*.comp under /root/reference), compiled
+as C++ through oracle/glsl_shim and executed on the CPU with the reference's descriptor bindings, dispatch sizes and
+push constants (oracle/ref.py).  Every plane of every frame must be bit-identical, including the BMFR feature buffer
+and the fitted weights.  oracle/_ref is built here (where the reference is mounted) by __graft_entry__.build(); the
+prebuilt library travels to the GPU box."""
+import numpy as np
+import pytest
+
+from vulkanpbrt_b200 import synth
+
+
+@pytest.fixture(scope="module")
+def ref(oracle):
+    from oracle import ref as R
+    try:
+        ok = R.build()
+    except Exception as e:      # pragma: no cover
+        pytest.fail(f"oracle/_ref failed to build: {e}")
+    if not ok:
+        pytest.skip("oracle/_ref is not built and /root/reference is not mounted: parity unpinned on this machine")
+    return R
+
+
+CASES = [
+    # W, H, denoiser, block, taa, frames, first frame, separate matrices, rgba16f input
+    (256, 256, "bmfr", 32, True, 4, 0, True, False),        # BASELINE configs[0] geometry
+    (250, 130, "bmfr", 32, True, 4, 7, True, False),        # ragged size, frames 8 / 9 leave rows 0-1 / column 0 unwritten
+    (208, 144, "bmfr", 16, False, 2, 8, True, False),
+    (200, 136, "bmfr", 8, True, 2, 0, True, False),
+    (160, 128, "bfr", 32, False, 2, 0, True, False),
+    (168, 104, "bfr", 16, False, 2, 0, True, False),
+    (128, 96, "bfr", 8, False, 2, 0, True, False),
+    (160, 128, "bfrx3", 32, True, 3, 0, True, False),       # BASELINE configs[2] structure: 3 x BFR + blender (+ TAA)
+    (256, 128, "bmfr", 32, True, 3, 0, False, False),       # accumulator.comp without SEPARATE_MATRICES
+    (256, 128, "bmfr", 32, False, 2, 0, True, True),        # rgba16f raw illumination
+]
+
+
+@pytest.mark.parametrize("W,H,den,block,taa,frames,f0,sep,f16", CASES)
+def test_oracle_equals_reference_shader_source(oracle, ref, W, H, den, block, taa, frames, f0, sep, f16):
+    a = oracle.OracleChain(W, H, den, block, use_taa=taa, separate_matrices=sep, raw_f16=f16)
+    b = ref.RefChain(W, H, den, block, use_taa=taa, separate_matrices=sep, raw_f16=f16)
+    for f in range(f0, f0 + frames):
+        fr = synth.render_frame(W, H, f)
+        if den.endswith("x3"):
+            av = oracle.f16_bits_to_f32(a.prev_illu)
+            sq = np.ascontiguousarray((av * av * 1.5 + 0.01).astype(np.float16).view(np.uint16))
+            a.average_squared[...] = sq
+            b.average_squared[...] = sq
+        a.run_frame(f, fr, keep_debug=True)
+        b.run_frame(f, fr, keep_debug=True)
+        for name in ("motion", "spp", "illum", "prev_depth", "blend_final", "taa_final", "taa_history"):
+            np.testing.assert_array_equal(getattr(a, name), getattr(b, name), err_msg=f"{name}, frame {f}")
+        for blk in a.blocks:
+            np.testing.assert_array_equal(a.denoised[blk], b.denoised[blk], err_msg=f"denoised b={blk}, frame {f}")
+            np.testing.assert_array_equal(a.finals[blk], b.finals[blk], err_msg=f"final b={blk}, frame {f}")
+        if den.startswith("bmfr"):
+            np.testing.assert_array_equal(a.features, b.features, err_msg=f"feature buffer, frame {f}")
+            np.testing.assert_array_equal(a.weights.view(np.uint32), b.weights.view(np.uint32), err_msg=f"weights, frame {f}")
