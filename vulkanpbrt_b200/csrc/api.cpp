@@ -841,6 +841,14 @@ int vkpbrt_bmfr_record(vkpbrt_bmfr_t b, const vkpbrt_push_constants* pc)
     p.blocks_x = (int)b->blocks_x; p.blocks_y = (int)b->blocks_y;
     p.block_row_begin = b->block_row_begin; p.block_row_end = b->block_row_end;
     p.frame = pc->frame_number;
+    {
+        // bmfrGeneral.comp:36 / bmfrPre.comp:16: float multiply, truncation toward zero
+        static const float offs[16][2] = {{.7f, .85f}, {.95f, .5f}, {.43f, .76f}, {.97f, .03f}, {.37f, .58f}, {.03f, .36f}, {.81f, .46f}, {0.f, .78f},
+                                          {.36f, -.08f}, {-.06f, 0.f}, {.95f, .1f}, {.85f, .61f}, {.06f, .1f}, {.43f, .16f}, {0.f, .5f}, {.73f, .38f}};
+        const float bw = (float)b->work;
+        p.off_x = (int)(bw * offs[pc->frame_number % 16][0]);
+        p.off_y = (int)(bw * offs[pc->frame_number % 16][1]);
+    }
     p.depth = (const float*)b->g->img[VKPBRT_GBUFFER_DEPTH]->data;
     p.normal = (const float2*)b->g->img[VKPBRT_GBUFFER_NORMAL]->data;
     p.albedo = (const uchar4*)b->g->img[VKPBRT_GBUFFER_ALBEDO]->data;

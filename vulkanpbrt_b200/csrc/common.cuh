@@ -86,11 +86,13 @@ VK_DEVICE float div_guarded(float a, float b, float rb, bool b_safe)
 // same order, so normals, features and tone-mapped texels are bit-identical on CPU and GPU.
 VK_DEVICE void vk_sincos(float x, float& sn, float& cs)
 {
-    const float ax = fabsf(x);
-    if (!(ax < 8192.0f)) { sn = cs = div_rn(sub_rn(x, x), sub_rn(x, x)); return; }
-    uint32_t j = (uint32_t)mul_rn(ax, 1.27323954473516f);
-    float y = (float)j;
-    if (j & 1u) { j += 1u; y = add_rn(y, 1.0f); }
+    // branch-free form of the oracle's vk_sincos: out-of-range arguments are evaluated on a dummy and replaced by
+    // the oracle's NaN at the end; "if (j & 1) { j += 1; y += 1; }" is j = (j + 1) & ~1 with y = float(j) (exact, j < 2^24)
+    const float ax0 = fabsf(x);
+    const bool in_range = ax0 < 8192.0f;
+    const float ax = in_range ? ax0 : 0.0f;
+    const uint32_t j = ((uint32_t)mul_rn(ax, 1.27323954473516f) + 1u) & ~1u;
+    const float y = (float)j;
     const float r = sub_rn(sub_rn(sub_rn(ax, mul_rn(y, 0.78515625f)), mul_rn(y, 2.4187564849853515625e-4f)), mul_rn(y, 3.77489497744594108e-8f));
     const float z = mul_rn(r, r);
     const float ps = add_rn(mul_rn(mul_rn(add_rn(mul_rn(add_rn(mul_rn(-1.9515295891e-4f, z), 8.3321608736e-3f), z), -1.6666654611e-1f), z), r), r);
@@ -100,35 +102,43 @@ VK_DEVICE void vk_sincos(float x, float& sn, float& cs)
     const uint32_t q = (j >> 1) & 3u;
     const float s = (q == 0u) ? ps : ((q == 1u) ? pc : ((q == 2u) ? -ps : -pc));
     const float c = (q == 0u) ? pc : ((q == 1u) ? -ps : ((q == 2u) ? -pc : ps));
-    sn = (x < 0.0f) ? -s : s;
-    cs = c;
+    const float nan = __uint_as_float(0x7fc00000u);
+    sn = in_range ? ((x < 0.0f) ? -s : s) : nan;
+    cs = in_range ? c : nan;
 }
 
-VK_DEVICE float vk_pow(float x, float y)
+VK_DEVICE float vk_pow(float x0, float y)
 {
-    if (!(x > 0.0f)) return (x == 0.0f) ? 0.0f : div_rn(sub_rn(x, x), sub_rn(x, x));
-    if (x > 3.0e38f) return x;
-    int e = 0;
-    if (x < 1.17549435e-38f) { x = mul_rn(x, 8388608.0f); e = -23; }
+    // branch-free form of the oracle's vk_pow (every early exit becomes a select on the final value)
+    const bool positive = x0 > 0.0f, huge = x0 > 3.0e38f;
+    float x = (positive && !huge) ? x0 : 1.0f;
+    const bool sub = x < 1.17549435e-38f;
+    x = sub ? mul_rn(x, 8388608.0f) : x;
     const uint32_t bits = __float_as_uint(x);
-    e += (int)((bits >> 23) & 255u) - 127;
+    int e = (sub ? -23 : 0) + (int)((bits >> 23) & 255u) - 127;
     float m = __uint_as_float((bits & 0x007fffffu) | 0x3f800000u);
-    if (m > 1.41421356f) { m = mul_rn(m, 0.5f); e += 1; }
+    const bool big = m > 1.41421356f;
+    m = big ? mul_rn(m, 0.5f) : m;
+    e += big ? 1 : 0;
     const float z = div_rn(sub_rn(m, 1.0f), add_rn(m, 1.0f));
     const float z2 = mul_rn(z, z);
     const float p = mul_rn(add_rn(mul_rn(add_rn(mul_rn(add_rn(mul_rn(add_rn(mul_rn(0.0909090909f, z2), 0.1111111111f), z2), 0.1428571429f), z2), 0.2f), z2), 0.3333333333f), z2);
     const float lnm = mul_rn(2.0f, add_rn(z, mul_rn(z, p)));
     const float lg = add_rn((float)e, mul_rn(lnm, 1.44269504089f));
-    const float t = mul_rn(y, lg);
-    if (t > 127.99f) return __uint_as_float(0x7f800000u);
-    if (t < -150.0f) return 0.0f;
+    const float t0 = mul_rn(y, lg);
+    const bool over = t0 > 127.99f, under = t0 < -150.0f;
+    const float t = (over || under) ? 0.0f : t0;
     const float n = rintf(t);
     const float f = sub_rn(t, n);
     const float px = add_rn(mul_rn(add_rn(mul_rn(add_rn(mul_rn(add_rn(mul_rn(add_rn(mul_rn(1.535336188319500e-4f, f), 1.339887440266574e-3f), f),
                                                                     9.618437357674640e-3f), f), 5.550332471162809e-2f), f), 2.402264791363012e-1f), f), 6.931472028550421e-1f);
     const float r = add_rn(1.0f, mul_rn(f, px));
     const int ni = (int)n, n1 = ni / 2, n2 = ni - n1;
-    return mul_rn(mul_rn(r, __uint_as_float((uint32_t)(n1 + 127) << 23)), __uint_as_float((uint32_t)(n2 + 127) << 23));
+    float res = mul_rn(mul_rn(r, __uint_as_float((uint32_t)(n1 + 127) << 23)), __uint_as_float((uint32_t)(n2 + 127) << 23));
+    res = over ? __uint_as_float(0x7f800000u) : (under ? 0.0f : res);
+    res = huge ? x0 : res;
+    // x <= 0 or NaN: pow(0, y) = 0, otherwise the oracle's (x - x) / (x - x) = NaN
+    return positive ? res : ((x0 == 0.0f) ? 0.0f : __uint_as_float(0x7fc00000u));
 }
 
 // mix(x, y, a) = x*(1-a) + y*a, no contraction
@@ -139,7 +149,7 @@ VK_DEVICE float f16_bits_to_f32(uint16_t h) { return __half2float(__ushort_as_ha
 
 VK_DEVICE uint8_t f32_to_unorm8(float c)
 {
-    if (!(c == c)) return 0;
+    c = (c == c) ? c : 0.0f;          // NaN -> 0
     c = c < 0.0f ? 0.0f : c;
     c = c > 1.0f ? 1.0f : c;
     return (uint8_t)add_rn(mul_rn(c, 255.0f), 0.5f);

@@ -46,6 +46,7 @@ struct BmfrParams {
     int blocks_x, blocks_y;       // W/b+2, H/b+2
     int block_row_begin, block_row_end;  // block rows processed (band sharding)
     uint32_t frame;
+    int off_x, off_y;             // ivec2(vec2(b, b) * pixelOffsets[frame % 16]) (bmfrPre.comp:16), evaluated on the host
     const float* depth;
     const float2* normal;
     const uchar4* albedo;
