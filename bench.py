@@ -59,30 +59,41 @@ def peaks():
 class ClockSampler(threading.Thread):
     """samples SM clock / throttle reasons during the timed region (nvml, falling back to nvidia-smi)"""
 
+    NAMES = {0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown",
+             0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown"}
+
     def __init__(self, device):
         super().__init__(daemon=True)
         self.device, self.samples, self.reasons, self.max_mhz, self._halt = device, [], set(), None, threading.Event()
-
-    def run(self):
-        try:
+        self._nv = self._h = None
+        try:        # NVML is initialised here, before the timed region: the region itself can be as short as 15 ms
             import pynvml as nv
             nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.device)
-            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-            names = {0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown",
-                     0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown"}
-            while not self._halt.is_set():
-                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
-                try:
-                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
-                except Exception:
-                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for bit, n in names.items():
-                    if r & bit:
-                        self.reasons.add(n)
-                time.sleep(0.004)
+            self._nv, self._h = nv, nv.nvmlDeviceGetHandleByIndex(device)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self._h, nv.NVML_CLOCK_SM)
         except Exception as e:  # pragma: no cover
             self.reasons.add(f"sampler_error:{type(e).__name__}")
+
+    def sample(self):
+        nv, h = self._nv, self._h
+        if nv is None:
+            return
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+            try:
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+            except Exception:
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            for bit, n in self.NAMES.items():
+                if r & bit:
+                    self.reasons.add(n)
+        except Exception as e:  # pragma: no cover
+            self.reasons.add(f"sampler_error:{type(e).__name__}")
+
+    def run(self):
+        while not self._halt.is_set():
+            self.sample()
+            time.sleep(0.001)
 
     def stop(self):
         self._halt.set()
@@ -360,6 +371,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--resident-frames", type=int, default=70)
+    ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: halo rows through NVLink peer memory (k_halo_push) or NCCL send/recv groups")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for cpu_baseline (0 = skip)")
     args = ap.parse_args()
     if args.warmup < 3:

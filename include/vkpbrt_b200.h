@@ -293,6 +293,43 @@ VKPBRT_API int vkpbrt_external_semaphore_wait(vkpbrt_external_semaphore_t s, uin
 VKPBRT_API int vkpbrt_external_semaphore_signal(vkpbrt_external_semaphore_t s, uint64_t value); /* on ctx stream */
 VKPBRT_API int vkpbrt_external_semaphore_destroy(vkpbrt_external_semaphore_t s);
 
+/* ---------------------------------------------------------------------------------------- */
+/* Band-sharded multi-GPU runs: halo rows over NVLink peer memory.    */
+/* No reference counterpart (the reference records one device's command graph,                */
+/* VulkanPBRT.cpp:551-618); the exchanged rows follow the shaders' read footprints            */
+/* (accumulator.comp:75-98, bmfrPost.comp:103-118, taa.comp:44-60).  One process per GPU:      */
+/* a rank exports the allocations its neighbours write into, the neighbours open them, and    */
+/* each exchange point is ONE kernel that stores the rows into the receivers' HBM and then    */
+/* publishes a frame counter to their flag words; receivers wait on their own flag words.     */
+/* ---------------------------------------------------------------------------------------- */
+#define VKPBRT_PEER_HANDLE_BYTES 64
+#define VKPBRT_HALO_MAX_PEERS 8
+typedef struct vkpbrt_halo_copy {       /* rows x row_bytes, pitched on both sides */
+    const void* src;                    /* local device address */
+    void* dst;                          /* address inside a vkpbrt_peer_open mapping (or local) */
+    uint64_t src_pitch, dst_pitch;
+    uint32_t row_bytes, rows;
+} vkpbrt_halo_copy;
+/* handle of the cudaMalloc allocation holding device_ptr + device_ptr's offset inside it (cudaIpcGetMemHandle) */
+VKPBRT_API int vkpbrt_peer_export(vkpbrt_context_t ctx, const void* device_ptr, uint8_t handle[VKPBRT_PEER_HANDLE_BYTES],
+                                  uint64_t* offset);
+/* maps another process's allocation (cudaIpcOpenMemHandle, peer access enabled lazily); open each handle once */
+VKPBRT_API int vkpbrt_peer_open(vkpbrt_context_t ctx, const uint8_t handle[VKPBRT_PEER_HANDLE_BYTES], void** base);
+VKPBRT_API int vkpbrt_peer_close(vkpbrt_context_t ctx, void* base);
+/* one launch on `stream` (a cudaStream_t; NULL = the context's stream):
+ *   spin until every ready_flags[i] (local words) >= value   (n_ready may be 0: no gate)
+ *   copy the n_copies blocks of the DEVICE table copies_device
+ *   store `value` to every done_flags[i] (receivers' words, peer mapped) after all copies have landed
+ * counter_device: one zero-initialised device word per concurrently running exchange point;
+ * error_device: device word set to 1 if a spin exceeded timeout_ms (the kernel then proceeds, it never hangs) */
+VKPBRT_API int vkpbrt_halo_push(vkpbrt_context_t ctx, void* stream, const vkpbrt_halo_copy* copies_device, uint32_t n_copies,
+                                const uint32_t* const* ready_flags, uint32_t n_ready, uint32_t* const* done_flags,
+                                uint32_t n_done, uint32_t value, uint32_t* counter_device, uint32_t* error_device,
+                                uint32_t timeout_ms);
+/* makes `stream` wait until every flags[i] (local device words) >= value */
+VKPBRT_API int vkpbrt_halo_wait(vkpbrt_context_t ctx, void* stream, const uint32_t* const* flags, uint32_t n, uint32_t value,
+                                uint32_t* error_device, uint32_t timeout_ms);
+
 #ifdef __cplusplus
 }
 #endif

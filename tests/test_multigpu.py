@@ -150,49 +150,79 @@ def test_two_rank_banded_chain_equals_single_rank(tmp_path, use_taa, W, H, frame
         _capi._lib = saved
 
 
-# ---- real GPUs: NCCL halo exchange over NVLink ------------------------------------------------------
-def _gpu_worker(rank, world, W, H, frames, use_taa, port, out_dir, direct):
+# ---- real GPUs: halo exchange over NVLink (peer memory / NCCL) ---------------------------------------
+def _gpu_worker(rank, world, W, H, frames, use_taa, port, out_dir, mode):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
     sys.path.insert(0, str(ROOT))
+    import time
+
     import torch
     import torch.distributed as dist
     from vulkanpbrt_b200 import Context, synth
-    from vulkanpbrt_b200.multigpu import BandedPipeline, NcclDirect, cuda_view
+    from vulkanpbrt_b200.multigpu import BandedPipeline, NcclDirect, PeerDirect, cuda_view
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
-    bp = BandedPipeline(W, H, rank, world, use_taa, Context(rank, stream.cuda_stream), cuda_view(dev), external_inputs=False, dist=dist,
-                        nccl=NcclDirect(dist, rank, world, dev) if direct else None)
+    ctx = Context(rank, stream.cuda_stream)
+    view = cuda_view(dev)
+    bp = BandedPipeline(W, H, rank, world, use_taa, ctx, view, external_inputs=(mode == "peer-async"), dist=dist,
+                        nccl=NcclDirect(dist, rank, world, dev) if mode == "nccl" else None,
+                        peer=PeerDirect(dist, rank, world, dev, ctx) if mode.startswith("peer") else None)
     lo, hi = bp.plan.input_rows(rank)
     finals = []
-    for f in range(frames):
-        fr = synth.render_frame(W, H, f, rows=(lo, hi))
-        bp.pipe.upload_frame(fr)
-        bp.run_frame(f, fr.camera)
+    if mode == "peer-async":
+        # no host synchronisation between frames and the ranks' hosts deliberately out of step: the only
+        # ordering left is the flag protocol.  Owned rows are snapshotted on the stream and read at the end.
+        seq = [synth.render_frame(W, H, f, rows=(lo, hi)) for f in range(frames)]
+        dseq = [{k: torch.from_numpy(np.ascontiguousarray(getattr(fr, k))).to(dev) for k in ("depth", "normal", "albedo", "illumination")}
+                for fr in seq]
         torch.cuda.synchronize()
-        o = bp.owned_rows(f)
-        finals.append((o, bp.pipe.final.download()[o[0]:o[1]].copy(), bp.bmfr.denoised.download()[(f & 1) ^ 1, o[0]:o[1]].copy()))
-    bp.flush()
-    torch.cuda.synchronize()
+        snaps = []
+        for f, fr in enumerate(seq):
+            d = dseq[f]
+            bp.pipe.bind_inputs(d["depth"].data_ptr(), d["normal"].data_ptr(), d["albedo"].data_ptr(), d["illumination"].data_ptr())
+            bp.run_frame(f, fr.camera)
+            o = bp.owned_rows(f)
+            layer = (f & 1) ^ 1
+            snaps.append((o, view(bp.pipe.final)[o[0]:o[1]].clone(), view(bp.bmfr.denoised)[layer, o[0]:o[1]].clone()))
+            if (f + rank) % 3 == 0:
+                time.sleep(0.02 * (1 + (rank + f) % 3))
+        bp.flush()
+        torch.cuda.synchronize()
+        bp.check()
+        for o, fin, den in snaps:
+            finals.append((o, fin.cpu().numpy().view(np.uint8).reshape(o[1] - o[0], W, 4), den.cpu().numpy().view(np.uint16).reshape(o[1] - o[0], W, 4)))
+    else:
+        for f in range(frames):
+            fr = synth.render_frame(W, H, f, rows=(lo, hi))
+            bp.pipe.upload_frame(fr)
+            bp.run_frame(f, fr.camera)
+            torch.cuda.synchronize()
+            o = bp.owned_rows(f)
+            finals.append((o, bp.pipe.final.download()[o[0]:o[1]].copy(), bp.bmfr.denoised.download()[(f & 1) ^ 1, o[0]:o[1]].copy()))
+        bp.flush()
+        torch.cuda.synchronize()
+        bp.check()
     np.save(os.path.join(out_dir, f"gpu_{rank}.npy"), np.array(finals, dtype=object), allow_pickle=True)
     dist.barrier()
     dist.destroy_process_group()
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("world,direct", [(2, True), (2, False), (4, True), (8, True)])
-def test_banded_chain_on_gpus_equals_single_gpu(tmp_path, world, direct):
-    """direct: NCCL groups issued through ctypes on a communication stream (the bench path); otherwise
-    torch.distributed's own P2P ops"""
+@pytest.mark.parametrize("world,mode", [(2, "peer"), (2, "peer-async"), (2, "nccl"), (2, "torch"), (4, "peer-async"), (8, "peer-async")])
+def test_banded_chain_on_gpus_equals_single_gpu(tmp_path, world, mode):
+    """peer: rows stored straight into the neighbours' HBM over NVLink + flag words (the bench path);
+    peer-async: the same without any host synchronisation between frames and with the ranks' hosts out of step;
+    nccl: NCCL groups issued through ctypes on a communication stream; torch: torch.distributed's own P2P ops"""
     import torch
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
-    W, H, frames = 1920, 1080, 12
+    W, H, frames = 1920, 1080, (20 if mode == "peer-async" else 12)
     port = 29500 + (os.getpid() % 2000)
-    mp.start_processes(_gpu_worker, args=(world, W, H, frames, True, port, str(tmp_path), direct), nprocs=world, join=True, start_method="spawn")
+    mp.start_processes(_gpu_worker, args=(world, W, H, frames, True, port, str(tmp_path), mode), nprocs=world, join=True, start_method="spawn")
     from vulkanpbrt_b200 import DenoisePipeline, synth
     pipe = DenoisePipeline(W, H, use_taa=True)
     per_rank = [np.load(tmp_path / f"gpu_{r}.npy", allow_pickle=True) for r in range(world)]

@@ -41,6 +41,8 @@ GBUFFER_DEPTH, GBUFFER_NORMAL, GBUFFER_MATERIAL, GBUFFER_ALBEDO = range(4)
 ILLUMINATION_FINAL, ILLUMINATION_DEMODULATED, ILLUMINATION_DEMODULATED_FLOAT, ILLUMINATION_FINAL_DEMODULATED = range(4)
 (ACC_PREV_ILLU, ACC_PREV_ILLU_SQUARED, ACC_PREV_DEPTH, ACC_PREV_NORMAL, ACC_SPP, ACC_PREV_SPP, ACC_MOTION, ACC_NEXT_DEPTH) = range(8)
 BMFR_IMAGE_DENOISED, BMFR_IMAGE_FEATURES, BMFR_IMAGE_WEIGHTS = range(3)
+PEER_HANDLE_BYTES = 64
+HALO_MAX_PEERS = 8
 
 
 class ImageInfo(C.Structure):
@@ -139,6 +141,11 @@ _PROTOS = {
     "vkpbrt_external_semaphore_wait": [H, u64],
     "vkpbrt_external_semaphore_signal": [H, u64],
     "vkpbrt_external_semaphore_destroy": [H],
+    "vkpbrt_peer_export": [H, C.c_void_p, C.c_void_p, C.POINTER(u64)],
+    "vkpbrt_peer_open": [H, C.c_void_p, PH],
+    "vkpbrt_peer_close": [H, C.c_void_p],
+    "vkpbrt_halo_push": [H, C.c_void_p, C.c_void_p, u32, C.c_void_p, u32, C.c_void_p, u32, u32, C.c_void_p, C.c_void_p, u32],
+    "vkpbrt_halo_wait": [H, C.c_void_p, C.c_void_p, u32, u32, C.c_void_p, u32],
 }
 _RESTYPES = {"vkpbrt_last_error": C.c_char_p, "vkpbrt_version": C.c_char_p, "vkpbrt_format_texel_size": u32}
 EXPORTS = sorted(list(_PROTOS) + list(_RESTYPES))

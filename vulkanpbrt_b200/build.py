@@ -33,6 +33,7 @@ UNITS = {
     "taa.cu": ["-fmad=false"],
     "bmfr.cu": [],
     "bfr.cu": [],
+    "halo.cu": [],
     "api.cpp": [],
 }
 

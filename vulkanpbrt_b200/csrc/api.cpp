@@ -1226,4 +1226,102 @@ int vkpbrt_external_semaphore_destroy(vkpbrt_external_semaphore_t s)
     return VKPBRT_OK;
 }
 
+// ---- band-sharded runs: NVLink peer memory -----------------------------------------------------------
+#ifndef VKPBRT_HOSTSIM
+using vkpbrt::HaloCopy;
+using vkpbrt::HaloPushParams;
+using vkpbrt::HaloWaitParams;
+using vkpbrt::kHaloMaxPeers;
+static_assert(sizeof(vkpbrt_halo_copy) == sizeof(HaloCopy) && VKPBRT_HALO_MAX_PEERS == kHaloMaxPeers, "halo table layout");
+static_assert(sizeof(cudaIpcMemHandle_t) == VKPBRT_PEER_HANDLE_BYTES, "IPC handle size");
+
+int vkpbrt_peer_export(vkpbrt_context_t ctx, const void* device_ptr, uint8_t handle[VKPBRT_PEER_HANDLE_BYTES], uint64_t* offset)
+{
+    VK_REQUIRE(ctx && device_ptr && handle && offset, "null argument");
+    VK_CUDA(cudaSetDevice(ctx->device));
+    // the handle names the whole allocation: find its base through the driver entry point the runtime already holds
+    typedef int (*range_fn)(unsigned long long*, size_t*, unsigned long long);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    VK_CUDA(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr));
+    VK_REQUIRE(fn && qr == cudaDriverEntryPointSuccess, "cuMemGetAddressRange is not available");
+    unsigned long long base = 0;
+    size_t size = 0;
+    const int rc = reinterpret_cast<range_fn>(fn)(&base, &size, (unsigned long long)(uintptr_t)device_ptr);
+    VK_REQUIRE(rc == 0 && base != 0, "not a device allocation");
+    cudaIpcMemHandle_t h;
+    VK_CUDA(cudaIpcGetMemHandle(&h, reinterpret_cast<void*>((uintptr_t)base)));
+    memcpy(handle, &h, sizeof(h));
+    *offset = (uint64_t)((uintptr_t)device_ptr - (uintptr_t)base);
+    return VKPBRT_OK;
+}
+
+int vkpbrt_peer_open(vkpbrt_context_t ctx, const uint8_t handle[VKPBRT_PEER_HANDLE_BYTES], void** base)
+{
+    VK_REQUIRE(ctx && handle && base, "null argument");
+    VK_CUDA(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    VK_CUDA(cudaIpcOpenMemHandle(base, h, cudaIpcMemLazyEnablePeerAccess));
+    return VKPBRT_OK;
+}
+
+int vkpbrt_peer_close(vkpbrt_context_t ctx, void* base)
+{
+    VK_REQUIRE(ctx, "null context");
+    if (!base) return VKPBRT_OK;
+    VK_CUDA(cudaSetDevice(ctx->device));
+    VK_CUDA(cudaIpcCloseMemHandle(base));
+    return VKPBRT_OK;
+}
+
+int vkpbrt_halo_push(vkpbrt_context_t ctx, void* stream, const vkpbrt_halo_copy* copies_device, uint32_t n_copies,
+                     const uint32_t* const* ready_flags, uint32_t n_ready, uint32_t* const* done_flags, uint32_t n_done,
+                     uint32_t value, uint32_t* counter_device, uint32_t* error_device, uint32_t timeout_ms)
+{
+    VK_REQUIRE(ctx && counter_device && error_device, "null argument");
+    VK_REQUIRE(n_copies == 0 || copies_device, "null copy table");
+    VK_REQUIRE(n_ready <= (uint32_t)kHaloMaxPeers && n_done <= (uint32_t)kHaloMaxPeers, "too many peers");
+    VK_REQUIRE((n_ready == 0 || ready_flags) && (n_done == 0 || done_flags), "null flag list");
+    HaloPushParams p{};
+    p.copies = reinterpret_cast<const HaloCopy*>(copies_device);
+    p.n_copies = (int)n_copies;
+    p.n_ready = (int)n_ready;
+    p.n_done = (int)n_done;
+    for (uint32_t i = 0; i < n_ready; ++i) p.ready_flags[i] = ready_flags[i];
+    for (uint32_t i = 0; i < n_done; ++i) p.done_flags[i] = done_flags[i];
+    p.value = value;
+    p.counter = counter_device;
+    p.error = error_device;
+    p.timeout_ns = (unsigned long long)timeout_ms * 1000000ull;
+    // 16 CTAs x 256 threads x 16 B x 4 in flight = 256 KB per sweep of one block of rows
+    VK_CUDA(vkpbrt::launch_halo_push(p, n_copies ? 16 : 1, stream ? (cudaStream_t)stream : ctx->stream));
+    ctx->launches++;
+    return VKPBRT_OK;
+}
+
+int vkpbrt_halo_wait(vkpbrt_context_t ctx, void* stream, const uint32_t* const* flags, uint32_t n, uint32_t value,
+                     uint32_t* error_device, uint32_t timeout_ms)
+{
+    VK_REQUIRE(ctx && flags && error_device, "null argument");
+    VK_REQUIRE(n >= 1 && n <= (uint32_t)kHaloMaxPeers, "1..8 flags");
+    HaloWaitParams p{};
+    p.n = (int)n;
+    for (uint32_t i = 0; i < n; ++i) p.flags[i] = flags[i];
+    p.value = value;
+    p.error = error_device;
+    p.timeout_ns = (unsigned long long)timeout_ms * 1000000ull;
+    VK_CUDA(vkpbrt::launch_halo_wait(p, stream ? (cudaStream_t)stream : ctx->stream));
+    ctx->launches++;
+    return VKPBRT_OK;
+}
+#else
+int vkpbrt_peer_export(vkpbrt_context_t, const void*, uint8_t*, uint64_t*) { return fail(VKPBRT_ERR_UNSUPPORTED, "peer memory needs CUDA devices"); }
+int vkpbrt_peer_open(vkpbrt_context_t, const uint8_t*, void**) { return fail(VKPBRT_ERR_UNSUPPORTED, "peer memory needs CUDA devices"); }
+int vkpbrt_peer_close(vkpbrt_context_t, void*) { return fail(VKPBRT_ERR_UNSUPPORTED, "peer memory needs CUDA devices"); }
+int vkpbrt_halo_push(vkpbrt_context_t, void*, const vkpbrt_halo_copy*, uint32_t, const uint32_t* const*, uint32_t, uint32_t* const*,
+                     uint32_t, uint32_t, uint32_t*, uint32_t*, uint32_t) { return fail(VKPBRT_ERR_UNSUPPORTED, "peer memory needs CUDA devices"); }
+int vkpbrt_halo_wait(vkpbrt_context_t, void*, const uint32_t* const*, uint32_t, uint32_t, uint32_t*, uint32_t) { return fail(VKPBRT_ERR_UNSUPPORTED, "peer memory needs CUDA devices"); }
+#endif
+
 }  // extern "C"

@@ -108,4 +108,33 @@ struct TaaParams {
 };
 cudaError_t launch_taa(const TaaParams& p, cudaStream_t stream);
 
+// ---- k_halo_push / k_halo_wait : band-sharded runs, halo rows over NVLink peer memory ------
+struct HaloCopy {                 // rows x row_bytes, pitched on both sides (same layout as vkpbrt_halo_copy)
+    const uint8_t* src;           // local
+    uint8_t* dst;                 // the receiver's buffer through its peer mapping
+    uint64_t src_pitch, dst_pitch;
+    uint32_t row_bytes, rows;
+};
+constexpr int kHaloMaxPeers = 8;
+struct HaloPushParams {
+    const HaloCopy* copies;       // device table
+    int n_copies;
+    int n_ready, n_done;
+    const uint32_t* ready_flags[kHaloMaxPeers];   // local words the receivers set when their halo rows may be overwritten
+    uint32_t* done_flags[kHaloMaxPeers];          // receivers' words (peer mapped), set to `value` once every copy has landed
+    uint32_t value;
+    uint32_t* counter;            // last-CTA detection, left at 0
+    uint32_t* error;              // set to 1 when a spin timed out
+    unsigned long long timeout_ns;
+};
+struct HaloWaitParams {
+    int n;
+    const uint32_t* flags[kHaloMaxPeers];
+    uint32_t value;
+    uint32_t* error;
+    unsigned long long timeout_ns;
+};
+cudaError_t launch_halo_push(const HaloPushParams& p, int parts, cudaStream_t stream);
+cudaError_t launch_halo_wait(const HaloWaitParams& p, cudaStream_t stream);
+
 }  // namespace vkpbrt

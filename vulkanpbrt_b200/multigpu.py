@@ -251,18 +251,117 @@ class NcclDirect:
             self.comm = None
 
 
+class PeerDirect:
+    """Halo exchange over NVLink peer memory (include/vkpbrt_b200.h, "Band-sharded multi-GPU runs"): every rank
+    maps the allocations it writes into (cudaIpc handles passed around through torch.distributed) and each exchange
+    point is ONE k_halo_push launch on a communication stream: it stores the rows straight into the receivers' HBM
+    and then publishes a sequence number to their flag words; the receiver's main stream runs k_halo_wait on its
+    own flag words before the consuming kernel.  No host synchronisation, no staging copies, no rendezvous except
+    for the end-of-frame exchange, whose receivers first tell the senders (a "ready" word) that their frame is over
+    -- the point at which NCCL would have posted the receive.
+
+    flag words of a rank: done[group][src] for group in A, B, F, then ready[dst]."""
+
+    GROUPS = {"A": 0, "B": 1, "F": 2}
+
+    def __init__(self, dist, rank: int, world: int, device, ctx, timeout_ms: int = 20000):
+        import ctypes as C
+
+        import torch
+
+        from . import _capi as capi
+        from .modules import DescriptorImage
+        if world > capi.HALO_MAX_PEERS:
+            raise ValueError(f"at most {capi.HALO_MAX_PEERS} ranks per node")
+        self.C, self.capi, self.dist, self.rank, self.world, self.ctx = C, capi, dist, rank, world, ctx
+        self.timeout_ms = timeout_ms
+        self.stream = torch.cuda.Stream(device=device)
+        self.device = device
+        self.flags = DescriptorImage.create(ctx, capi.FORMAT_R32_SFLOAT, max(16, 4 * world), 1)
+        self.flags.compile()            # allocates, zero-initialised
+        self.scratch = torch.zeros(8, dtype=torch.int32, device=device)      # counters of A, B, F, B-ready; [7] = error
+        ctx.synchronize()
+        self._opened: Dict = {}         # (rank, handle bytes) -> mapped base
+        self.seq = {"A": 0, "B": 0, "F": 0}
+        mine = self.export(self.flags.device_ptr)
+        everyone = self.all_gather(mine)
+        self.peer_flags = [self.flags.device_ptr if r == rank else self.map(r, everyone[r]) for r in range(world)]
+
+    # ---- mappings ---------------------------------------------------------------------------------------
+    def export(self, device_ptr: int):
+        C = self.C
+        h = (C.c_uint8 * self.capi.PEER_HANDLE_BYTES)()
+        off = C.c_uint64()
+        self.capi.call("vkpbrt_peer_export", self.ctx.handle, C.c_void_p(device_ptr), h, C.byref(off))
+        return bytes(h), int(off.value)
+
+    def map(self, rank: int, exported) -> int:
+        C = self.C
+        h, off = exported
+        base = self._opened.get((rank, h))
+        if base is None:
+            out = C.c_void_p()
+            buf = (C.c_uint8 * self.capi.PEER_HANDLE_BYTES).from_buffer_copy(h)
+            self.capi.call("vkpbrt_peer_open", self.ctx.handle, buf, C.byref(out))
+            base = self._opened[(rank, h)] = int(out.value)
+        return base + off
+
+    def all_gather(self, obj):
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj)
+        return out
+
+    # ---- flag addresses ---------------------------------------------------------------------------------
+    def done_word(self, owner: int, group: str, src: int) -> int:
+        return self.peer_flags[owner] + 4 * (self.GROUPS[group] * self.world + src)
+
+    def ready_word(self, owner: int, dst: int) -> int:
+        return self.peer_flags[owner] + 4 * (3 * self.world + dst)
+
+    # ---- launches ---------------------------------------------------------------------------------------
+    def _ptr_array(self, addrs):
+        return (self.C.c_void_p * max(1, len(addrs)))(*addrs)
+
+    def push(self, table, n_copies: int, ready, done, value: int, counter: int) -> None:
+        C = self.C
+        self.capi.call("vkpbrt_halo_push", self.ctx.handle, C.c_void_p(self.stream.cuda_stream),
+                       C.c_void_p(table.data_ptr() if table is not None else 0), n_copies,
+                       self._ptr_array(ready), len(ready), self._ptr_array(done), len(done), value,
+                       C.c_void_p(self.scratch.data_ptr() + 4 * counter), C.c_void_p(self.scratch.data_ptr() + 28), self.timeout_ms)
+
+    def wait(self, stream_handle: int, flags, value: int) -> None:
+        C = self.C
+        self.capi.call("vkpbrt_halo_wait", self.ctx.handle, C.c_void_p(stream_handle), self._ptr_array(flags), len(flags), value,
+                       C.c_void_p(self.scratch.data_ptr() + 28), self.timeout_ms)
+
+    def check(self) -> None:
+        """synchronises and raises if any flag wait timed out (a peer died or fell out of step)"""
+        if int(self.scratch[7].item()) != 0:
+            raise RuntimeError("halo exchange: a flag wait timed out (peer rank lost or out of step)")
+
+    def close(self) -> None:
+        for base in self._opened.values():
+            try:
+                self.capi.call("vkpbrt_peer_close", self.ctx.handle, self.C.c_void_p(base))
+            except Exception:
+                pass
+        self._opened = {}
+
+
 class BandedPipeline:
     """One rank of the band-sharded chain.  `view(image)` must return a uint8 torch tensor aliasing the image's
     CURRENT device buffer as raw bytes, shaped [layers?][H][row bytes] (cuda_view() below on a GPU)."""
 
     def __init__(self, width: int, height: int, rank: int, world: int, use_taa: bool, ctx, view: Callable,
-                 max_disp_rows: int = 24, external_inputs: bool = True, dist=None, nccl: "NcclDirect" = None):
+                 max_disp_rows: int = 24, external_inputs: bool = True, dist=None, nccl: "NcclDirect" = None,
+                 peer: "PeerDirect" = None):
         self.rank, self.world, self.view = rank, world, view
         self.plan = BandPlan(width, height, world, 32, max_disp_rows, use_taa)
         self.pipe = DenoisePipeline(width, height, DenoisingType.BMFR, DenoisingBlockSize.X32, use_taa=use_taa, ctx=ctx,
                                     external_inputs=external_inputs)
         self.dist = dist
         self.nccl = nccl                      # direct NCCL issue path (GPU); None: torch.distributed P2P ops (gloo tests)
+        self.peer = peer                      # NVLink peer-memory path (GPU, one node): takes precedence over nccl
         self.bmfr = self.pipe.modules[0]
         self.bmfr.set_block_row_range(*self.plan.block_rows(rank))
         c = self.pipe.commands.children
@@ -318,11 +417,49 @@ class BandedPipeline:
                     self._keep.append(buf)
         return (ops, gather, scatter, nbytes, raw)
 
+    def _build_peer(self, kind: str, transfers: List[Transfer], images: Dict[str, list]):
+        """copy table of this rank's outgoing blocks of rows (device resident), the ranks it sends to / receives
+        from.  Collective: every rank builds the same key at the same frame and contributes its image handles."""
+        import torch
+        pd, g = self.peer, self.rank
+        entries = {}
+        exported = []
+        for name, lst in images.items():
+            entries[name] = []
+            for img, ncol in lst:
+                im, layer = (img if isinstance(img, tuple) else (img, 0))
+                i = im.info()
+                entries[name].append((len(exported), i.data, layer * i.layer_pitch, i.row_pitch, ncol))
+                exported.append(pd.export(i.data))
+        everyone = pd.all_gather(exported)
+        rows_of, send_to, recv_from, nbytes = [], set(), set(), 0
+        for t in transfers:
+            if t.src == t.dst:
+                continue
+            for idx, base, layer_off, pitch, ncol in entries[t.plane]:
+                rb = pitch if ncol is None else ncol
+                off = layer_off + t.rows[0] * pitch
+                if t.src == g:
+                    rows_of.append((base + off, pd.map(t.dst, everyone[t.dst][idx]) + off, pitch, pitch, rb, t.rows[1] - t.rows[0]))
+                    send_to.add(t.dst)
+                elif t.dst == g:
+                    recv_from.add(t.src)
+                    nbytes += rb * (t.rows[1] - t.rows[0])
+        table = None
+        if rows_of:
+            a = np.zeros(len(rows_of), dtype=np.dtype([("src", "<u8"), ("dst", "<u8"), ("sp", "<u8"), ("dp", "<u8"), ("rb", "<u4"), ("rows", "<u4")]))
+            for k, r in enumerate(rows_of):
+                a[k] = r
+            table = torch.from_numpy(a.view(np.uint8).copy()).to(pd.device)
+        return ("peer", kind, table, len(rows_of), sorted(send_to), sorted(recv_from), nbytes)
+
     def _exchange_desc(self, kind: str, frame: int, images: Dict[str, list], transfers_fn):
         """images: plane name -> [(DescriptorImage or (DescriptorImage, layer), ncol_bytes)]"""
         ptrs = tuple((img[0] if isinstance(img, tuple) else img).info().data for lst in images.values() for img, _ in lst)
         key = (kind, frame % 16, ptrs)
         d = self._desc.get(key)
+        if d is None and self.peer is not None:
+            d = self._desc[key] = self._build_peer(kind, transfers_fn(), images)
         if d is None:
             planes = {}
             for name, lst in images.items():
@@ -349,6 +486,8 @@ class BandedPipeline:
         group started right after a kernel overlaps whatever is enqueued next."""
         if self.world == 1 or desc is None:
             return None
+        if desc[0] == "peer":
+            return self._start_peer(desc)
         ops, gather, scatter, nbytes, raw = desc
         if not raw:
             return None
@@ -367,10 +506,39 @@ class BandedPipeline:
             return (done, scatter)
         return (self.dist.batch_isend_irecv(ops), scatter)
 
-    @staticmethod
-    def _finish(pending) -> None:
+    def _start_peer(self, desc):
+        """one k_halo_push on the communication stream, ordered after the work already on the current stream"""
+        import torch
+        _, kind, table, n, send_to, recv_from, nbytes = desc
+        pd, g = self.peer, self.rank
+        pd.seq[kind] += 1
+        value = pd.seq[kind]
+        if not send_to and not recv_from:
+            return None
+        self.bytes_exchanged += nbytes
+        cur = torch.cuda.current_stream()
+        ready = self._event()
+        ready.record(cur)
+        pd.stream.wait_event(ready)
+        gate = []
+        if kind == "B":
+            # the receivers' frame is over: let the senders overwrite the halo rows (what posting the receive
+            # did with NCCL); our own push is gated on the same word from each of its receivers
+            if recv_from:
+                pd.push(None, 0, [], [pd.ready_word(s, g) for s in recv_from], value, 3)
+            gate = [pd.ready_word(g, d) for d in send_to]
+        if send_to:
+            pd.push(table, n, gate, [pd.done_word(d, kind, g) for d in send_to], value, pd.GROUPS[kind])
+        return ("peer", [pd.done_word(g, kind, s) for s in recv_from], value)
+
+    def _finish(self, pending) -> None:
         """makes the current stream wait for a group started by _start (stream-side wait for NCCL)"""
         if pending is None:
+            return
+        if pending[0] == "peer":
+            import torch
+            if pending[1]:
+                self.peer.wait(torch.cuda.current_stream().cuda_stream, pending[1], pending[2])
             return
         works, scatter = pending
         if isinstance(works, list):
@@ -431,6 +599,11 @@ class BandedPipeline:
         self._finish(self._pending_b)
         self._pending_a = self._pending_b = None
 
+    def check(self) -> None:
+        """after a device synchronisation: raises if the peer-memory flag protocol reported a timeout"""
+        if self.peer is not None:
+            self.peer.check()
+
     def owned_rows(self, frame: int) -> Rows:
         return self.plan.owned_rows(self.rank, frame)
 
@@ -467,7 +640,10 @@ def bench_multi(args, rank: int, world: int, local: int):
     ctx = Context(local, stream.cuda_stream)
     assert ctx.stream == stream.cuda_stream
     view = cuda_view(dev)
-    bp = BandedPipeline(W, H, rank, world, taa, ctx, view, dist=dist, nccl=NcclDirect(dist, rank, world, dev))
+    halo = getattr(args, "halo", "peer")
+    bp = BandedPipeline(W, H, rank, world, taa, ctx, view, dist=dist,
+                        nccl=NcclDirect(dist, rank, world, dev) if halo == "nccl" else None,
+                        peer=PeerDirect(dist, rank, world, dev, ctx) if halo == "peer" else None)
     lo, hi = bp.plan.input_rows(rank)
     rows = hi - lo
     # band-local resident sequence; the kernels index absolute rows through a virtual full-frame base pointer
@@ -498,7 +674,15 @@ def bench_multi(args, rank: int, world: int, local: int):
         bind(dseq, i)
         bp.run_frame(f, cams[i])
 
-    for f in range(Wm):
+    # set-up, not warm-up: the exchange descriptors (row ranges x ping-pong buffers: period 32 frames) are built
+    # -- and for the peer path the neighbours' allocations mapped -- the first time each one is needed
+    PRE = 32
+    for f in range(PRE):
+        frame(f)
+    torch.cuda.synchronize()
+    bp.check()
+    dist.barrier()
+    for f in range(PRE, PRE + Wm):
         frame(f)
     torch.cuda.synchronize()
     dist.barrier()
@@ -508,12 +692,13 @@ def bench_multi(args, rank: int, world: int, local: int):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     t_host = time.perf_counter()
-    for f in range(Wm, Wm + K):
+    for f in range(PRE + Wm, PRE + Wm + K):
         frame(f)
     bp.flush()
     e1.record(stream)
     t_host = (time.perf_counter() - t_host) / K * 1e3      # host time to ENQUEUE one frame (no sync inside)
     torch.cuda.synchronize()
+    bp.check()
     dist.barrier()
     clocks = sampler.stop()
     t = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -548,7 +733,7 @@ def bench_multi(args, rank: int, world: int, local: int):
 
     for s in range(2):
         consumed[s].record(stream)
-    f0 = Wm + K
+    f0 = PRE + Wm + K
     issue_copy(f0)
     for f in range(f0, f0 + 3):
         issue_copy(f + 1)
@@ -562,12 +747,13 @@ def bench_multi(args, rank: int, world: int, local: int):
     bp.flush()
     e1.record(stream)
     torch.cuda.synchronize()
+    bp.check()
     dist.barrier()
     t = torch.tensor([e0.elapsed_time(e1)], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item())
-    halo = torch.tensor([bp.bytes_exchanged], device=dev, dtype=torch.float64)
-    dist.all_reduce(halo)
+    halo_bytes = torch.tensor([bp.bytes_exchanged], device=dev, dtype=torch.float64)
+    dist.all_reduce(halo_bytes)
     if rank == 0:
         hbm_peak, peak_src = B.peaks()
         chain = (B.BYTES_ACCUMULATE + B.BYTES_BMFR + (B.BYTES_TAA if taa else 0))
@@ -578,7 +764,9 @@ def bench_multi(args, rank: int, world: int, local: int):
                 "config": {"workload": name + ("" if strong else "_bands"), "description": desc + f"; band-sharded over {world} GPUs"
                            + ("" if strong else f" (weak scaling: one {W}x{Hband} band per GPU, frame {W}x{H})"),
                            "width": W, "height": H, "block": 32, "taa": taa, "band_block_rows": bp.plan.brow,
-                           "halo": f"history rows +-{bp.plan.D + 1} (+ REPEAT wrap row) per boundary, NCCL send/recv per frame",
+                           "halo": f"history rows +-{bp.plan.D + 1} (+ REPEAT wrap row) per boundary, "
+                                   + ("stored into the neighbours' HBM over NVLink peer mappings by k_halo_push, flag words for ordering"
+                                      if halo == "peer" else "NCCL send/recv groups per frame"),
                            "l2": f"inputs larger than L2: {R} resident band frames, each read once per step",
                            "sequence_generation_s": round(t_gen, 1)},
                 "e2e": {"value": round(W * H * K / (e2e_ms * 1e-3) / 1e6, 1), "unit": "MPix/s",
@@ -589,7 +777,7 @@ def bench_multi(args, rank: int, world: int, local: int):
                              "achieved": round(gbs, 1), "peak": hbm_peak * world, "unit": "GB/s",
                              "frac": round(gbs / (hbm_peak * world), 4), "traffic": None, "peak_source": peak_src,
                              "note": "aggregate over ranks; per-kernel fractions are reported by the N=1 run"},
-                "halo_bytes_per_step": float(halo.item()) / (2 * K + Wm + 3), "host_enqueue_ms_per_step": round(t_host, 4),
+                "halo_bytes_per_step": float(halo_bytes.item()) / (PRE + 2 * K + Wm + 3), "host_enqueue_ms_per_step": round(t_host, 4),
                 "cpu_baseline": None}
     else:
         line = None
