@@ -220,7 +220,9 @@ VKPBRT_API int vkpbrt_bmfr_create(vkpbrt_context_t ctx, uint32_t width, uint32_t
                                   uint32_t work_height, vkpbrt_gbuffer_t g, vkpbrt_illumination_buffer_t illumination,
                                   vkpbrt_accumulation_buffer_t acc, uint32_t fitting_kernel, vkpbrt_bmfr_t* out);
 /* the fused kernel keeps the feature matrix and the weights on chip; enable to also materialise
- * the reference's featureBuffer (r16f x13, padded) and weights (r32f x30) images for parity tests */
+ * the reference's featureBuffer (r16f x13, padded) and weights (r32f x30) images for parity tests.
+ * enable bit 0: those images; bit 1: every block takes the out-of-line IEEE-division fit (the path a block
+ * falls back to when an operand leaves the range the reciprocal division is proven exact for) */
 VKPBRT_API int vkpbrt_bmfr_set_debug_outputs(vkpbrt_bmfr_t b, int enable);
 VKPBRT_API int vkpbrt_bmfr_compile(vkpbrt_bmfr_t b);
 VKPBRT_API int vkpbrt_bmfr_record(vkpbrt_bmfr_t b, const vkpbrt_push_constants* pc); /* pre+fit+post, one launch */

@@ -43,6 +43,13 @@ def test_bmfr_other_block_sizes(backend, oracle, block, W, H):
     run_sequence(oracle, W, H, 3, first=7, denoiser="bmfr", block=block, debug=True)
 
 
+@pytest.mark.parametrize("block,W,H", [(32, 160, 96), (8, 72, 40)])
+def test_bmfr_out_of_line_generic_fit(backend, oracle, block, W, H):
+    """debug bit 1: every block redoes its fit in qr_generic (IEEE division, rolled loops) -- the path a block takes
+    when an operand leaves the proven range of the reciprocal division; same bits required"""
+    run_sequence(oracle, W, H, 3, first=8, denoiser="bmfr", block=block, debug=3)
+
+
 def test_bmfr_combined_matrices_mode(backend, oracle):
     """accumulator.comp without SEPARATE_MATRICES (offline mode, :56-64)"""
     run_sequence(oracle, 256, 128, 3, denoiser="bmfr", block=32, use_taa=True, separate_matrices=False)

@@ -7,8 +7,9 @@ i=0
 for V in "$@"; do
   i=$((i+1))
   nvcc -std=c++17 -O3 -lineinfo -ccbin /usr/bin/g++ -Xcompiler -fPIC,-fvisibility=hidden,-ffp-contract=off -gencode arch=compute_100a,code=sm_100a $V -x cu -c $CS/bmfr.cu -o build/obj/bmfr.cu.o 2>&1 | grep -E "error" 
-  nvcc -shared -ccbin /usr/bin/g++ -gencode arch=compute_100a,code=sm_100a -cudart static -o vulkanpbrt_b200/lib/libvkpbrt_b200.so build/obj/accumulate.cu.o build/obj/taa.cu.o build/obj/bmfr.cu.o build/obj/bfr.cu.o build/obj/api.cpp.o
+  nvcc -shared -ccbin /usr/bin/g++ -gencode arch=compute_100a,code=sm_100a -cudart static -o vulkanpbrt_b200/lib/libvkpbrt_b200.so build/obj/accumulate.cu.o build/obj/taa.cu.o build/obj/bmfr.cu.o build/obj/bfr.cu.o build/obj/halo.cu.o build/obj/api.cpp.o
   echo "== variant $i: $V"
+  timeout 300 python -m pytest tests/test_parity.py -m gpu -x -q -k "256x256 or generic or 1080p_chain" 2>&1 | tail -1
   python bench.py --steps 60 --warmup 10 --cpu-budget 0 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('   ms/frame',d['ms_per_step'], {k:v['ms'] for k,v in d['kernels'].items()})"
   python bench.py --workload bmfr_taa_4k --steps 30 --warmup 5 --resident-frames 35 --cpu-budget 0 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('   4k ms/frame',d['ms_per_step'], {k:v['ms'] for k,v in d['kernels'].items()})"
 done

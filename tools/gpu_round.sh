@@ -23,6 +23,11 @@ grep -E "k_accumulate|k_bmfr|k_taa" gpurun_out/launches_$TAG.csv | tail -12
 echo "== ncu full"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_bmfr_block|k_accumulate" -s 12 -c 4 -f -o gpurun_out/prof_$TAG \
     python bench.py --steps 6 --warmup 3 --cpu-budget 0 > gpurun_out/ncu_full_$TAG.log 2>&1
+echo "== ncu full (taa 4k, bfr)"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_taa" -s 8 -c 2 -f -o gpurun_out/prof_taa_$TAG \
+    python bench.py --workload bmfr_taa_4k --steps 6 --warmup 3 --resident-frames 10 --cpu-budget 0 > gpurun_out/ncu_taa_$TAG.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_bfr_bl" -s 16 -c 4 -f -o gpurun_out/prof_bfr_$TAG \
+    python bench.py --workload bfr_blend_1080p --steps 6 --warmup 3 --resident-frames 10 --cpu-budget 0 > gpurun_out/ncu_bfr_$TAG.log 2>&1
 ls -la gpurun_out/ | tail -12
 echo "== compute-sanitizer (smoke)"
 timeout 60 true # --print-limit 5 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -6

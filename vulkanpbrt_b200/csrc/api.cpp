@@ -155,7 +155,7 @@ struct vkpbrt_bmfr_s {
     vkpbrt_illumination_buffer_t illum;
     vkpbrt_accumulation_buffer_t acc;
     vkpbrt_image_t denoised = nullptr, final_image = nullptr, features = nullptr, weights = nullptr;
-    bool debug = false, compiled = false;
+    bool debug = false, force_generic = false, compiled = false;
     int block_row_begin, block_row_end;
 };
 
@@ -805,7 +805,8 @@ int vkpbrt_bmfr_set_debug_outputs(vkpbrt_bmfr_t b, int enable)
 {
     VK_REQUIRE(b, "null bmfr");
     VK_REQUIRE(!b->compiled, "vkpbrt_bmfr_set_debug_outputs must precede compile()");
-    b->debug = enable != 0;
+    b->debug = (enable & 1) != 0;
+    b->force_generic = (enable & 2) != 0;
     return VKPBRT_OK;
 }
 
@@ -862,6 +863,7 @@ int vkpbrt_bmfr_record(vkpbrt_bmfr_t b, const vkpbrt_push_constants* pc)
     p.final_bgra = (uint32_t*)b->final_image->data;
     p.dbg_features = b->debug ? (uint16_t*)b->features->data : nullptr;
     p.dbg_weights = b->debug ? (float*)b->weights->data : nullptr;
+    p.force_generic = b->force_generic ? 1 : 0;
     VK_CUDA(cudaSetDevice(b->ctx->device));
     VK_CUDA(vkpbrt::launch_bmfr(p, b->ctx->stream));
     b->ctx->launches++;

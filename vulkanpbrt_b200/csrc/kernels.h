@@ -58,6 +58,7 @@ struct BmfrParams {
     uint32_t* final_bgra;
     uint16_t* dbg_features;       // optional r16f [13][Hp][Wp]
     float* dbg_weights;           // optional r32f [30][blocks_y][blocks_x]
+    int force_generic;            // debug: every block takes the out-of-line IEEE-division fit (test coverage of the cold path)
 };
 cudaError_t launch_bmfr(const BmfrParams& p, cudaStream_t stream);
 

@@ -506,14 +506,16 @@ class BMFR(_BlockDenoiser):
 
     def __init__(self, width: int, height: int, work_width: int, work_height: int, g_buffer: GBuffer,
                  illu_buffer: IlluminationBuffer, acc_buffer: AccumulationBuffer, fitting_kernel: int = 256,
-                 debug_outputs: bool = False):
+                 debug_outputs: int = 0):
+        """debug_outputs: bit 0 materialises the reference's feature buffer / weights images, bit 1 routes every block
+        through the out-of-line IEEE-division fit (qr_generic in bmfr.cu) so tests can cover it"""
         self.ctx = g_buffer.ctx
         self._keep = (g_buffer, illu_buffer, acc_buffer)
         self._h = C.c_void_p()
         capi.call("vkpbrt_bmfr_create", self.ctx.handle, width, height, work_width, work_height, g_buffer.handle,
                   illu_buffer.handle, acc_buffer.handle, fitting_kernel, C.byref(self._h))
         if debug_outputs:
-            capi.call("vkpbrt_bmfr_set_debug_outputs", self._h, 1)
+            capi.call("vkpbrt_bmfr_set_debug_outputs", self._h, int(debug_outputs))
         self.kernel_name = f"k_bmfr_block<{work_width},{fitting_kernel}>"
         self._final = _borrow(self.ctx, "vkpbrt_bmfr_final_image", self._h)
 

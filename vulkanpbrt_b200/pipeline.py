@@ -63,7 +63,7 @@ class DenoisePipeline:
         if denoiser == DenoisingType.BMFR and block_size != DenoisingBlockSize.X8X16X32 and bmfr_debug_outputs:
             b = {DenoisingBlockSize.X8: 8, DenoisingBlockSize.X16: 16, DenoisingBlockSize.X32: 32}[block_size]
             d = BMFR.create(width, height, b, b, self.g_buffer, self.illumination_buffer, self.accumulation_buffer,
-                            64 if b == 8 else 256, debug_outputs=True)
+                            64 if b == 8 else 256, debug_outputs=int(bmfr_debug_outputs))
             d.compile(ctx)
             d.add_dispatch_to_command_graph(self.commands, self.push_constants)
             self.final, self.modules = d.get_final_descriptor_image(), [d]
