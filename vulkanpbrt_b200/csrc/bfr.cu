@@ -6,8 +6,8 @@
 // pays, per step, 22 subgroupAdds + a serial fold over up to 32 subgroups + 2 barriers.  Here a
 // thread owns S pixels (T = 256 / 64 / 32 threads for B = 32 / 16 / 8) laid out so that a warp's 32
 // lanes are exactly one of the reference's subgroups for each s; the 21 gradient terms + the L1
-// count of a subgroup are reduced by ONE transposing shuffle network (31 shuffles, total j on lane
-// j) instead of 22 butterflies, and 21 lanes of warp 0 own one (feature, channel) coefficient
+// count of a subgroup are reduced by ONE transposing shuffle network (23 shuffles) instead of 22
+// butterflies, and 21 lanes of warp 0 own one (feature, channel) coefficient
 // each, like bfr.comp's "ID < ALPHA_SIZE" invocations own one vec3.  For B = 8 the block is a
 // single warp.  The sums follow the oracle's order exactly (xor-butterfly per subgroup, serial fold
 // over subgroups, no FMA contraction), so the descent trajectory -- which contains a sign()
@@ -25,53 +25,38 @@ __constant__ int c_bfr_offsets[16][2] = {{-7, -11}, {-14, -8}, {-5, -12}, {-15, 
                                          {-14, -7}, {0, -13},  {-5, -1},  {-1, 0},   {-15, -2}, {-14, -10},
                                          {-1, -1},  {-6, -3},  {0, -8},   {-10, -4}};
 
-// 32 values per lane in, total j on lane j out: 16 + 8 + 4 + 2 + 1 shuffles.
-VK_DEVICE float warp_reduce32(float (&v)[32], int lane)
+// Transposing warp reduction of N values per lane (N need not be a power of two): at each of the five xor stages
+// the lower half of the lanes keeps the first ceil(N/2) values and the upper half the rest (an odd count is padded
+// with a zero), so 22 values cost 11 + 6 + 3 + 2 + 1 = 23 shuffles instead of 22 x 5.  Every total is summed along
+// the xor-butterfly tree (lane^16, ^8, ^4, ^2, ^1): bit-identical to 22 separate subgroupAdds.
+template <int N, int OFF>
+struct ReduceN {
+    static VK_DEVICE float run(const float* v, int lane)
+    {
+        if constexpr (OFF == 0) {
+            return v[0];
+        } else {
+            constexpr int h = (N + 1) / 2;
+            const bool up = (lane & OFF) != 0;
+            float nv[h];
+#pragma unroll
+            for (int j = 0; j < h; ++j) {
+                const float lo = v[j];
+                const float hi = (j + h < N) ? v[j + h] : 0.0f;
+                const float send = up ? lo : hi;
+                const float keep = up ? hi : lo;
+                nv[j] = add_rn(keep, __shfl_xor_sync(0xffffffffu, send, OFF));
+            }
+            return ReduceN<h, OFF / 2>::run(nv, lane);
+        }
+    }
+};
+// which of the 22 totals a lane ends up with (22 -> 11 -> 6 -> 3 -> 2 -> 1), or -1 for the lanes left with padding
+VK_DEVICE int reduce22_slot(int lane)
 {
-    float a[16];
-    {
-        const bool up = (lane & 16) != 0;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const float send = up ? v[j] : v[j + 16];
-            const float keep = up ? v[j + 16] : v[j];
-            a[j] = add_rn(keep, __shfl_xor_sync(0xffffffffu, send, 16));
-        }
-    }
-    float b[8];
-    {
-        const bool up = (lane & 8) != 0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float send = up ? a[j] : a[j + 8];
-            const float keep = up ? a[j + 8] : a[j];
-            b[j] = add_rn(keep, __shfl_xor_sync(0xffffffffu, send, 8));
-        }
-    }
-    float c[4];
-    {
-        const bool up = (lane & 4) != 0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float send = up ? b[j] : b[j + 4];
-            const float keep = up ? b[j + 4] : b[j];
-            c[j] = add_rn(keep, __shfl_xor_sync(0xffffffffu, send, 4));
-        }
-    }
-    float d[2];
-    {
-        const bool up = (lane & 2) != 0;
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const float send = up ? c[j] : c[j + 2];
-            const float keep = up ? c[j + 2] : c[j];
-            d[j] = add_rn(keep, __shfl_xor_sync(0xffffffffu, send, 2));
-        }
-    }
-    const bool up = (lane & 1) != 0;
-    const float send = up ? d[0] : d[1];
-    const float keep = up ? d[1] : d[0];
-    return add_rn(keep, __shfl_xor_sync(0xffffffffu, send, 1));
+    const int p3 = (lane & 1) + 2 * ((lane >> 1) & 1);          // position among the 3 values before the last two stages
+    const int p1 = p3 + 3 * ((lane >> 2) & 1) + 6 * ((lane >> 3) & 1);
+    return (p3 < 3 && p1 < 11) ? p1 + 11 * ((lane >> 4) & 1) : -1;
 }
 
 template <int NSG>
@@ -83,8 +68,16 @@ struct BfrShared {
     int stop;
 };
 
+// occupancy targets (CTAs per SM) of the three instantiations; A/B-tested on B200 (tools/bfr_variants.sh)
+#ifndef BFR_CTAS_B32
+#define BFR_CTAS_B32 2
+#endif
+#ifndef BFR_CTAS_B16
+#define BFR_CTAS_B16 9
+#endif
+
 template <int B, int T>
-__global__ void __launch_bounds__(T) k_bfr_block(const BfrParams p)
+__global__ void __launch_bounds__(T, (T == 256 ? BFR_CTAS_B32 : (T == 64 ? BFR_CTAS_B16 : 32))) k_bfr_block(const BfrParams p)
 {
     constexpr int N = B * B;
     constexpr int S = N / T;
@@ -159,6 +152,7 @@ __global__ void __launch_bounds__(T) k_bfr_block(const BfrParams p)
 
     // ---- :260-278 gradient descent ---------------------------------------------------------
     float m = 0.0f, v = 0.0f;          // Adam moments of coefficient t (threads 0..20)
+    const int slot = reduce22_slot(lane);
     float al[21];
     for (int it = 0; it < 40; ++it) {
 #pragma unroll
@@ -176,16 +170,14 @@ __global__ void __launch_bounds__(T) k_bfr_block(const BfrParams p)
                 if (l1[s]) d = (d > 0.0f) ? 1.0f : ((d < 0.0f) ? -1.0f : 0.0f);  // sign(), :267-268
                 r[c] = d;
             }
-            float part[32];
+            float part[22];
 #pragma unroll
             for (int j = 0; j < 7; ++j)
 #pragma unroll
                 for (int c = 0; c < 3; ++c) part[j * 3 + c] = mul_rn(f[j], r[c]);                // :272-274
             part[21] = l1[s] ? 1.0f : 0.0f;
-#pragma unroll
-            for (int j = 22; j < 32; ++j) part[j] = 0.0f;
-            const float tot = warp_reduce32(part, lane);                         // subgroupAdd x22 (:101-104)
-            if (lane < 22) sm.red[lane][warp + s * NW] = tot;
+            const float tot = ReduceN<22, 16>::run(part, lane);                  // subgroupAdd x22 (:101-104)
+            if (slot >= 0) sm.red[slot][warp + s * NW] = tot;
         }
         __syncthreads();
         if (t < 21) {
@@ -294,9 +286,9 @@ __global__ void __launch_bounds__(256) k_bfr_blend(const BlendParams p)
     uint32_t out = 0xff000000u;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {      // c indexes BGRA8 memory bytes; the blend is per channel
-        const float den2 = unorm8_to_f32((d0 >> (8 * c)) & 0xffu);              // :50-52 binding swap
-        const float den1 = unorm8_to_f32((d1 >> (8 * c)) & 0xffu);
-        const float den0 = unorm8_to_f32((d2 >> (8 * c)) & 0xffu);
+        const float den2 = unorm8_byte_to_f32(d0, c);                           // :50-52 binding swap
+        const float den1 = unorm8_byte_to_f32(d1, c);
+        const float den0 = unorm8_byte_to_f32(d2, c);
         out |= (uint32_t)f32_to_unorm8(mix3(den0, den1, den2, std_dev, .5f, 1.0f)) << (8 * c);
     }
     p.final_bgra[pix] = out;

@@ -154,8 +154,23 @@ VK_DEVICE uint8_t f32_to_unorm8(float c)
     c = c > 1.0f ? 1.0f : c;
     return (uint8_t)add_rn(mul_rn(c, 255.0f), 0.5f);
 }
-// c / 255.0f, exactly rounded (checked for all 256 codes by tests/test_oracle_kat.py against the oracle)
-VK_DEVICE float unorm8_to_f32(uint32_t c) { return div_by_rcp((float)c, 255.0f, 0.0039215688593685627f); }
+// c / 255.0f, exactly rounded for every code 0..255 (checked by tests/test_oracle_kat.py against the oracle's
+// division): with 1/255 = RH + RL as a double-float, c*RH + (c*RL) rounds to the quotient -- two operations
+VK_DEVICE float unorm8_scale(float cf)
+{
+    return fmaf(cf, 0x1.010102p-8f, mul_rn(cf, -0x1.fdfdfep-33f));
+}
+VK_DEVICE float unorm8_to_f32(uint32_t c) { return unorm8_scale((float)c); }
+// byte K of a packed texel: one PRMT builds 2^23 + byte as a float, one subtraction makes it the integer value
+VK_DEVICE float unorm8_byte_to_f32(uint32_t texel, int k)
+{
+#ifndef VKPBRT_HOSTSIM
+    const uint32_t bits = __byte_perm(texel, 0x4b000000u, 0x7650u + (uint32_t)k);
+#else
+    const uint32_t bits = 0x4b000000u | ((texel >> (8 * k)) & 0xffu);
+#endif
+    return unorm8_scale(sub_rn(__uint_as_float(bits), 8388608.0f));
+}
 
 // bmfrGeneral.comp:93-97 / bfr.comp:192-196
 VK_DEVICE int mirror(int x, int s)

@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(TAA_BX* TAA_BY) k_taa(const TaaParams p)
         sx = sx < 0 ? 0 : (sx >= W ? W - 1 : sx);
         sy = sy < 0 ? 0 : (sy >= H ? H - 1 : sy);
         const uint32_t sb = __ldg(p.denoised + (size_t)sy * W + sx);          // BGRA8: byte0 = B
-        ycocg(unorm8_to_f32((sb >> 16) & 0xffu), unorm8_to_f32((sb >> 8) & 0xffu), unorm8_to_f32(sb & 0xffu),
+        ycocg(unorm8_byte_to_f32(sb, 2), unorm8_byte_to_f32(sb, 1), unorm8_byte_to_f32(sb, 0),
               s_y[ty][tx], s_co[ty][tx], s_cg[ty][tx]);
     }
     __syncthreads();
@@ -84,9 +84,8 @@ __global__ void __launch_bounds__(TAA_BX* TAA_BY) k_taa(const TaaParams p)
     float prev[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        const int sh = 8 * (p.fix_swizzle ? (2 - c) : c);
-        prev[c] = bilin_mix(bl, unorm8_to_f32((h00 >> sh) & 0xffu), unorm8_to_f32((h10 >> sh) & 0xffu),
-                            unorm8_to_f32((h01 >> sh) & 0xffu), unorm8_to_f32((h11 >> sh) & 0xffu));
+        const int k = p.fix_swizzle ? (2 - c) : c;
+        prev[c] = bilin_mix(bl, unorm8_byte_to_f32(h00, k), unorm8_byte_to_f32(h10, k), unorm8_byte_to_f32(h01, k), unorm8_byte_to_f32(h11, k));
     }
     // history is a bilinear mix of unorm8 values: finite and non-negative as well
     float pyc[3];
@@ -101,7 +100,7 @@ __global__ void __launch_bounds__(TAA_BX* TAA_BY) k_taa(const TaaParams p)
         p.final_bgra[pix] = cur_bits | 0xff000000u;
         return;
     }
-    const float cur[3] = {unorm8_to_f32((cur_bits >> 16) & 0xffu), unorm8_to_f32((cur_bits >> 8) & 0xffu), unorm8_to_f32(cur_bits & 0xffu)};
+    const float cur[3] = {unorm8_byte_to_f32(cur_bits, 2), unorm8_byte_to_f32(cur_bits, 1), unorm8_byte_to_f32(cur_bits, 0)};
     float res[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) res[c] = add_rn(mul_rn(.4f, cur[c]), mul_rn((1 - .4f), prev[c]));
