@@ -371,6 +371,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--resident-frames", type=int, default=70)
+    ap.add_argument("--replicas", action="store_true", help="N > 1: N independent sequences of the workload, one per GPU")
     ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
                     help="N > 1: halo rows through NVLink peer memory (k_halo_push) or NCCL send/recv groups")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for cpu_baseline (0 = skip)")

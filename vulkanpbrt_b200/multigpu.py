@@ -630,8 +630,10 @@ def bench_multi(args, rank: int, world: int, local: int):
 
     name = args.workload or "bmfr_1080p"
     W, Hband, taa, desc = B.WORKLOADS[name]
-    strong = name != "bmfr_1080p"
-    H = Hband if strong else Hband * world
+    replicas = bool(getattr(args, "replicas", False))     # N independent sequences, one per GPU: no communication
+    strong = name != "bmfr_1080p" and not replicas
+    H = Hband if (strong or replicas) else Hband * world
+    prank, pworld = (0, 1) if replicas else (rank, world)
     K, Wm = args.steps, args.warmup
     R = min(K + Wm, args.resident_frames)
     dev = torch.device("cuda", local)
@@ -641,10 +643,10 @@ def bench_multi(args, rank: int, world: int, local: int):
     assert ctx.stream == stream.cuda_stream
     view = cuda_view(dev)
     halo = getattr(args, "halo", "peer")
-    bp = BandedPipeline(W, H, rank, world, taa, ctx, view, dist=dist,
-                        nccl=NcclDirect(dist, rank, world, dev) if halo == "nccl" else None,
-                        peer=PeerDirect(dist, rank, world, dev, ctx) if halo == "peer" else None)
-    lo, hi = bp.plan.input_rows(rank)
+    bp = BandedPipeline(W, H, prank, pworld, taa, ctx, view, dist=dist,
+                        nccl=NcclDirect(dist, rank, world, dev) if (halo == "nccl" and not replicas) else None,
+                        peer=PeerDirect(dist, rank, world, dev, ctx) if (halo == "peer" and not replicas) else None)
+    lo, hi = bp.plan.input_rows(prank)
     rows = hi - lo
     # band-local resident sequence; the kernels index absolute rows through a virtual full-frame base pointer
     mk = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True)
@@ -705,7 +707,8 @@ def bench_multi(args, rank: int, world: int, local: int):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     launches = ctx.launch_count - launches0
-    value = W * H * K / (ms * 1e-3) / 1e6
+    jobs = world if replicas else 1
+    value = jobs * W * H * K / (ms * 1e-3) / 1e6
 
     # ---- e2e: per-rank band uploaded from pinned host memory every frame, owned rows of the result read back ----
     copy_stream = torch.cuda.Stream()
@@ -757,20 +760,23 @@ def bench_multi(args, rank: int, world: int, local: int):
     if rank == 0:
         hbm_peak, peak_src = B.peaks()
         chain = (B.BYTES_ACCUMULATE + B.BYTES_BMFR + (B.BYTES_TAA if taa else 0))
-        gbs = chain * W * H / (ms / K * 1e-3) / 1e9
+        gbs = jobs * chain * W * H / (ms / K * 1e-3) / 1e9
         line = {"metric": "BMFR denoised MPix/s", "value": round(value, 1), "unit": "MPix/s", "n_gpus": world, "steps": K, "warmup": Wm,
                 "ms_per_step": round(ms / K, 5), "higher_is_better": True, "scaling": "strong" if strong else "weak",
+                "replicas": jobs if replicas else None,
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": name + ("" if strong else "_bands"), "description": desc + f"; band-sharded over {world} GPUs"
-                           + ("" if strong else f" (weak scaling: one {W}x{Hband} band per GPU, frame {W}x{H})"),
+                "config": {"workload": name + ("_replicas" if replicas else ("" if strong else "_bands")),
+                           "description": desc + (f"; {world} independent sequences, one per GPU, no communication" if replicas
+                                                  else f"; band-sharded over {world} GPUs"
+                                                  + ("" if strong else f" (weak scaling: one {W}x{Hband} band per GPU, frame {W}x{H})")),
                            "width": W, "height": H, "block": 32, "taa": taa, "band_block_rows": bp.plan.brow,
                            "halo": f"history rows +-{bp.plan.D + 1} (+ REPEAT wrap row) per boundary, "
                                    + ("stored into the neighbours' HBM over NVLink peer mappings by k_halo_push, flag words for ordering"
                                       if halo == "peer" else "NCCL send/recv groups per frame"),
                            "l2": f"inputs larger than L2: {R} resident band frames, each read once per step",
                            "sequence_generation_s": round(t_gen, 1)},
-                "e2e": {"value": round(W * H * K / (e2e_ms * 1e-3) / 1e6, 1), "unit": "MPix/s",
-                        "h2d_bytes_per_step": B.INPUT_BYTES * W * rows * world, "d2h_bytes_per_step": 4 * W * H,
+                "e2e": {"value": round(jobs * W * H * K / (e2e_ms * 1e-3) / 1e6, 1), "unit": "MPix/s",
+                        "h2d_bytes_per_step": B.INPUT_BYTES * W * rows * world, "d2h_bytes_per_step": 4 * W * H * jobs,
                         "ms_per_step": round(e2e_ms / K, 5)},
                 "gpu_launches": int(launches) * world, "clocks": clocks,
                 "roofline": {"kernel": "chain (k_accumulate + k_bmfr_block" + (" + k_taa)" if taa else ")"), "bound": "hbm",
