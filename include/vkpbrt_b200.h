@@ -318,19 +318,36 @@ VKPBRT_API int vkpbrt_peer_export(vkpbrt_context_t ctx, const void* device_ptr, 
 /* maps another process's allocation (cudaIpcOpenMemHandle, peer access enabled lazily); open each handle once */
 VKPBRT_API int vkpbrt_peer_open(vkpbrt_context_t ctx, const uint8_t handle[VKPBRT_PEER_HANDLE_BYTES], void** base);
 VKPBRT_API int vkpbrt_peer_close(vkpbrt_context_t ctx, void* base);
-/* one launch on `stream` (a cudaStream_t; NULL = the context's stream):
- *   spin until every ready_flags[i] (local words) >= value   (n_ready may be 0: no gate)
- *   copy the n_copies blocks of the DEVICE table copies_device
- *   store `value` to every done_flags[i] (receivers' words, peer mapped) after all copies have landed
- * counter_device: one zero-initialised device word per concurrently running exchange point;
- * error_device: device word set to 1 if a spin exceeded timeout_ms (the kernel then proceeds, it never hangs) */
-VKPBRT_API int vkpbrt_halo_push(vkpbrt_context_t ctx, void* stream, const vkpbrt_halo_copy* copies_device, uint32_t n_copies,
-                                const uint32_t* const* ready_flags, uint32_t n_ready, uint32_t* const* done_flags,
-                                uint32_t n_done, uint32_t value, uint32_t* counter_device, uint32_t* error_device,
-                                uint32_t timeout_ms);
-/* makes `stream` wait until every flags[i] (local device words) >= value */
-VKPBRT_API int vkpbrt_halo_wait(vkpbrt_context_t ctx, void* stream, const uint32_t* const* flags, uint32_t n, uint32_t value,
-                                uint32_t* error_device, uint32_t timeout_ms);
+/* An exchange point: everything one rank does at one point of the frame for one (jitter phase, ping-pong parity),
+ * built once and replayed.  `start` is ONE kernel launch on the communication stream, ordered after the work already
+ * enqueued on `after_stream`:
+ *   1. store `value` to every announce_flags[i]   (senders' words, peer mapped: "my halo rows may be overwritten")
+ *   2. spin until every ready_flags[i] >= value    (local words the receivers announce to; n_ready may be 0: no gate)
+ *   3. copy the blocks of rows of `copies`         (16-byte stores into the receivers' HBM)
+ *   4. store `value` to every done_flags[i]        (receivers' words, peer mapped) once every copy has landed
+ * `wait` makes a stream spin until every wait_flags[i] (local words) >= value, in front of the consuming kernel.
+ * Spins are bounded by timeout_ms: on expiry an error word is set (see `stats`) and the kernel proceeds -- it never
+ * hangs the GPU.  `value` must grow from call to call (a frame or sequence counter). */
+typedef struct vkpbrt_halo_exchange_s* vkpbrt_halo_exchange_t;
+typedef struct vkpbrt_halo_exchange_desc {
+    const vkpbrt_halo_copy* copies;      /* host array; copied to the device by create */
+    uint32_t n_copies;
+    uint32_t* const* announce_flags;
+    uint32_t n_announce;
+    const uint32_t* const* ready_flags;
+    uint32_t n_ready;
+    uint32_t* const* done_flags;
+    uint32_t n_done;
+    const uint32_t* const* wait_flags;
+    uint32_t n_wait;
+} vkpbrt_halo_exchange_desc;
+VKPBRT_API int vkpbrt_halo_exchange_create(vkpbrt_context_t ctx, const vkpbrt_halo_exchange_desc* desc, uint32_t timeout_ms,
+                                           vkpbrt_halo_exchange_t* out);
+VKPBRT_API int vkpbrt_halo_exchange_start(vkpbrt_halo_exchange_t x, void* comm_stream, void* after_stream, uint32_t value);
+VKPBRT_API int vkpbrt_halo_exchange_wait(vkpbrt_halo_exchange_t x, void* stream, uint32_t value);
+/* synchronises the device; nanoseconds spent spinning in step 2 and in `wait` since creation, and the error word */
+VKPBRT_API int vkpbrt_halo_exchange_stats(vkpbrt_halo_exchange_t x, uint64_t* gate_ns, uint64_t* wait_ns, uint32_t* error);
+VKPBRT_API int vkpbrt_halo_exchange_destroy(vkpbrt_halo_exchange_t x);
 
 #ifdef __cplusplus
 }

@@ -51,6 +51,19 @@ class ImageInfo(C.Structure):
                 ("size_bytes", C.c_uint64), ("owned", C.c_int32)]
 
 
+class HaloCopy(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("src_pitch", C.c_uint64), ("dst_pitch", C.c_uint64),
+                ("row_bytes", C.c_uint32), ("rows", C.c_uint32)]
+
+
+class HaloExchangeDesc(C.Structure):
+    _fields_ = [("copies", C.POINTER(HaloCopy)), ("n_copies", C.c_uint32),
+                ("announce_flags", C.POINTER(C.c_void_p)), ("n_announce", C.c_uint32),
+                ("ready_flags", C.POINTER(C.c_void_p)), ("n_ready", C.c_uint32),
+                ("done_flags", C.POINTER(C.c_void_p)), ("n_done", C.c_uint32),
+                ("wait_flags", C.POINTER(C.c_void_p)), ("n_wait", C.c_uint32)]
+
+
 class PushConstants(C.Structure):
     """RayTracingPushConstants (source/renderModules/PipelineStructs.hpp:6-13)."""
     _fields_ = [("view_inverse", C.c_float * 16), ("proj_inverse", C.c_float * 16), ("prev_view", C.c_float * 16),
@@ -144,8 +157,11 @@ _PROTOS = {
     "vkpbrt_peer_export": [H, C.c_void_p, C.c_void_p, C.POINTER(u64)],
     "vkpbrt_peer_open": [H, C.c_void_p, PH],
     "vkpbrt_peer_close": [H, C.c_void_p],
-    "vkpbrt_halo_push": [H, C.c_void_p, C.c_void_p, u32, C.c_void_p, u32, C.c_void_p, u32, u32, C.c_void_p, C.c_void_p, u32],
-    "vkpbrt_halo_wait": [H, C.c_void_p, C.c_void_p, u32, u32, C.c_void_p, u32],
+    "vkpbrt_halo_exchange_create": [H, C.c_void_p, u32, PH],
+    "vkpbrt_halo_exchange_start": [H, C.c_void_p, C.c_void_p, u32],
+    "vkpbrt_halo_exchange_wait": [H, C.c_void_p, u32],
+    "vkpbrt_halo_exchange_stats": [H, C.POINTER(u64), C.POINTER(u64), C.POINTER(u32)],
+    "vkpbrt_halo_exchange_destroy": [H],
 }
 _RESTYPES = {"vkpbrt_last_error": C.c_char_p, "vkpbrt_version": C.c_char_p, "vkpbrt_format_texel_size": u32}
 EXPORTS = sorted(list(_PROTOS) + list(_RESTYPES))

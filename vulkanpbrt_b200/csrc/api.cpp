@@ -1277,53 +1277,121 @@ int vkpbrt_peer_close(vkpbrt_context_t ctx, void* base)
     return VKPBRT_OK;
 }
 
-int vkpbrt_halo_push(vkpbrt_context_t ctx, void* stream, const vkpbrt_halo_copy* copies_device, uint32_t n_copies,
-                     const uint32_t* const* ready_flags, uint32_t n_ready, uint32_t* const* done_flags, uint32_t n_done,
-                     uint32_t value, uint32_t* counter_device, uint32_t* error_device, uint32_t timeout_ms)
+struct vkpbrt_halo_exchange_s {
+    vkpbrt_context_t ctx = nullptr;
+    HaloPushParams push{};
+    HaloWaitParams wait{};
+    bool has_start = false;
+    void* device_block = nullptr;      // [copy table][counter u32, error u32][gate_ns u64 x2][wait_ns u64 x2]
+    cudaEvent_t ordered = nullptr;
+};
+
+int vkpbrt_halo_exchange_create(vkpbrt_context_t ctx, const vkpbrt_halo_exchange_desc* d, uint32_t timeout_ms, vkpbrt_halo_exchange_t* out)
 {
-    VK_REQUIRE(ctx && counter_device && error_device, "null argument");
-    VK_REQUIRE(n_copies == 0 || copies_device, "null copy table");
-    VK_REQUIRE(n_ready <= (uint32_t)kHaloMaxPeers && n_done <= (uint32_t)kHaloMaxPeers, "too many peers");
-    VK_REQUIRE((n_ready == 0 || ready_flags) && (n_done == 0 || done_flags), "null flag list");
-    HaloPushParams p{};
-    p.copies = reinterpret_cast<const HaloCopy*>(copies_device);
-    p.n_copies = (int)n_copies;
-    p.n_ready = (int)n_ready;
-    p.n_done = (int)n_done;
-    for (uint32_t i = 0; i < n_ready; ++i) p.ready_flags[i] = ready_flags[i];
-    for (uint32_t i = 0; i < n_done; ++i) p.done_flags[i] = done_flags[i];
-    p.value = value;
-    p.counter = counter_device;
-    p.error = error_device;
+    VK_REQUIRE(ctx && d && out, "null argument");
+    VK_REQUIRE(d->n_copies == 0 || d->copies, "null copy table");
+    VK_REQUIRE(d->n_announce <= (uint32_t)kHaloMaxPeers && d->n_ready <= (uint32_t)kHaloMaxPeers &&
+                   d->n_done <= (uint32_t)kHaloMaxPeers && d->n_wait <= (uint32_t)kHaloMaxPeers, "too many peers");
+    VK_REQUIRE((d->n_announce == 0 || d->announce_flags) && (d->n_ready == 0 || d->ready_flags) &&
+                   (d->n_done == 0 || d->done_flags) && (d->n_wait == 0 || d->wait_flags), "null flag list");
+    VK_CUDA(cudaSetDevice(ctx->device));
+    auto* x = new vkpbrt_halo_exchange_s();
+    x->ctx = ctx;
+    const size_t table_bytes = (size_t)d->n_copies * sizeof(HaloCopy);
+    const size_t tail = (table_bytes + 15) / 16 * 16;
+    cudaError_t e = cudaMalloc(&x->device_block, tail + 48);
+    if (e == cudaSuccess) e = cudaMemset(x->device_block, 0, tail + 48);
+    if (e == cudaSuccess && table_bytes) e = cudaMemcpy(x->device_block, d->copies, table_bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&x->ordered, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        if (x->device_block) cudaFree(x->device_block);
+        delete x;
+        return fail_cuda(e, "vkpbrt_halo_exchange_create");
+    }
+    auto* base = static_cast<unsigned char*>(x->device_block);
+    HaloPushParams& p = x->push;
+    p.copies = reinterpret_cast<const HaloCopy*>(base);
+    p.n_copies = (int)d->n_copies;
+    p.n_announce = (int)d->n_announce;
+    p.n_ready = (int)d->n_ready;
+    p.n_done = (int)d->n_done;
+    for (uint32_t i = 0; i < d->n_announce; ++i) p.announce_flags[i] = d->announce_flags[i];
+    for (uint32_t i = 0; i < d->n_ready; ++i) p.ready_flags[i] = d->ready_flags[i];
+    for (uint32_t i = 0; i < d->n_done; ++i) p.done_flags[i] = d->done_flags[i];
+    p.counter = reinterpret_cast<uint32_t*>(base + tail);
+    p.error = p.counter + 1;
+    p.gate_ns = reinterpret_cast<unsigned long long*>(base + tail + 16);
     p.timeout_ns = (unsigned long long)timeout_ms * 1000000ull;
-    // 16 CTAs x 256 threads x 16 B x 4 in flight = 256 KB per sweep of one block of rows
-    VK_CUDA(vkpbrt::launch_halo_push(p, n_copies ? 16 : 1, stream ? (cudaStream_t)stream : ctx->stream));
-    ctx->launches++;
+    x->has_start = d->n_copies || d->n_announce || d->n_done;
+    HaloWaitParams& w = x->wait;
+    w.n = (int)d->n_wait;
+    for (uint32_t i = 0; i < d->n_wait; ++i) w.flags[i] = d->wait_flags[i];
+    w.error = p.error;
+    w.wait_ns = reinterpret_cast<unsigned long long*>(base + tail + 32);
+    w.timeout_ns = p.timeout_ns;
+    *out = x;
     return VKPBRT_OK;
 }
 
-int vkpbrt_halo_wait(vkpbrt_context_t ctx, void* stream, const uint32_t* const* flags, uint32_t n, uint32_t value,
-                     uint32_t* error_device, uint32_t timeout_ms)
+int vkpbrt_halo_exchange_start(vkpbrt_halo_exchange_t x, void* comm_stream, void* after_stream, uint32_t value)
 {
-    VK_REQUIRE(ctx && flags && error_device, "null argument");
-    VK_REQUIRE(n >= 1 && n <= (uint32_t)kHaloMaxPeers, "1..8 flags");
-    HaloWaitParams p{};
-    p.n = (int)n;
-    for (uint32_t i = 0; i < n; ++i) p.flags[i] = flags[i];
-    p.value = value;
-    p.error = error_device;
-    p.timeout_ns = (unsigned long long)timeout_ms * 1000000ull;
-    VK_CUDA(vkpbrt::launch_halo_wait(p, stream ? (cudaStream_t)stream : ctx->stream));
-    ctx->launches++;
+    VK_REQUIRE(x, "null exchange");
+    if (!x->has_start) return VKPBRT_OK;
+    cudaStream_t comm = comm_stream ? (cudaStream_t)comm_stream : x->ctx->stream;
+    cudaStream_t after = after_stream ? (cudaStream_t)after_stream : x->ctx->stream;
+    if (comm != after) {
+        VK_CUDA(cudaEventRecord(x->ordered, after));
+        VK_CUDA(cudaStreamWaitEvent(comm, x->ordered, 0));
+    }
+    x->push.value = value;
+    // 16 CTAs x 256 threads x 16 B x 4 in flight = 256 KB per sweep of one block of rows
+    VK_CUDA(vkpbrt::launch_halo_push(x->push, x->push.n_copies ? 16 : 1, comm));
+    x->ctx->launches++;
+    return VKPBRT_OK;
+}
+
+int vkpbrt_halo_exchange_wait(vkpbrt_halo_exchange_t x, void* stream, uint32_t value)
+{
+    VK_REQUIRE(x, "null exchange");
+    if (x->wait.n == 0) return VKPBRT_OK;
+    x->wait.value = value;
+    VK_CUDA(vkpbrt::launch_halo_wait(x->wait, stream ? (cudaStream_t)stream : x->ctx->stream));
+    x->ctx->launches++;
+    return VKPBRT_OK;
+}
+
+int vkpbrt_halo_exchange_stats(vkpbrt_halo_exchange_t x, uint64_t* gate_ns, uint64_t* wait_ns, uint32_t* error)
+{
+    VK_REQUIRE(x, "null exchange");
+    VK_CUDA(cudaSetDevice(x->ctx->device));
+    VK_CUDA(cudaDeviceSynchronize());
+    unsigned long long host[4] = {0, 0, 0, 0};
+    uint32_t words[2] = {0, 0};
+    VK_CUDA(cudaMemcpy(host, x->push.gate_ns, sizeof(host), cudaMemcpyDeviceToHost));
+    VK_CUDA(cudaMemcpy(words, x->push.counter, sizeof(words), cudaMemcpyDeviceToHost));
+    if (gate_ns) *gate_ns = host[0];
+    if (wait_ns) *wait_ns = host[2];
+    if (error) *error = words[1];
+    return VKPBRT_OK;
+}
+
+int vkpbrt_halo_exchange_destroy(vkpbrt_halo_exchange_t x)
+{
+    if (!x) return VKPBRT_OK;
+    if (x->ordered) cudaEventDestroy(x->ordered);
+    if (x->device_block) cudaFree(x->device_block);
+    delete x;
     return VKPBRT_OK;
 }
 #else
 int vkpbrt_peer_export(vkpbrt_context_t, const void*, uint8_t*, uint64_t*) { return fail(VKPBRT_ERR_UNSUPPORTED, "peer memory needs CUDA devices"); }
 int vkpbrt_peer_open(vkpbrt_context_t, const uint8_t*, void**) { return fail(VKPBRT_ERR_UNSUPPORTED, "peer memory needs CUDA devices"); }
 int vkpbrt_peer_close(vkpbrt_context_t, void*) { return fail(VKPBRT_ERR_UNSUPPORTED, "peer memory needs CUDA devices"); }
-int vkpbrt_halo_push(vkpbrt_context_t, void*, const vkpbrt_halo_copy*, uint32_t, const uint32_t* const*, uint32_t, uint32_t* const*,
-                     uint32_t, uint32_t, uint32_t*, uint32_t*, uint32_t) { return fail(VKPBRT_ERR_UNSUPPORTED, "peer memory needs CUDA devices"); }
-int vkpbrt_halo_wait(vkpbrt_context_t, void*, const uint32_t* const*, uint32_t, uint32_t, uint32_t*, uint32_t) { return fail(VKPBRT_ERR_UNSUPPORTED, "peer memory needs CUDA devices"); }
+int vkpbrt_halo_exchange_create(vkpbrt_context_t, const vkpbrt_halo_exchange_desc*, uint32_t, vkpbrt_halo_exchange_t*) { return fail(VKPBRT_ERR_UNSUPPORTED, "peer memory needs CUDA devices"); }
+int vkpbrt_halo_exchange_start(vkpbrt_halo_exchange_t, void*, void*, uint32_t) { return fail(VKPBRT_ERR_UNSUPPORTED, "peer memory needs CUDA devices"); }
+int vkpbrt_halo_exchange_wait(vkpbrt_halo_exchange_t, void*, uint32_t) { return fail(VKPBRT_ERR_UNSUPPORTED, "peer memory needs CUDA devices"); }
+int vkpbrt_halo_exchange_stats(vkpbrt_halo_exchange_t, uint64_t*, uint64_t*, uint32_t*) { return fail(VKPBRT_ERR_UNSUPPORTED, "peer memory needs CUDA devices"); }
+int vkpbrt_halo_exchange_destroy(vkpbrt_halo_exchange_t) { return VKPBRT_OK; }
 #endif
 
 }  // extern "C"

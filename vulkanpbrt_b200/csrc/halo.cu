@@ -4,7 +4,7 @@
 // (accumulator.comp:75-98 history taps, bmfrPost.comp:103-118 / taa.comp:44-60 neighbourhoods),
 // see vulkanpbrt_b200/multigpu.py BandPlan.
 //
-//   k_halo_push   [gate on the receivers' "ready" flags] -> copy every block of rows of the table
+//   k_halo_push   [announce "ready" to the senders] -> [gate on the receivers' "ready" flags] -> copy every block of rows of the table
 //                 with 16-byte peer stores -> the last CTA publishes `value` to the receivers'
 //                 "done" flags (release at system scope).  One launch per exchange point.
 //   k_halo_wait   one warp; lane i spins (acquire at system scope) until flag i >= value.
@@ -37,16 +37,19 @@ __device__ __forceinline__ unsigned long long global_timer_ns()
     return t;
 }
 
-__device__ void spin_until(const uint32_t* flag, uint32_t value, unsigned long long timeout_ns, uint32_t* error)
+// returns the nanoseconds spent spinning
+__device__ unsigned long long spin_until(const uint32_t* flag, uint32_t value, unsigned long long timeout_ns, uint32_t* error)
 {
+    if ((int32_t)(ld_acquire_sys(flag) - value) >= 0) return 0ull;
     const unsigned long long t0 = global_timer_ns();
     while ((int32_t)(ld_acquire_sys(flag) - value) < 0) {
         if (global_timer_ns() - t0 > timeout_ns) {
             atomicExch(error, 1u);
-            return;
+            break;
         }
         __nanosleep(40);
     }
+    return global_timer_ns() - t0;
 }
 
 template <typename V>
@@ -82,8 +85,12 @@ __device__ __forceinline__ void copy_block(const HaloCopy& hc, uint32_t rows, ui
 // grid = (parts per block of rows, blocks of rows in the table)
 __global__ void __launch_bounds__(256) k_halo_push(const HaloPushParams p)
 {
+    if (blockIdx.x == 0 && blockIdx.y == 0 && (int)threadIdx.x < p.n_announce) st_release_sys(p.announce_flags[threadIdx.x], p.value);
     if (p.n_ready > 0) {
-        if ((int)threadIdx.x < p.n_ready) spin_until(p.ready_flags[threadIdx.x], p.value, p.timeout_ns, p.error);
+        if ((int)threadIdx.x < p.n_ready) {
+            const unsigned long long ns = spin_until(p.ready_flags[threadIdx.x], p.value, p.timeout_ns, p.error);
+            if (ns && blockIdx.x == 0 && blockIdx.y == 0) atomicMax(p.gate_ns + 1, ns), atomicAdd(p.gate_ns, ns);
+        }
         __syncthreads();
     }
     if ((int)blockIdx.y < p.n_copies) {
@@ -114,7 +121,10 @@ __global__ void __launch_bounds__(256) k_halo_push(const HaloPushParams p)
 
 __global__ void __launch_bounds__(32) k_halo_wait(const HaloWaitParams p)
 {
-    if ((int)threadIdx.x < p.n) spin_until(p.flags[threadIdx.x], p.value, p.timeout_ns, p.error);
+    if ((int)threadIdx.x < p.n) {
+        const unsigned long long ns = spin_until(p.flags[threadIdx.x], p.value, p.timeout_ns, p.error);
+        if (ns) atomicMax(p.wait_ns + 1, ns), atomicAdd(p.wait_ns, ns);
+    }
 }
 
 cudaError_t launch_halo_push(const HaloPushParams& p, int parts, cudaStream_t stream)

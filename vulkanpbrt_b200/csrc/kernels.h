@@ -120,12 +120,14 @@ constexpr int kHaloMaxPeers = 8;
 struct HaloPushParams {
     const HaloCopy* copies;       // device table
     int n_copies;
-    int n_ready, n_done;
+    int n_announce, n_ready, n_done;
+    uint32_t* announce_flags[kHaloMaxPeers];      // senders' words (peer mapped): set first
     const uint32_t* ready_flags[kHaloMaxPeers];   // local words the receivers set when their halo rows may be overwritten
     uint32_t* done_flags[kHaloMaxPeers];          // receivers' words (peer mapped), set to `value` once every copy has landed
     uint32_t value;
     uint32_t* counter;            // last-CTA detection, left at 0
     uint32_t* error;              // set to 1 when a spin timed out
+    unsigned long long* gate_ns;  // statistics: time CTA 0 spent in the gate
     unsigned long long timeout_ns;
 };
 struct HaloWaitParams {
@@ -133,6 +135,7 @@ struct HaloWaitParams {
     const uint32_t* flags[kHaloMaxPeers];
     uint32_t value;
     uint32_t* error;
+    unsigned long long* wait_ns;  // statistics
     unsigned long long timeout_ns;
 };
 cudaError_t launch_halo_push(const HaloPushParams& p, int parts, cudaStream_t stream);

@@ -279,8 +279,11 @@ class PeerDirect:
         self.device = device
         self.flags = DescriptorImage.create(ctx, capi.FORMAT_R32_SFLOAT, max(16, 4 * world), 1)
         self.flags.compile()            # allocates, zero-initialised
-        self.scratch = torch.zeros(8, dtype=torch.int32, device=device)      # counters of A, B, F, B-ready; [7] = error
         ctx.synchronize()
+        self._exchanges: list = []
+        lib = capi.lib()
+        self._start_fn, self._wait_fn = lib.vkpbrt_halo_exchange_start, lib.vkpbrt_halo_exchange_wait
+        self._comm = self.stream.cuda_stream
         self._opened: Dict = {}         # (rank, handle bytes) -> mapped base
         self.seq = {"A": 0, "B": 0, "F": 0}
         mine = self.export(self.flags.device_ptr)
@@ -318,28 +321,54 @@ class PeerDirect:
     def ready_word(self, owner: int, dst: int) -> int:
         return self.peer_flags[owner] + 4 * (3 * self.world + dst)
 
-    # ---- launches ---------------------------------------------------------------------------------------
-    def _ptr_array(self, addrs):
-        return (self.C.c_void_p * max(1, len(addrs)))(*addrs)
+    # ---- exchange points --------------------------------------------------------------------------------
+    def make_exchange(self, kind: str, copies, announce, ready, done, wait):
+        """copies: [(src, dst, src_pitch, dst_pitch, row_bytes, rows)]; the four flag lists are device addresses.
+        Returns the opaque exchange handle (vkpbrt_halo_exchange_create); everything is resolved here, once."""
+        C, capi = self.C, self.capi
+        table = (capi.HaloCopy * max(1, len(copies)))()
+        for k, c in enumerate(copies):
+            table[k] = capi.HaloCopy(*c)
+        arrays = [(C.c_void_p * max(1, len(lst)))(*lst) for lst in (announce, ready, done, wait)]
+        d = capi.HaloExchangeDesc(table, len(copies), arrays[0], len(announce), arrays[1], len(ready), arrays[2], len(done),
+                                  arrays[3], len(wait))
+        h = C.c_void_p()
+        capi.call("vkpbrt_halo_exchange_create", self.ctx.handle, C.byref(d), self.timeout_ms, C.byref(h))
+        self._exchanges.append((kind, h))
+        return h
 
-    def push(self, table, n_copies: int, ready, done, value: int, counter: int) -> None:
-        C = self.C
-        self.capi.call("vkpbrt_halo_push", self.ctx.handle, C.c_void_p(self.stream.cuda_stream),
-                       C.c_void_p(table.data_ptr() if table is not None else 0), n_copies,
-                       self._ptr_array(ready), len(ready), self._ptr_array(done), len(done), value,
-                       C.c_void_p(self.scratch.data_ptr() + 4 * counter), C.c_void_p(self.scratch.data_ptr() + 28), self.timeout_ms)
+    def start(self, x, after_stream: int, value: int) -> None:
+        rc = self._start_fn(x, self._comm, after_stream, value)
+        if rc:
+            self.capi.check(rc)
 
-    def wait(self, stream_handle: int, flags, value: int) -> None:
+    def wait(self, x, stream: int, value: int) -> None:
+        rc = self._wait_fn(x, stream, value)
+        if rc:
+            self.capi.check(rc)
+
+    def stats(self):
+        """synchronises; {kind: (ms spent in the start kernels' gate, ms spent in the wait kernels)} and the error flag"""
         C = self.C
-        self.capi.call("vkpbrt_halo_wait", self.ctx.handle, C.c_void_p(stream_handle), self._ptr_array(flags), len(flags), value,
-                       C.c_void_p(self.scratch.data_ptr() + 28), self.timeout_ms)
+        out, err = {}, 0
+        for kind, h in self._exchanges:
+            g, w, e = C.c_uint64(), C.c_uint64(), C.c_uint32()
+            self.capi.call("vkpbrt_halo_exchange_stats", h, C.byref(g), C.byref(w), C.byref(e))
+            a = out.setdefault(kind, [0.0, 0.0])
+            a[0] += g.value * 1e-6
+            a[1] += w.value * 1e-6
+            err |= e.value
+        return out, err
 
     def check(self) -> None:
         """synchronises and raises if any flag wait timed out (a peer died or fell out of step)"""
-        if int(self.scratch[7].item()) != 0:
+        if self.stats()[1]:
             raise RuntimeError("halo exchange: a flag wait timed out (peer rank lost or out of step)")
 
     def close(self) -> None:
+        for _, h in self._exchanges:
+            self.capi.call("vkpbrt_halo_exchange_destroy", h)
+        self._exchanges = []
         for base in self._opened.values():
             try:
                 self.capi.call("vkpbrt_peer_close", self.ctx.handle, self.C.c_void_p(base))
@@ -370,6 +399,8 @@ class BandedPipeline:
         self._back_cmd = c[-1]
         self.bytes_exchanged = 0
         self._pending_a = self._pending_b = None
+        self._main_stream = ctx.stream          # the stream the modules record on
+        self._swaps = 0                         # copy_to_back pointer swaps so far: selects the ping-pong buffers
         self._views: Dict = {}
         self._desc: Dict = {}
         self._keep: list = []
@@ -445,21 +476,38 @@ class BandedPipeline:
                 elif t.dst == g:
                     recv_from.add(t.src)
                     nbytes += rb * (t.rows[1] - t.rows[0])
-        table = None
-        if rows_of:
-            a = np.zeros(len(rows_of), dtype=np.dtype([("src", "<u8"), ("dst", "<u8"), ("sp", "<u8"), ("dp", "<u8"), ("rb", "<u4"), ("rows", "<u4")]))
-            for k, r in enumerate(rows_of):
-                a[k] = r
-            table = torch.from_numpy(a.view(np.uint8).copy()).to(pd.device)
-        return ("peer", kind, table, len(rows_of), sorted(send_to), sorted(recv_from), nbytes)
+        send_to, recv_from = sorted(send_to), sorted(recv_from)
+        # the end-of-frame group rewrites texels the receiver still reads during its frame: receivers announce the end
+        # of their frame to the senders, whose copy is gated on it (the point where NCCL would have posted the receive)
+        handshake = kind == "B"
+        x = pd.make_exchange(kind, rows_of,
+                             announce=[pd.ready_word(s_, g) for s_ in recv_from] if handshake else [],
+                             ready=[pd.ready_word(g, d_) for d_ in send_to] if handshake else [],
+                             done=[pd.done_word(d_, kind, g) for d_ in send_to],
+                             wait=[pd.done_word(g, kind, s_) for s_ in recv_from])
+        return ("peer", kind, x, bool(send_to or recv_from), nbytes)
 
-    def _exchange_desc(self, kind: str, frame: int, images: Dict[str, list], transfers_fn):
-        """images: plane name -> [(DescriptorImage or (DescriptorImage, layer), ncol_bytes)]"""
+    def _exchange_desc(self, kind: str, frame: int, images_fn, transfers_fn):
+        """images_fn() -> plane name -> [(DescriptorImage or (DescriptorImage, layer), ncol_bytes)]"""
+        if self.peer is not None:
+            # every buffer involved alternates with the copy_to_back swaps (and the denoised layer with the frame
+            # parity): no per-frame queries; the addresses a cached entry was built for are re-checked on its first reuses
+            key = (kind, frame % 16, self._swaps & 1, frame & 1)
+            entry = self._desc.get(key)
+            if entry is None or entry[1] < 2:
+                images = images_fn()
+                ptrs = tuple((img[0] if isinstance(img, tuple) else img).info().data for lst in images.values() for img, _ in lst)
+                if entry is None:
+                    entry = self._desc[key] = [self._build_peer(kind, transfers_fn(), images), 0, ptrs]
+                else:
+                    if entry[2] != ptrs:
+                        raise RuntimeError("halo exchange: image buffers do not follow the ping-pong schedule the cache assumes")
+                    entry[1] += 1
+            return entry[0]
+        images = images_fn()
         ptrs = tuple((img[0] if isinstance(img, tuple) else img).info().data for lst in images.values() for img, _ in lst)
         key = (kind, frame % 16, ptrs)
         d = self._desc.get(key)
-        if d is None and self.peer is not None:
-            d = self._desc[key] = self._build_peer(kind, transfers_fn(), images)
         if d is None:
             planes = {}
             for name, lst in images.items():
@@ -507,38 +555,23 @@ class BandedPipeline:
         return (self.dist.batch_isend_irecv(ops), scatter)
 
     def _start_peer(self, desc):
-        """one k_halo_push on the communication stream, ordered after the work already on the current stream"""
-        import torch
-        _, kind, table, n, send_to, recv_from, nbytes = desc
-        pd, g = self.peer, self.rank
+        """one k_halo_push on the communication stream, ordered after the work already on the main stream"""
+        _, kind, x, active, nbytes = desc
+        pd = self.peer
         pd.seq[kind] += 1
-        value = pd.seq[kind]
-        if not send_to and not recv_from:
+        if not active:
             return None
+        value = pd.seq[kind]
         self.bytes_exchanged += nbytes
-        cur = torch.cuda.current_stream()
-        ready = self._event()
-        ready.record(cur)
-        pd.stream.wait_event(ready)
-        gate = []
-        if kind == "B":
-            # the receivers' frame is over: let the senders overwrite the halo rows (what posting the receive
-            # did with NCCL); our own push is gated on the same word from each of its receivers
-            if recv_from:
-                pd.push(None, 0, [], [pd.ready_word(s, g) for s in recv_from], value, 3)
-            gate = [pd.ready_word(g, d) for d in send_to]
-        if send_to:
-            pd.push(table, n, gate, [pd.done_word(d, kind, g) for d in send_to], value, pd.GROUPS[kind])
-        return ("peer", [pd.done_word(g, kind, s) for s in recv_from], value)
+        pd.start(x, self._main_stream, value)
+        return ("peer", x, value)
 
     def _finish(self, pending) -> None:
         """makes the current stream wait for a group started by _start (stream-side wait for NCCL)"""
         if pending is None:
             return
         if pending[0] == "peer":
-            import torch
-            if pending[1]:
-                self.peer.wait(torch.cuda.current_stream().cuda_stream, pending[1], pending[2])
+            self.peer.wait(pending[1], self._main_stream, pending[2])
             return
         works, scatter = pending
         if isinstance(works, list):
@@ -566,8 +599,9 @@ class BandedPipeline:
         self._acc_cmd(p.commands)
         if multi:
             # pre-swap handles: what k_accumulate just wrote becomes prev_depth / prev_illu / prev_spp at copy_to_back
-            da = self._exchange_desc("A", frame, {"acc": [(acc.next_depth, None), (p.illumination_buffer.illumination_images[0], None),
-                                                          (acc.spp, None)]},
+            da = self._exchange_desc("A", frame,
+                                     lambda: {"acc": [(acc.next_depth, None), (p.illumination_buffer.illumination_images[0], None),
+                                                      (acc.spp, None)]},
                                      lambda: [t for t in plan.history_transfers(frame + 1) if t.plane == "acc"])
             self._pending_a = self._start(da)
         self._finish(self._pending_b)
@@ -575,19 +609,23 @@ class BandedPipeline:
         self._bmfr_cmd(p.commands)
         if p.taa is not None:
             if multi:
-                df = self._exchange_desc("F", frame, {"final": [(p.denoiser_final, None)]}, lambda: plan.final_transfers(frame))
+                df = self._exchange_desc("F", frame, lambda: {"final": [(p.denoiser_final, None)]}, lambda: plan.final_transfers(frame))
                 self._finish(self._start(df))
             p.taa.set_row_range(*plan.owned_rows(g, frame))
             self._taa_cmd(p.commands)
         self._back_cmd(p.commands)
         p.end_frame(cam)
+        self._swaps += 1
         if multi:
             layer = (frame & 1) ^ 1
-            images_b = {"denoised": [((self.bmfr.denoised, layer), None)],
-                        "final_col0": [(p.denoiser_final, 4)],                     # 1 BGRA8 texel
-                        "denoised_col0": [((self.bmfr.denoised, layer), 8)]}       # 1 rgba16f texel
-            if p.taa is not None:
-                images_b["taa"] = [(p.taa.history, None)]
+
+            def images_b():
+                im = {"denoised": [((self.bmfr.denoised, layer), None)],
+                      "final_col0": [(p.denoiser_final, 4)],                     # 1 BGRA8 texel
+                      "denoised_col0": [((self.bmfr.denoised, layer), 8)]}       # 1 rgba16f texel
+                if p.taa is not None:
+                    im["taa"] = [(p.taa.history, None)]
+                return im
             db = self._exchange_desc("B", frame, images_b,
                                      lambda: [t for t in plan.history_transfers(frame + 1) if t.plane != "acc"]
                                      + plan.stale_column_transfers(frame))
@@ -688,8 +726,10 @@ def bench_multi(args, rank: int, world: int, local: int):
         frame(f)
     torch.cuda.synchronize()
     dist.barrier()
-    sampler = B.ClockSampler(local)
-    sampler.start()
+    stats0 = bp.peer.stats()[0] if bp.peer is not None else {}
+    sampler = B.ClockSampler(local) if rank == 0 else None       # rank 0's GPU is the one reported
+    if sampler:
+        sampler.start()
     launches0 = ctx.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -702,7 +742,16 @@ def bench_multi(args, rank: int, world: int, local: int):
     torch.cuda.synchronize()
     bp.check()
     dist.barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler else None
+    # time each rank's streams spent spinning on flag words inside the timed region, per exchange group:
+    # [gate of the end-of-frame push, wait in front of the consumer]; rank 0 reports every rank's
+    spin = {}
+    if bp.peer is not None:
+        for kind, (g_ms, w_ms) in bp.peer.stats()[0].items():
+            g0, w0 = stats0.get(kind, (0.0, 0.0))
+            spin[kind] = [round((g_ms - g0) / K, 4), round((w_ms - w0) / K, 4)]
+    spins = [None] * world
+    dist.all_gather_object(spins, spin)
     t = torch.tensor([e0.elapsed_time(e1)], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
@@ -784,7 +833,7 @@ def bench_multi(args, rank: int, world: int, local: int):
                              "frac": round(gbs / (hbm_peak * world), 4), "traffic": None, "peak_source": peak_src,
                              "note": "aggregate over ranks; per-kernel fractions are reported by the N=1 run"},
                 "halo_bytes_per_step": float(halo_bytes.item()) / (PRE + 2 * K + Wm + 3), "host_enqueue_ms_per_step": round(t_host, 4),
-                "cpu_baseline": None}
+                "halo_spin_ms_per_step_by_rank": spins, "cpu_baseline": None}
     else:
         line = None
     dist.barrier()
