@@ -19,6 +19,8 @@ BandPlan is pure integer geometry (tested on CPU); BandedPipeline drives one ran
 """
 from __future__ import annotations
 
+import os
+
 import json
 import time
 from dataclasses import dataclass
@@ -725,9 +727,11 @@ def bench_multi(args, rank: int, world: int, local: int):
     for f in range(PRE, PRE + Wm):
         frame(f)
     torch.cuda.synchronize()
-    dist.barrier()
     stats0 = bp.peer.stats()[0] if bp.peer is not None else {}
-    sampler = B.ClockSampler(local) if rank == 0 else None       # rank 0's GPU is the one reported
+    # rank 0's GPU is the one whose clocks are reported.  NVML is initialised BEFORE the barrier: a rank that enters
+    # the timed region late makes its neighbours' clocks run while they wait for its halos
+    sampler = B.ClockSampler(local) if rank == 0 else None
+    dist.barrier()
     if sampler:
         sampler.start()
     launches0 = ctx.launch_count
@@ -753,6 +757,8 @@ def bench_multi(args, rank: int, world: int, local: int):
     spins = [None] * world
     dist.all_gather_object(spins, spin)
     t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    per_rank_ms = [None] * world
+    dist.all_gather_object(per_rank_ms, round(float(t.item()) / K, 5))
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     launches = ctx.launch_count - launches0
@@ -833,7 +839,7 @@ def bench_multi(args, rank: int, world: int, local: int):
                              "frac": round(gbs / (hbm_peak * world), 4), "traffic": None, "peak_source": peak_src,
                              "note": "aggregate over ranks; per-kernel fractions are reported by the N=1 run"},
                 "halo_bytes_per_step": float(halo_bytes.item()) / (PRE + 2 * K + Wm + 3), "host_enqueue_ms_per_step": round(t_host, 4),
-                "halo_spin_ms_per_step_by_rank": spins, "cpu_baseline": None}
+                "halo_spin_ms_per_step_by_rank": spins, "ms_per_step_by_rank": per_rank_ms, "cpu_baseline": None}
     else:
         line = None
     dist.barrier()
