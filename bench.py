@@ -57,7 +57,7 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """samples SM clock / throttle reasons during the timed region (nvml, falling back to nvidia-smi)"""
+    """samples SM clock / throttle reasons during the timed region (NVML)"""
 
     NAMES = {0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown",
              0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown"}

@@ -223,6 +223,8 @@ public:
     }
     ref_ptr<IlluminationBuffer> accumulated_illumination;
     ref_ptr<AccumulationBuffer> accumulation_buffer;
+    // band-sharded runs (not in the reference): rows this device accumulates
+    void set_row_range(int row_begin, int row_end) { check(vkpbrt_accumulator_set_row_range(handle, row_begin, row_end)); }
     vkpbrt_accumulator_t handle = nullptr;
 private:
     // every bundle remembers the context it was created in through its first image
@@ -257,6 +259,8 @@ public:
         command_graph->addChild([h, push_constants](Commands& c) { c.bound_push_constants = push_constants; check(vkpbrt_bmfr_record(h, push_constants->c())); });
     }
     ref_ptr<DescriptorImage> get_final_descriptor_image() const { return _final; }
+    // band-sharded runs (not in the reference): block rows of the jittered grid this device fits
+    void set_block_row_range(int begin, int end) { check(vkpbrt_bmfr_set_block_row_range(handle, begin, end)); }
     vkpbrt_bmfr_t handle = nullptr;
 private:
     struct Keep { ref_ptr<GBuffer> g; ref_ptr<IlluminationBuffer> i; ref_ptr<AccumulationBuffer> a; } _keep;
@@ -340,6 +344,8 @@ public:
         });
     }
     ref_ptr<DescriptorImage> get_final_descriptor_image() const { return _final; }
+    // band-sharded runs (not in the reference)
+    void set_row_range(int row_begin, int row_end) { check(vkpbrt_taa_set_row_range(handle, row_begin, row_end)); }
     vkpbrt_taa_t handle = nullptr;
 private:
     ref_ptr<GBuffer> _g;
@@ -390,5 +396,57 @@ inline void add_denoiser_to_commands(DenoisingType denoising_type, DenoisingBloc
     }
     }
 }
+
+// ---- band-sharded multi-GPU runs (no reference counterpart; include/vkpbrt_b200.h, "Band-sharded multi-GPU runs") --------
+// One process per GPU.  PeerMemory maps a neighbour's allocation; HaloExchange is one exchange point of the frame
+// (rows to store into the receivers' HBM + the flag words that order them), built once and replayed every frame.
+struct PeerHandle {
+    uint8_t bytes[VKPBRT_PEER_HANDLE_BYTES];
+    uint64_t offset = 0;
+};
+inline PeerHandle peer_export(Context& ctx, const void* device_ptr)
+{
+    PeerHandle h;
+    check(vkpbrt_peer_export(ctx.handle, device_ptr, h.bytes, &h.offset));
+    return h;
+}
+class PeerMemory : public Inherit<PeerMemory> {
+public:
+    PeerMemory(ref_ptr<Context> ctx, const PeerHandle& h) : _ctx(ctx), _offset(h.offset) { check(vkpbrt_peer_open(ctx->handle, h.bytes, &_base)); }
+    ~PeerMemory() { vkpbrt_peer_close(_ctx->handle, _base); }
+    PeerMemory(const PeerMemory&) = delete;
+    void* data() const { return static_cast<uint8_t*>(_base) + _offset; }   // the address the exporter passed to peer_export
+private:
+    ref_ptr<Context> _ctx;
+    void* _base = nullptr;
+    uint64_t _offset;
+};
+class HaloExchange : public Inherit<HaloExchange> {
+public:
+    HaloExchange(Context& ctx, const std::vector<vkpbrt_halo_copy>& copies, const std::vector<uint32_t*>& announce_flags,
+                 const std::vector<const uint32_t*>& ready_flags, const std::vector<uint32_t*>& done_flags,
+                 const std::vector<const uint32_t*>& wait_flags, uint32_t timeout_ms = 20000)
+    {
+        vkpbrt_halo_exchange_desc d{};
+        d.copies = copies.data();
+        d.n_copies = (uint32_t)copies.size();
+        d.announce_flags = announce_flags.data();
+        d.n_announce = (uint32_t)announce_flags.size();
+        d.ready_flags = ready_flags.data();
+        d.n_ready = (uint32_t)ready_flags.size();
+        d.done_flags = done_flags.data();
+        d.n_done = (uint32_t)done_flags.size();
+        d.wait_flags = wait_flags.data();
+        d.n_wait = (uint32_t)wait_flags.size();
+        check(vkpbrt_halo_exchange_create(ctx.handle, &d, timeout_ms, &handle));
+    }
+    ~HaloExchange() { vkpbrt_halo_exchange_destroy(handle); }
+    HaloExchange(const HaloExchange&) = delete;
+    // one launch on comm_stream, ordered after the work already enqueued on after_stream (cudaStream_t; nullptr = the context's)
+    void start(void* comm_stream, void* after_stream, uint32_t value) { check(vkpbrt_halo_exchange_start(handle, comm_stream, after_stream, value)); }
+    // in front of the consuming kernel
+    void wait(void* stream, uint32_t value) { check(vkpbrt_halo_exchange_wait(handle, stream, value)); }
+    vkpbrt_halo_exchange_t handle = nullptr;
+};
 
 }  // namespace vkpbrt

@@ -19,9 +19,6 @@ BandPlan is pure integer geometry (tested on CPU); BandedPipeline drives one ran
 """
 from __future__ import annotations
 
-import os
-
-import json
 import time
 from dataclasses import dataclass
 from typing import Callable, Dict, List, Tuple
