@@ -50,6 +50,37 @@ def test_unorm8(oracle):
         assert L.vkpbrt_oracle_f32_to_unorm8(c / 255.0) == c
 
 
+def _round_f32(x):
+    """Fraction -> nearest-even binary32, exactly"""
+    from fractions import Fraction
+    if x == 0:
+        return np.float32(0.0)
+    near = np.float32(float(x))
+    best = None
+    for c in (near, np.nextafter(near, np.float32(np.inf)), np.nextafter(near, np.float32(-np.inf))):
+        d = abs(Fraction(float(c)) - x)
+        even = (int(np.float32(c).view(np.uint32)) & 1) == 0
+        if best is None or d < best[0] or (d == best[0] and even):
+            best = (d, np.float32(c))
+    return best[1]
+
+
+def test_kernel_unorm8_decode_is_the_exact_quotient_for_all_codes():
+    """csrc/common.cuh unorm8_scale: fma(c, RH, c * RL) with 1/255 = RH + RL must equal the oracle's c / 255.0f
+    (an IEEE division) for every code; the constants are read from the source so the test follows the kernel"""
+    import re
+    from fractions import Fraction
+    src = (Path(__file__).resolve().parents[1] / "vulkanpbrt_b200" / "csrc" / "common.cuh").read_text()
+    m = re.search(r"fmaf\(cf, (-?0x[0-9a-fA-F.]+p[-+]?\d+)f, mul_rn\(cf, (-?0x[0-9a-fA-F.]+p[-+]?\d+)f\)\)", src)
+    assert m, "unorm8_scale not found in common.cuh"
+    rh, rl = (Fraction(float.fromhex(g)) for g in m.groups())
+    assert float(np.float32(float(rh))) == float(rh) and float(np.float32(float(rl))) == float(rl)   # binary32 constants
+    for c in range(256):
+        t = _round_f32(Fraction(c) * rl)
+        q = _round_f32(Fraction(c) * rh + Fraction(float(t)))
+        assert q == np.float32(c) / np.float32(255.0), c
+
+
 # SURVEY.md App. A.2: ivec2(vec2(b, b) * pixelOffsets[f % 16]) for the table of bmfrGeneral.comp:36
 BMFR_OFFSETS = {
     32: [(22, 27), (30, 16), (13, 24), (31, 0), (11, 18), (0, 11), (25, 14), (0, 24), (11, -2), (-1, 0), (30, 3), (27, 19),
@@ -164,3 +195,62 @@ def test_oracle_matches_committed_golden_hashes(oracle, name):
     spec = json.loads((GOLDEN / f"{name}.json").read_text())
     got = run_case(oracle, CASES[name])
     assert got["frames"] == spec["frames"]
+
+
+# ---- the transposing shuffle networks of bmfr.cu / bfr.cu, restated symbolically ----------------------
+def _network(n_values, lanes=32, plain_tail=False):
+    """ReduceN<N, 16> of bfr.cu, or with plain_tail MultiReduce<N, 16> of bmfr.cu (N a power of two; once one value
+    is left every lane keeps adding its partner's copy).  Returns per lane the expression tree it ends with; a sum is
+    a frozenset of its two operands (IEEE addition is commutative, not associative)."""
+    vals = [[("x", lane, j) for j in range(n_values)] for lane in range(lanes)]
+    n, off = n_values, lanes // 2
+    while off >= 1:
+        h = (n + 1) // 2
+        new = []
+        for lane in range(lanes):
+            up = bool(lane & off)
+            row = []
+            if plain_tail and n == 1:
+                new.append([frozenset([vals[lane][0], vals[lane ^ off][0]])])
+                continue
+            for j in range(h):
+                mine, theirs = vals[lane], vals[lane ^ off]
+                zero = ("zero",)
+                keep = (mine[j + h] if j + h < n else zero) if up else mine[j]
+                recv = (theirs[j + h] if j + h < n else zero) if up else theirs[j]     # the partner sends what I keep
+                row.append(frozenset([keep, recv]) if keep != recv else ("dbl", keep))
+            new.append(row)
+        vals, n, off = new, h, off // 2
+    return [v[0] for v in vals]
+
+
+def _butterfly(j, lanes=32):
+    x = [("x", lane, j) for lane in range(lanes)]
+    off = lanes // 2
+    while off >= 1:
+        x = [frozenset([x[lane], x[lane ^ off]]) for lane in range(lanes)]
+        off //= 2
+    return x
+
+
+def _slot22(lane):      # bfr.cu reduce22_slot
+    p3 = (lane & 1) + 2 * ((lane >> 1) & 1)
+    p1 = p3 + 3 * ((lane >> 2) & 1) + 6 * ((lane >> 3) & 1)
+    return p1 + 11 * ((lane >> 4) & 1) if (p3 < 3 and p1 < 11) else -1
+
+
+def test_transposing_networks_sum_along_the_butterfly_tree():
+    """every total leaves the network as exactly the expression tree of a plain xor-butterfly subgroupAdd, and the
+    lane -> slot maps the kernels use are the right ones"""
+    got = _network(22)
+    slots = [_slot22(lane) for lane in range(32)]
+    assert sorted(s for s in slots if s >= 0) == list(range(22))
+    for lane, s in enumerate(slots):
+        if s >= 0:
+            assert got[lane] == _butterfly(s)[lane], (lane, s)
+    for n in (16, 8, 4, 2):             # bmfr.cu MultiReduce<KP, 16>: value j on the lanes with lane >> (5 - log2 KP) == j
+        got = _network(n, plain_tail=True)
+        shift = 5 - n.bit_length() + 1
+        for lane in range(32):
+            j = lane >> shift
+            assert got[lane] == _butterfly(j)[lane], (n, lane)
