@@ -264,7 +264,7 @@ def main_ours(args):
     # ---- per-kernel times (CUDA events around each recorded command), same steady state ---------------------
     ncmd = len(pipe.commands.children)
     names = pipe.command_labels
-    acc_ms = [0.0] * ncmd
+    probe_ms = [[] for _ in range(ncmd)]
     frame_lat = []
     nprobe = min(60, K)
     for f in range(Wm + K, Wm + K + nprobe):
@@ -279,8 +279,9 @@ def main_ours(args):
         pipe.end_frame(seq["cams"][i])
         torch.cuda.synchronize()
         for c in range(ncmd):
-            acc_ms[c] += evs[c].elapsed_time(evs[c + 1]) / nprobe
+            probe_ms[c].append(evs[c].elapsed_time(evs[c + 1]))
         frame_lat.append(evs[0].elapsed_time(evs[ncmd]))
+    acc_ms = [sorted(v)[len(v) // 2] for v in probe_ms]       # median over the probe frames: robust against a one-off hiccup
     frame_lat.sort()
     # one frame at a time (device idle before each): the latency a frame-by-frame caller sees (median, p95)
     latency = {"median": round(frame_lat[len(frame_lat) // 2], 5), "p95": round(frame_lat[min(len(frame_lat) - 1, int(0.95 * len(frame_lat)))], 5),
