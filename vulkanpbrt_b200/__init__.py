@@ -7,4 +7,5 @@ from .modules import (BFR, BMFR, Accumulator, AccumulationBuffer, BFRBlender, Ca
                       DenoisingBlockSize, DenoisingType, DescriptorImage, GBuffer, IlluminationBuffer,
                       IlluminationBufferDemodulated, IlluminationBufferDemodulatedFloat, IlluminationBufferFinal,
                       IlluminationBufferFinalDemodulated, PushConstants, Taa, add_denoiser_to_commands)
+from .matrix_io import export_matrices, import_matrices  # noqa: F401
 from .pipeline import DenoisePipeline  # noqa: F401

@@ -116,6 +116,22 @@ class DenoisePipeline:
         self.push_constants.value.prev_view = capi.mat16(cam.view)    # :591
         self._prev_camera = cam
 
+    def run_frame_with_matrices(self, frame_index: int, frame, matrices) -> None:
+        """offline mode as main() drives it (VulkanPBRT.cpp:566-573): the frame's planes are staged and the accumulator
+        gets camera_matrices[f] and camera_matrices[f-1] straight from the imported file (matrix_io.import_matrices)"""
+        self.upload_frame(frame)
+        cur = matrices[frame_index]
+        prev = matrices[frame_index - 1] if frame_index > 0 else cur
+        pc = self.push_constants.value
+        pc.view_inverse = capi.mat16(cur.inv_view)
+        if cur.inv_proj is not None:
+            pc.proj_inverse = capi.mat16(cur.inv_proj)
+        pc.frame_number = frame_index
+        pc.sample_number = 0
+        self.accumulator.set_camera_matrices(frame_index, cur, prev)
+        self.record()
+        pc.prev_view = capi.mat16(cur.view)
+
     def upload_frame(self, frame) -> None:
         """stager->transfer_staging_data_from(frame) (:568-569)"""
         self.g_buffer.depth.upload(frame.depth, sync=False)
