@@ -150,6 +150,13 @@ inline float __shfl_sync(unsigned, float v, int src)
     return v;
 }
 
+inline int __all_sync(unsigned, int pred)
+{
+    uint32_t v = pred ? 1u : 0u;
+    for (int off = 16; off >= 1; off >>= 1) v &= hostsim::warp_exchange(v, hostsim::blk()->cur->lane ^ off);
+    return (int)v;
+}
+
 // ---- intrinsics ---------------------------------------------------------------------------------------
 // (the emulator build uses -ffp-contract=off, so plain operators are the _rn forms)
 inline float __fmul_rn(float a, float b) { return a * b; }
