@@ -81,6 +81,21 @@ def test_kernel_unorm8_decode_is_the_exact_quotient_for_all_codes():
         assert q == np.float32(c) / np.float32(255.0), c
 
 
+def test_block_coordinate_division_by_reciprocal_is_exact():
+    """bmfr.cu evaluates i / (B - 1), i = 0 .. B-1, as q0 = i*r, e = fma(-q0, B-1, i), q = fma(e, r, q0) with r = RN(1/(B-1)):
+    must equal the IEEE quotient the oracle computes, for every block size"""
+    from fractions import Fraction
+    for B in (8, 16, 32):
+        b = Fraction(B - 1)
+        r = Fraction(float(np.float32(1.0) / np.float32(B - 1)))
+        for i in range(B):
+            a = Fraction(i)
+            q0 = Fraction(float(_round_f32(a * r)))
+            e = Fraction(float(_round_f32(a - q0 * b)))
+            q = _round_f32(e * r + q0)
+            assert q == np.float32(i) / np.float32(B - 1), (B, i)
+
+
 # SURVEY.md App. A.2: ivec2(vec2(b, b) * pixelOffsets[f % 16]) for the table of bmfrGeneral.comp:36
 BMFR_OFFSETS = {
     32: [(22, 27), (30, 16), (13, 24), (31, 0), (11, 18), (0, 11), (25, 14), (0, 24), (11, -2), (-1, 0), (30, 3), (27, 19),
