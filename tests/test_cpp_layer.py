@@ -45,3 +45,33 @@ def test_cpp_layer_on_emulator(tmp_path, oracle, denoiser, taa):
 @pytest.mark.parametrize("denoiser,taa", [("bmfr", True), ("bfr", False)])
 def test_cpp_layer_on_gpu(tmp_path, oracle, denoiser, taa):
     _run(tmp_path, oracle, ROOT / "vulkanpbrt_b200" / "lib", "vkpbrt_b200", denoiser, taa, W=640, H=360, frames=4)
+
+
+@pytest.mark.parametrize("W,H,world,taa", [(1920, 1080, 2, True), (1920, 2160, 2, False), (3840, 2160, 4, True), (3840, 2160, 8, True),
+                                           (1920, 8640, 8, False), (7680, 4320, 8, False), (640, 360, 4, True)])
+def test_cpp_band_plan_equals_the_python_plan(tmp_path, W, H, world, taa):
+    """include/vkpbrt/band_plan.hpp (what a C++ host shards with) against vulkanpbrt_b200/multigpu.py BandPlan: band
+    boundaries, owned / accumulated / input rows and every transfer list, over a full jitter period"""
+    from vulkanpbrt_b200.multigpu import BandPlan
+    exe = tmp_path / "band_plan_dump"
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-I", str(ROOT / "include"), str(ROOT / "examples" / "band_plan_dump.cpp"), "-o", str(exe)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    frames = 17
+    got = subprocess.run([str(exe), str(W), str(H), str(world), "1" if taa else "0", str(frames)], capture_output=True, text=True).stdout.split("\n")
+    try:
+        plan = BandPlan(W, H, world, 32, 24, taa)
+    except ValueError as e:
+        assert got[0].startswith("error"), got[0]
+        assert "edge regions" in str(e)
+        return
+    want = [f"brow {b}" for b in plan.brow]
+    want += [f"input {g} {plan.input_rows(g)[0]} {plan.input_rows(g)[1]}" for g in range(world)]
+    for f in range(frames):
+        for g in range(world):
+            o, a = plan.owned_rows(g, f), plan.accumulate_rows(g, f)
+            want.append(f"rows {f} {g} {o[0]} {o[1]} {a[0]} {a[1]}")
+        want += [f"history {f + 1} {t.src} {t.dst} {t.plane} {t.rows[0]} {t.rows[1]}" for t in plan.history_transfers(f + 1)]
+        want += [f"stale {f} {t.src} {t.dst} {t.plane} {t.rows[0]} {t.rows[1]}" for t in plan.stale_column_transfers(f)]
+        want += [f"final {f} {t.src} {t.dst} {t.plane} {t.rows[0]} {t.rows[1]}" for t in plan.final_transfers(f)]
+    assert [line for line in got if line] == want
