@@ -155,4 +155,5 @@ void launch(dim3 grid, dim3 block, const std::function<void()>& body)
 #include "../../vulkanpbrt_b200/csrc/bmfr.cu"
 #include "../../vulkanpbrt_b200/csrc/bfr.cu"
 #include "../../vulkanpbrt_b200/csrc/taa.cu"
+#include "../../vulkanpbrt_b200/csrc/halo.cu"
 #include "../../vulkanpbrt_b200/csrc/api.cpp"

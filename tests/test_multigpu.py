@@ -234,3 +234,88 @@ def test_banded_chain_on_gpus_equals_single_gpu(tmp_path, world, mode):
             (lo, hi), band_f, band_d = per_rank[r][f]
             np.testing.assert_array_equal(band_f, full_final[lo:hi], err_msg=f"final, frame {f}, rank {r}")
             np.testing.assert_array_equal(band_d, full_den[lo:hi], err_msg=f"denoised, frame {f}, rank {r}")
+
+
+# ---- the NVLink peer-memory exchange protocol on the CPU: ranks are THREADS over the test emulator ----------------
+class _ThreadGroup:
+    """all_gather_object for ranks that are threads of this process"""
+
+    def __init__(self, world):
+        import threading
+        self.world, self.slots, self.barrier = world, [None] * world, threading.Barrier(world)
+
+    def rank_view(self, rank):
+        group = self
+
+        class _Dist:
+            def all_gather_object(self, out, obj):
+                group.slots[rank] = obj
+                group.barrier.wait()
+                out[:] = list(group.slots)
+                group.barrier.wait()
+        return _Dist()
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("world,use_taa,W,H,frames", [(2, True, 64, 416, 20), (3, True, 64, 416, 20), (3, False, 96, 384, 12)])
+def test_peer_memory_exchange_protocol_on_the_emulator(world, use_taa, W, H, frames):
+    """PeerDirect + vkpbrt_halo_exchange_* + k_halo_push / k_halo_wait, compiled for the CPU: every rank is an OS thread
+    with its own context and pipeline, "peer" memory is the shared address space, flag words are real atomics and the
+    ranks run at whatever speed the scheduler gives them.  The banded result must equal the single-rank one bit for
+    bit (a protocol error shows up as stale halo rows, or as a flag wait running into its timeout)."""
+    import subprocess
+    import threading
+    import time
+    subprocess.run(["make", "-C", str(ROOT / "tests" / "hostsim")], check=True, capture_output=True)
+    from vulkanpbrt_b200 import Context, DenoisePipeline, _capi, synth
+    from vulkanpbrt_b200.multigpu import BandedPipeline, PeerDirect
+    saved = _capi._lib
+    _capi._lib = _capi.configure(ctypes.CDLL(str(ROOT / "tests" / "hostsim" / "libvkpbrt_hostsim.so")))
+    try:
+        group = _ThreadGroup(world)
+        results, errors = [None] * world, []
+
+        def rank_main(rank):
+            try:
+                ctx = Context(0)
+                peer = PeerDirect(group.rank_view(rank), rank, world, None, ctx, timeout_ms=120000, comm_stream=0)
+                bp = BandedPipeline(W, H, rank, world, use_taa, ctx, None, max_disp_rows=12, external_inputs=False, peer=peer)
+                lo, hi = bp.plan.input_rows(rank)
+                out = []
+                for f in range(frames):
+                    fr = synth.render_frame(W, H, f, rows=(lo, hi))
+                    bp.pipe.upload_frame(fr)
+                    bp.run_frame(f, fr.camera)
+                    o = bp.owned_rows(f)
+                    out.append((o, bp.pipe.final.download()[o[0]:o[1]].copy(), bp.bmfr.denoised.download()[(f & 1) ^ 1, o[0]:o[1]].copy()))
+                    if (f + rank) % 3 == 0:         # keep the ranks out of step
+                        time.sleep(0.004 * (1 + (rank + f) % 4))
+                bp.flush()
+                bp.check()
+                results[rank] = (out, bp, peer)       # handles stay alive until every rank is done writing into them
+            except BaseException as e:      # noqa: BLE001 -- reported by the main thread
+                errors.append((rank, e))
+                group.barrier.abort()
+
+        threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        assert not errors, errors
+        pipe = DenoisePipeline(W, H, use_taa=use_taa)
+        for f in range(frames):
+            pipe.run_frame(f, synth.render_frame(W, H, f))
+            full_final = pipe.final.download()
+            full_den = pipe.modules[0].denoised.download()[(f & 1) ^ 1]
+            for r in range(world):
+                (lo, hi), band_f, band_d = results[r][0][f]
+                np.testing.assert_array_equal(band_f, full_final[lo:hi], err_msg=f"final, frame {f}, rank {r}")
+                np.testing.assert_array_equal(band_d, full_den[lo:hi], err_msg=f"denoised, frame {f}, rank {r}")
+        for r in range(world):
+            results[r][2].close()
+        del pipe, results
+    finally:
+        import gc
+        gc.collect()
+        _capi._lib = saved

@@ -1229,7 +1229,6 @@ int vkpbrt_external_semaphore_destroy(vkpbrt_external_semaphore_t s)
 }
 
 // ---- band-sharded runs: NVLink peer memory -----------------------------------------------------------
-#ifndef VKPBRT_HOSTSIM
 using vkpbrt::HaloCopy;
 using vkpbrt::HaloPushParams;
 using vkpbrt::HaloWaitParams;
@@ -1241,6 +1240,9 @@ int vkpbrt_peer_export(vkpbrt_context_t ctx, const void* device_ptr, uint8_t han
 {
     VK_REQUIRE(ctx && device_ptr && handle && offset, "null argument");
     VK_CUDA(cudaSetDevice(ctx->device));
+#ifdef VKPBRT_HOSTSIM
+    unsigned long long base = (unsigned long long)(uintptr_t)device_ptr;     // test emulator: one address space
+#else
     // the handle names the whole allocation: find its base through the driver entry point the runtime already holds
     typedef int (*range_fn)(unsigned long long*, size_t*, unsigned long long);
     void* fn = nullptr;
@@ -1251,6 +1253,7 @@ int vkpbrt_peer_export(vkpbrt_context_t ctx, const void* device_ptr, uint8_t han
     size_t size = 0;
     const int rc = reinterpret_cast<range_fn>(fn)(&base, &size, (unsigned long long)(uintptr_t)device_ptr);
     VK_REQUIRE(rc == 0 && base != 0, "not a device allocation");
+#endif
     cudaIpcMemHandle_t h;
     VK_CUDA(cudaIpcGetMemHandle(&h, reinterpret_cast<void*>((uintptr_t)base)));
     memcpy(handle, &h, sizeof(h));
@@ -1383,15 +1386,6 @@ int vkpbrt_halo_exchange_destroy(vkpbrt_halo_exchange_t x)
     delete x;
     return VKPBRT_OK;
 }
-#else
-int vkpbrt_peer_export(vkpbrt_context_t, const void*, uint8_t*, uint64_t*) { return fail(VKPBRT_ERR_UNSUPPORTED, "peer memory needs CUDA devices"); }
-int vkpbrt_peer_open(vkpbrt_context_t, const uint8_t*, void**) { return fail(VKPBRT_ERR_UNSUPPORTED, "peer memory needs CUDA devices"); }
-int vkpbrt_peer_close(vkpbrt_context_t, void*) { return fail(VKPBRT_ERR_UNSUPPORTED, "peer memory needs CUDA devices"); }
-int vkpbrt_halo_exchange_create(vkpbrt_context_t, const vkpbrt_halo_exchange_desc*, uint32_t, vkpbrt_halo_exchange_t*) { return fail(VKPBRT_ERR_UNSUPPORTED, "peer memory needs CUDA devices"); }
-int vkpbrt_halo_exchange_start(vkpbrt_halo_exchange_t, void*, void*, uint32_t) { return fail(VKPBRT_ERR_UNSUPPORTED, "peer memory needs CUDA devices"); }
-int vkpbrt_halo_exchange_wait(vkpbrt_halo_exchange_t, void*, uint32_t) { return fail(VKPBRT_ERR_UNSUPPORTED, "peer memory needs CUDA devices"); }
-int vkpbrt_halo_exchange_stats(vkpbrt_halo_exchange_t, uint64_t*, uint64_t*, uint32_t*) { return fail(VKPBRT_ERR_UNSUPPORTED, "peer memory needs CUDA devices"); }
-int vkpbrt_halo_exchange_destroy(vkpbrt_halo_exchange_t) { return VKPBRT_OK; }
-#endif
+
 
 }  // extern "C"

@@ -18,6 +18,7 @@ namespace vkpbrt {
 
 namespace {
 
+#ifndef VKPBRT_HOSTSIM
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
 {
     uint32_t v;
@@ -36,6 +37,16 @@ __device__ __forceinline__ unsigned long long global_timer_ns()
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+#else   // test emulator: ranks are OS threads of one process
+inline uint32_t ld_acquire_sys(const uint32_t* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+inline void st_release_sys(uint32_t* p, uint32_t v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+inline unsigned long long global_timer_ns()
+{
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (unsigned long long)ts.tv_sec * 1000000000ull + (unsigned long long)ts.tv_nsec;
+}
+#endif
 
 // returns the nanoseconds spent spinning
 __device__ unsigned long long spin_until(const uint32_t* flag, uint32_t value, unsigned long long timeout_ns, uint32_t* error)
@@ -130,13 +141,13 @@ __global__ void __launch_bounds__(32) k_halo_wait(const HaloWaitParams p)
 cudaError_t launch_halo_push(const HaloPushParams& p, int parts, cudaStream_t stream)
 {
     dim3 grid((unsigned)parts, (unsigned)(p.n_copies > 0 ? p.n_copies : 1));
-    k_halo_push<<<grid, 256, 0, stream>>>(p);
+    VKPBRT_LAUNCH(k_halo_push, grid, dim3(256, 1, 1), 0, stream, p);
     return cudaGetLastError();
 }
 
 cudaError_t launch_halo_wait(const HaloWaitParams& p, cudaStream_t stream)
 {
-    k_halo_wait<<<1, 32, 0, stream>>>(p);
+    VKPBRT_LAUNCH(k_halo_wait, dim3(1, 1, 1), dim3(32, 1, 1), 0, stream, p);
     return cudaGetLastError();
 }
 

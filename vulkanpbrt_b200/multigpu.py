@@ -263,10 +263,10 @@ class PeerDirect:
 
     GROUPS = {"A": 0, "B": 1, "F": 2}
 
-    def __init__(self, dist, rank: int, world: int, device, ctx, timeout_ms: int = 20000):
+    def __init__(self, dist, rank: int, world: int, device, ctx, timeout_ms: int = 20000, comm_stream: int = None):
+        """dist: anything with all_gather_object(out_list, obj) (torch.distributed on GPUs).  comm_stream: a cudaStream_t to
+        use instead of creating a high-priority torch stream (the CPU tests pass 0)."""
         import ctypes as C
-
-        import torch
 
         from . import _capi as capi
         from .modules import DescriptorImage
@@ -274,18 +274,23 @@ class PeerDirect:
             raise ValueError(f"at most {capi.HALO_MAX_PEERS} ranks per node")
         self.C, self.capi, self.dist, self.rank, self.world, self.ctx = C, capi, dist, rank, world, ctx
         self.timeout_ms = timeout_ms
-        # high priority: an exchange kernel is launched while the main stream keeps all SMs busy (k_bmfr_block, or the next
-        # frame's k_accumulate) and its few CTAs should be dispatched ahead of the main kernel's pending ones
-        # (measured at N = 2: no difference either way -- the remaining ~25 us per banded frame are kernel boundaries)
-        self.stream = torch.cuda.Stream(device=device, priority=-1)
         self.device = device
+        if comm_stream is None:
+            import torch
+            # high priority: an exchange kernel is launched while the main stream keeps all SMs busy (k_bmfr_block, or the
+            # next frame's k_accumulate) and its few CTAs should be dispatched ahead of the main kernel's pending ones
+            # (measured at N = 2: no difference either way -- the remaining ~25 us per banded frame are kernel boundaries)
+            self.stream = torch.cuda.Stream(device=device, priority=-1)
+            comm_stream = self.stream.cuda_stream
+        else:
+            self.stream = None
         self.flags = DescriptorImage.create(ctx, capi.FORMAT_R32_SFLOAT, max(16, 4 * world), 1)
         self.flags.compile()            # allocates, zero-initialised
         ctx.synchronize()
         self._exchanges: list = []
         lib = capi.lib()
         self._start_fn, self._wait_fn = lib.vkpbrt_halo_exchange_start, lib.vkpbrt_halo_exchange_wait
-        self._comm = self.stream.cuda_stream
+        self._comm = comm_stream
         self._opened: Dict = {}         # (rank, handle bytes) -> mapped base
         self.seq = {"A": 0, "B": 0, "F": 0}
         mine = self.export(self.flags.device_ptr)
