@@ -416,6 +416,7 @@ public:
     ~PeerMemory() { vkpbrt_peer_close(_ctx->handle, _base); }
     PeerMemory(const PeerMemory&) = delete;
     void* data() const { return static_cast<uint8_t*>(_base) + _offset; }   // the address the exporter passed to peer_export
+    void* base() const { return _base; }   // start of the exporter's allocation: open each allocation ONCE, add PeerHandle::offset per pointer
 private:
     ref_ptr<Context> _ctx;
     void* _base = nullptr;

@@ -75,3 +75,32 @@ def test_cpp_band_plan_equals_the_python_plan(tmp_path, W, H, world, taa):
         want += [f"stale {f} {t.src} {t.dst} {t.plane} {t.rows[0]} {t.rows[1]}" for t in plan.stale_column_transfers(f)]
         want += [f"final {f} {t.src} {t.dst} {t.plane} {t.rows[0]} {t.rows[1]}" for t in plan.final_transfers(f)]
     assert [line for line in got if line] == want
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("world,taa", [(2, True), (3, True), (3, False)])
+def test_cpp_banded_ranks_on_emulator(tmp_path, oracle, world, taa):
+    """examples/cpp_banded_ranks.cpp: BandPlan + PeerMemory + HaloExchange + the modules' band ranges, ranks as threads
+    over the test emulator; the frame assembled from the ranks' owned rows must equal the oracle bit for bit"""
+    subprocess.run(["make", "-C", str(ROOT / "tests" / "hostsim")], check=True, capture_output=True)
+    libdir = ROOT / "tests" / "hostsim"
+    exe = tmp_path / "cpp_banded_ranks"
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-I", str(ROOT / "include"), str(ROOT / "examples" / "cpp_banded_ranks.cpp"), "-o", str(exe),
+                        f"-L{libdir}", "-lvkpbrt_hostsim", f"-Wl,-rpath,{libdir}", "-lpthread"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    W, H, frames = 64, 416, 19
+    orc = oracle.OracleChain(W, H, "bmfr", 32, use_taa=taa)
+    want = []
+    for f in range(frames):
+        fr = synth.render_frame(W, H, f)
+        base = tmp_path / f"frame_{f}"
+        fr.depth.tofile(str(base) + ".depth"); fr.normal.tofile(str(base) + ".normal")
+        fr.albedo.tofile(str(base) + ".albedo"); fr.illumination.tofile(str(base) + ".illum")
+        np.concatenate([fr.camera.view, fr.camera.inv_view, fr.camera.proj, fr.camera.inv_proj]).astype(np.float32).tofile(str(base) + ".cam")
+        orc.run_frame(f, fr)
+        want.append(orc.final().copy())
+    r = subprocess.run([str(exe), str(tmp_path), str(W), str(H), str(frames), str(world), "1" if taa else "0"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    for f in range(frames):
+        got = np.fromfile(tmp_path / f"final_{f}.bgra", dtype=np.uint8).reshape(H, W, 4)
+        np.testing.assert_array_equal(got, want[f], err_msg=f"frame {f}")
