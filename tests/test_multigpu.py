@@ -257,7 +257,8 @@ class _ThreadGroup:
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("world,use_taa,W,H,frames", [(2, True, 64, 416, 20), (3, True, 64, 416, 20), (3, False, 96, 384, 12)])
+@pytest.mark.parametrize("world,use_taa,W,H,frames", [(2, True, 64, 416, 20), (3, True, 64, 416, 20), (3, False, 96, 384, 12),
+                                                       (2, True, 101, 400, 12)])      # odd width: unaligned rows take the 4-byte / 1-byte copy paths
 def test_peer_memory_exchange_protocol_on_the_emulator(world, use_taa, W, H, frames):
     """PeerDirect + vkpbrt_halo_exchange_* + k_halo_push / k_halo_wait, compiled for the CPU: every rank is an OS thread
     with its own context and pipeline, "peer" memory is the shared address space, flag words are real atomics and the
