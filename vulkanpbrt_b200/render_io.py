@@ -1,0 +1,246 @@
+"""Offline sequence I/O: the reference's way of feeding pre-rendered sequences.
+
+Host-side mirror of `GBufferIO` and `IlluminationBufferIO` (source/io/RenderIO.cpp:6-158 import, :212-327 export,
+:329-398 conversions, :501-591 illumination): printf-style per-frame file names, OpenEXR planes, and the conversions
+between what is stored (world position / cartesian normal / float albedo, all rgba32f) and what the G-buffer holds
+(Euclidean depth r32f, spherical normal rg32f, albedo rgba8).  The EXR codec is OpenCV's bundled OpenEXR (the
+reference uses vsgXchange::openexr); planes come back in R, G, B, A channel order, row 0 at the top.
+
+The conversions run in binary32 like the reference's loops.  `acos` / `atan2` / `sin` / `cos` are the platform's libm
+in the reference and numpy's here: results agree to an ulp or two, which is below the fp16 / unorm8 storage of
+everything downstream -- but it means imported planes are inputs, not something parity is asserted on; parity is
+asserted on what the modules compute FROM the imported planes (tests/test_render_io.py).
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+from typing import List, Optional
+
+import numpy as np
+
+from .modules import CameraMatrices
+
+os.environ.setdefault("OPENCV_IO_ENABLE_OPENEXR", "1")     # OpenCV ships the codec disabled by default
+
+
+def _cv2():
+    import cv2
+    return cv2
+
+
+@dataclass
+class OfflineGBuffer:           # source/io/RenderIO.hpp: depth / normal / material / albedo as uploaded to the GBuffer
+    depth: Optional[np.ndarray] = None          # float32 [H][W]
+    normal: Optional[np.ndarray] = None         # float32 [H][W][2]  (theta, phi)
+    material: Optional[np.ndarray] = None       # uint8   [H][W][4]
+    albedo: Optional[np.ndarray] = None         # uint8   [H][W][4]
+
+
+@dataclass
+class OfflineIllumination:
+    noisy: Optional[np.ndarray] = None          # float32 [H][W][4]
+
+
+# ---- EXR planes --------------------------------------------------------------------------------------------------
+def read_exr(path) -> Optional[np.ndarray]:
+    """float32 [H][W] or [H][W][C] with channels in R, G, B, A order; None when the file cannot be read"""
+    cv2 = _cv2()
+    img = cv2.imread(str(path), cv2.IMREAD_UNCHANGED)
+    if img is None:
+        return None
+    img = np.asarray(img, dtype=np.float32)
+    if img.ndim == 3 and img.shape[2] >= 3:
+        img = img[..., [2, 1, 0] + list(range(3, img.shape[2]))]        # OpenCV hands back B, G, R(, A)
+    return np.ascontiguousarray(img)
+
+
+def write_exr(path, plane: np.ndarray) -> bool:
+    cv2 = _cv2()
+    a = np.asarray(plane, dtype=np.float32)
+    if a.ndim == 3 and a.shape[2] == 2:
+        raise ValueError("two-channel planes are converted before they are stored (spherical_to_cartesian)")
+    if a.ndim == 3 and a.shape[2] >= 3:
+        a = a[..., [2, 1, 0] + list(range(3, a.shape[2]))]
+    return bool(cv2.imwrite(str(path), np.ascontiguousarray(a), [cv2.IMWRITE_EXR_TYPE, cv2.IMWRITE_EXR_TYPE_FLOAT]))
+
+
+def _rgba(img: np.ndarray) -> np.ndarray:
+    """vec4Array2D view of whatever the file held (3-channel files get w = 1)"""
+    if img.ndim == 2:
+        img = img[..., None]
+    if img.shape[2] == 4:
+        return img
+    out = np.ones(img.shape[:2] + (4,), np.float32)
+    out[..., :min(3, img.shape[2])] = img[..., :3]
+    return out
+
+
+# ---- conversions (RenderIO.cpp:160-211, :329-398) -------------------------------------------------------------------
+class GBufferIO:
+    @staticmethod
+    def convert_normal_to_spherical(normals: np.ndarray) -> np.ndarray:
+        """:160-178  (theta, phi) = (acos(n.z), atan2(n.y, n.x))"""
+        n = _rgba(normals).astype(np.float32)
+        with np.errstate(invalid="ignore"):
+            return np.stack([np.arccos(n[..., 2]), np.arctan2(n[..., 1], n[..., 0])], axis=-1).astype(np.float32)
+
+    @staticmethod
+    def spherical_to_cartesian(normals: np.ndarray) -> np.ndarray:
+        """:329-346"""
+        t, p = normals[..., 0].astype(np.float32), normals[..., 1].astype(np.float32)
+        out = np.empty(normals.shape[:2] + (4,), np.float32)
+        out[..., 0] = np.cos(p) * np.sin(t)
+        out[..., 1] = np.sin(p) * np.sin(t)
+        out[..., 2] = np.cos(t)
+        out[..., 3] = 1.0
+        return out
+
+    @staticmethod
+    def compress_albedo(albedo: np.ndarray) -> np.ndarray:
+        """:180-211  float (or half) rgba -> rgba8 by `ubvec4 = vec4 * 255.0F`: the C++ conversion TRUNCATES; integer
+        inputs are taken as they are"""
+        a = np.asarray(albedo)
+        if a.dtype.kind in "ui":
+            return _rgba(a.astype(np.float32)).astype(np.uint8) if a.ndim == 3 and a.shape[2] != 4 else a.astype(np.uint8)
+        scaled = _rgba(a.astype(np.float32)) * np.float32(255.0)
+        return np.clip(np.trunc(scaled), 0, 255).astype(np.uint8)      # out-of-range values are undefined in the reference
+
+    @staticmethod
+    def unorm_to_float(array: np.ndarray) -> np.ndarray:
+        """:348-363"""
+        return (array.astype(np.float32) / np.float32(255.0)).astype(np.float32)
+
+    @staticmethod
+    def position_to_depth(position: np.ndarray, matrices: CameraMatrices) -> np.ndarray:
+        """:101-118  depth = |camera - p| with the camera position taken as column 2 of inv_view divided by its w: the
+        offline matrices are combined view-projections, for which that column of the inverse is the eye point"""
+        iv = np.asarray(matrices.inv_view, dtype=np.float32).reshape(4, 4)      # [col][row]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            cam = (iv[2] / iv[2][3])[:3].astype(np.float32)
+        d = cam[None, None, :] - _rgba(position)[..., :3].astype(np.float32)
+        return np.sqrt((d * d).sum(axis=-1, dtype=np.float32)).astype(np.float32)
+
+    @staticmethod
+    def depth_to_position(depth: np.ndarray, matrices: CameraMatrices) -> Optional[np.ndarray]:
+        """:365-398  needs separate view / projection matrices"""
+        if matrices.proj is None or matrices.inv_proj is None:
+            print("GBufferIO::depthToPosition: Camera matrix in wrong layout. Expected camera matrix with separate projection matrix")
+            return None
+        f = np.float32
+        H, W = depth.shape
+        ip = np.asarray(matrices.inv_proj, dtype=f).reshape(4, 4)       # [col][row]
+        iv = np.asarray(matrices.inv_view, dtype=f).reshape(4, 4)
+        x = ((np.arange(W, dtype=f) + f(.5)) / f(W) * f(2) - f(1))[None, :].repeat(H, 0)
+        y = ((np.arange(H, dtype=f) + f(.5)) / f(H) * f(2) - f(1))[:, None].repeat(W, 1)
+        clip = np.stack([x, y, np.ones_like(x), np.ones_like(x)], axis=-1)
+        d = np.einsum("cr,hwc->hwr", ip, clip).astype(f)                # m * v = sum_c col[c] * v[c]
+        d[..., 3] = 0
+        d = d / np.sqrt((d * d).sum(axis=-1, keepdims=True, dtype=f))
+        direction = np.einsum("cr,hwc->hwr", iv, d).astype(f)[..., :3] * depth[..., None].astype(f)
+        out = np.ones((H, W, 4), f)
+        out[..., :3] = iv[3][:3][None, None, :] + direction
+        return out
+
+    # ---- files -----------------------------------------------------------------------------------------------------
+    @staticmethod
+    def import_g_buffer_depth(depth_format: str, normal_format: str, material_format: str, albedo_format: str, num_frames: int,
+                              verbosity: int = 1) -> List[OfflineGBuffer]:
+        """:6-69  (the reference loads no material plane either)"""
+        out = []
+        for f in range(num_frames):
+            g = OfflineGBuffer()
+            out.append(g)
+            depth = read_exr(depth_format % f)
+            if depth is None:
+                print(f"Failed to load image: {depth_format % f}")
+                continue
+            g.depth = np.ascontiguousarray(depth[..., 0] if depth.ndim == 3 else depth)
+            if not GBufferIO._load_normal_albedo(g, normal_format % f, albedo_format % f):
+                continue
+        return out
+
+    @staticmethod
+    def import_g_buffer_position(position_format: str, normal_format: str, material_format: str, albedo_format: str,
+                                 matrices: List[CameraMatrices], num_frames: int, verbosity: int = 1) -> List[OfflineGBuffer]:
+        """:71-158"""
+        out = []
+        for f in range(num_frames):
+            g = OfflineGBuffer()
+            out.append(g)
+            pos = read_exr(position_format % f)
+            if pos is None:
+                print(f"Failed to load image: {position_format % f}")
+                continue
+            if pos.ndim != 3 or pos.shape[2] < 3:
+                print("Unexpected position format")
+                continue
+            g.depth = GBufferIO.position_to_depth(pos, matrices[f])
+            GBufferIO._load_normal_albedo(g, normal_format % f, albedo_format % f)
+        return out
+
+    @staticmethod
+    def _load_normal_albedo(g: OfflineGBuffer, normal_path: str, albedo_path: str) -> bool:
+        normal = read_exr(normal_path)
+        if normal is None:
+            print(f"Failed to load image: {normal_path}")
+            return False
+        g.normal = GBufferIO.convert_normal_to_spherical(normal)
+        albedo = read_exr(albedo_path)
+        if albedo is None:
+            print(f"Failed to load image: {albedo_path}")
+            return False
+        g.albedo = GBufferIO.compress_albedo(albedo)
+        g.material = np.zeros(g.albedo.shape, np.uint8)
+        return True
+
+    @staticmethod
+    def export_g_buffer(position_format: str, depth_format: str, normal_format: str, material_format: str, albedo_format: str,
+                        num_frames: int, g_buffers: List[OfflineGBuffer], matrices: List[CameraMatrices], verbosity: int = 1) -> bool:
+        """:212-327  empty format strings skip a plane"""
+        fine = True
+        for f in range(num_frames):
+            g = g_buffers[f]
+            jobs = []
+            if depth_format:
+                jobs.append((depth_format % f, g.depth))
+            if position_format:
+                jobs.append((position_format % f, GBufferIO.depth_to_position(g.depth, matrices[f])))
+            if normal_format:
+                jobs.append((normal_format % f, GBufferIO.spherical_to_cartesian(g.normal)))
+            if material_format:
+                jobs.append((material_format % f, GBufferIO.unorm_to_float(g.material)))
+            if albedo_format:
+                jobs.append((albedo_format % f, GBufferIO.unorm_to_float(g.albedo)))
+            for path, plane in jobs:
+                if plane is None or not write_exr(path, plane):
+                    print(f"Failed to store image: {path}")
+                    fine = False
+                    break
+        return fine
+
+
+class IlluminationBufferIO:
+    @staticmethod
+    def import_illumination(illumination_format: str, num_frames: int, verbosity: int = 1) -> List[OfflineIllumination]:
+        """:501-548"""
+        out = []
+        for f in range(num_frames):
+            illu = OfflineIllumination()
+            out.append(illu)
+            img = read_exr(illumination_format % f)
+            if img is None:
+                print(f"Failed to load image: {illumination_format % f}")
+                continue
+            illu.noisy = np.ascontiguousarray(_rgba(img))
+        return out
+
+    @staticmethod
+    def export_illumination(illumination_format: str, num_frames: int, illus: List[OfflineIllumination], verbosity: int = 1) -> bool:
+        """:550-591"""
+        fine = True
+        for f in range(num_frames):
+            if not write_exr(illumination_format % f, illus[f].noisy):
+                print(f"Faled to store image: {illumination_format % f}")
+                fine = False
+        return fine
