@@ -68,7 +68,7 @@ def test_position_round_trip_recovers_depth(tmp_path):
     assert GBufferIO.depth_to_position(fr.depth, CameraMatrices(view=c.view, inv_view=c.inv_view)) is None
 
 
-@pytest.mark.parametrize("backend", backend_params(), indirect=True)
+@pytest.mark.parametrize("backend", backend_params()[:1], indirect=True)      # host-side I/O: the emulator backend is enough
 def test_exported_sequence_imports_and_drives_the_modules(tmp_path, backend, oracle, capsys):
     """export a synthetic sequence the way the reference stores it (EXR: depth, cartesian normals, float albedo, 1-spp
     illumination), import it back and denoise it: every plane equals the oracle fed with the same imported planes"""
