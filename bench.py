@@ -312,6 +312,22 @@ def main_ours(args):
                 "chain_fused_bytes_per_pixel": BYTES_CHAIN_FUSED,
                 "chain_achieved_gbs": round(BYTES_CHAIN_FUSED * W * H / (ms / K * 1e-3) / 1e9, 1)}
 
+    # the dominant kernel is bound by instruction issue, not by HBM: report that roofline too.  Warp instructions per
+    # launch come from the committed ncu capture of this workload (like `traffic`); peak = SMs x 4 schedulers x clock.
+    try:
+        ip = ROOT / "profiles" / "roofline_instructions.json"
+        inst = json.loads(ip.read_text()).get(name, {}).get(dom) if ip.exists() else None
+        mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz")
+        if inst and mhz:
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            peak = sms * 4 * mhz * 1e6
+            achieved = inst / (kernels[dom]["ms"] * 1e-3)
+            roofline["issue"] = {"warp_instructions_per_launch": int(inst), "achieved_ginst_per_s": round(achieved / 1e9, 1),
+                                 "peak_ginst_per_s": round(peak / 1e9, 1), "frac": round(achieved / peak, 3),
+                                 "source": "smsp__inst_executed.sum of profiles/*_ncu_summary (same workload), SMs x 4 issue slots x SM clock"}
+    except Exception as e:  # pragma: no cover -- never let a reporting extra break the line
+        roofline["issue"] = {"error": type(e).__name__}
+
     # ---- e2e: host buffers, H2D + D2H inside the timed region ------------------------------------------------
     del pipe
     pipe = make_pipe()

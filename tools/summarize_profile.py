@@ -50,6 +50,7 @@ def main():
     md = [f"# ncu --set full summary ({tag}, workload {workload})", "",
           f"Source report: `{Path(rep).name}` (scratch, not tracked); command: see tools/gpu_round.sh.", ""]
     traffic = {}
+    instructions = {}
     seen = set()
     for r in rows[2:]:
         name = r[idx["Kernel Name"]]
@@ -67,6 +68,8 @@ def main():
             return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
         short = name.split("(")[0].replace("void ", "").replace("vkpbrt::", "").replace(" ", "")
         traffic[short] = int(num("dram__bytes_read.sum") + num("dram__bytes_write.sum"))
+        if "smsp__inst_executed.sum" in idx:
+            instructions[short] = int(float(r[idx["smsp__inst_executed.sum"]].replace(",", "")))
     (out / f"{tag}_ncu_summary_{workload}.md").write_text("\n".join(md))
     # launch list: per-kernel statistics + the raw csv
     lr = [r for r in csv.reader(open(launches)) if len(r) > 10 and r[0].isdigit()]
@@ -85,6 +88,10 @@ def main():
     allt = json.loads(tp.read_text()) if tp.exists() else {}
     allt[workload] = {("k_bmfr_block<32,256>" if "bmfr" in k else k): v for k, v in traffic.items()}
     tp.write_text(json.dumps(allt, indent=1))
+    ip = out / "roofline_instructions.json"       # warp instructions per launch: bench.py's issue-slot roofline
+    alli = json.loads(ip.read_text()) if ip.exists() else {}
+    alli[workload] = {("k_bmfr_block<32,256>" if "bmfr" in k else k): v for k, v in instructions.items()}
+    ip.write_text(json.dumps(alli, indent=1))
     print("\n".join(lines))
 
 
