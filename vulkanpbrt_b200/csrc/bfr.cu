@@ -90,6 +90,8 @@ __global__ void __launch_bounds__(T, (T == 256 ? BFR_CTAS_B32 : (T == 64 ? BFR_C
     const int W = p.W, H = p.H;
     const uint32_t frame = p.frame;
     const int ox = c_bfr_offsets[frame & 15u][0], oy = c_bfr_offsets[frame & 15u][1];
+    // a block with no pixel inside the image stores nothing (bfr.comp:293 drops its pixels): skip its 40 descent steps
+    if (bx * B + ox >= p.W || bx * B + ox + B <= 0 || by * B + oy >= p.H || by * B + oy + B <= 0) return;
 
     // pixel q = t + s*T of the block (gl_LocalInvocationIndex = ly*B + lx): subgroup q / 32 = warp + s*NW,
     // lane q % 32 = lane
