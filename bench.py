@@ -302,7 +302,15 @@ def main_ours(args):
     if tp.exists():
         traffic = json.loads(tp.read_text()).get(name, {}).get(dom)
     # FP32 work of the fit (4.05e5 FLOP per 32x32 block as FMAs; executed as separate mul/add)
-    nblocks = (W // 32 + 2) * (H // 32 + 2)
+    # blocks of the padded, jittered grid that hold at least one image pixel (the others are not fitted), mean over the 16 phases
+    from vulkanpbrt_b200.multigpu import block_offset
+
+    def fitted(frame):
+        ox, oy = block_offset(32, frame)
+        nx = sum(1 for bx in range(W // 32 + 2) if bx * 32 - ox < W and bx * 32 - ox + 32 > 0)
+        ny = sum(1 for by in range(H // 32 + 2) if by * 32 - oy < H and by * 32 - oy + 32 > 0)
+        return nx * ny
+    nblocks = sum(fitted(f) for f in range(16)) / 16.0
     roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
                 "frac": round(kernels[dom]["achieved_gbs"] / hbm_peak, 4), "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": per_kernel_bytes[dom] * W * H,
