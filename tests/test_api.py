@@ -36,6 +36,22 @@ def test_product_library_has_no_cpu_fallback():
     assert e.value.code == _capi.ERR_NO_DEVICE
 
 
+def test_halo_entry_points_reject_null_arguments_without_a_device():
+    """argument checks of the multi-GPU entry points come before any CUDA call: callable on a machine without a GPU"""
+    from vulkanpbrt_b200 import _capi
+    lib = _capi.configure(ctypes.CDLL(str(ROOT / "vulkanpbrt_b200" / "lib" / "libvkpbrt_b200.so")))
+    out = ctypes.c_void_p()
+    off = ctypes.c_uint64()
+    buf = (ctypes.c_uint8 * 64)()
+    assert lib.vkpbrt_peer_export(None, None, buf, ctypes.byref(off)) == _capi.ERR_INVALID_ARGUMENT
+    assert lib.vkpbrt_peer_open(None, buf, ctypes.byref(out)) == _capi.ERR_INVALID_ARGUMENT
+    assert lib.vkpbrt_halo_exchange_create(None, None, 1000, ctypes.byref(out)) == _capi.ERR_INVALID_ARGUMENT
+    assert lib.vkpbrt_halo_exchange_start(None, None, None, 1) == _capi.ERR_INVALID_ARGUMENT
+    assert lib.vkpbrt_halo_exchange_wait(None, None, 1) == _capi.ERR_INVALID_ARGUMENT
+    assert lib.vkpbrt_halo_exchange_destroy(None) == _capi.OK
+    assert b"null" in lib.vkpbrt_last_error()
+
+
 def test_product_library_contains_sm100a_code_only():
     import shutil
     import subprocess
