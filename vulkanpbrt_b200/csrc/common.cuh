@@ -69,14 +69,17 @@ VK_DEVICE bool in_pow2_range(float x, uint32_t lo_bits, uint32_t hi_bits)   // l
 VK_DEVICE bool safe_divisor(float b) { return in_pow2_range(b, 0x2b800000u, 0x53800000u); }        // 2^-40 .. 2^40
 VK_DEVICE bool safe_factor(float x)                                                               // 0 or 2^-30 .. 2^30
 {
-    return (__float_as_uint(x) & 0x7fffffffu) == 0u || in_pow2_range(x, 0x30800000u, 0x4e800000u);
+    // '|' on purpose: a short-circuit '||' (and '&&' chains of these tests in the callers) compiles to a branch inside a
+    // convergence-barrier region per test, which costs far more in the unrolled Householder stream than the test itself
+    const uint32_t a = __float_as_uint(x) & 0x7fffffffu;
+    return (a == 0u) | ((a - 0x30800000u) <= (0x4e800000u - 0x30800000u));
 }
 // a / b for a divisor whose reciprocal is reused: exact fast path when both operands are in range
 VK_DEVICE float div_guarded(float a, float b, float rb, bool b_safe)
 {
     const uint32_t ia = __float_as_uint(a) & 0x7fffffffu;
-    if (b_safe && (ia == 0u || (ia - 0x21800000u) <= (0x5d800000u - 0x21800000u)))     // 0 or 2^-60 .. 2^60
-        return div_by_rcp(a, b, rb);
+    const bool ok = b_safe & ((ia == 0u) | ((ia - 0x21800000u) <= (0x5d800000u - 0x21800000u)));     // 0 or 2^-60 .. 2^60; one branch
+    if (ok) return div_by_rcp(a, b, rb);
     return div_rn_cold(a, b);
 }
 
