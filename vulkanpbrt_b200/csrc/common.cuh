@@ -178,9 +178,8 @@ VK_DEVICE float unorm8_byte_to_f32(uint32_t texel, int k)
 // bmfrGeneral.comp:93-97 / bfr.comp:192-196
 VK_DEVICE int mirror(int x, int s)
 {
-    if (x < 0) return -x - 1;
-    if (x >= s) return 2 * s - x - 1;
-    return x;
+    const int below = -x - 1, above = 2 * s - x - 1;        // both candidates, then selects: no branch per pixel
+    return x < 0 ? below : (x >= s ? above : x);
 }
 
 // ---- bilinear sampler, REPEAT addressing, normalised coordinates ----
