@@ -168,9 +168,9 @@ __global__ void __launch_bounds__(T, (T == 256 ? BFR_CTAS_B32 : (T == 64 ? BFR_C
                 float pred = 0.0f;
 #pragma unroll
                 for (int j = 0; j < 7; ++j) pred = add_rn(pred, mul_rn(f[j], al[j * 3 + c]));   // :262-264
-                float d = sub_rn(noisy[s][c], pred);
-                if (l1[s]) d = (d > 0.0f) ? 1.0f : ((d < 0.0f) ? -1.0f : 0.0f);  // sign(), :267-268
-                r[c] = d;
+                const float d = sub_rn(noisy[s][c], pred);
+                const float sgn = (d > 0.0f) ? 1.0f : ((d < 0.0f) ? -1.0f : 0.0f);          // sign(), :267-268
+                r[c] = l1[s] ? sgn : d;                                                      // selects: no branch per pixel and step
             }
             float part[22];
 #pragma unroll
