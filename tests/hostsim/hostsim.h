@@ -40,7 +40,8 @@ struct dim3 {
     dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
 };
 struct uint2 { uint32_t x, y; };
-struct float2 { float x, y; };
+struct alignas(8) float2 { float x, y; };
+inline float2 make_float2(float x, float y) { return float2{x, y}; }
 struct alignas(16) float4 { float x, y, z, w; };
 struct uchar4 { uint8_t x, y, z, w; };
 struct alignas(16) uint4 { uint32_t x, y, z, w; };

@@ -157,6 +157,9 @@ struct vkpbrt_bmfr_s {
     vkpbrt_image_t denoised = nullptr, final_image = nullptr, features = nullptr, weights = nullptr;
     bool debug = false, force_generic = false, compiled = false;
     int block_row_begin, block_row_end;
+    // block-invariant per-frame table (csrc/bmfr.cu), double-buffered: slot f & 1 holds frame table_frame[f & 1]
+    float* table[2] = {nullptr, nullptr};
+    int64_t table_frame[2] = {-1, -1};
 };
 
 struct vkpbrt_bfr_s {
@@ -821,6 +824,13 @@ int vkpbrt_bmfr_compile(vkpbrt_bmfr_t b)
         if (!rc) rc = vkpbrt_image_compile(b->features);
         if (!rc) rc = vkpbrt_image_compile(b->weights);
     }
+    if (!rc && !b->table[0]) {
+        VK_CUDA(cudaSetDevice(b->ctx->device));
+        for (int i = 0; i < 2; ++i) {
+            VK_CUDA(cudaMalloc((void**)&b->table[i], vkpbrt::bmfr_table_floats((int)b->work) * sizeof(float)));
+            b->table_frame[i] = -1;
+        }
+    }
     if (!rc) b->compiled = true;
     return rc;
 }
@@ -864,8 +874,20 @@ int vkpbrt_bmfr_record(vkpbrt_bmfr_t b, const vkpbrt_push_constants* pc)
     p.dbg_features = b->debug ? (uint16_t*)b->features->data : nullptr;
     p.dbg_weights = b->debug ? (float*)b->weights->data : nullptr;
     p.force_generic = b->force_generic ? 1 : 0;
+    p.one = 1.0f; p.neg_one = -1.0f;
     VK_CUDA(cudaSetDevice(b->ctx->device));
+    // the frame's block-invariant table: normally written by the previous frame's launch (its spare CTAs produce the
+    // table of frame + 1); the first frame, or a frame number that does not follow the previous one, builds it here
+    const int slot = (int)(pc->frame_number & 1u);
+    if (b->table_frame[slot] != (int64_t)pc->frame_number) {
+        VK_CUDA(vkpbrt::launch_bmfr_table((int)b->work, b->table[slot], pc->frame_number, b->ctx->stream));
+        b->ctx->launches++;
+        b->table_frame[slot] = (int64_t)pc->frame_number;
+    }
+    p.table = b->table[slot];
+    p.table_next = b->table[slot ^ 1];
     VK_CUDA(vkpbrt::launch_bmfr(p, b->ctx->stream));
+    b->table_frame[slot ^ 1] = (int64_t)(uint32_t)(pc->frame_number + 1u);
     b->ctx->launches++;
     return VKPBRT_OK;
 }
@@ -897,6 +919,8 @@ int vkpbrt_bmfr_destroy(vkpbrt_bmfr_t b)
     vkpbrt_image_release(b->final_image);
     vkpbrt_image_release(b->features);
     vkpbrt_image_release(b->weights);
+    for (int i = 0; i < 2; ++i)
+        if (b->table[i]) cudaFree(b->table[i]);
     delete b;
     return VKPBRT_OK;
 }

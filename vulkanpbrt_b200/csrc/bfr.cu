@@ -66,6 +66,7 @@ struct BfrShared {
     float zmin[NSG], zmax[NSG];
     float zrange[2];
     int stop;
+    uint32_t thr[256];       // tone-map thresholds (common.cuh: tonemap_code)
 };
 
 // occupancy targets (CTAs per SM) of the three instantiations; A/B-tested on B200 (tools/bfr_variants.sh)
@@ -137,6 +138,7 @@ __global__ void __launch_bounds__(T, (T == 256 ? BFR_CTAS_B32 : (T == 64 ? BFR_C
     }
     if (lane == 0) { sm.zmin[warp] = zmin; sm.zmax[warp] = zmax; }
     if (t < 24) sm.alpha[t] = 0.0f;                                              // :235-237
+    for (int i = t; i < 256; i += T) sm.thr[i] = __ldg(c_tonemap_thr + i);
     if (t == 0) sm.stop = 0;
     __syncthreads();
     if (t == 0) {
@@ -236,7 +238,7 @@ __global__ void __launch_bounds__(T, (T == 256 ? BFR_CTAS_B32 : (T == 64 ? BFR_C
         cb = gl_clamp(cb, 0.0f, 10.0f);
         const size_t pix = pixs[s];
         denoise_epilogue(cr, cg, cb, frame, pix, W, H, __ldg(p.motion + pix), (uint32_t)__ldg(p.spp + pix),
-                         __ldg(p.albedo + pix), p.denoised_prev, p.denoised_next, p.final_bgra);
+                         __ldg(p.albedo + pix), p.denoised_prev, p.denoised_next, p.final_bgra, sm.thr);
     }
 }
 

@@ -83,6 +83,33 @@ VK_DEVICE float div_guarded(float a, float b, float rb, bool b_safe)
     return div_rn_cold(a, b);
 }
 
+// ---- packed fp32 pairs (sm_100: FMUL2 / FFMA2 issue two IEEE binary32 operations per instruction) ---------------
+// The block kernels are bound by instruction ISSUE, not by the FP32 pipe, so pairing independent operations halves
+// the slots their arithmetic needs while every lane still performs the same correctly rounded operation.
+// Two rules keep the results bit-identical to the scalar sequence:
+//   * ptxas contracts mul.rn.f32x2 followed by add.rn.f32x2 into one FFMA2 (single rounding) even with --fmad=false
+//     and even when the addition is written as fma(x, 1.0, y) with a literal 1.0, so an addition that consumes a
+//     product is issued as f2_fma(product, ONE, addend) with ONE = (1.0f, 1.0f) taken from a KERNEL PARAMETER:
+//     RN(product * 1 + addend) is the addition, and the assembler cannot see the multiplier;
+//   * a - b is f2_fma(b, NEG_ONE, a) for the same reason (no separate negation instruction either).
+#ifndef VKPBRT_HOSTSIM
+struct f2 { unsigned long long v; };
+VK_DEVICE f2 f2_make(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi)); return r; }
+VK_DEVICE float f2_lo(f2 a) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); (void)hi; return lo; }
+VK_DEVICE float f2_hi(f2 a) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); (void)lo; return hi; }
+VK_DEVICE f2 f2_mul(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+VK_DEVICE f2 f2_fma(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r; }
+#else
+struct f2 { float lo, hi; };
+inline f2 f2_make(float lo, float hi) { return f2{lo, hi}; }
+inline float f2_lo(f2 a) { return a.lo; }
+inline float f2_hi(f2 a) { return a.hi; }
+inline f2 f2_mul(f2 a, f2 b) { return f2{a.lo * b.lo, a.hi * b.hi}; }
+inline f2 f2_fma(f2 a, f2 b, f2 c) { return f2{fmaf(a.lo, b.lo, c.lo), fmaf(a.hi, b.hi, c.hi)}; }
+#endif
+VK_DEVICE f2 f2_dup(float x) { return f2_make(x, x); }
+VK_DEVICE f2 f2_select(bool c, f2 a, f2 b) { return f2_make(c ? f2_lo(a) : f2_lo(b), c ? f2_hi(a) : f2_hi(b)); }
+
 // ---- deterministic sin / cos / pow ------------------------------------------------------------
 // GLSL leaves their precision to the implementation; the oracle (oracle/vkpbrt_oracle.c: vk_sincos,
 // vk_pow) fixes them as plain-IEEE Cephes-style algorithms and these are the same operations in the
@@ -254,12 +281,40 @@ VK_DEVICE void sample_rgb16f(const uint2* __restrict__ plane, const Bilin& bl, i
     b = bilin_mix(bl, b00, b10, b01, b11);
 }
 
+// ---- tone-map quantiser: unorm8(clamp(pow(x, .454545), 0, 1)) as a threshold search ------------------------------
+// With the oracle's deterministic vk_pow the stored code is a monotone function of the single binary32 input
+// (verified over ALL 2^31 - 2^23 + 1 non-negative inputs, tests/tools/pow_unorm8_sweep.c, which also generates the
+// table): thr[k] is the bit pattern of the smallest x whose code is >= k.  The kernels estimate the code with the
+// hardware log2 / exp2 approximations (error << 1 code) and correct it by +-1 with two exact integer compares, so
+// the result is bit-identical to evaluating vk_pow and costs ~15 instead of ~60 instructions per channel.
+// x must not be NaN (callers pass gl_max(0, .), which maps NaN to 0).  `thr` may point to shared or global memory.
+static __device__ const uint32_t c_tonemap_thr[256] = {
+#include "tonemap_thresholds.inc"
+};
+VK_DEVICE uint32_t tonemap_code(float x, const uint32_t* thr)
+{
+#ifndef VKPBRT_HOSTSIM
+    const float est = exp2f(mul_rn(.454545f, __log2f(x)));      // ex2.approx(lg2.approx): pow(0) = 0, pow(inf) = inf
+#else
+    const float est = x > 0.0f ? exp2f(.454545f * log2f(x)) : 0.0f;
+#endif
+    int k = (int)fmaf(fminf(est, 1.0f), 255.0f, 0.5f);           // any rounding: only has to land within one code
+    const uint32_t xb = __float_as_uint(x);
+    const int kn = k < 255 ? k + 1 : 255;
+    const uint32_t t_hi = thr[kn], t_lo = thr[k];
+    k = (xb >= t_hi) ? kn : k;
+    k = (xb < t_lo) ? k - 1 : k;                                   // thr[0] = 0: never below code 0
+    return (uint32_t)k;
+}
+// the reference form, kept for the exhaustive device-side equivalence test (vkpbrt_debug_tonemap_sweep)
+VK_DEVICE uint32_t tonemap_code_reference(float x) { return (uint32_t)f32_to_unorm8(gl_clamp(vk_pow(x, .454545f), 0.0f, 1.0f)); }
+
 // ---- epilogue shared by bmfrPost.comp:105-123 and bfr.comp:293-308 ----
 // color: clamped regression output.  Writes the rgba16f history texel and the BGRA8 tone-mapped
 // texel for image pixel `pix`.
 VK_DEVICE void denoise_epilogue(float cr, float cg, float cb, uint32_t frame, size_t pix, int W, int H, uint32_t motion_bits,
                                 uint32_t spp_code, uchar4 alb, const uint2* __restrict__ denoised_prev,
-                                uint2* __restrict__ denoised_next, uint32_t* __restrict__ final_bgra)
+                                uint2* __restrict__ denoised_next, uint32_t* __restrict__ final_bgra, const uint32_t* thr)
 {
     float uvx = f16_bits_to_f32((uint16_t)(motion_bits & 0xffffu));
     float uvy = f16_bits_to_f32((uint16_t)(motion_bits >> 16));
@@ -277,11 +332,11 @@ VK_DEVICE void denoise_epilogue(float cr, float cg, float cb, uint32_t frame, si
     cb = add_rn(mul_rn(blend, cb), mul_rn(omb, pb));
     denoised_next[pix] = pack_rgba16f(cr, cg, cb, 1.0f);
     float ar = add_rn(unorm8_to_f32(alb.x), 1e-6f), ag = add_rn(unorm8_to_f32(alb.y), 1e-6f), ab = add_rn(unorm8_to_f32(alb.z), 1e-6f);
-    float tr = gl_clamp(vk_pow(gl_max(0.0f, mul_rn(ar, cr)), .454545f), 0.0f, 1.0f);
-    float tg = gl_clamp(vk_pow(gl_max(0.0f, mul_rn(ag, cg)), .454545f), 0.0f, 1.0f);
-    float tb = gl_clamp(vk_pow(gl_max(0.0f, mul_rn(ab, cb)), .454545f), 0.0f, 1.0f);
+    const uint32_t tr = tonemap_code(gl_max(0.0f, mul_rn(ar, cr)), thr);
+    const uint32_t tg = tonemap_code(gl_max(0.0f, mul_rn(ag, cg)), thr);
+    const uint32_t tb = tonemap_code(gl_max(0.0f, mul_rn(ab, cb)), thr);
     // B8G8R8A8_UNORM memory order
-    final_bgra[pix] = (uint32_t)f32_to_unorm8(tb) | ((uint32_t)f32_to_unorm8(tg) << 8) | ((uint32_t)f32_to_unorm8(tr) << 16) | 0xff000000u;
+    final_bgra[pix] = tb | (tg << 8) | (tr << 16) | 0xff000000u;
 }
 
 }  // namespace vkpbrt

@@ -59,8 +59,13 @@ struct BmfrParams {
     uint16_t* dbg_features;       // optional r16f [13][Hp][Wp]
     float* dbg_weights;           // optional r32f [30][blocks_y][blocks_x]
     int force_generic;            // debug: every block takes the out-of-line IEEE-division fit (test coverage of the cold path)
+    const float* table;           // this frame's block-invariant table (bmfr.cu), 10 * block^2 floats
+    float* table_next;            // where the launch's spare CTAs write the table of frame + 1 (may be null)
+    float one, neg_one;           // 1.0f / -1.0f as run-time values (common.cuh: packed pairs)
 };
+constexpr size_t bmfr_table_floats(int block) { return (size_t)10 * block * block; }
 cudaError_t launch_bmfr(const BmfrParams& p, cudaStream_t stream);
+cudaError_t launch_bmfr_table(int block, float* table, uint32_t frame, cudaStream_t stream);
 
 // ---- k_bfr_block : shaders/bfr.comp ------------------------------------------------------
 struct BfrParams {
