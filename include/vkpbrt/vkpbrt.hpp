@@ -225,6 +225,7 @@ public:
     ref_ptr<AccumulationBuffer> accumulation_buffer;
     // band-sharded runs (not in the reference): rows this device accumulates
     void set_row_range(int row_begin, int row_end) { check(vkpbrt_accumulator_set_row_range(handle, row_begin, row_end)); }
+    void set_force_scalar(bool enable) { check(vkpbrt_accumulator_set_force_scalar(handle, enable ? 1 : 0)); }
     vkpbrt_accumulator_t handle = nullptr;
 private:
     // every bundle remembers the context it was created in through its first image
@@ -346,6 +347,7 @@ public:
     ref_ptr<DescriptorImage> get_final_descriptor_image() const { return _final; }
     // band-sharded runs (not in the reference)
     void set_row_range(int row_begin, int row_end) { check(vkpbrt_taa_set_row_range(handle, row_begin, row_end)); }
+    void set_force_scalar(bool enable) { check(vkpbrt_taa_set_force_scalar(handle, enable ? 1 : 0)); }
     vkpbrt_taa_t handle = nullptr;
 private:
     ref_ptr<GBuffer> _g;

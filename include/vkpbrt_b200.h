@@ -206,6 +206,9 @@ VKPBRT_API int vkpbrt_accumulator_set_camera_matrices(vkpbrt_accumulator_t a, in
 VKPBRT_API int vkpbrt_accumulator_record(vkpbrt_accumulator_t a);
 /* restrict the dispatch to image rows [row_begin, row_end) (multi-GPU band sharding) */
 VKPBRT_API int vkpbrt_accumulator_set_row_range(vkpbrt_accumulator_t a, int row_begin, int row_end);
+/* debug / test switch: non-zero = run the one-pixel-per-thread kernel with the IEEE library routines instead of the
+ * packed two-pixel kernel (both are bit-identical; the tests run both) */
+VKPBRT_API int vkpbrt_accumulator_set_force_scalar(vkpbrt_accumulator_t a, int enable);
 VKPBRT_API int vkpbrt_accumulator_destroy(vkpbrt_accumulator_t a);
 
 /* ---------------------------------------------------------------------------------------- */
@@ -271,6 +274,8 @@ VKPBRT_API int vkpbrt_taa_create(vkpbrt_context_t ctx, uint32_t width, uint32_t 
                                  vkpbrt_image_t denoised, vkpbrt_taa_t* out);
 /* 0 (default): reproduce the reference's R/B-swapped history; 1: fix it */
 VKPBRT_API int vkpbrt_taa_set_fix_swizzle(vkpbrt_taa_t t, int fix);
+/* debug / test switch: the one-pixel-per-thread kernel (bit-identical to the default two-column kernel) */
+VKPBRT_API int vkpbrt_taa_set_force_scalar(vkpbrt_taa_t t, int enable);
 VKPBRT_API int vkpbrt_taa_compile(vkpbrt_taa_t t);
 /* dispatch + final->history hand-over (Taa.cpp:99-107).  The reference never pushes constants for
  * TAA and inherits the denoiser's (App. C-10); here they are passed explicitly. */

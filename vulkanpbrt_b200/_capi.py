@@ -120,6 +120,7 @@ _PROTOS = {
     "vkpbrt_accumulator_set_camera_matrices": [H, i32, C.POINTER(CameraMatrices), C.POINTER(CameraMatrices)],
     "vkpbrt_accumulator_record": [H],
     "vkpbrt_accumulator_set_row_range": [H, i32, i32],
+    "vkpbrt_accumulator_set_force_scalar": [H, i32],
     "vkpbrt_accumulator_destroy": [H],
     "vkpbrt_bmfr_create": [H, u32, u32, u32, u32, H, H, H, u32, PH],
     "vkpbrt_bmfr_set_debug_outputs": [H, i32],
@@ -143,6 +144,7 @@ _PROTOS = {
     "vkpbrt_taa_create": [H, u32, u32, u32, u32, H, H, H, PH],
     "vkpbrt_taa_set_fix_swizzle": [H, i32],
     "vkpbrt_taa_compile": [H],
+    "vkpbrt_taa_set_force_scalar": [H, i32],
     "vkpbrt_taa_record": [H, C.POINTER(PushConstants)],
     "vkpbrt_taa_set_row_range": [H, i32, i32],
     "vkpbrt_taa_final_image": [H, PH],

@@ -146,6 +146,7 @@ struct vkpbrt_accumulator_s {
     // Accumulator::PushConstants (Accumulator.hpp:28-33)
     float pc_view[16], pc_inv_view[16], pc_prev_view[16], pc_prev_pos[4];
     int pc_frame_number = 0;
+    bool force_scalar = false;
 };
 
 struct vkpbrt_bmfr_s {
@@ -189,6 +190,7 @@ struct vkpbrt_taa_s {
     vkpbrt_image_t final_image = nullptr, history = nullptr;   // handles; data flips between buf[0..1]
     void* buf[2] = {nullptr, nullptr};
     int fix_swizzle = 0;
+    int force_scalar = 0;
     bool compiled = false;
     int row_begin, row_end;
 };
@@ -705,6 +707,13 @@ int vkpbrt_accumulator_set_row_range(vkpbrt_accumulator_t a, int row_begin, int 
     return VKPBRT_OK;
 }
 
+int vkpbrt_accumulator_set_force_scalar(vkpbrt_accumulator_t a, int enable)
+{
+    VK_REQUIRE(a, "null accumulator");
+    a->force_scalar = enable != 0;
+    return VKPBRT_OK;
+}
+
 int vkpbrt_accumulator_record(vkpbrt_accumulator_t a)
 {
     VK_REQUIRE(a, "null accumulator");
@@ -743,6 +752,8 @@ int vkpbrt_accumulator_record(vkpbrt_accumulator_t a)
     p.spp = (uint8_t*)a->acc->img[VKPBRT_ACC_SPP]->data;
     p.illum = (uint2*)a->accumulated->images[0]->data;
     p.depth_history = (float*)a->acc->depth_next->data;
+    p.one = 1.0f; p.neg_one = -1.0f;
+    p.force_scalar = a->force_scalar ? 1 : 0;
     VK_CUDA(cudaSetDevice(a->ctx->device));
     VK_CUDA(vkpbrt::launch_accumulate(p, a->ctx->stream));
     a->ctx->launches++;
@@ -1106,6 +1117,13 @@ int vkpbrt_taa_set_fix_swizzle(vkpbrt_taa_t t, int fix)
     return VKPBRT_OK;
 }
 
+int vkpbrt_taa_set_force_scalar(vkpbrt_taa_t t, int enable)
+{
+    VK_REQUIRE(t, "null taa");
+    t->force_scalar = enable ? 1 : 0;
+    return VKPBRT_OK;
+}
+
 int vkpbrt_taa_compile(vkpbrt_taa_t t)
 {
     VK_REQUIRE(t, "null taa");
@@ -1146,6 +1164,8 @@ int vkpbrt_taa_record(vkpbrt_taa_t t, const vkpbrt_push_constants* pc)
     p.history = (const uint32_t*)in;
     p.final_bgra = (uint32_t*)outb;
     VK_REQUIRE(p.motion && p.denoised, "Taa: an input image is not compiled");
+    p.one = 1.0f; p.neg_one = -1.0f;
+    p.force_scalar = t->force_scalar;
     VK_CUDA(cudaSetDevice(t->ctx->device));
     VK_CUDA(vkpbrt::launch_taa(p, t->ctx->stream));
     t->ctx->launches++;

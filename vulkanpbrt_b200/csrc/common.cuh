@@ -108,6 +108,20 @@ inline f2 f2_mul(f2 a, f2 b) { return f2{a.lo * b.lo, a.hi * b.hi}; }
 inline f2 f2_fma(f2 a, f2 b, f2 c) { return f2{fmaf(a.lo, b.lo, c.lo), fmaf(a.hi, b.hi, c.hi)}; }
 #endif
 VK_DEVICE f2 f2_dup(float x) { return f2_make(x, x); }
+// arithmetic context of a kernel that works on pairs: the run-time 1.0 / -1.0
+struct Pk {
+    f2 one, neg_one;
+    VK_DEVICE f2 add(f2 a, f2 b) const { return f2_fma(a, one, b); }              // RN(a + b)
+    VK_DEVICE f2 sub(f2 a, f2 b) const { return f2_fma(b, neg_one, a); }          // RN(a - b)
+    VK_DEVICE f2 neg(f2 a) const { return f2_mul(a, neg_one); }                   // exact
+    // a / b from rb = RN(1 / b): div_by_rcp on both lanes
+    VK_DEVICE f2 div_by_rcp(f2 a, f2 b, f2 rb) const
+    {
+        const f2 q0 = f2_mul(a, rb);
+        const f2 e = f2_fma(q0, neg(b), a);
+        return f2_fma(e, rb, q0);
+    }
+};
 VK_DEVICE f2 f2_select(bool c, f2 a, f2 b) { return f2_make(c ? f2_lo(a) : f2_lo(b), c ? f2_hi(a) : f2_hi(b)); }
 
 // ---- deterministic sin / cos / pow ------------------------------------------------------------

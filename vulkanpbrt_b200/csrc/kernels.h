@@ -35,6 +35,8 @@ struct AccumulateParams {
     uint8_t* spp;                 // r8
     uint2* illum;                 // rgba16f
     float* depth_history;         // r32f: next frame's prev_depth (fused copy_to_back), may be null
+    float one, neg_one;           // 1.0f / -1.0f as run-time values (common.cuh: packed pairs)
+    int force_scalar;             // debug: one pixel per thread with the IEEE library routines (k_accumulate_scalar)
 };
 cudaError_t launch_accumulate(const AccumulateParams& p, cudaStream_t stream);
 
@@ -111,6 +113,8 @@ struct TaaParams {
     const uint32_t* denoised;     // BGRA8 final of the denoiser
     const uint32_t* history;      // previous TAA final, bytes as written (BGRA8) viewed as RGBA8
     uint32_t* final_bgra;         // this frame's TAA final == next frame's history (ping-pong)
+    float one, neg_one;           // 1.0f / -1.0f as run-time values (common.cuh: packed pairs)
+    int force_scalar;             // debug: the one-pixel-per-thread kernel
 };
 cudaError_t launch_taa(const TaaParams& p, cudaStream_t stream);
 

@@ -468,6 +468,10 @@ class Accumulator:
     def set_row_range(self, row_begin: int, row_end: int) -> None:
         capi.call("vkpbrt_accumulator_set_row_range", self._h, row_begin, row_end)
 
+    def set_force_scalar(self, enable: bool) -> None:
+        """debug / test switch: the one-pixel-per-thread kernel with the IEEE library routines"""
+        capi.call("vkpbrt_accumulator_set_force_scalar", self._h, 1 if enable else 0)
+
     def __del__(self):
         try:
             capi.lib().vkpbrt_accumulator_destroy(self._h)   # also frees the two bundles it owns
@@ -630,6 +634,10 @@ class Taa:
 
     def set_row_range(self, row_begin: int, row_end: int) -> None:
         capi.call("vkpbrt_taa_set_row_range", self._h, row_begin, row_end)
+
+    def set_force_scalar(self, enable: bool) -> None:
+        """debug / test switch: the one-pixel-per-thread kernel"""
+        capi.call("vkpbrt_taa_set_force_scalar", self._h, 1 if enable else 0)
 
     def add_dispatch_to_command_graph(self, command_graph: Commands) -> None:
         def rec(c: Commands):
