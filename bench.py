@@ -3,11 +3,13 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
 
-A "step" is one frame through the hot path: accumulate -> fused BMFR (pre + fit + post) [-> TAA].
-N = 1 runs BASELINE.json configs[1]: BMFR 1920x1080, 1 spp, camera motion.  For N > 1 (torchrun, one
-rank per GPU) the frame is partitioned into horizontal block bands, one 1920x1080 band per GPU
-(weak scaling: the frame is 1920 x 1080*N), with the history halo rows exchanged over NCCL/NVLink
-every frame (vulkanpbrt_b200/multigpu.py).
+A "step" is one frame through the hot path: accumulate -> fused BMFR (pre + fit + post) -> TAA.
+The default workload, for every N, is BASELINE.json configs[3] -- the full chain at 3840x2160, the configuration the
+north star's "< 1 ms per frame" is quoted on.  N = 1 denoises whole frames; N > 1 (torchrun, one rank per GPU) is
+STRONG scaling: the same 4K frame cut into horizontal block bands, the history halo rows pushed into the neighbours'
+HBM over NVLink every frame (vulkanpbrt_b200/multigpu.py).  The other BASELINE configurations are measured in the same
+run and nested under "also": N = 1 adds BMFR 1080p (configs[1]), BFR x3 + blender 1080p (configs[2]) and BMFR 8K;
+N = 8 adds the 8K frame band-sharded over the 8 GPUs (configs[4]).
 
 value   whole-job MPix/s with the input sequence already resident in HBM (each frame's planes are
         distinct buffers, read once: inputs larger than L2)
@@ -15,8 +17,9 @@ e2e     the same metric through the public API with HOST buffers: per frame the 
         illumination are copied from pinned host memory and the BGRA8 result is read back, inside the
         timed region (2-deep copy/compute overlap)
 roofline  the dominant kernel's algorithmic bytes / its CUDA-event time, against MEASURED_PEAKS.json
-cpu_baseline  the oracle (CPU restatement of the reference shaders) on the host cores, bounded sample
---impl reference  times the reference's CPU path (oracle/_ref when built, else the oracle port) alone
+cpu_baseline  the reference's shader source compiled for the host cores (oracle/_ref), bounded sample
+--impl reference  times the reference's CPU path (oracle/_ref when built, else the oracle port) alone, on the SAME
+        workload at its real size, with every host core
 """
 import argparse
 import json
@@ -46,6 +49,25 @@ BYTES_BMFR = 37 + 12           # reads depth 4 + normal 8 + noisyAcc 8 + albedo 
 BYTES_TAA = 12 + 4             # reads denoised 4 + motion 4 + history 4; writes final 4
 BYTES_CHAIN_FUSED = 78         # ideal fully fused chain, the figure BASELINE.md quotes
 INPUT_BYTES = 4 + 8 + 4 + 16   # depth + normal + albedo + raw rgba32f per pixel (host -> device per frame)
+DEFAULT_WORKLOAD = "bmfr_taa_4k"
+
+
+def seq_index(f, R):
+    """frame number -> resident frame: the sequence is walked forwards and backwards (0 .. R-1, R-2 .. 1, 0 ..), so that
+    consecutive frames are always neighbours on the camera path -- cycling f % R would jump the camera back to the start
+    every R frames (a full-frame disocclusion, and more reprojection displacement than a band's halo covers)"""
+    if R < 2:
+        return 0
+    m = f % (2 * R - 2)
+    return m if m < R else 2 * R - 2 - m
+
+
+def config_of(name):
+    """the workload description both arms print verbatim (the driver compares the two `config` objects)"""
+    W, H, taa, desc = WORKLOADS[name]
+    return {"workload": name, "description": desc, "width": W, "height": H, "block": 32, "taa": taa,
+            "sequence": "deterministic synthetic G-buffer sequence (analytic scene, 1-spp noise, camera motion), frames at full size",
+            "l2": "GPU arms: every frame's input planes are distinct resident buffers read once per step (inputs larger than L2)"}
 
 
 def peaks():
@@ -136,27 +158,42 @@ def cpu_chain(W, H, taa):
     return O, O.OracleChain(W, H, "bmfr", 32, use_taa=taa), "port"
 
 
-def run_cpu(W, H, taa, frames, budget_s=None, warmup=0, sample_scale=1):
-    """times the CPU chain on `frames` synthetic frames of (W / sample_scale) x (H / sample_scale) -- MPix/s does not
-    depend on the frame size -- and stops early once budget_s is spent"""
+def use_all_host_cores():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arms use every core of the box.  Must run before the
+    oracle libraries are loaded (libgomp reads the variable once)."""
+    n = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    os.environ.pop("OMP_THREAD_LIMIT", None)
+    return n
+
+
+def run_cpu(name, frames, budget_s=None, warmup=0):
+    """times the CPU chain on `frames` synthetic frames of the workload at its REAL size; stops early once budget_s is
+    spent (cpu_baseline leg: a bounded sample)"""
+    use_all_host_cores()
     from vulkanpbrt_b200 import synth
-    w, h = (W // sample_scale) // 32 * 32, (H // sample_scale) // 4 * 4
-    O, chain, kind = cpu_chain(w, h, taa)
-    fs = [synth.render_frame(w, h, f) for f in range(min(frames + warmup, 8))]
+    W, H, taa, _ = WORKLOADS[name]
+    O, chain, kind = cpu_chain(W, H, taa)
+    try:
+        O.lib().vkpbrt_oracle_set_num_threads(os.cpu_count() or 1)
+    except AttributeError:
+        pass
+    nf = max(1, min(frames + warmup, 4))
+    fs = [synth.render_frame(W, H, f) for f in range(nf)]
     for f in range(warmup):
-        chain.run_frame(f, fs[f % len(fs)])
+        chain.run_frame(f, fs[f % nf])
     t0 = time.perf_counter()
     done = 0
     for f in range(warmup, warmup + frames):
-        chain.run_frame(f, fs[f % len(fs)])
+        chain.run_frame(f, fs[f % nf])
         done += 1
-        if budget_s is not None and time.perf_counter() - t0 > budget_s and done >= 2:
+        if budget_s is not None and time.perf_counter() - t0 > budget_s:
             break
     dt = time.perf_counter() - t0
     what = ("reference shader source (shaders/*.comp) compiled for the CPU via oracle/glsl_shim" if kind == "reference"
             else "oracle/vkpbrt_oracle.c")
-    return {"value": w * h * done / dt / 1e6, "unit": "MPix/s", "cores": int(O.lib().vkpbrt_oracle_num_threads()),
-            "kind": kind, "sample": f"{done} frames of {w}x{h} ({what}, OpenMP over workgroups), {dt:.1f} s",
+    return {"value": W * H * done / dt / 1e6, "unit": "MPix/s", "cores": int(O.lib().vkpbrt_oracle_num_threads()),
+            "kind": kind, "sample": f"{done} frames of {W}x{H} ({what}, OpenMP over workgroups), {dt:.1f} s",
             "ms_per_frame": dt / done * 1e3}
 
 
@@ -164,13 +201,14 @@ def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    W, H, taa, desc = WORKLOADS[args.workload or "bmfr_1080p"]
-    r = run_cpu(W, H, taa, args.steps, warmup=min(args.warmup, 3), sample_scale=2)      # bounded sample: quarter-size frames
+    name = args.workload or DEFAULT_WORKLOAD
+    r = run_cpu(name, args.steps, warmup=min(args.warmup, 2))
     line = {"impl": "reference", "metric": "BMFR denoised MPix/s", "value": r["value"], "unit": "MPix/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_frame"], "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload or "bmfr_1080p", "description": desc, "width": W, "height": H,
-                       "note": "reference CPU path (no Vulkan ICD / lavapipe on this machine): " + r["sample"]},
+            "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_of(name),
+            "note": "the reference's CPU path (no Vulkan ICD / lavapipe on this machine): " + r["sample"]
+                    + f"; {min(args.warmup, 2)} untimed warm-up frames",
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "MPix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -179,35 +217,13 @@ def main_reference(args):
 # ---------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------
-def main_ours(args):
+def measure_single(args, name, K, Wm, R, local, with_e2e=True, cpu_budget=0.0):
+    """one workload on ONE GPU: resident-input throughput, per-kernel times, roofline, (optionally) the end-to-end leg"""
     import torch
-    import torch.distributed as dist
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus and world > 1:
-        args.gpus = world
-    torch.cuda.set_device(local)
-    if world > 1:
-        # exactly ONE line on stdout (the JSON): library chatter such as NCCL's version banner goes to stderr
-        real_stdout = os.dup(1)
-        os.dup2(2, 1)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        from vulkanpbrt_b200.multigpu import bench_multi
-        line = bench_multi(args, rank, world, local)
-        sys.stdout.flush()
-        os.dup2(real_stdout, 1)
-        if line is not None:
-            print(json.dumps(line), flush=True)
-        return
 
     from vulkanpbrt_b200 import Context, DenoisePipeline, DenoisingBlockSize, DenoisingType
 
-    name = args.workload or "bmfr_1080p"
     W, H, taa, desc = WORKLOADS[name]
-    K, Wm = args.steps, args.warmup
-    R = min(K + Wm, args.resident_frames)        # frames kept resident; longer runs cycle through them
     dev = torch.device("cuda", local)
     # an explicit stream: the library records on the stream it is handed and the CUDA events below must sit on the same one
     stream = torch.cuda.Stream(device=dev)
@@ -236,7 +252,7 @@ def main_ours(args):
     pipe = make_pipe()
 
     def frame_resident(f):
-        i = f % R
+        i = seq_index(f, R)
         bind(pipe, dseq, i)
         pipe.set_frame_constants(f, seq["cams"][i])
         pipe.record()
@@ -256,7 +272,6 @@ def main_ours(args):
     e1.record(stream)
     t_host = (time.perf_counter() - t_host) / K * 1e3          # host time to ENQUEUE one frame (no sync inside)
     torch.cuda.synchronize()
-    clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
     launches = ctx.launch_count - launches0
     value = W * H * K / (ms * 1e-3) / 1e6
@@ -266,9 +281,9 @@ def main_ours(args):
     names = pipe.command_labels
     probe_ms = [[] for _ in range(ncmd)]
     frame_lat = []
-    nprobe = min(60, K)
+    nprobe = min(60, max(K, 12))
     for f in range(Wm + K, Wm + K + nprobe):
-        i = f % R
+        i = seq_index(f, R)
         bind(pipe, dseq, i)
         pipe.set_frame_constants(f, seq["cams"][i])
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(ncmd + 1)]
@@ -281,6 +296,7 @@ def main_ours(args):
         for c in range(ncmd):
             probe_ms[c].append(evs[c].elapsed_time(evs[c + 1]))
         frame_lat.append(evs[0].elapsed_time(evs[ncmd]))
+    clocks = sampler.stop()          # sampled over the timed region AND the per-kernel probes (both run the same kernels)
     acc_ms = [sorted(v)[len(v) // 2] for v in probe_ms]       # median over the probe frames: robust against a one-off hiccup
     frame_lat.sort()
     # one frame at a time (device idle before each): the latency a frame-by-frame caller sees (median, p95)
@@ -314,8 +330,8 @@ def main_ours(args):
     roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
                 "frac": round(kernels[dom]["achieved_gbs"] / hbm_peak, 4), "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": per_kernel_bytes[dom] * W * H,
-                "note": "k_bmfr_block is FP32-pipe/latency bound (batched Householder QR), see fit_gflops; the streaming "
-                        "kernels' HBM fractions are under 'kernels'",
+                "note": "k_bmfr_block is bound by instruction issue (batched Householder QR on the FP32 pipe, no tensor cores by "
+                        "design), see `issue` and fit_gflops; the streaming kernels' HBM fractions are under 'kernels'",
                 "fit_gflops": round(nblocks * 4.05e5 / (kernels[dom]["ms"] * 1e-3) / 1e9, 1) if "bmfr" in dom else None,
                 "chain_fused_bytes_per_pixel": BYTES_CHAIN_FUSED,
                 "chain_achieved_gbs": round(BYTES_CHAIN_FUSED * W * H / (ms / K * 1e-3) / 1e9, 1)}
@@ -336,80 +352,143 @@ def main_ours(args):
     except Exception as e:  # pragma: no cover -- never let a reporting extra break the line
         roofline["issue"] = {"error": type(e).__name__}
 
+    res = {"workload": name, "value": round(value, 1), "unit": "MPix/s", "ms_per_step": round(ms / K, 5), "steps": K, "warmup": Wm,
+           "gpu_launches": int(launches), "host_enqueue_ms_per_step": round(t_host, 4), "frame_latency_ms": latency, "clocks": clocks,
+           "roofline": roofline, "kernels": kernels, "resident_frames": R, "sequence_generation_s": round(t_gen, 1), "e2e": None,
+           "cpu_baseline": None}
+
     # ---- e2e: host buffers, H2D + D2H inside the timed region ------------------------------------------------
     del pipe
-    pipe = make_pipe()
-    copy_stream = torch.cuda.Stream()
-    dbuf = [{k: torch.empty_like(dseq[k][0]) for k in ("depth", "normal", "albedo", "illum")} for _ in range(2)]
-    out_host = [torch.empty((H, W, 4), dtype=torch.uint8, pin_memory=True) for _ in range(2)]
-    copied = [torch.cuda.Event() for _ in range(2)]
-    consumed = [torch.cuda.Event() for _ in range(2)]
-    final_view = lambda: torch.as_tensor(pipe.final, device=dev)
+    if with_e2e:
+        pipe = make_pipe()
+        copy_stream = torch.cuda.Stream()
+        dbuf = [{k: torch.empty_like(dseq[k][0]) for k in ("depth", "normal", "albedo", "illum")} for _ in range(2)]
+        out_host = [torch.empty((H, W, 4), dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+        copied = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
+        final_view = lambda: torch.as_tensor(pipe.final, device=dev)
 
-    def issue_copy(f):
-        s = f % 2
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[s])
-            for k in ("depth", "normal", "albedo", "illum"):
-                dbuf[s][k].copy_(seq[k][f % R], non_blocking=True)
-            copied[s].record(copy_stream)
+        def issue_copy(f):
+            s = f % 2
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[s])
+                for k in ("depth", "normal", "albedo", "illum"):
+                    dbuf[s][k].copy_(seq[k][seq_index(f, R)], non_blocking=True)
+                copied[s].record(copy_stream)
 
-    def frame_e2e(f):
-        s = f % 2
-        stream.wait_event(copied[s])
-        pipe.bind_inputs(dbuf[s]["depth"].data_ptr(), dbuf[s]["normal"].data_ptr(), dbuf[s]["albedo"].data_ptr(),
-                         dbuf[s]["illum"].data_ptr())
-        pipe.set_frame_constants(f, seq["cams"][f % R])
-        pipe.record()
-        pipe.end_frame(seq["cams"][f % R])
-        consumed[s].record(stream)
-        out_host[s].copy_(final_view(), non_blocking=True)       # the step's result, read back every frame
+        def frame_e2e(f):
+            s = f % 2
+            stream.wait_event(copied[s])
+            pipe.bind_inputs(dbuf[s]["depth"].data_ptr(), dbuf[s]["normal"].data_ptr(), dbuf[s]["albedo"].data_ptr(),
+                             dbuf[s]["illum"].data_ptr())
+            pipe.set_frame_constants(f, seq["cams"][seq_index(f, R)])
+            pipe.record()
+            pipe.end_frame(seq["cams"][seq_index(f, R)])
+            consumed[s].record(stream)
+            out_host[s].copy_(final_view(), non_blocking=True)       # the step's result, read back every frame
 
-    for s in range(2):
-        consumed[s].record(stream)
-    issue_copy(0)
-    for f in range(Wm):
-        issue_copy(f + 1)
-        frame_e2e(f)
+        for s in range(2):
+            consumed[s].record(stream)
+        issue_copy(0)
+        for f in range(Wm):
+            issue_copy(f + 1)
+            frame_e2e(f)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for f in range(Wm, Wm + K):
+            issue_copy(f + 1)
+            frame_e2e(f)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        e2e_ms = max(e0.elapsed_time(e1), 0.0)
+        e2e_value = W * H * K / (e2e_ms * 1e-3) / 1e6
+        res["e2e"] = {"value": round(e2e_value, 1), "unit": "MPix/s", "h2d_bytes_per_step": INPUT_BYTES * W * H,
+                      "d2h_bytes_per_step": 4 * W * H, "ms_per_step": round(e2e_ms / K, 5), "wall_ms_per_step": round(wall_ms / K, 5),
+                      "h2d_gb_per_s": round(INPUT_BYTES * W * H / (e2e_ms / K * 1e-3) / 1e9, 1)}
+        del pipe, dbuf, out_host
+    del dseq, seq
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    e0.record(stream)
-    for f in range(Wm, Wm + K):
-        issue_copy(f + 1)
-        frame_e2e(f)
-    e1.record(stream)
-    torch.cuda.synchronize()
-    wall_ms = (time.perf_counter() - t0) * 1e3
-    e2e_ms = max(e0.elapsed_time(e1), 0.0)
-    e2e_value = W * H * K / (e2e_ms * 1e-3) / 1e6
+    torch.cuda.empty_cache()
+    if cpu_budget > 0 and not bfr:
+        res["cpu_baseline"] = run_cpu(name, frames=64, budget_s=cpu_budget, warmup=1)
+    return res
 
-    cpu = run_cpu(W, H, taa, frames=64, budget_s=args.cpu_budget, warmup=1, sample_scale=2) if (args.cpu_budget > 0 and not bfr) else None
 
-    line = {"metric": ("BFR+blend" if bfr else "BMFR") + " denoised MPix/s", "value": round(value, 1), "unit": "MPix/s", "n_gpus": 1, "steps": K, "warmup": Wm,
-            "ms_per_step": round(ms / K, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": name, "description": desc, "width": W, "height": H, "block": 32, "taa": taa,
-                       "l2": f"inputs larger than L2: {R} resident frames x {INPUT_BYTES * W * H / 1e6:.0f} MB, each read once per step",
-                       "resident_frames": R, "sequence_generation_s": round(t_gen, 1)},
-            "e2e": {"value": round(e2e_value, 1), "unit": "MPix/s", "h2d_bytes_per_step": INPUT_BYTES * W * H,
-                    "d2h_bytes_per_step": 4 * W * H, "ms_per_step": round(e2e_ms / K, 5), "wall_ms_per_step": round(wall_ms / K, 5),
-                    "h2d_gb_per_s": round(INPUT_BYTES * W * H / (e2e_ms / K * 1e-3) / 1e9, 1)},
-            "gpu_launches": int(launches), "host_enqueue_ms_per_step": round(t_host, 4), "frame_latency_ms": latency, "clocks": clocks, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu}
+def also_entry(r):
+    """the nested form of a secondary workload's result"""
+    return {"config": config_of(r["workload"]), "value": r["value"], "unit": r["unit"], "ms_per_step": r["ms_per_step"], "steps": r["steps"],
+            "warmup": r["warmup"], "kernels": r["kernels"], "roofline": {k: r["roofline"][k] for k in ("kernel", "achieved", "peak", "frac")},
+            "gpu_launches": r["gpu_launches"], "e2e": r["e2e"], "clocks": r["clocks"]}
+
+
+def main_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    torch.cuda.set_device(local)
+    if world > 1:
+        # exactly ONE line on stdout (the JSON): library chatter such as NCCL's version banner goes to stderr
+        real_stdout = os.dup(1)
+        os.dup2(2, 1)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        from vulkanpbrt_b200.multigpu import bench_multi
+        line = bench_multi(args, rank, world, local)
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        if line is not None:
+            print(json.dumps(line), flush=True)
+        return
+
+    name = args.workload or DEFAULT_WORKLOAD
+    W, H, taa, desc = WORKLOADS[name]
+    K, Wm = args.steps, args.warmup
+    R = min(K + Wm, args.resident_frames)        # frames kept resident; longer runs cycle through them
+    if name == "bmfr_8k":
+        R = min(R, 8)                            # 1 GB of input planes per frame
+    r = measure_single(args, name, K, Wm, R, local, with_e2e=True, cpu_budget=args.cpu_budget)
+    also = {}
+    if not args.no_also and args.workload is None:
+        # the other BASELINE configurations, shorter runs of the same measurement
+        for other, k2, w2, r2 in (("bmfr_1080p", 20, 5, 25), ("bfr_blend_1080p", 10, 3, 13), ("bmfr_8k", 8, 3, 6)):
+            try:
+                also[other] = also_entry(measure_single(args, other, k2, w2, r2, local, with_e2e=(other != "bmfr_8k"), cpu_budget=0.0))
+            except Exception as e:  # pragma: no cover -- a secondary workload must not cost the headline line
+                also[other] = {"error": f"{type(e).__name__}: {e}"}
+    bfr = name.startswith("bfr")
+    cfg = config_of(name)
+    line = {"metric": ("BFR+blend" if bfr else "BMFR") + " denoised MPix/s", "value": r["value"], "unit": "MPix/s", "n_gpus": 1, "steps": K, "warmup": Wm,
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": cfg,
+            "run": {"resident_frames": r["resident_frames"], "sequence_generation_s": r["sequence_generation_s"],
+                    "l2": f"inputs larger than L2: {r['resident_frames']} resident frames x {INPUT_BYTES * W * H / 1e6:.0f} MB, each read once per step"},
+            "e2e": r["e2e"], "gpu_launches": r["gpu_launches"], "host_enqueue_ms_per_step": r["host_enqueue_ms_per_step"],
+            "frame_latency_ms": r["frame_latency_ms"], "clocks": r["clocks"], "roofline": r["roofline"], "kernels": r["kernels"],
+            "cpu_baseline": r["cpu_baseline"], "also": also}
     print(json.dumps(line), flush=True)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=60)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
-    ap.add_argument("--resident-frames", type=int, default=70)
+    ap.add_argument("--resident-frames", type=int, default=48)
     ap.add_argument("--replicas", action="store_true", help="N > 1: N independent sequences of the workload, one per GPU")
+    ap.add_argument("--weak", action="store_true", help="N > 1: weak scaling (one band of the workload's height per GPU) instead of strong")
+    ap.add_argument("--no-verify", dest="no_verify", action="store_true", help="N > 1: skip the banded == single-GPU comparison")
     ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
                     help="N > 1: halo rows through NVLink peer memory (k_halo_push) or NCCL send/recv groups")
-    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for cpu_baseline (0 = skip)")
+    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline (0 = skip)")
+    ap.add_argument("--no-also", action="store_true", help="skip the secondary workloads nested under 'also'")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

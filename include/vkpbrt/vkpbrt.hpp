@@ -226,6 +226,8 @@ public:
     // band-sharded runs (not in the reference): rows this device accumulates
     void set_row_range(int row_begin, int row_end) { check(vkpbrt_accumulator_set_row_range(handle, row_begin, row_end)); }
     void set_force_scalar(bool enable) { check(vkpbrt_accumulator_set_force_scalar(handle, enable ? 1 : 0)); }
+    void set_max_displacement_rows(int rows) { check(vkpbrt_accumulator_set_max_displacement_rows(handle, rows)); }
+    uint32_t displacement_violations() const { uint32_t n = 0; check(vkpbrt_accumulator_displacement_violations(handle, &n)); return n; }
     vkpbrt_accumulator_t handle = nullptr;
 private:
     // every bundle remembers the context it was created in through its first image

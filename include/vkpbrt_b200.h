@@ -209,6 +209,12 @@ VKPBRT_API int vkpbrt_accumulator_set_row_range(vkpbrt_accumulator_t a, int row_
 /* debug / test switch: non-zero = run the one-pixel-per-thread kernel with the IEEE library routines instead of the
  * packed two-pixel kernel (both are bit-identical; the tests run both) */
 VKPBRT_API int vkpbrt_accumulator_set_force_scalar(vkpbrt_accumulator_t a, int enable);
+/* Band-sharded runs: a rank holds history rows only within `rows` (+ 1 bilinear row) of the rows it computes.  With the
+ * guard on (rows > 0) every reprojection tap further away than that -- other than through the sampler's REPEAT wrap --
+ * is counted instead of silently reading rows the rank never received; ..._displacement_violations() synchronises
+ * the context's stream and returns the count since the guard was switched on. */
+VKPBRT_API int vkpbrt_accumulator_set_max_displacement_rows(vkpbrt_accumulator_t a, int rows);
+VKPBRT_API int vkpbrt_accumulator_displacement_violations(vkpbrt_accumulator_t a, uint32_t* count);
 VKPBRT_API int vkpbrt_accumulator_destroy(vkpbrt_accumulator_t a);
 
 /* ---------------------------------------------------------------------------------------- */

@@ -64,6 +64,7 @@ def lib():
         l.vkpbrt_oracle_bfr_blender.argtypes = [i32, i32, i32] + [vp] * 6; l.vkpbrt_oracle_bfr_blender.restype = None
         l.vkpbrt_oracle_taa.argtypes = [i32, i32, u32, i32] + [vp] * 4; l.vkpbrt_oracle_taa.restype = None
         l.vkpbrt_oracle_num_threads.argtypes = []; l.vkpbrt_oracle_num_threads.restype = i32
+        l.vkpbrt_oracle_set_num_threads.argtypes = [i32]; l.vkpbrt_oracle_set_num_threads.restype = None
         _lib = l
     return _lib
 

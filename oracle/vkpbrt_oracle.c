@@ -1004,3 +1004,13 @@ ORACLE_API int vkpbrt_oracle_num_threads(void)
     return 1;
 #endif
 }
+
+/* the worker-thread count of the CPU arms (bench.py): launchers such as torchrun export OMP_NUM_THREADS=1 */
+ORACLE_API void vkpbrt_oracle_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}

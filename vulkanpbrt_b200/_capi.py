@@ -121,6 +121,8 @@ _PROTOS = {
     "vkpbrt_accumulator_record": [H],
     "vkpbrt_accumulator_set_row_range": [H, i32, i32],
     "vkpbrt_accumulator_set_force_scalar": [H, i32],
+    "vkpbrt_accumulator_set_max_displacement_rows": [H, i32],
+    "vkpbrt_accumulator_displacement_violations": [H, C.POINTER(u32)],
     "vkpbrt_accumulator_destroy": [H],
     "vkpbrt_bmfr_create": [H, u32, u32, u32, u32, H, H, H, u32, PH],
     "vkpbrt_bmfr_set_debug_outputs": [H, i32],

@@ -147,6 +147,8 @@ struct vkpbrt_accumulator_s {
     float pc_view[16], pc_inv_view[16], pc_prev_view[16], pc_prev_pos[4];
     int pc_frame_number = 0;
     bool force_scalar = false;
+    int max_disp_rows = 0;
+    uint32_t* disp_violations = nullptr;    // device word, allocated when the guard is switched on
 };
 
 struct vkpbrt_bmfr_s {
@@ -714,6 +716,29 @@ int vkpbrt_accumulator_set_force_scalar(vkpbrt_accumulator_t a, int enable)
     return VKPBRT_OK;
 }
 
+int vkpbrt_accumulator_set_max_displacement_rows(vkpbrt_accumulator_t a, int rows)
+{
+    VK_REQUIRE(a && rows >= 0, "vkpbrt_accumulator_set_max_displacement_rows: bad argument");
+    if (rows > 0 && !a->disp_violations) {
+        VK_CUDA(cudaSetDevice(a->ctx->device));
+        VK_CUDA(cudaMalloc((void**)&a->disp_violations, sizeof(uint32_t)));
+        VK_CUDA(cudaMemsetAsync(a->disp_violations, 0, sizeof(uint32_t), a->ctx->stream));
+    }
+    a->max_disp_rows = rows;
+    return VKPBRT_OK;
+}
+
+int vkpbrt_accumulator_displacement_violations(vkpbrt_accumulator_t a, uint32_t* count)
+{
+    VK_REQUIRE(a && count, "null argument");
+    *count = 0;
+    if (!a->disp_violations) return VKPBRT_OK;
+    VK_CUDA(cudaSetDevice(a->ctx->device));
+    VK_CUDA(cudaMemcpyAsync(count, a->disp_violations, sizeof(uint32_t), cudaMemcpyDeviceToHost, a->ctx->stream));
+    VK_CUDA(cudaStreamSynchronize(a->ctx->stream));
+    return VKPBRT_OK;
+}
+
 int vkpbrt_accumulator_record(vkpbrt_accumulator_t a)
 {
     VK_REQUIRE(a, "null accumulator");
@@ -754,6 +779,8 @@ int vkpbrt_accumulator_record(vkpbrt_accumulator_t a)
     p.depth_history = (float*)a->acc->depth_next->data;
     p.one = 1.0f; p.neg_one = -1.0f;
     p.force_scalar = a->force_scalar ? 1 : 0;
+    p.max_disp_rows = a->disp_violations ? a->max_disp_rows : 0;
+    p.disp_violations = a->disp_violations;
     VK_CUDA(cudaSetDevice(a->ctx->device));
     VK_CUDA(vkpbrt::launch_accumulate(p, a->ctx->stream));
     a->ctx->launches++;
@@ -766,6 +793,7 @@ int vkpbrt_accumulator_destroy(vkpbrt_accumulator_t a)
     if (!a) return VKPBRT_OK;
     vkpbrt_illumination_buffer_destroy(a->accumulated);
     vkpbrt_accumulation_buffer_destroy(a->acc);
+    if (a->disp_violations) cudaFree(a->disp_violations);
     delete a;
     return VKPBRT_OK;
 }

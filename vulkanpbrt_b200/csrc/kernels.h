@@ -37,6 +37,11 @@ struct AccumulateParams {
     float* depth_history;         // r32f: next frame's prev_depth (fused copy_to_back), may be null
     float one, neg_one;           // 1.0f / -1.0f as run-time values (common.cuh: packed pairs)
     int force_scalar;             // debug: one pixel per thread with the IEEE library routines (k_accumulate_scalar)
+    // band-sharded runs: a rank only holds history rows within max_disp_rows (+1 bilinear row) of the rows it computes.
+    // A reprojection tap further away (other than through the REPEAT wrap at the image edge) would read rows this rank
+    // never received: it is counted in *disp_violations instead of passing silently (0 / null = no check).
+    int max_disp_rows;
+    uint32_t* disp_violations;
 };
 cudaError_t launch_accumulate(const AccumulateParams& p, cudaStream_t stream);
 

@@ -472,6 +472,15 @@ class Accumulator:
         """debug / test switch: the one-pixel-per-thread kernel with the IEEE library routines"""
         capi.call("vkpbrt_accumulator_set_force_scalar", self._h, 1 if enable else 0)
 
+    def set_max_displacement_rows(self, rows: int) -> None:
+        """band-sharded runs: count reprojection taps that leave the rows this rank holds (0 = off)"""
+        capi.call("vkpbrt_accumulator_set_max_displacement_rows", self._h, int(rows))
+
+    def displacement_violations(self) -> int:
+        n = C.c_uint32(0)
+        capi.call("vkpbrt_accumulator_displacement_violations", self._h, C.byref(n))
+        return int(n.value)
+
     def __del__(self):
         try:
             capi.lib().vkpbrt_accumulator_destroy(self._h)   # also frees the two bundles it owns

@@ -400,6 +400,10 @@ class BandedPipeline:
         self.peer = peer                      # NVLink peer-memory path (GPU, one node): takes precedence over nccl
         self.bmfr = self.pipe.modules[0]
         self.bmfr.set_block_row_range(*self.plan.block_rows(rank))
+        if world > 1:
+            # a rank holds history rows within D (+1) rows of the rows it computes: taps beyond that are counted, not
+            # silently served from stale rows (check() raises)
+            self.pipe.accumulator.set_max_displacement_rows(max_disp_rows)
         c = self.pipe.commands.children
         self._acc_cmd, self._bmfr_cmd = c[0], c[1]
         self._taa_cmd = c[2] if use_taa else None
@@ -645,9 +649,15 @@ class BandedPipeline:
         self._pending_a = self._pending_b = None
 
     def check(self) -> None:
-        """after a device synchronisation: raises if the peer-memory flag protocol reported a timeout"""
+        """after a device synchronisation: raises if the peer-memory flag protocol reported a timeout, or if a
+        reprojection left the history rows this rank holds (camera motion larger than the plan's max_disp_rows)"""
         if self.peer is not None:
             self.peer.check()
+        if self.world > 1:
+            n = self.pipe.accumulator.displacement_violations()
+            if n:
+                raise RuntimeError(f"band-sharded run: {n} reprojection taps moved more than max_disp_rows = {self.plan.D} rows; "
+                                   "the halo does not cover this camera motion (rebuild the BandPlan with a larger max_disp_rows)")
 
     def owned_rows(self, frame: int) -> Rows:
         return self.plan.owned_rows(self.rank, frame)
@@ -663,24 +673,26 @@ def cuda_view(device):
 
 
 # ---------------------------------------------------------------------------------------------------
-# bench.py --gpus N (N > 1): weak scaling, one 1920x1080 band per GPU
+# bench.py --gpus N (N > 1): strong scaling (the workload's frame cut into N bands); --weak: one 1080p band per GPU
 # ---------------------------------------------------------------------------------------------------
-def bench_multi(args, rank: int, world: int, local: int):
+def _sha(t) -> str:
+    import hashlib
+    return hashlib.sha256(t.contiguous().cpu().numpy().tobytes()).hexdigest()
+
+
+def measure_banded(args, name: str, K: int, Wm: int, R: int, rank: int, world: int, local: int, weak: bool, replicas: bool, with_e2e: bool):
+    """one workload band-sharded over the ranks.  Returns the result dict on rank 0, None elsewhere."""
     import torch
     import torch.distributed as dist
 
     from . import synth
     from .modules import Context
-    import bench as B     # the repo-root bench.py (constants, sampler, cpu baseline)
+    import bench as B     # the repo-root bench.py (constants, sampler)
 
-    name = args.workload or "bmfr_1080p"
     W, Hband, taa, desc = B.WORKLOADS[name]
-    replicas = bool(getattr(args, "replicas", False))     # N independent sequences, one per GPU: no communication
-    strong = name != "bmfr_1080p" and not replicas
+    strong = not weak and not replicas
     H = Hband if (strong or replicas) else Hband * world
     prank, pworld = (0, 1) if replicas else (rank, world)
-    K, Wm = args.steps, args.warmup
-    R = min(K + Wm, args.resident_frames)
     dev = torch.device("cuda", local)
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
@@ -688,11 +700,17 @@ def bench_multi(args, rank: int, world: int, local: int):
     assert ctx.stream == stream.cuda_stream
     view = cuda_view(dev)
     halo = getattr(args, "halo", "peer")
-    bp = BandedPipeline(W, H, prank, pworld, taa, ctx, view, dist=dist,
+    # reprojection displacement grows with the resolution: 24 rows per 1080 rows of image height
+    max_disp = max(24, -(-24 * Hband // 1080))
+    bp = BandedPipeline(W, H, prank, pworld, taa, ctx, view, max_disp_rows=max_disp, dist=dist,
                         nccl=NcclDirect(dist, rank, world, dev) if (halo == "nccl" and not replicas) else None,
                         peer=PeerDirect(dist, rank, world, dev, ctx) if (halo == "peer" and not replicas) else None)
     lo, hi = bp.plan.input_rows(prank)
     rows = hi - lo
+    # Parity evidence that travels with the number: rank 0 ALSO runs the same frames through a plain single-GPU pipeline
+    # (outside every timed region) and the ranks' owned rows are compared with it after the set-up frames.
+    verify = (not replicas) and not getattr(args, "no_verify", False)
+    keep_full = verify and rank == 0
     # band-local resident sequence; the kernels index absolute rows through a virtual full-frame base pointer
     mk = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True)
     host = {"depth": mk((R, rows, W), torch.float32), "normal": mk((R, rows, W, 2), torch.float32),
@@ -700,13 +718,17 @@ def bench_multi(args, rank: int, world: int, local: int):
     cams = []
     full = synth.Frame(0, np.zeros((H, W), np.float32), np.zeros((H, W, 2), np.float32), np.zeros((H, W, 4), np.uint8),
                        np.zeros((H, W, 4), np.uint8), np.zeros((H, W, 4), np.float32), None)
+    dfull = {k: [] for k in host}
     t_gen = time.perf_counter()
     for i in range(R):
-        synth.render_frame(W, H, i, rows=(lo, hi), out=full)
+        synth.render_frame(W, H, i, rows=None if keep_full else (lo, hi), out=full)
         host["depth"][i].numpy()[...] = full.depth[lo:hi]
         host["normal"][i].numpy()[...] = full.normal[lo:hi]
         host["albedo"][i].numpy()[...] = full.albedo[lo:hi]
         host["illum"][i].numpy()[...] = full.illumination[lo:hi]
+        if keep_full:
+            for k, a in (("depth", full.depth), ("normal", full.normal), ("albedo", full.albedo), ("illum", full.illumination)):
+                dfull[k].append(torch.from_numpy(a).to(dev))
         cams.append(full.camera)
     t_gen = time.perf_counter() - t_gen
     dseq = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
@@ -717,7 +739,7 @@ def bench_multi(args, rank: int, world: int, local: int):
         bp.pipe.bind_inputs(*[bufs[k][i].data_ptr() - lo * pitch[k] for k in ("depth", "normal", "albedo", "illum")])
 
     def frame(f):
-        i = f % R
+        i = B.seq_index(f, R)
         bind(dseq, i)
         bp.run_frame(f, cams[i])
 
@@ -726,8 +748,38 @@ def bench_multi(args, rank: int, world: int, local: int):
     PRE = 32
     for f in range(PRE):
         frame(f)
+    bp.flush()
     torch.cuda.synchronize()
     bp.check()
+    # ---- banded == single (every jitter phase has been through the exchange twice by now) -----------------------
+    equal = None
+    if verify:
+        layer = ((PRE - 1) & 1) ^ 1
+        mine = bp.owned_rows(PRE - 1)
+        fin = view(bp.pipe.final)                       # [H][W*4]
+        den = view(bp.bmfr.denoised)                    # [2][H][W*8]
+        my_hash = (_sha(fin[mine[0]:mine[1]]), _sha(den[layer, mine[0]:mine[1]]))
+        hashes = [None] * world
+        dist.all_gather_object(hashes, my_hash)
+        if rank == 0:
+            from .pipeline import DenoisePipeline
+            sctx = Context(local, stream.cuda_stream)
+            sp = DenoisePipeline(W, H, DenoisingType.BMFR, DenoisingBlockSize.X32, use_taa=taa, ctx=sctx, external_inputs=True)
+            for f in range(PRE):
+                i = B.seq_index(f, R)
+                sp.bind_inputs(*[dfull[k][i].data_ptr() for k in ("depth", "normal", "albedo", "illum")])
+                sp.set_frame_constants(f, cams[i])
+                sp.record()
+                sp.end_frame(cams[i])
+            torch.cuda.synchronize()
+            sfin, sden = view(sp.final), view(sp.modules[0].denoised)
+            equal = True
+            for g in range(world):
+                o = bp.plan.owned_rows(g, PRE - 1)
+                equal = equal and hashes[g] == (_sha(sfin[o[0]:o[1]]), _sha(sden[layer, o[0]:o[1]]))
+            del sp, sfin, sden
+        dfull.clear()
+        torch.cuda.empty_cache()
     dist.barrier()
     for f in range(PRE, PRE + Wm):
         frame(f)
@@ -771,82 +823,133 @@ def bench_multi(args, rank: int, world: int, local: int):
     value = jobs * W * H * K / (ms * 1e-3) / 1e6
 
     # ---- e2e: per-rank band uploaded from pinned host memory every frame, owned rows of the result read back ----
-    copy_stream = torch.cuda.Stream()
-    dbuf = [{k: torch.empty_like(dseq[k][0]) for k in host} for _ in range(2)]
-    out_host = torch.empty((H, W * 4), dtype=torch.uint8, pin_memory=True)
-    copied = [torch.cuda.Event() for _ in range(2)]
-    consumed = [torch.cuda.Event() for _ in range(2)]
+    e2e = None
+    nframes = PRE + Wm + K
+    if with_e2e:
+        copy_stream = torch.cuda.Stream()
+        dbuf = [{k: torch.empty_like(dseq[k][0]) for k in host} for _ in range(2)]
+        out_host = torch.empty((H, W * 4), dtype=torch.uint8, pin_memory=True)
+        copied = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
 
-    def issue_copy(f):
-        s = f % 2
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[s])
-            for k in host:
-                dbuf[s][k].copy_(host[k][f % R], non_blocking=True)
-            copied[s].record(copy_stream)
+        def issue_copy(f):
+            s = f % 2
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[s])
+                for k in host:
+                    dbuf[s][k].copy_(host[k][B.seq_index(f, R)], non_blocking=True)
+                copied[s].record(copy_stream)
 
-    def frame_e2e(f):
-        s = f % 2
-        stream.wait_event(copied[s])
-        bp.pipe.bind_inputs(*[dbuf[s][k].data_ptr() - lo * pitch[k] for k in ("depth", "normal", "albedo", "illum")])
-        bp.run_frame(f, cams[f % R])
-        consumed[s].record(stream)
-        o = bp.owned_rows(f)
-        out_host[o[0]:o[1]].copy_(view(bp.pipe.final)[o[0]:o[1]], non_blocking=True)     # [H][W*4] bytes
+        def frame_e2e(f):
+            s = f % 2
+            stream.wait_event(copied[s])
+            bp.pipe.bind_inputs(*[dbuf[s][k].data_ptr() - lo * pitch[k] for k in ("depth", "normal", "albedo", "illum")])
+            bp.run_frame(f, cams[B.seq_index(f, R)])
+            consumed[s].record(stream)
+            o = bp.owned_rows(f)
+            out_host[o[0]:o[1]].copy_(view(bp.pipe.final)[o[0]:o[1]], non_blocking=True)     # [H][W*4] bytes
 
-    for s in range(2):
-        consumed[s].record(stream)
-    f0 = PRE + Wm + K
-    issue_copy(f0)
-    for f in range(f0, f0 + 3):
-        issue_copy(f + 1)
-        frame_e2e(f)
-    torch.cuda.synchronize()
-    dist.barrier()
-    e0.record(stream)
-    for f in range(f0 + 3, f0 + 3 + K):
-        issue_copy(f + 1)
-        frame_e2e(f)
-    bp.flush()
-    e1.record(stream)
-    torch.cuda.synchronize()
-    bp.check()
-    dist.barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item())
+        for s in range(2):
+            consumed[s].record(stream)
+        f0 = PRE + Wm + K
+        issue_copy(f0)
+        for f in range(f0, f0 + 3):
+            issue_copy(f + 1)
+            frame_e2e(f)
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0.record(stream)
+        for f in range(f0 + 3, f0 + 3 + K):
+            issue_copy(f + 1)
+            frame_e2e(f)
+        bp.flush()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        bp.check()
+        dist.barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+        nframes += 3 + K
+        e2e = {"value": round(jobs * W * H * K / (e2e_ms * 1e-3) / 1e6, 1), "unit": "MPix/s",
+               "h2d_bytes_per_step": B.INPUT_BYTES * W * rows * world, "d2h_bytes_per_step": 4 * W * H * jobs,
+               "ms_per_step": round(e2e_ms / K, 5)}
+        del dbuf, out_host
     halo_bytes = torch.tensor([bp.bytes_exchanged], device=dev, dtype=torch.float64)
     dist.all_reduce(halo_bytes)
+    res = None
     if rank == 0:
         hbm_peak, peak_src = B.peaks()
         chain = (B.BYTES_ACCUMULATE + B.BYTES_BMFR + (B.BYTES_TAA if taa else 0))
         gbs = jobs * chain * W * H / (ms / K * 1e-3) / 1e9
-        line = {"metric": "BMFR denoised MPix/s", "value": round(value, 1), "unit": "MPix/s", "n_gpus": world, "steps": K, "warmup": Wm,
-                "ms_per_step": round(ms / K, 5), "higher_is_better": True, "scaling": "strong" if strong else "weak",
-                "replicas": jobs if replicas else None,
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": name + ("_replicas" if replicas else ("" if strong else "_bands")),
-                           "description": desc + (f"; {world} independent sequences, one per GPU, no communication" if replicas
-                                                  else f"; band-sharded over {world} GPUs"
-                                                  + ("" if strong else f" (weak scaling: one {W}x{Hband} band per GPU, frame {W}x{H})")),
-                           "width": W, "height": H, "block": 32, "taa": taa, "band_block_rows": bp.plan.brow,
-                           "halo": f"history rows +-{bp.plan.D + 1} (+ REPEAT wrap row) per boundary, "
-                                   + ("stored into the neighbours' HBM over NVLink peer mappings by k_halo_push, flag words for ordering"
-                                      if halo == "peer" else "NCCL send/recv groups per frame"),
-                           "l2": f"inputs larger than L2: {R} resident band frames, each read once per step",
-                           "sequence_generation_s": round(t_gen, 1)},
-                "e2e": {"value": round(jobs * W * H * K / (e2e_ms * 1e-3) / 1e6, 1), "unit": "MPix/s",
-                        "h2d_bytes_per_step": B.INPUT_BYTES * W * rows * world, "d2h_bytes_per_step": 4 * W * H * jobs,
-                        "ms_per_step": round(e2e_ms / K, 5)},
-                "gpu_launches": int(launches) * world, "clocks": clocks,
-                "roofline": {"kernel": "chain (k_accumulate + k_bmfr_block" + (" + k_taa)" if taa else ")"), "bound": "hbm",
-                             "achieved": round(gbs, 1), "peak": hbm_peak * world, "unit": "GB/s",
-                             "frac": round(gbs / (hbm_peak * world), 4), "traffic": None, "peak_source": peak_src,
-                             "note": "aggregate over ranks; per-kernel fractions are reported by the N=1 run"},
-                "halo_bytes_per_step": float(halo_bytes.item()) / (PRE + 2 * K + Wm + 3), "host_enqueue_ms_per_step": round(t_host, 4),
-                "halo_spin_ms_per_step_by_rank": spins, "ms_per_step_by_rank": per_rank_ms, "cpu_baseline": None}
-    else:
-        line = None
+        res = {"workload": name, "value": round(value, 1), "unit": "MPix/s", "ms_per_step": round(ms / K, 5), "steps": K, "warmup": Wm,
+               "scaling": "strong" if strong else "weak", "replicas": jobs if replicas else None,
+               "width": W, "height": H,
+               "sharding": {"mode": ("replicas" if replicas else ("strong" if strong else "weak")) ,
+                            "description": (f"{world} independent sequences, one per GPU, no communication" if replicas
+                                            else f"frame {W}x{H} cut into {world} horizontal block bands"
+                                            + ("" if strong else f" (weak scaling: one {W}x{Hband} band per GPU)")),
+                            "band_block_rows": bp.plan.brow,
+                            "halo": f"history rows +-{bp.plan.D + 1} (+ REPEAT wrap row) per boundary, "
+                                    + ("stored into the neighbours' HBM over NVLink peer mappings by k_halo_push, flag words for ordering"
+                                       if halo == "peer" else "NCCL send/recv groups per frame"),
+                            "resident_band_frames": R, "sequence_generation_s": round(t_gen, 1)},
+               "banded_equals_single": equal,
+               "banded_equals_single_note": (f"after {PRE} frames (every jitter phase twice): each rank's owned rows of the final image and of the "
+                                             "denoised history, SHA-256, against a single-GPU run of the same frames on rank 0" if verify else None),
+               "e2e": e2e, "gpu_launches": int(launches) * world, "clocks": clocks,
+               "roofline": {"kernel": "chain (k_accumulate + k_bmfr_block" + (" + k_taa)" if taa else ")"), "bound": "hbm",
+                            "achieved": round(gbs, 1), "peak": hbm_peak * world, "unit": "GB/s",
+                            "frac": round(gbs / (hbm_peak * world), 4), "traffic": None, "peak_source": peak_src,
+                            "note": "aggregate over ranks; per-kernel fractions are reported by the N=1 run"},
+               "halo_bytes_per_step": float(halo_bytes.item()) / nframes, "host_enqueue_ms_per_step": round(t_host, 4),
+               "halo_spin_ms_per_step_by_rank": spins, "ms_per_step_by_rank": per_rank_ms}
+    dist.barrier()
+    if bp.peer is not None:
+        bp.peer.close()
+    del bp, dseq, host
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    return res
+
+
+def bench_multi(args, rank: int, world: int, local: int):
+    import torch.distributed as dist
+
+    import bench as B
+
+    name = args.workload or B.DEFAULT_WORKLOAD
+    replicas = bool(getattr(args, "replicas", False))     # N independent sequences, one per GPU: no communication
+    weak = bool(getattr(args, "weak", False))
+    K, Wm = args.steps, args.warmup
+    R = min(K + Wm, args.resident_frames)
+    if name == "bmfr_8k":
+        R = min(R, 8)
+    r = measure_banded(args, name, K, Wm, R, rank, world, local, weak, replicas, with_e2e=True)
+    also = {}
+    if world == 8 and args.workload is None and not getattr(args, "no_also", False) and not replicas and not weak:
+        # BASELINE configs[4]: the 8K frame across the 8 GPUs
+        try:
+            r8 = measure_banded(args, "bmfr_8k", 10, 3, 6, rank, world, local, False, False, with_e2e=False)
+            if r8 is not None:
+                also["bmfr_8k"] = {"config": B.config_of("bmfr_8k"), **{k: r8[k] for k in
+                                   ("value", "unit", "ms_per_step", "steps", "warmup", "scaling", "sharding", "banded_equals_single",
+                                    "roofline", "halo_spin_ms_per_step_by_rank", "ms_per_step_by_rank", "gpu_launches")}}
+        except Exception as e:  # pragma: no cover -- a secondary workload must not cost the headline line
+            also["bmfr_8k"] = {"error": f"{type(e).__name__}: {e}"}
+    line = None
+    if rank == 0:
+        cfg = B.config_of(name)
+        if r["height"] != cfg["height"]:
+            cfg = dict(cfg, workload=name + "_bands", height=r["height"])
+        line = {"metric": "BMFR denoised MPix/s", "value": r["value"], "unit": "MPix/s", "n_gpus": world, "steps": K, "warmup": Wm,
+                "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": r["scaling"], "replicas": r["replicas"],
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg, "sharding": r["sharding"],
+                "banded_equals_single": r["banded_equals_single"], "banded_equals_single_note": r["banded_equals_single_note"],
+                "e2e": r["e2e"], "gpu_launches": r["gpu_launches"], "clocks": r["clocks"], "roofline": r["roofline"],
+                "halo_bytes_per_step": r["halo_bytes_per_step"], "host_enqueue_ms_per_step": r["host_enqueue_ms_per_step"],
+                "halo_spin_ms_per_step_by_rank": r["halo_spin_ms_per_step_by_rank"], "ms_per_step_by_rank": r["ms_per_step_by_rank"],
+                "cpu_baseline": None, "also": also}
     dist.barrier()
     dist.destroy_process_group()
     return line
