@@ -66,6 +66,10 @@ VKPBRT_API int vkpbrt_context_synchronize(vkpbrt_context_t ctx);
 VKPBRT_API int vkpbrt_context_stream(vkpbrt_context_t ctx, void** cuda_stream);
 /* number of kernels this context has launched so far (bench.py's gpu_launches)               */
 VKPBRT_API int vkpbrt_context_launch_count(vkpbrt_context_t ctx, uint64_t* out);
+/* Device-side self check (tests): evaluates the tone-map quantiser of bmfrPost.comp:121-123 / bfr.comp:306-308 for
+ * EVERY non-negative binary32 input both ways -- the kernels' threshold search and the pow form -- and returns the
+ * number of inputs on which they differ (must be 0) and the smallest such bit pattern. */
+VKPBRT_API int vkpbrt_debug_tonemap_sweep(vkpbrt_context_t ctx, uint64_t* mismatches, uint32_t* first_mismatch);
 
 /* ---------------------------------------------------------------------------------------- */
 /* images  ~ vsg::ref_ptr<vsg::DescriptorImage>                                              */

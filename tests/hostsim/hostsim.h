@@ -89,6 +89,12 @@ inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
 // atomics / fences / timer used by the halo kernels (ranks = OS threads: real concurrency)
 inline uint32_t atomicAdd(uint32_t* p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline uint32_t atomicMin(uint32_t* p, uint32_t v)
+{
+    uint32_t old = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (old > v && !__atomic_compare_exchange_n(p, &old, v, true, __ATOMIC_SEQ_CST, __ATOMIC_RELAXED)) {}
+    return old;
+}
 inline uint32_t atomicExch(uint32_t* p, uint32_t v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
 inline unsigned long long atomicMax(unsigned long long* p, unsigned long long v)
 {

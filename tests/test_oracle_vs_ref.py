@@ -32,6 +32,7 @@ CASES = [
     (168, 104, "bfr", 16, False, 2, 0, True, False),
     (128, 96, "bfr", 8, False, 2, 0, True, False),
     (160, 128, "bfrx3", 32, True, 3, 0, True, False),       # BASELINE configs[2] structure: 3 x BFR + blender (+ TAA)
+    (160, 128, "bmfrx3", 32, True, 3, 7, True, False),      # 3 x BMFR + blender (DenoiserUtils.cpp:106-124), frames 7-9
     (256, 128, "bmfr", 32, True, 3, 0, False, False),       # accumulator.comp without SEPARATE_MATRICES
     (256, 128, "bmfr", 32, False, 2, 0, True, True),        # rgba16f raw illumination
 ]

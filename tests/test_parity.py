@@ -76,6 +76,25 @@ def test_bfr_x8x16x32_blender_taa(backend, oracle):
     run_sequence(oracle, 160, 128, 3, denoiser="bfrx3", block=32, use_taa=True)
 
 
+def test_bmfr_x8x16x32_blender_taa(backend, oracle):
+    """three BMFRs (b = 8 / 16 / 32) + BFRBlender (+ TAA): the BMFR branch of add_denoiser_to_commands
+    (DenoiserUtils.cpp:106-124); frames 7-9 include both negative-jitter phases"""
+    run_sequence(oracle, 160, 128, 3, first=7, denoiser="bmfrx3", block=32, use_taa=True)
+
+
+def test_one_pixel_per_thread_kernels(backend, oracle):
+    """the scalar k_accumulate / k_taa (odd widths, unaligned planes; selectable through the C ABI) against the oracle,
+    i.e. bit-identical to the default two-pixel packed kernels; second case: an odd width, which selects them by itself"""
+    W, H = 192, 96
+    pipe, orc = make_pair(oracle, W, H, denoiser="bmfr", block=32, use_taa=True)
+    pipe.accumulator.set_force_scalar(True)
+    pipe.taa.set_force_scalar(True)
+    for f in range(3):
+        step_both(oracle, pipe, orc, W, H, f)
+        assert_frame_equal(pipe, orc, f)
+    run_sequence(oracle, 161, 97, 3, first=8, denoiser="bmfr", block=32, use_taa=True)
+
+
 def test_bfr_l1_branch_after_ten_samples(backend, oracle):
     """after ~10 accumulated frames pixel_spp >= SPP_THRESH switches residuals to sign() (bfr.comp:267-268)"""
     W, H = 96, 64
@@ -114,19 +133,50 @@ def test_bfr_blender_1080p(backend, oracle):
     run_sequence(oracle, 1920, 1080, 2, denoiser="bfrx3", block=32, use_taa=False)
 
 
-def test_replay_is_deterministic_8k(backend, oracle):
-    """size-independent property at the largest BASELINE size: two independent pipelines fed the same
-    7680x4320 frames produce identical bytes (no atomics / scheduling dependence in any kernel)"""
+def test_bmfr_8k_two_frames(backend, oracle):
+    """BASELINE.json configs[4] at full size, 7680x4320, against the oracle: frames 8 and 9 (the two negative-jitter
+    phases: rows 0-1 / column 0 stay unwritten), every plane bit for bit"""
     _gpu_only(backend)
-    from vulkanpbrt_b200 import DenoisePipeline, synth
-    W, H = 7680, 4320
-    outs = []
-    for _ in range(2):
-        pipe = DenoisePipeline(W, H, use_taa=True)
-        for f in range(2):
-            pipe.run_frame(f, synth.render_frame(W, H, f))
-        pipe.ctx.synchronize()
-        outs.append((pipe.final.download(), pipe.modules[0].denoised.download()))
-        del pipe
-    np.testing.assert_array_equal(outs[0][0], outs[1][0])
-    np.testing.assert_array_equal(outs[0][1], outs[1][1])
+    pipe, orc = run_sequence(oracle, 7680, 4320, 2, first=8, denoiser="bmfr", block=32, use_taa=True)
+    frac, p = tolerance_report(oracle, pipe.modules[0].denoised.download(), orc.denoised[32])
+    assert frac >= 0.999 and p >= 60.0
+
+
+def test_bmfr_256x256_60_frames(backend, oracle):
+    """BASELINE.json configs[0] at its full length: 60 frames of the 256x256 chain + TAA -- all 16 jitter phases several
+    times over, sample counts far past the L1 threshold; every plane of every frame bit for bit"""
+    _gpu_only(backend)
+    run_sequence(oracle, 256, 256, 60, denoiser="bmfr", block=32, use_taa=True)
+
+
+def test_sample_count_saturation_300_frames(backend, oracle):
+    """spp counts in units of 1/255 and saturates after 255 accumulated frames: 300 frames of a
+    static camera at 64x64, final frame compared plane by plane"""
+    _gpu_only(backend)
+    from vulkanpbrt_b200 import synth
+    W, H = 64, 64
+    pipe, orc = make_pair(oracle, W, H, denoiser="bmfr", block=32, use_taa=True)
+    fr0 = synth.render_frame(W, H, 0)
+    for f in range(300):
+        fr = synth.render_frame(W, H, f)
+        fr.camera = fr0.camera                      # static camera: every pixel keeps reprojecting onto itself
+        fr.depth[...] = fr0.depth
+        fr.normal[...] = fr0.normal
+        fr.albedo[...] = fr0.albedo
+        pipe.run_frame(f, fr)
+        orc.run_frame(f, fr)
+    pipe.ctx.synchronize()
+    assert int(orc.spp.max()) == 255
+    assert_frame_equal(pipe, orc, 299)
+
+
+def test_tonemap_threshold_search_equals_pow_for_every_input(backend, oracle):
+    """common.cuh tonemap_code (estimate + two threshold compares) against the vk_pow form, on the device, for ALL
+    2^31 - 2^23 + 1 non-negative binary32 inputs"""
+    _gpu_only(backend)
+    import ctypes as C
+    from vulkanpbrt_b200 import Context, _capi
+    ctx = Context(0)
+    bad, first = C.c_uint64(0), C.c_uint32(0)
+    _capi.call("vkpbrt_debug_tonemap_sweep", ctx.handle, C.byref(bad), C.byref(first))
+    assert bad.value == 0, f"{bad.value} inputs differ, first bit pattern 0x{first.value:08x}"

@@ -87,6 +87,7 @@ _PROTOS = {
     "vkpbrt_context_synchronize": [H],
     "vkpbrt_context_stream": [H, PH],
     "vkpbrt_context_launch_count": [H, C.POINTER(u64)],
+    "vkpbrt_debug_tonemap_sweep": [H, C.POINTER(u64), C.POINTER(u32)],
     "vkpbrt_image_create": [H, u32, u32, u32, u32, PH],
     "vkpbrt_image_wrap": [H, u32, u32, u32, u32, C.c_void_p, PH],
     "vkpbrt_image_set_data": [H, C.c_void_p],

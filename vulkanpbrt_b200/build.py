@@ -34,6 +34,7 @@ UNITS = {
     "bmfr.cu": [],
     "bfr.cu": [],
     "halo.cu": [],
+    "debug.cu": [],
     "api.cpp": [],
 }
 

@@ -297,6 +297,30 @@ int vkpbrt_context_launch_count(vkpbrt_context_t ctx, uint64_t* out)
     return VKPBRT_OK;
 }
 
+// ---- device-side self checks ---------------------------------------------------------------------
+int vkpbrt_debug_tonemap_sweep(vkpbrt_context_t ctx, uint64_t* mismatches, uint32_t* first_mismatch)
+{
+    VK_REQUIRE(ctx && mismatches && first_mismatch, "vkpbrt_debug_tonemap_sweep: null argument");
+    VK_CUDA(cudaSetDevice(ctx->device));
+    unsigned long long* d_bad = nullptr;
+    VK_CUDA(cudaMalloc((void**)&d_bad, 16));
+    uint32_t* d_first = reinterpret_cast<uint32_t*>(d_bad + 1);
+    const unsigned long long zero = 0;
+    const uint32_t none = 0xffffffffu;
+    VK_CUDA(cudaMemcpyAsync(d_bad, &zero, 8, cudaMemcpyHostToDevice, ctx->stream));
+    VK_CUDA(cudaMemcpyAsync(d_first, &none, 4, cudaMemcpyHostToDevice, ctx->stream));
+    cudaError_t e = vkpbrt::launch_tonemap_sweep(d_bad, d_first, ctx->stream);
+    unsigned long long bad = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, d_bad, 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(first_mismatch, d_first, 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_bad);
+    VK_CUDA(e);
+    *mismatches = bad;
+    ctx->launches++;
+    return VKPBRT_OK;
+}
+
 // ---- images ------------------------------------------------------------------------------------
 int vkpbrt_image_create(vkpbrt_context_t ctx, uint32_t format, uint32_t width, uint32_t height, uint32_t layers,
                         vkpbrt_image_t* out)

@@ -152,6 +152,9 @@ struct HaloWaitParams {
     unsigned long long* wait_ns;  // statistics
     unsigned long long timeout_ns;
 };
+// ---- device-side self checks (debug.cu) ----------------------------------------------------------
+cudaError_t launch_tonemap_sweep(unsigned long long* bad, uint32_t* first_bad, cudaStream_t stream);
+
 cudaError_t launch_halo_push(const HaloPushParams& p, int parts, cudaStream_t stream);
 cudaError_t launch_halo_wait(const HaloWaitParams& p, cudaStream_t stream);
 
