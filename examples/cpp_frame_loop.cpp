@@ -48,13 +48,11 @@ int main(int argc, char** argv)
         auto accumulation_buffer = accumulator->accumulation_buffer;
         // :443
         ref_ptr<DescriptorImage> final_descriptor_image;
-        std::vector<std::shared_ptr<void>> modules;
         add_denoiser_to_commands(denoising_type, DenoisingBlockSize::X32, commands, context, width, height, ray_tracing_push_constants,
-                                 g_buffer, illumination_buffer, accumulation_buffer, final_descriptor_image, modules);
-        // :448-456
-        ref_ptr<Taa> taa;
+                                 g_buffer, illumination_buffer, accumulation_buffer, final_descriptor_image);
+        // :448-456 -- a block-local ref_ptr, exactly as in the reference: the command graph keeps the module alive
         if (use_taa) {
-            taa = Taa::create(width, height, 16, 16, g_buffer, accumulation_buffer, final_descriptor_image);
+            auto taa = Taa::create(width, height, 16, 16, g_buffer, accumulation_buffer, final_descriptor_image);
             taa->compile(context);
             taa->update_image_layouts(context);
             taa->add_dispatch_to_command_graph(commands);

@@ -33,10 +33,16 @@ inline void check(int rc)
     if (rc != VKPBRT_OK) throw std::runtime_error(std::string("vkpbrt: ") + vkpbrt_last_error());
 }
 
+// vsg::Inherit stand-in.  Objects made by T::create() are shared-owned, and -- like vsg nodes -- whatever they add to
+// a command graph keeps them alive: the recorded closures capture keep_alive(), so a module held only by a block-local
+// ref_ptr (auto taa = Taa::create(...), VulkanPBRT.cpp:450; the denoisers of util/DenoiserUtils.cpp) lives as long as
+// the Commands object that replays it.
 template <typename T>
-struct Inherit {
+struct Inherit : std::enable_shared_from_this<T> {
     template <typename... Args>
     static ref_ptr<T> create(Args&&... args) { return std::make_shared<T>(std::forward<Args>(args)...); }
+protected:
+    std::shared_ptr<void> keep_alive() { return this->weak_from_this().lock(); }     // null for objects not made by create()
 };
 
 struct mat4 {
@@ -214,7 +220,7 @@ public:
     void add_dispatch_to_command_graph(ref_ptr<Commands> command_graph)
     {
         auto h = handle;
-        command_graph->addChild([h](Commands&) { check(vkpbrt_accumulator_record(h)); });
+        command_graph->addChild([h, keep = keep_alive()](Commands&) { check(vkpbrt_accumulator_record(h)); });
     }
     void set_camera_matrices(int frame_index, const CameraMatrices& cur, const CameraMatrices& prev)
     {
@@ -259,11 +265,13 @@ public:
     void add_dispatch_to_command_graph(ref_ptr<Commands> command_graph, ref_ptr<PushConstants> push_constants)
     {
         auto h = handle;
-        command_graph->addChild([h, push_constants](Commands& c) { c.bound_push_constants = push_constants; check(vkpbrt_bmfr_record(h, push_constants->c())); });
+        command_graph->addChild([h, push_constants, keep = keep_alive()](Commands& c) { c.bound_push_constants = push_constants; check(vkpbrt_bmfr_record(h, push_constants->c())); });
     }
     ref_ptr<DescriptorImage> get_final_descriptor_image() const { return _final; }
     // band-sharded runs (not in the reference): block rows of the jittered grid this device fits
     void set_block_row_range(int begin, int end) { check(vkpbrt_bmfr_set_block_row_range(handle, begin, end)); }
+    // 0: the context's stream; 1, 2: a side lane, concurrent with the other denoisers of the frame (not in the reference)
+    void set_lane(int lane) { check(vkpbrt_bmfr_set_lane(handle, lane)); }
     vkpbrt_bmfr_t handle = nullptr;
 private:
     struct Keep { ref_ptr<GBuffer> g; ref_ptr<IlluminationBuffer> i; ref_ptr<AccumulationBuffer> a; } _keep;
@@ -287,9 +295,10 @@ public:
     void add_dispatch_to_command_graph(ref_ptr<Commands> command_graph, ref_ptr<PushConstants> push_constants)
     {
         auto h = handle;
-        command_graph->addChild([h, push_constants](Commands& c) { c.bound_push_constants = push_constants; check(vkpbrt_bfr_record(h, push_constants->c())); });
+        command_graph->addChild([h, push_constants, keep = keep_alive()](Commands& c) { c.bound_push_constants = push_constants; check(vkpbrt_bfr_record(h, push_constants->c())); });
     }
     ref_ptr<DescriptorImage> get_final_descriptor_image() const { return _final; }
+    void set_lane(int lane) { check(vkpbrt_bfr_set_lane(handle, lane)); }     // see BMFR::set_lane
     vkpbrt_bfr_t handle = nullptr;
 private:
     struct Keep { ref_ptr<GBuffer> g; ref_ptr<IlluminationBuffer> i; ref_ptr<AccumulationBuffer> a; } _keep;
@@ -315,7 +324,7 @@ public:
     void add_dispatch_to_command_graph(ref_ptr<Commands> command_graph)
     {
         auto h = handle;
-        command_graph->addChild([h](Commands&) { check(vkpbrt_bfr_blender_record(h)); });
+        command_graph->addChild([h, keep = keep_alive()](Commands&) { check(vkpbrt_bfr_blender_record(h)); });
     }
     ref_ptr<DescriptorImage> get_final_descriptor_image() const { return _final; }
     vkpbrt_bfr_blender_t handle = nullptr;
@@ -341,7 +350,7 @@ public:
     void add_dispatch_to_command_graph(ref_ptr<Commands> command_graph)
     {
         auto h = handle;
-        command_graph->addChild([h](Commands& c) {
+        command_graph->addChild([h, keep = keep_alive()](Commands& c) {
             if (!c.bound_push_constants) throw std::runtime_error("Taa: no push constants bound; record a denoiser first (Taa.cpp:99-107)");
             check(vkpbrt_taa_record(h, c.bound_push_constants->c()));
         });
@@ -357,20 +366,19 @@ private:
     ref_ptr<DescriptorImage> _den, _final;
 };
 
-// source/util/DenoiserUtils.hpp:11-15.  `compile` is the context the reference reaches through
-// vsg::CompileTraversal::context; `modules` keeps the created modules alive (the reference leaks them into the graph).
+// source/util/DenoiserUtils.hpp:11-15 -- the reference's signature (`compile` is the context the reference reaches
+// through vsg::CompileTraversal::context).  The created modules are owned by `commands`, as in the reference, where the
+// vsg command graph keeps them.
 inline void add_denoiser_to_commands(DenoisingType denoising_type, DenoisingBlockSize denoising_size, ref_ptr<Commands>& commands,
                                      Context& compile, int width, int height, ref_ptr<PushConstants> compute_constants,
                                      ref_ptr<GBuffer>& g_buffer, ref_ptr<IlluminationBuffer>& illumination_buffer,
-                                     ref_ptr<AccumulationBuffer>& accumulation_buffer, ref_ptr<DescriptorImage>& final_descriptor_image,
-                                     std::vector<std::shared_ptr<void>>& modules)
+                                     ref_ptr<AccumulationBuffer>& accumulation_buffer, ref_ptr<DescriptorImage>& final_descriptor_image)
 {
     auto one = [&](auto mod) {
         mod->compile(compile);
         mod->update_image_layouts(compile);
         mod->add_dispatch_to_command_graph(commands, compute_constants);
         final_descriptor_image = mod->get_final_descriptor_image();
-        modules.push_back(mod);
     };
     auto size_of = [&]() { return denoising_size == DenoisingBlockSize::X8 ? 8u : denoising_size == DenoisingBlockSize::X16 ? 16u : 32u; };
     switch (denoising_type) {
@@ -380,17 +388,20 @@ inline void add_denoiser_to_commands(DenoisingType denoising_type, DenoisingBloc
     case DenoisingType::BMFR: {
         const bool bmfr = denoising_type == DenoisingType::BMFR;
         if (denoising_size == DenoisingBlockSize::X8X16X32) {
+            // DenoiserUtils.cpp:48-70 / :106-124.  The three block sizes are independent: b = 16 and b = 32 run on side
+            // lanes, concurrently with b = 8; the blender (context stream) waits for all three.
             std::vector<ref_ptr<DescriptorImage>> finals;
+            int lane = 0;
             for (uint32_t b : {8u, 16u, 32u}) {
-                if (bmfr) { auto m = BMFR::create(width, height, b, b, g_buffer, illumination_buffer, accumulation_buffer, b == 8 ? 64u : 256u); m->compile(compile); m->add_dispatch_to_command_graph(commands, compute_constants); finals.push_back(m->get_final_descriptor_image()); modules.push_back(m); }
-                else { auto m = BFR::create(width, height, b, b, g_buffer, illumination_buffer, accumulation_buffer); m->compile(compile); m->add_dispatch_to_command_graph(commands, compute_constants); finals.push_back(m->get_final_descriptor_image()); modules.push_back(m); }
+                if (bmfr) { auto m = BMFR::create(width, height, b, b, g_buffer, illumination_buffer, accumulation_buffer, b == 8 ? 64u : 256u); m->set_lane(lane); m->compile(compile); m->add_dispatch_to_command_graph(commands, compute_constants); finals.push_back(m->get_final_descriptor_image()); }
+                else { auto m = BFR::create(width, height, b, b, g_buffer, illumination_buffer, accumulation_buffer); m->set_lane(lane); m->compile(compile); m->add_dispatch_to_command_graph(commands, compute_constants); finals.push_back(m->get_final_descriptor_image()); }
+                ++lane;
             }
             auto blender = BFRBlender::create(width, height, illumination_buffer->illumination_images[0], illumination_buffer->illumination_images[1],
                                               finals[0], finals[1], finals[2]);
             blender->compile(compile);
             blender->add_dispatch_to_command_graph(commands);
             final_descriptor_image = blender->get_final_descriptor_image();
-            modules.push_back(blender);
         } else if (bmfr) {
             one(BMFR::create(width, height, size_of(), size_of(), g_buffer, illumination_buffer, accumulation_buffer, size_of() == 8 ? 64u : 256u));
         } else {
@@ -399,6 +410,16 @@ inline void add_denoiser_to_commands(DenoisingType denoising_type, DenoisingBloc
         break;
     }
     }
+}
+// round-1 form with an explicit keep-alive list: the commands own the modules now, the list stays empty
+inline void add_denoiser_to_commands(DenoisingType denoising_type, DenoisingBlockSize denoising_size, ref_ptr<Commands>& commands,
+                                     Context& compile, int width, int height, ref_ptr<PushConstants> compute_constants,
+                                     ref_ptr<GBuffer>& g_buffer, ref_ptr<IlluminationBuffer>& illumination_buffer,
+                                     ref_ptr<AccumulationBuffer>& accumulation_buffer, ref_ptr<DescriptorImage>& final_descriptor_image,
+                                     std::vector<std::shared_ptr<void>>&)
+{
+    add_denoiser_to_commands(denoising_type, denoising_size, commands, compile, width, height, compute_constants, g_buffer, illumination_buffer,
+                             accumulation_buffer, final_descriptor_image);
 }
 
 // ---- band-sharded multi-GPU runs (no reference counterpart; include/vkpbrt_b200.h, "Band-sharded multi-GPU runs") --------

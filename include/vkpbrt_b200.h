@@ -237,6 +237,11 @@ VKPBRT_API int vkpbrt_bmfr_create(vkpbrt_context_t ctx, uint32_t width, uint32_t
  * enable bit 0: those images; bit 1: every block takes the out-of-line IEEE-division fit (the path a block
  * falls back to when an operand leaves the range the reciprocal division is proven exact for) */
 VKPBRT_API int vkpbrt_bmfr_set_debug_outputs(vkpbrt_bmfr_t b, int enable);
+/* Side lanes.  Denoisers of one frame that do not depend on each other (the three block sizes of X8X16X32) can run
+ * concurrently: lane 0 (default) records on the context's stream, lanes 1 and 2 on streams of their own that are forked
+ * from the context's stream at record() and joined back into it before whatever is recorded on it next (blender, TAA,
+ * copies, synchronize).  The reference serialises them with COMPUTE->COMPUTE barriers (DenoiserUtils.cpp:48-70). */
+VKPBRT_API int vkpbrt_bmfr_set_lane(vkpbrt_bmfr_t b, int lane);
 VKPBRT_API int vkpbrt_bmfr_compile(vkpbrt_bmfr_t b);
 VKPBRT_API int vkpbrt_bmfr_record(vkpbrt_bmfr_t b, const vkpbrt_push_constants* pc); /* pre+fit+post, one launch */
 VKPBRT_API int vkpbrt_bmfr_set_block_row_range(vkpbrt_bmfr_t b, int block_row_begin, int block_row_end);
@@ -252,6 +257,7 @@ typedef struct vkpbrt_bfr_s* vkpbrt_bfr_t;
 VKPBRT_API int vkpbrt_bfr_create(vkpbrt_context_t ctx, uint32_t width, uint32_t height, uint32_t work_width,
                                  uint32_t work_height, vkpbrt_gbuffer_t g, vkpbrt_illumination_buffer_t illumination,
                                  vkpbrt_accumulation_buffer_t acc, vkpbrt_bfr_t* out);
+VKPBRT_API int vkpbrt_bfr_set_lane(vkpbrt_bfr_t b, int lane);     /* see vkpbrt_bmfr_set_lane */
 VKPBRT_API int vkpbrt_bfr_compile(vkpbrt_bfr_t b);
 VKPBRT_API int vkpbrt_bfr_record(vkpbrt_bfr_t b, const vkpbrt_push_constants* pc);
 VKPBRT_API int vkpbrt_bfr_final_image(vkpbrt_bfr_t b, vkpbrt_image_t* out);

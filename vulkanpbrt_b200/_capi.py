@@ -128,6 +128,7 @@ _PROTOS = {
     "vkpbrt_bmfr_create": [H, u32, u32, u32, u32, H, H, H, u32, PH],
     "vkpbrt_bmfr_set_debug_outputs": [H, i32],
     "vkpbrt_bmfr_compile": [H],
+    "vkpbrt_bmfr_set_lane": [H, i32],
     "vkpbrt_bmfr_record": [H, C.POINTER(PushConstants)],
     "vkpbrt_bmfr_set_block_row_range": [H, i32, i32],
     "vkpbrt_bmfr_final_image": [H, PH],
@@ -135,6 +136,7 @@ _PROTOS = {
     "vkpbrt_bmfr_destroy": [H],
     "vkpbrt_bfr_create": [H, u32, u32, u32, u32, H, H, H, PH],
     "vkpbrt_bfr_compile": [H],
+    "vkpbrt_bfr_set_lane": [H, i32],
     "vkpbrt_bfr_record": [H, C.POINTER(PushConstants)],
     "vkpbrt_bfr_final_image": [H, PH],
     "vkpbrt_bfr_denoised_image": [H, PH],

@@ -15,6 +15,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -99,6 +100,12 @@ struct vkpbrt_context_s {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     std::atomic<uint64_t> launches{0};
+    // side lanes: independent denoisers of one frame (the three block sizes of X8X16X32) run concurrently on their
+    // own streams, forked from / joined back into `stream` with events
+    static constexpr int kLanes = 2;
+    cudaStream_t lane[kLanes] = {nullptr, nullptr};
+    cudaEvent_t fork_ev[kLanes] = {nullptr, nullptr}, join_ev[kLanes] = {nullptr, nullptr};
+    bool lane_pending[kLanes] = {false, false};
 };
 
 struct vkpbrt_image_s {
@@ -163,6 +170,8 @@ struct vkpbrt_bmfr_s {
     // block-invariant per-frame table (csrc/bmfr.cu), double-buffered: slot f & 1 holds frame table_frame[f & 1]
     float* table[2] = {nullptr, nullptr};
     int64_t table_frame[2] = {-1, -1};
+    int lane = 0;                 // as vkpbrt_bfr_s::lane
+    bool tma_enabled = true;      // interior blocks stage their input tiles through TMA (VKPBRT_BMFR_TMA=0 switches it off)
 };
 
 struct vkpbrt_bfr_s {
@@ -173,6 +182,7 @@ struct vkpbrt_bfr_s {
     vkpbrt_accumulation_buffer_t acc;
     vkpbrt_image_t denoised = nullptr, final_image = nullptr;
     bool compiled = false;
+    int lane = 0;                 // 0: the context's stream; 1, 2: a side lane (runs concurrently with the other denoisers of the frame)
     float lr_exp[40], lr_sqrt[40], lr_den[40];
 };
 
@@ -207,6 +217,45 @@ struct vkpbrt_external_semaphore_s {
     cudaExternalSemaphore_t sem;
     bool timeline;
 };
+
+// the context's stream with every side lane joined back into it: all work recorded so far is ordered before whatever
+// the caller enqueues next
+static cudaStream_t joined(vkpbrt_context_t ctx)
+{
+    for (int i = 0; i < vkpbrt_context_s::kLanes; ++i)
+        if (ctx->lane_pending[i]) {
+            cudaStreamWaitEvent(ctx->stream, ctx->join_ev[i], 0);
+            ctx->lane_pending[i] = false;
+        }
+    return ctx->stream;
+}
+// stream of lane `lane` (1-based; 0 = the context's stream), ordered after everything recorded on the context's stream
+static cudaError_t fork_lane(vkpbrt_context_t ctx, int lane, cudaStream_t* out)
+{
+    if (lane <= 0 || lane > vkpbrt_context_s::kLanes) { *out = joined(ctx); return cudaSuccess; }
+    const int i = lane - 1;
+    cudaError_t e = cudaSuccess;
+    if (!ctx->lane[i]) {
+        e = cudaStreamCreateWithFlags(&ctx->lane[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->fork_ev[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->join_ev[i], cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+    }
+    // the lane's previous work (last frame) is already joined or still pending: either way stream order on the lane
+    // itself keeps its launches in sequence
+    e = cudaEventRecord(ctx->fork_ev[i], ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->lane[i], ctx->fork_ev[i], 0);
+    *out = ctx->lane[i];
+    return e;
+}
+static cudaError_t lane_done(vkpbrt_context_t ctx, int lane)
+{
+    if (lane <= 0 || lane > vkpbrt_context_s::kLanes) return cudaSuccess;
+    const int i = lane - 1;
+    cudaError_t e = cudaEventRecord(ctx->join_ev[i], ctx->lane[i]);
+    if (e == cudaSuccess) ctx->lane_pending[i] = true;
+    return e;
+}
 
 // ------------------------------------------------------------------------------------------------
 extern "C" {
@@ -271,6 +320,11 @@ int vkpbrt_context_create(int device, void* cuda_stream, vkpbrt_context_t* out)
 int vkpbrt_context_destroy(vkpbrt_context_t ctx)
 {
     if (!ctx) return VKPBRT_OK;
+    for (int i = 0; i < vkpbrt_context_s::kLanes; ++i) {
+        if (ctx->lane[i]) cudaStreamDestroy(ctx->lane[i]);
+        if (ctx->fork_ev[i]) cudaEventDestroy(ctx->fork_ev[i]);
+        if (ctx->join_ev[i]) cudaEventDestroy(ctx->join_ev[i]);
+    }
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return VKPBRT_OK;
@@ -279,7 +333,7 @@ int vkpbrt_context_destroy(vkpbrt_context_t ctx)
 int vkpbrt_context_synchronize(vkpbrt_context_t ctx)
 {
     VK_REQUIRE(ctx, "null context");
-    VK_CUDA(cudaStreamSynchronize(ctx->stream));
+    VK_CUDA(cudaStreamSynchronize(joined(ctx)));
     return VKPBRT_OK;
 }
 
@@ -307,13 +361,13 @@ int vkpbrt_debug_tonemap_sweep(vkpbrt_context_t ctx, uint64_t* mismatches, uint3
     uint32_t* d_first = reinterpret_cast<uint32_t*>(d_bad + 1);
     const unsigned long long zero = 0;
     const uint32_t none = 0xffffffffu;
-    VK_CUDA(cudaMemcpyAsync(d_bad, &zero, 8, cudaMemcpyHostToDevice, ctx->stream));
-    VK_CUDA(cudaMemcpyAsync(d_first, &none, 4, cudaMemcpyHostToDevice, ctx->stream));
-    cudaError_t e = vkpbrt::launch_tonemap_sweep(d_bad, d_first, ctx->stream);
+    VK_CUDA(cudaMemcpyAsync(d_bad, &zero, 8, cudaMemcpyHostToDevice, joined(ctx)));
+    VK_CUDA(cudaMemcpyAsync(d_first, &none, 4, cudaMemcpyHostToDevice, joined(ctx)));
+    cudaError_t e = vkpbrt::launch_tonemap_sweep(d_bad, d_first, joined(ctx));
     unsigned long long bad = 0;
-    if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, d_bad, 8, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(first_mismatch, d_first, 4, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, d_bad, 8, cudaMemcpyDeviceToHost, joined(ctx));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(first_mismatch, d_first, 4, cudaMemcpyDeviceToHost, joined(ctx));
+    if (e == cudaSuccess) e = cudaStreamSynchronize(joined(ctx));
     cudaFree(d_bad);
     VK_CUDA(e);
     *mismatches = bad;
@@ -366,7 +420,7 @@ int vkpbrt_image_compile(vkpbrt_image_t img)
     VK_CUDA(cudaMalloc(&img->allocation, img->size_bytes()));
     img->data = img->allocation;
     // the reference leaves new images undefined; zero is the documented initial history
-    VK_CUDA(cudaMemsetAsync(img->data, 0, img->size_bytes(), img->ctx->stream));
+    VK_CUDA(cudaMemsetAsync(img->data, 0, img->size_bytes(), joined(img->ctx)));
     return VKPBRT_OK;
 }
 
@@ -388,7 +442,7 @@ int vkpbrt_image_upload(vkpbrt_image_t img, const void* host, uint64_t bytes)
     VK_REQUIRE(img && host, "null argument");
     VK_REQUIRE(img->data, "vkpbrt_image_upload: image not compiled");
     VK_REQUIRE(bytes <= img->size_bytes(), "vkpbrt_image_upload: size exceeds image");
-    VK_CUDA(cudaMemcpyAsync(img->data, host, bytes, cudaMemcpyHostToDevice, img->ctx->stream));
+    VK_CUDA(cudaMemcpyAsync(img->data, host, bytes, cudaMemcpyHostToDevice, joined(img->ctx)));
     return VKPBRT_OK;
 }
 
@@ -397,14 +451,14 @@ int vkpbrt_image_download(vkpbrt_image_t img, void* host, uint64_t bytes)
     VK_REQUIRE(img && host, "null argument");
     VK_REQUIRE(img->data, "vkpbrt_image_download: image not compiled");
     VK_REQUIRE(bytes <= img->size_bytes(), "vkpbrt_image_download: size exceeds image");
-    VK_CUDA(cudaMemcpyAsync(host, img->data, bytes, cudaMemcpyDeviceToHost, img->ctx->stream));
+    VK_CUDA(cudaMemcpyAsync(host, img->data, bytes, cudaMemcpyDeviceToHost, joined(img->ctx)));
     return VKPBRT_OK;
 }
 
 int vkpbrt_image_clear(vkpbrt_image_t img)
 {
     VK_REQUIRE(img && img->data, "vkpbrt_image_clear: image not compiled");
-    VK_CUDA(cudaMemsetAsync(img->data, 0, img->size_bytes(), img->ctx->stream));
+    VK_CUDA(cudaMemsetAsync(img->data, 0, img->size_bytes(), joined(img->ctx)));
     return VKPBRT_OK;
 }
 
@@ -605,7 +659,7 @@ static int swap_or_copy(vkpbrt_image_t cur, vkpbrt_image_t prev)
         std::swap(cur->data, prev->data);
         std::swap(cur->allocation, prev->allocation);
     } else {
-        VK_CUDA(cudaMemcpyAsync(prev->data, cur->data, cur->size_bytes(), cudaMemcpyDeviceToDevice, cur->ctx->stream));
+        VK_CUDA(cudaMemcpyAsync(prev->data, cur->data, cur->size_bytes(), cudaMemcpyDeviceToDevice, joined(cur->ctx)));
     }
     return VKPBRT_OK;
 }
@@ -624,7 +678,7 @@ int vkpbrt_accumulation_buffer_copy_to_back_images(vkpbrt_accumulation_buffer_t 
     } else {
         vkpbrt_image_t d = g->img[VKPBRT_GBUFFER_DEPTH], pd = b->img[VKPBRT_ACC_PREV_DEPTH];
         VK_REQUIRE(d->data && pd->data, "copy_to_back_images: depth image not compiled");
-        VK_CUDA(cudaMemcpyAsync(pd->data, d->data, pd->size_bytes(), cudaMemcpyDeviceToDevice, b->ctx->stream));
+        VK_CUDA(cudaMemcpyAsync(pd->data, d->data, pd->size_bytes(), cudaMemcpyDeviceToDevice, joined(b->ctx)));
     }
     int rc = swap_or_copy(b->img[VKPBRT_ACC_SPP], b->img[VKPBRT_ACC_PREV_SPP]);
     if (rc) return rc;
@@ -746,7 +800,7 @@ int vkpbrt_accumulator_set_max_displacement_rows(vkpbrt_accumulator_t a, int row
     if (rows > 0 && !a->disp_violations) {
         VK_CUDA(cudaSetDevice(a->ctx->device));
         VK_CUDA(cudaMalloc((void**)&a->disp_violations, sizeof(uint32_t)));
-        VK_CUDA(cudaMemsetAsync(a->disp_violations, 0, sizeof(uint32_t), a->ctx->stream));
+        VK_CUDA(cudaMemsetAsync(a->disp_violations, 0, sizeof(uint32_t), joined(a->ctx)));
     }
     a->max_disp_rows = rows;
     return VKPBRT_OK;
@@ -758,8 +812,8 @@ int vkpbrt_accumulator_displacement_violations(vkpbrt_accumulator_t a, uint32_t*
     *count = 0;
     if (!a->disp_violations) return VKPBRT_OK;
     VK_CUDA(cudaSetDevice(a->ctx->device));
-    VK_CUDA(cudaMemcpyAsync(count, a->disp_violations, sizeof(uint32_t), cudaMemcpyDeviceToHost, a->ctx->stream));
-    VK_CUDA(cudaStreamSynchronize(a->ctx->stream));
+    VK_CUDA(cudaMemcpyAsync(count, a->disp_violations, sizeof(uint32_t), cudaMemcpyDeviceToHost, joined(a->ctx)));
+    VK_CUDA(cudaStreamSynchronize(joined(a->ctx)));
     return VKPBRT_OK;
 }
 
@@ -806,7 +860,7 @@ int vkpbrt_accumulator_record(vkpbrt_accumulator_t a)
     p.max_disp_rows = a->disp_violations ? a->max_disp_rows : 0;
     p.disp_violations = a->disp_violations;
     VK_CUDA(cudaSetDevice(a->ctx->device));
-    VK_CUDA(vkpbrt::launch_accumulate(p, a->ctx->stream));
+    VK_CUDA(vkpbrt::launch_accumulate(p, joined(a->ctx)));
     a->ctx->launches++;
     a->acc->depth_next_valid = true;
     return VKPBRT_OK;
@@ -860,6 +914,7 @@ int vkpbrt_bmfr_create(vkpbrt_context_t ctx, uint32_t width, uint32_t height, ui
     b->blocks_y = height / work_height + 2;
     b->g = g; b->illum = illumination; b->acc = acc;
     b->block_row_begin = 0; b->block_row_end = (int)b->blocks_y;
+    if (const char* e = std::getenv("VKPBRT_BMFR_TMA")) b->tma_enabled = std::atoi(e) != 0;
     rc = make_image(ctx, VKPBRT_FORMAT_R16G16B16A16_SFLOAT, width, height, 2, &b->denoised);     // BMFR.cpp:56-75
     if (!rc) rc = make_image(ctx, VKPBRT_FORMAT_B8G8R8A8_UNORM, width, height, 1, &b->final_image);   // :78-93
     if (rc) { vkpbrt_bmfr_destroy(b); return rc; }
@@ -873,6 +928,13 @@ int vkpbrt_bmfr_set_debug_outputs(vkpbrt_bmfr_t b, int enable)
     VK_REQUIRE(!b->compiled, "vkpbrt_bmfr_set_debug_outputs must precede compile()");
     b->debug = (enable & 1) != 0;
     b->force_generic = (enable & 2) != 0;
+    return VKPBRT_OK;
+}
+
+int vkpbrt_bmfr_set_lane(vkpbrt_bmfr_t b, int lane)
+{
+    VK_REQUIRE(b && lane >= 0 && lane <= vkpbrt_context_s::kLanes, "vkpbrt_bmfr_set_lane: lane must be 0, 1 or 2");
+    b->lane = lane;
     return VKPBRT_OK;
 }
 
@@ -942,14 +1004,18 @@ int vkpbrt_bmfr_record(vkpbrt_bmfr_t b, const vkpbrt_push_constants* pc)
     // the frame's block-invariant table: normally written by the previous frame's launch (its spare CTAs produce the
     // table of frame + 1); the first frame, or a frame number that does not follow the previous one, builds it here
     const int slot = (int)(pc->frame_number & 1u);
+    cudaStream_t st = nullptr;
+    VK_CUDA(fork_lane(b->ctx, b->lane, &st));
     if (b->table_frame[slot] != (int64_t)pc->frame_number) {
-        VK_CUDA(vkpbrt::launch_bmfr_table((int)b->work, b->table[slot], pc->frame_number, b->ctx->stream));
+        VK_CUDA(vkpbrt::launch_bmfr_table((int)b->work, b->table[slot], pc->frame_number, st));
         b->ctx->launches++;
         b->table_frame[slot] = (int64_t)pc->frame_number;
     }
     p.table = b->table[slot];
     p.table_next = b->table[slot ^ 1];
-    VK_CUDA(vkpbrt::launch_bmfr(p, b->ctx->stream));
+    if (b->tma_enabled) vkpbrt::bmfr_encode_tma(p);     // descriptors follow the planes bound for this frame
+    VK_CUDA(vkpbrt::launch_bmfr(p, st));
+    VK_CUDA(lane_done(b->ctx, b->lane));
     b->table_frame[slot ^ 1] = (int64_t)(uint32_t)(pc->frame_number + 1u);
     b->ctx->launches++;
     return VKPBRT_OK;
@@ -1017,6 +1083,13 @@ int vkpbrt_bfr_create(vkpbrt_context_t ctx, uint32_t width, uint32_t height, uin
     return VKPBRT_OK;
 }
 
+int vkpbrt_bfr_set_lane(vkpbrt_bfr_t b, int lane)
+{
+    VK_REQUIRE(b && lane >= 0 && lane <= vkpbrt_context_s::kLanes, "vkpbrt_bfr_set_lane: lane must be 0, 1 or 2");
+    b->lane = lane;
+    return VKPBRT_OK;
+}
+
 int vkpbrt_bfr_compile(vkpbrt_bfr_t b)
 {
     VK_REQUIRE(b, "null bfr");
@@ -1049,7 +1122,10 @@ int vkpbrt_bfr_record(vkpbrt_bfr_t b, const vkpbrt_push_constants* pc)
     p.denoised_next = (uint2*)((char*)b->denoised->data + (uint64_t)((pc->frame_number & 1u) ^ 1u) * layer);
     p.final_bgra = (uint32_t*)b->final_image->data;
     VK_CUDA(cudaSetDevice(b->ctx->device));
-    VK_CUDA(vkpbrt::launch_bfr(p, b->ctx->stream));
+    cudaStream_t st = nullptr;
+    VK_CUDA(fork_lane(b->ctx, b->lane, &st));
+    VK_CUDA(vkpbrt::launch_bfr(p, st));
+    VK_CUDA(lane_done(b->ctx, b->lane));
     b->ctx->launches++;
     return VKPBRT_OK;
 }
@@ -1120,9 +1196,10 @@ int vkpbrt_bfr_blender_record(vkpbrt_bfr_blender_t b)
     p.denoised1 = (const uint32_t*)b->den[1]->data;
     p.denoised2 = (const uint32_t*)b->den[2]->data;
     p.final_bgra = (uint32_t*)b->final_image->data;
+    p.one = 1.0f; p.neg_one = -1.0f;
     VK_REQUIRE(p.average && p.average_squared && p.denoised0 && p.denoised1 && p.denoised2, "BFRBlender: an input image is not compiled");
     VK_CUDA(cudaSetDevice(b->ctx->device));
-    VK_CUDA(vkpbrt::launch_bfr_blend(p, b->ctx->stream));
+    VK_CUDA(vkpbrt::launch_bfr_blend(p, joined(b->ctx)));
     b->ctx->launches++;
     return VKPBRT_OK;
 }
@@ -1184,7 +1261,7 @@ int vkpbrt_taa_compile(vkpbrt_taa_t t)
     VK_CUDA(cudaSetDevice(t->ctx->device));
     for (auto& b : t->buf) {
         VK_CUDA(cudaMalloc(&b, bytes));
-        VK_CUDA(cudaMemsetAsync(b, 0, bytes, t->ctx->stream));
+        VK_CUDA(cudaMemsetAsync(b, 0, bytes, joined(t->ctx)));
     }
     t->final_image->data = t->buf[1];
     t->history->data = t->buf[0];
@@ -1219,7 +1296,7 @@ int vkpbrt_taa_record(vkpbrt_taa_t t, const vkpbrt_push_constants* pc)
     p.one = 1.0f; p.neg_one = -1.0f;
     p.force_scalar = t->force_scalar;
     VK_CUDA(cudaSetDevice(t->ctx->device));
-    VK_CUDA(vkpbrt::launch_taa(p, t->ctx->stream));
+    VK_CUDA(vkpbrt::launch_taa(p, joined(t->ctx)));
     t->ctx->launches++;
     // Taa.cpp:106 copy final -> history: both handles now view this frame's output
     t->final_image->data = outb;
@@ -1303,7 +1380,7 @@ int vkpbrt_external_semaphore_wait(vkpbrt_external_semaphore_t s, uint64_t value
     VK_REQUIRE(s, "null semaphore");
     cudaExternalSemaphoreWaitParams wp{};
     wp.params.fence.value = value;
-    VK_CUDA(cudaWaitExternalSemaphoresAsync(&s->sem, &wp, 1, s->ctx->stream));
+    VK_CUDA(cudaWaitExternalSemaphoresAsync(&s->sem, &wp, 1, joined(s->ctx)));
     return VKPBRT_OK;
 }
 
@@ -1312,7 +1389,7 @@ int vkpbrt_external_semaphore_signal(vkpbrt_external_semaphore_t s, uint64_t val
     VK_REQUIRE(s, "null semaphore");
     cudaExternalSemaphoreSignalParams sp{};
     sp.params.fence.value = value;
-    VK_CUDA(cudaSignalExternalSemaphoresAsync(&s->sem, &sp, 1, s->ctx->stream));
+    VK_CUDA(cudaSignalExternalSemaphoresAsync(&s->sem, &sp, 1, joined(s->ctx)));
     return VKPBRT_OK;
 }
 
@@ -1436,8 +1513,8 @@ int vkpbrt_halo_exchange_start(vkpbrt_halo_exchange_t x, void* comm_stream, void
 {
     VK_REQUIRE(x, "null exchange");
     if (!x->has_start) return VKPBRT_OK;
-    cudaStream_t comm = comm_stream ? (cudaStream_t)comm_stream : x->ctx->stream;
-    cudaStream_t after = after_stream ? (cudaStream_t)after_stream : x->ctx->stream;
+    cudaStream_t comm = comm_stream ? (cudaStream_t)comm_stream : joined(x->ctx);
+    cudaStream_t after = after_stream ? (cudaStream_t)after_stream : joined(x->ctx);
     if (comm != after) {
         VK_CUDA(cudaEventRecord(x->ordered, after));
         VK_CUDA(cudaStreamWaitEvent(comm, x->ordered, 0));
@@ -1454,7 +1531,7 @@ int vkpbrt_halo_exchange_wait(vkpbrt_halo_exchange_t x, void* stream, uint32_t v
     VK_REQUIRE(x, "null exchange");
     if (x->wait.n == 0) return VKPBRT_OK;
     x->wait.value = value;
-    VK_CUDA(vkpbrt::launch_halo_wait(x->wait, stream ? (cudaStream_t)stream : x->ctx->stream));
+    VK_CUDA(vkpbrt::launch_halo_wait(x->wait, stream ? (cudaStream_t)stream : joined(x->ctx)));
     x->ctx->launches++;
     return VKPBRT_OK;
 }

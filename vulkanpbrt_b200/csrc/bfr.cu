@@ -276,7 +276,98 @@ VK_DEVICE float lum3(float r, float g, float b)
     return add_rn(add_rn(mul_rn(r, third), mul_rn(g, third)), mul_rn(b, third));
 }
 
+// Round 2: the window statistics from a shared LUMINANCE tile.  The first version (k_bfr_blend_generic below, still
+// used for radii other than 1..3) gathered the (2r+1)^2 rgba16f texels per pixel from global memory, converted and
+// averaged each of them again for every pixel that touches it and divided by the running count with an IEEE division
+// per tap: 1500 instructions per pixel, 10 % of the HBM roofline.  Here a CTA stages the luminance of its 64 x 8 pixels
+// plus an r-texel apron ONCE per texel, every thread folds the windows of two pixels (x and x + 32) at a time in packed
+// fp32 pairs, and the weights 1/n and 1 - 1/n are compile-time constants (same bits as the division: correctly rounded
+// either way).  mix3's divisions by mid = 0.5, 1 - mid = 0.5 and max_dev = 1.0 are exact scalings, written as such.
+template <int R>
+struct BlendWeights {           // w[n-1] = RN(1 / n), omw[n-1] = RN(1 - w), n = 1 .. (2R+1)^2
+    float w[(2 * R + 1) * (2 * R + 1)], omw[(2 * R + 1) * (2 * R + 1)];
+    constexpr BlendWeights() : w{}, omw{}
+    {
+        for (int n = 1; n <= (2 * R + 1) * (2 * R + 1); ++n) {
+            w[n - 1] = 1.0f / (float)n;
+            omw[n - 1] = 1.0f - w[n - 1];
+        }
+    }
+};
+
+VK_DEVICE float mix3_half(float a, float b, float c, float t)      // mix3(a, b, c, t, mid = .5, max_dev = 1)
+{
+    t = gl_min(t, 1.0f);                                            // t / 1.0f == t
+    const float t2 = mul_rn(t, 2.0f);                               // t / 0.5f, exact
+    const float a_fac = gl_max(sub_rn(1.0f, t2), 0.0f);
+    const float b_fac = (t < .5f) ? t2 : sub_rn(1.0f, mul_rn(sub_rn(t, .5f), 2.0f));
+    const float c_fac = sub_rn(sub_rn(1.0f, a_fac), b_fac);
+    return add_rn(add_rn(mul_rn(a_fac, a), mul_rn(b_fac, b)), mul_rn(c_fac, c));
+}
+
+template <int R>
 __global__ void __launch_bounds__(256) k_bfr_blend(const BlendParams p)
+{
+    constexpr int TW = 64 + 2 * R, TH = 8 + 2 * R;
+    __shared__ float lum[TH][TW];
+    const int W = p.W, H = p.H;
+    const int x0 = blockIdx.x * 64, y0 = blockIdx.y * 8;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    for (int i = tid; i < TW * TH; i += 256) {
+        const int ty = i / TW, tx = i - ty * TW;
+        const int sx = x0 + tx - R, sy = y0 + ty - R;
+        float cr = 0.0f, cg = 0.0f, cb = 0.0f;                                  // out of range: robust-access 0
+        if (sx >= 0 && sy >= 0 && sx < W && sy < H) load_rgb16f(p.average, (size_t)sy * W + sx, cr, cg, cb);
+        lum[ty][tx] = lum3(cr, cg, cb);
+    }
+    __syncthreads();
+    const int gx = x0 + threadIdx.x, gy = y0 + threadIdx.y;                     // pixels (gx, gy) and (gx + 32, gy)
+    if (gy >= H || gx >= W) return;                                             // bfrBlender.comp:32
+    const bool has1 = gx + 32 < W;
+    const Pk k{f2_dup(p.one), f2_dup(p.neg_one)};
+    constexpr BlendWeights<R> wt{};
+    f2 sq = f2_make(0.0f, 0.0f), av = sq;
+#pragma unroll
+    for (int dy = 0; dy <= 2 * R; ++dy)
+#pragma unroll
+        for (int dx = 0; dx <= 2 * R; ++dx) {
+            constexpr int dummy = 0; (void)dummy;
+            const int n = dy * (2 * R + 1) + dx;                                // taps in the shader's order: y outer, x inner
+            const f2 cur = f2_make(lum[threadIdx.y + dy][threadIdx.x + dx], lum[threadIdx.y + dy][threadIdx.x + 32 + dx]);
+            const f2 w = f2_dup(wt.w[n]), omw = f2_dup(wt.omw[n]);
+            sq = k.add(f2_mul(sq, omw), f2_mul(f2_mul(cur, cur), w));           // :42-43 mix(x, y, 1/n) = x * (1 - 1/n) + y * (1/n)
+            av = k.add(f2_mul(av, omw), f2_mul(cur, w));
+        }
+    const size_t pix0 = (size_t)gy * W + gx, pix1 = has1 ? pix0 + 32 : pix0;
+    float ar0, ag0, ab0, qr0, qg0, qb0, ar1, ag1, ab1, qr1, qg1, qb1;
+    load_rgb16f(p.average_squared, pix0, qr0, qg0, qb0);
+    load_rgb16f(p.average_squared, pix1, qr1, qg1, qb1);
+    load_rgb16f(p.average, pix0, ar0, ag0, ab0);
+    load_rgb16f(p.average, pix1, ar1, ag1, ab1);
+    const f2 hf = f2_make(.5f, .5f);
+    av = k.add(f2_mul(av, hf), f2_mul(f2_make(lum3(ar0, ag0, ab0), lum3(ar1, ag1, ab1)), hf));       // :46-49 (1 - .5 == .5)
+    sq = k.add(f2_mul(sq, hf), f2_mul(f2_make(lum3(qr0, qg0, qb0), lum3(qr1, qg1, qb1)), hf));
+    const f2 var = k.sub(sq, f2_mul(av, av));
+    const float sd[2] = {__fsqrt_rn(f2_lo(var)), __fsqrt_rn(f2_hi(var))};       // :58 (NaN for a negative argument, as in the shader)
+#pragma unroll
+    for (int l = 0; l < 2; ++l) {
+        if (l == 1 && !has1) break;
+        const size_t pix = l ? pix1 : pix0;
+        const uint32_t d0 = __ldg(p.denoised0 + pix), d1 = __ldg(p.denoised1 + pix), d2 = __ldg(p.denoised2 + pix);
+        uint32_t out = 0xff000000u;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {      // c indexes BGRA8 memory bytes; the blend is per channel
+            const float den2 = unorm8_byte_to_f32(d0, c);                       // :50-52 binding swap
+            const float den1 = unorm8_byte_to_f32(d1, c);
+            const float den0 = unorm8_byte_to_f32(d2, c);
+            out |= (uint32_t)f32_to_unorm8(mix3_half(den0, den1, den2, sd[l])) << (8 * c);
+        }
+        p.final_bgra[pix] = out;
+    }
+}
+
+// any radius: one pixel per thread, global gathers (first version)
+__global__ void __launch_bounds__(256) k_bfr_blend_generic(const BlendParams p)
 {
     const int gx = blockIdx.x * 32 + threadIdx.x, gy = blockIdx.y * 8 + threadIdx.y;
     if (gx >= p.W || gy >= p.H) return;                                         // bfrBlender.comp:32
@@ -315,8 +406,16 @@ __global__ void __launch_bounds__(256) k_bfr_blend(const BlendParams p)
 
 cudaError_t launch_bfr_blend(const BlendParams& p, cudaStream_t stream)
 {
-    dim3 block(32, 8, 1), grid((p.W + 31) / 32, (p.H + 7) / 8, 1);
-    VKPBRT_LAUNCH(k_bfr_blend, grid, block, 0, stream, p);
+    if (p.one != 1.0f || p.neg_one != -1.0f) return cudaErrorInvalidValue;
+    if (p.radius >= 1 && p.radius <= 3) {
+        dim3 block(32, 8, 1), grid((p.W + 63) / 64, (p.H + 7) / 8, 1);
+        if (p.radius == 1) { VKPBRT_LAUNCH((k_bfr_blend<1>), grid, block, 0, stream, p); }
+        else if (p.radius == 2) { VKPBRT_LAUNCH((k_bfr_blend<2>), grid, block, 0, stream, p); }
+        else { VKPBRT_LAUNCH((k_bfr_blend<3>), grid, block, 0, stream, p); }
+    } else {
+        dim3 block(32, 8, 1), grid((p.W + 31) / 32, (p.H + 7) / 8, 1);
+        VKPBRT_LAUNCH(k_bfr_blend_generic, grid, block, 0, stream, p);
+    }
     return cudaGetLastError();
 }
 

@@ -46,6 +46,10 @@ struct AccumulateParams {
 cudaError_t launch_accumulate(const AccumulateParams& p, cudaStream_t stream);
 
 // ---- k_bmfr_block : bmfrPre.comp + bmfrFit.comp + bmfrPost.comp, one launch ---------------
+// a CUtensorMap (TMA descriptor) as plain bytes, so that this header does not need cuda.h
+struct alignas(64) TmaDesc {
+    unsigned char bytes[128];
+};
 struct BmfrParams {
     int W, H;
     int block;                    // work_width == work_height: 8, 16 or 32
@@ -69,7 +73,14 @@ struct BmfrParams {
     const float* table;           // this frame's block-invariant table (bmfr.cu), 10 * block^2 floats
     float* table_next;            // where the launch's spare CTAs write the table of frame + 1 (may be null)
     float one, neg_one;           // 1.0f / -1.0f as run-time values (common.cuh: packed pairs)
+    // TMA descriptors of the stage-1 input planes (32 x 32 texel boxes): blocks whose footprint lies inside the image
+    // fetch their depth / normal / noisy tiles with three cp.async.bulk.tensor.2d instead of per-thread loads
+    int use_tma;
+    TmaDesc tma_depth, tma_normal, tma_noisy;
 };
+// encodes the three descriptors for the planes currently in `p` (host; needs the driver's cuTensorMapEncodeTiled).
+// Leaves use_tma = 0 when a plane cannot be described (row pitch not a multiple of 16 bytes, unaligned base, block != 32).
+void bmfr_encode_tma(BmfrParams& p);
 constexpr size_t bmfr_table_floats(int block) { return (size_t)10 * block * block; }
 cudaError_t launch_bmfr(const BmfrParams& p, cudaStream_t stream);
 cudaError_t launch_bmfr_table(int block, float* table, uint32_t frame, cudaStream_t stream);
@@ -105,6 +116,7 @@ struct BlendParams {
     const uint32_t* denoised1;    // BGRA8 (b = 16)
     const uint32_t* denoised2;    // BGRA8 (b = 32)
     uint32_t* final_bgra;
+    float one, neg_one;           // 1.0f / -1.0f as run-time values (common.cuh: packed pairs)
 };
 cudaError_t launch_bfr_blend(const BlendParams& p, cudaStream_t stream);
 

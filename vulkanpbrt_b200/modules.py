@@ -536,6 +536,10 @@ class BMFR(_BlockDenoiser):
     def create(cls, *a, **k):
         return cls(*a, **k)
 
+    def set_lane(self, lane: int) -> None:
+        """0: the context's stream; 1, 2: a side lane that runs concurrently with the other denoisers of the frame"""
+        capi.call("vkpbrt_bmfr_set_lane", self._h, int(lane))
+
     def set_block_row_range(self, begin: int, end: int) -> None:
         capi.call("vkpbrt_bmfr_set_block_row_range", self._h, begin, end)
 
@@ -572,6 +576,10 @@ class BFR(_BlockDenoiser):
     @classmethod
     def create(cls, *a, **k):
         return cls(*a, **k)
+
+    def set_lane(self, lane: int) -> None:
+        """0: the context's stream; 1, 2: a side lane that runs concurrently with the other denoisers of the frame"""
+        capi.call("vkpbrt_bfr_set_lane", self._h, int(lane))
 
     @property
     def denoised(self) -> DescriptorImage:
@@ -699,6 +707,9 @@ def add_denoiser_to_commands(denoising_type: DenoisingType, denoising_size: Deno
         return d.get_final_descriptor_image(), [d]
     if denoising_size == DenoisingBlockSize.X8X16X32:
         d8, d16, d32 = make(8), make(16), make(32)
+        # the three block sizes are independent: b = 16 and b = 32 run on side lanes, concurrently with b = 8
+        d16.set_lane(1)
+        d32.set_lane(2)
         avg = illumination_buffer.illumination_images[0]
         avg_sq = average_squared_image if average_squared_image is not None else illumination_buffer.illumination_images[1]
         blender = BFRBlender.create(width, height, avg, avg_sq, d8.get_final_descriptor_image(),
