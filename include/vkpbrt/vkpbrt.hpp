@@ -272,6 +272,8 @@ public:
     void set_block_row_range(int begin, int end) { check(vkpbrt_bmfr_set_block_row_range(handle, begin, end)); }
     // 0: the context's stream; 1, 2: a side lane, concurrent with the other denoisers of the frame (not in the reference)
     void set_lane(int lane) { check(vkpbrt_bmfr_set_lane(handle, lane)); }
+    // the shaders' POSITION_TYPE specialisation constant (bmfrGeneral.comp:30-31); 0 = POSITION_DEPTH is what BMFR.cpp runs
+    void set_position_type(int position_type) { check(vkpbrt_bmfr_set_position_type(handle, position_type)); }
     vkpbrt_bmfr_t handle = nullptr;
 private:
     struct Keep { ref_ptr<GBuffer> g; ref_ptr<IlluminationBuffer> i; ref_ptr<AccumulationBuffer> a; } _keep;

@@ -237,6 +237,14 @@ VKPBRT_API int vkpbrt_bmfr_create(vkpbrt_context_t ctx, uint32_t width, uint32_t
  * enable bit 0: those images; bit 1: every block takes the out-of-line IEEE-division fit (the path a block
  * falls back to when an operand leaves the range the reciprocal division is proven exact for) */
 VKPBRT_API int vkpbrt_bmfr_set_debug_outputs(vkpbrt_bmfr_t b, int enable);
+/* The shaders' POSITION_TYPE specialisation constant (bmfrGeneral.comp:30-31; bmfrPre.comp:36-76, bmfrPost.comp:31-71):
+ * 0 POSITION_DEPTH (default -- the only mode the reference's BMFR.cpp instantiates), 1 POSITION_WORLD_DEPTH_NORM,
+ * 2 POSITION_WORLD.  The WORLD modes build the three position features from the camera ray through the pixel and read
+ * view_inverse / proj_inverse of the push constants handed to vkpbrt_bmfr_record. */
+#define VKPBRT_BMFR_POSITION_DEPTH 0
+#define VKPBRT_BMFR_POSITION_WORLD_DEPTH_NORM 1
+#define VKPBRT_BMFR_POSITION_WORLD 2
+VKPBRT_API int vkpbrt_bmfr_set_position_type(vkpbrt_bmfr_t b, int position_type);
 /* Side lanes.  Denoisers of one frame that do not depend on each other (the three block sizes of X8X16X32) can run
  * concurrently: lane 0 (default) records on the context's stream, lanes 1 and 2 on streams of their own that are forked
  * from the context's stream at record() and joined back into it before whatever is recorded on it next (blender, TAA,

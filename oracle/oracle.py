@@ -59,6 +59,8 @@ def lib():
         l.vkpbrt_oracle_bmfr_pre.argtypes = [i32, i32, i32, u32, vp, vp, vp, vp]; l.vkpbrt_oracle_bmfr_pre.restype = None
         l.vkpbrt_oracle_bmfr_fit.argtypes = [i32, i32, i32, i32, u32, vp, vp]; l.vkpbrt_oracle_bmfr_fit.restype = None
         l.vkpbrt_oracle_bmfr_post.argtypes = [i32, i32, i32, u32] + [vp] * 9; l.vkpbrt_oracle_bmfr_post.restype = None
+        l.vkpbrt_oracle_bmfr_pre_ex.argtypes = [i32, i32, i32, u32, i32, vp, vp, vp, vp, vp, vp]; l.vkpbrt_oracle_bmfr_pre_ex.restype = None
+        l.vkpbrt_oracle_bmfr_post_ex.argtypes = [i32, i32, i32, u32, i32, vp, vp] + [vp] * 9; l.vkpbrt_oracle_bmfr_post_ex.restype = None
         l.vkpbrt_oracle_bfr.argtypes = [i32, i32, i32, u32] + [vp] * 8; l.vkpbrt_oracle_bfr.restype = None
         l.vkpbrt_oracle_bfr_lr.argtypes = [i32]; l.vkpbrt_oracle_bfr_lr.restype = C.c_float
         l.vkpbrt_oracle_bfr_blender.argtypes = [i32, i32, i32] + [vp] * 6; l.vkpbrt_oracle_bfr_blender.restype = None
@@ -110,11 +112,12 @@ class OracleChain:
 
     def __init__(self, width: int, height: int, denoiser: str = "bmfr", block: int = 32, use_taa: bool = False,
                  separate_matrices: bool = True, raw_f16: bool = False, fix_taa_swizzle: bool = False,
-                 blend_radius: int = 2):
+                 blend_radius: int = 2, position_type: int = 0):
         W, H = width, height
         self.W, self.H, self.denoiser, self.block = W, H, denoiser, block
         self.use_taa, self.separate, self.raw_f16, self.fix_swz = use_taa, separate_matrices, raw_f16, fix_taa_swizzle
         self.blend_radius = blend_radius
+        self.position_type = position_type      # bmfrGeneral.comp:30-31 POSITION_TYPE (BMFR only)
         z = np.zeros
         # AccumulationBuffer (AccumulationBuffer.cpp:245-339) + accumulated illumination; zero-initialised
         self.prev_depth = z((H, W), np.float32)
@@ -189,10 +192,13 @@ class OracleChain:
                 Wb, Hb = W // b + 2, H // b + 2
                 feat = np.zeros((13, Hb * b, Wb * b), np.uint16)
                 wts = np.zeros((30, Hb, Wb), np.float32)
-                L.vkpbrt_oracle_bmfr_pre(W, H, b, frame_index, _p(self.illum), _p(depth), _p(normal), _p(feat))
+                iv = np.ascontiguousarray(frame.camera.inv_view, dtype=np.float32)      # RayTracingPushConstants (VulkanPBRT.cpp:561)
+                ip = np.ascontiguousarray(frame.camera.inv_proj, dtype=np.float32)
+                L.vkpbrt_oracle_bmfr_pre_ex(W, H, b, frame_index, self.position_type, _p(iv), _p(ip), _p(self.illum), _p(depth), _p(normal),
+                                            _p(feat))
                 L.vkpbrt_oracle_bmfr_fit(W, H, b, T, frame_index, _p(feat), _p(wts))
-                L.vkpbrt_oracle_bmfr_post(W, H, b, frame_index, _p(self.illum), _p(depth), _p(normal), _p(albedo),
-                                          _p(self.motion), _p(self.spp), _p(wts), _p(self.denoised[b]), _p(self.finals[b]))
+                L.vkpbrt_oracle_bmfr_post_ex(W, H, b, frame_index, self.position_type, _p(iv), _p(ip), _p(self.illum), _p(depth), _p(normal),
+                                             _p(albedo), _p(self.motion), _p(self.spp), _p(wts), _p(self.denoised[b]), _p(self.finals[b]))
                 if keep_debug:
                     self.features, self.weights = feat, wts
             else:

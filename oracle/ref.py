@@ -124,9 +124,10 @@ class RefChain(O.OracleChain):
                 ent = dict(common)
                 ent[10] = (feat, F_R16F)
                 ent[11] = (wts, F_R32F)
-                dispatch("bmfrPre", (b, b, b), W, H, 0, self.rt, Wb, Hb, ent)       # BMFR.cpp:203-230: pre, fit, post
+                sfx = {0: "", 1: "_w1", 2: "_w2"}[self.position_type]                # POSITION_TYPE instantiation (oracle/glsl_shim/Makefile)
+                dispatch("bmfrPre" + sfx, (b, b, b), W, H, 0, self.rt, Wb, Hb, ent)       # BMFR.cpp:203-230: pre, fit, post
                 dispatch("bmfrFit", (T, 1, b), W, H, 0, self.rt, Wb, Hb, ent)
-                dispatch("bmfrPost", (b, b, b), W, H, 0, self.rt, Wb, Hb, ent)
+                dispatch("bmfrPost" + sfx, (b, b, b), W, H, 0, self.rt, Wb, Hb, ent)
                 if keep_debug:
                     self.features, self.weights = feat, wts
             else:

@@ -470,10 +470,27 @@ typedef struct {
     float pos[3];
 } bmfr_px_t;
 
+/* camParams of the BMFR shaders (bmfrGeneral.comp:18-24: RayTracingPushConstants); only the WORLD position modes read
+ * the matrices */
+typedef struct {
+    int position_type;          /* bmfrGeneral.comp:30-31: 0 POSITION_DEPTH, 1 POSITION_WORLD_DEPTH_NORM, 2 POSITION_WORLD */
+    const float* inv_view;      /* camParams.inverseViewMatrix, column-major */
+    const float* inv_proj;      /* camParams.inverseProjectionMatrix */
+} bmfr_cam_t;
+
+/* normalize(v.xyz): GLSL leaves the precision open; fixed as v * (1 / sqrt(dot(v, v))), dot summed left to right */
+static inline void normalize3(const float* v, float* o)
+{
+    float inv = 1.0f / sqrtf((v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]);
+    o[0] = v[0] * inv; o[1] = v[1] * inv; o[2] = v[2] * inv;
+}
+
 static void bmfr_block_features(int W, int H, int b, int ox, int oy, int bx, int by,
-                                const uint16_t* noisy_acc, const float* depth, const float* normal, bmfr_px_t* px)
+                                const uint16_t* noisy_acc, const float* depth, const float* normal, const bmfr_cam_t* cam,
+                                bmfr_px_t* px)
 {
     float zmin = 0, zmax = 0;
+    const int ptype = cam ? cam->position_type : 0;
     /* invocation order inside the workgroup: local index = ly*b + lx */
     for (int ly = 0; ly < b; ++ly)
         for (int lx = 0; lx < b; ++lx) {
@@ -493,31 +510,81 @@ static void bmfr_block_features(int W, int H, int b, int ox, int oy, int bx, int
             q->n[1] = sph * sth;
             q->n[2] = cth;
         }
-    /* parallel_reduction_min / max: exact, order-independent */
-    zmin = zmax = px[0].pos[2];
-    for (int i = 1; i < b * b; ++i) {
-        zmin = gl_min(px[i].pos[2], zmin);
-        zmax = gl_max(px[i].pos[2], zmax);
+    if (ptype == 0 || ptype == 1) {
+        /* bmfrPre.comp:37-41 / :45-49: parallel_reduction_min / max are exact and order-independent */
+        zmin = zmax = px[0].pos[2];
+        for (int i = 1; i < b * b; ++i) {
+            zmin = gl_min(px[i].pos[2], zmin);
+            zmax = gl_max(px[i].pos[2], zmax);
+        }
     }
     for (int ly = 0; ly < b; ++ly)
         for (int lx = 0; lx < b; ++lx) {
             bmfr_px_t* q = &px[ly * b + lx];
             float z = q->pos[2];
-            z -= zmin;
-            z /= zmax - zmin + 1e-6f;
+            if (ptype == 0 || ptype == 1) {
+                z -= zmin;
+                z /= zmax - zmin + 1e-6f;
+            }
             q->pos[2] = z;
-            q->pos[0] = (float)lx / ((float)b - 1.0f);
-            q->pos[1] = (float)ly / ((float)b - 1.0f);
+            if (ptype == 0) {
+                q->pos[0] = (float)lx / ((float)b - 1.0f);                     /* :42 */
+                q->pos[1] = (float)ly / ((float)b - 1.0f);
+                continue;
+            }
+            /* bmfrPre.comp:50-57 / :61-67 (same text in bmfrPost.comp:45-52 / :56-62) */
+            float clip[4], wsp[4], vsd[4], nrm[4], wsd[4];
+            const float origin[4] = {0.f, 0.f, 0.f, 1.f};
+            clip[0] = (((float)q->img_x + .5f) / (float)W) * 2.0f - 1.0f;
+            clip[1] = (((float)q->img_y + .5f) / (float)H) * 2.0f - 1.0f;
+            clip[2] = 1.f; clip[3] = 1.f;
+            mat_vec(cam->inv_view, origin, wsp);
+            mat_vec(cam->inv_proj, clip, vsd);
+            normalize3(vsd, nrm);
+            nrm[3] = 0.f;
+            mat_vec(cam->inv_view, nrm, wsd);
+            if (ptype == 1) {
+                for (int i = 0; i < 3; ++i) q->pos[i] = wsd[i] * z;          /* :57 (z: the normalised depth) */
+            } else {
+                for (int i = 0; i < 3; ++i) q->pos[i] = wsp[i] + wsd[i] * z; /* :67 (z: the raw depth) */
+            }
         }
+    if (ptype == 2) {
+        for (int i = 0; i < 3; ++i) {                                       /* :68-73 */
+            float mn = px[0].pos[i], mx = px[0].pos[i];
+            for (int k = 1; k < b * b; ++k) {
+                mn = gl_min(px[k].pos[i], mn);
+                mx = gl_max(px[k].pos[i], mx);
+            }
+            for (int k = 0; k < b * b; ++k) {
+                float v = px[k].pos[i];
+                v -= mn;
+                v /= mx - mn + 1e-6f;
+                px[k].pos[i] = v;
+            }
+        }
+    }
 }
 
 /* ------------------------------------------------------------------------------------ */
 /* bmfrPre.comp:5-97 (POSITION_DEPTH), SURVEY.md App. A.4                               */
 /* feature: r16f [13][Hp][Wp], Hp = (H/b+2)*b, Wp = (W/b+2)*b  (BMFR.cpp:12-13, 99-104) */
 /* ------------------------------------------------------------------------------------ */
+ORACLE_API void vkpbrt_oracle_bmfr_pre_ex(int W, int H, int b, uint32_t frame, int position_type, const float* inv_view,
+                                          const float* inv_proj, const uint16_t* noisy_acc, const float* depth, const float* normal,
+                                          uint16_t* feature);
 ORACLE_API void vkpbrt_oracle_bmfr_pre(int W, int H, int b, uint32_t frame, const uint16_t* noisy_acc,
                                        const float* depth, const float* normal, uint16_t* feature)
 {
+    vkpbrt_oracle_bmfr_pre_ex(W, H, b, frame, 0, NULL, NULL, noisy_acc, depth, normal, feature);
+}
+/* bmfrPre.comp with POSITION_TYPE = position_type (specialisation constant 5, bmfrGeneral.comp:30) */
+ORACLE_API void vkpbrt_oracle_bmfr_pre_ex(int W, int H, int b, uint32_t frame, int position_type, const float* inv_view,
+                                          const float* inv_proj, const uint16_t* noisy_acc, const float* depth, const float* normal,
+                                          uint16_t* feature)
+{
+    const bmfr_cam_t camv = {position_type, inv_view, inv_proj};
+    const bmfr_cam_t* cam = &camv;
     const int Wb = W / b + 2, Hb = H / b + 2, Wp = Wb * b, Hp = Hb * b;
     int ox, oy;
     vkpbrt_oracle_bmfr_block_offset(b, b, frame, &ox, &oy);
@@ -527,7 +594,7 @@ ORACLE_API void vkpbrt_oracle_bmfr_pre(int W, int H, int b, uint32_t frame, cons
 #pragma omp for schedule(static) collapse(2)
         for (int by = 0; by < Hb; ++by)
             for (int bx = 0; bx < Wb; ++bx) {
-                bmfr_block_features(W, H, b, ox, oy, bx, by, noisy_acc, depth, normal, px);
+                bmfr_block_features(W, H, b, ox, oy, bx, by, noisy_acc, depth, normal, cam, px);
                 for (int ly = 0; ly < b; ++ly)
                     for (int lx = 0; lx < b; ++lx) {
                         const bmfr_px_t* q = &px[ly * b + lx];
@@ -681,11 +748,24 @@ static inline float sane(float w) { return (isinf(w) || isnan(w)) ? 0.0f : w; }
 /* ------------------------------------------------------------------------------------ */
 /* bmfrPost.comp:5-124, SURVEY.md App. A.6                                              */
 /* ------------------------------------------------------------------------------------ */
+ORACLE_API void vkpbrt_oracle_bmfr_post_ex(int W, int H, int b, uint32_t frame, int position_type, const float* inv_view,
+                                           const float* inv_proj, const uint16_t* noisy_acc, const float* depth, const float* normal,
+                                           const uint8_t* albedo, const uint16_t* motion, const uint8_t* spp, const float* weights,
+                                           uint16_t* denoised, uint8_t* final_bgra);
 ORACLE_API void vkpbrt_oracle_bmfr_post(int W, int H, int b, uint32_t frame, const uint16_t* noisy_acc,
                                         const float* depth, const float* normal, const uint8_t* albedo,
                                         const uint16_t* motion, const uint8_t* spp, const float* weights,
                                         uint16_t* denoised, uint8_t* final_bgra)
 {
+    vkpbrt_oracle_bmfr_post_ex(W, H, b, frame, 0, NULL, NULL, noisy_acc, depth, normal, albedo, motion, spp, weights, denoised, final_bgra);
+}
+ORACLE_API void vkpbrt_oracle_bmfr_post_ex(int W, int H, int b, uint32_t frame, int position_type, const float* inv_view,
+                                           const float* inv_proj, const uint16_t* noisy_acc, const float* depth, const float* normal,
+                                           const uint8_t* albedo, const uint16_t* motion, const uint8_t* spp, const float* weights,
+                                           uint16_t* denoised, uint8_t* final_bgra)
+{
+    const bmfr_cam_t camv = {position_type, inv_view, inv_proj};
+    const bmfr_cam_t* cam = &camv;
     const int Wb = W / b + 2, Hb = H / b + 2;
     int ox, oy;
     vkpbrt_oracle_bmfr_block_offset(b, b, frame, &ox, &oy);
@@ -695,7 +775,7 @@ ORACLE_API void vkpbrt_oracle_bmfr_post(int W, int H, int b, uint32_t frame, con
 #pragma omp for schedule(static) collapse(2)
         for (int by = 0; by < Hb; ++by)
             for (int bx = 0; bx < Wb; ++bx) {
-                bmfr_block_features(W, H, b, ox, oy, bx, by, noisy_acc, depth, normal, px);
+                bmfr_block_features(W, H, b, ox, oy, bx, by, noisy_acc, depth, normal, cam, px);
                 float w[10][3];
                 for (int f = 0; f < 10; ++f)
                     for (int k = 0; k < 3; ++k)

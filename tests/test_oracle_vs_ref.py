@@ -59,3 +59,25 @@ def test_oracle_equals_reference_shader_source(oracle, ref, W, H, den, block, ta
         if den.startswith("bmfr"):
             np.testing.assert_array_equal(a.features, b.features, err_msg=f"feature buffer, frame {f}")
             np.testing.assert_array_equal(a.weights.view(np.uint32), b.weights.view(np.uint32), err_msg=f"weights, frame {f}")
+
+
+@pytest.mark.parametrize("ptype,block,W,H", [(1, 32, 160, 128), (2, 32, 160, 128), (1, 16, 112, 80), (2, 16, 112, 80)])
+def test_world_position_modes(oracle, ref, ptype, block, W, H):
+    """bmfrPre.comp:45-76 / bmfrPost.comp:40-71 with POSITION_TYPE = 1 (POSITION_WORLD_DEPTH_NORM) and 2 (POSITION_WORLD):
+    the feature buffer now depends on the camera matrices of the push constants; frames 7-9 cover both negative jitters"""
+    a = oracle.OracleChain(W, H, "bmfr", block, use_taa=False, position_type=ptype)
+    b = ref.RefChain(W, H, "bmfr", block, use_taa=False, position_type=ptype)
+    for f in range(7, 10):
+        fr = synth.render_frame(W, H, f)
+        a.run_frame(f, fr, keep_debug=True)
+        b.run_frame(f, fr, keep_debug=True)
+        np.testing.assert_array_equal(a.features, b.features, err_msg=f"feature buffer, frame {f}")
+        np.testing.assert_array_equal(a.weights.view(np.uint32), b.weights.view(np.uint32), err_msg=f"weights, frame {f}")
+        np.testing.assert_array_equal(a.denoised[block], b.denoised[block], err_msg=f"denoised, frame {f}")
+        np.testing.assert_array_equal(a.finals[block], b.finals[block], err_msg=f"final, frame {f}")
+    # the modes are not degenerate copies of POSITION_DEPTH
+    c = oracle.OracleChain(W, H, "bmfr", block, use_taa=False)
+    c.run_frame(7, synth.render_frame(W, H, 7), keep_debug=True)
+    a2 = oracle.OracleChain(W, H, "bmfr", block, use_taa=False, position_type=ptype)
+    a2.run_frame(7, synth.render_frame(W, H, 7), keep_debug=True)
+    assert not np.array_equal(a2.features[4:7], c.features[4:7])

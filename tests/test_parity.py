@@ -82,6 +82,13 @@ def test_bmfr_x8x16x32_blender_taa(backend, oracle):
     run_sequence(oracle, 160, 128, 3, first=7, denoiser="bmfrx3", block=32, use_taa=True)
 
 
+@pytest.mark.parametrize("ptype,block,W,H", [(1, 32, 160, 128), (2, 32, 160, 128), (2, 16, 112, 80), (1, 8, 72, 56)])
+def test_bmfr_world_position_modes(backend, oracle, ptype, block, W, H):
+    """POSITION_WORLD_DEPTH_NORM / POSITION_WORLD (bmfrPre.comp:45-76, bmfrPost.comp:40-71): position features from the
+    camera ray, three block min / max reductions; feature buffer, weights and every plane bit for bit"""
+    run_sequence(oracle, W, H, 3, first=7, denoiser="bmfr", block=block, use_taa=True, debug=True, position_type=ptype)
+
+
 def test_one_pixel_per_thread_kernels(backend, oracle):
     """the scalar k_accumulate / k_taa (odd widths, unaligned planes; selectable through the C ABI) against the oracle,
     i.e. bit-identical to the default two-pixel packed kernels; second case: an odd width, which selects them by itself"""

@@ -7,15 +7,15 @@ BS = {8: DenoisingBlockSize.X8, 16: DenoisingBlockSize.X16, 32: DenoisingBlockSi
 
 
 def make_pair(oracle, W, H, denoiser="bmfr", block=32, use_taa=False, separate_matrices=True, raw_f16=False,
-              fix_taa_swizzle=False, debug=False):
+              fix_taa_swizzle=False, debug=False, position_type=0):
     """(CUDA pipeline, oracle chain) configured identically"""
     x3 = denoiser.endswith("x3")
     dt = DenoisingType.BMFR if denoiser.startswith("bmfr") else DenoisingType.BFR
     bs = DenoisingBlockSize.X8X16X32 if x3 else BS[block]
     pipe = DenoisePipeline(W, H, dt, bs, use_taa=use_taa, separate_matrices=separate_matrices, raw_f16=raw_f16,
-                           fix_taa_swizzle=fix_taa_swizzle, bmfr_debug_outputs=debug, average_squared=x3)
+                           fix_taa_swizzle=fix_taa_swizzle, bmfr_debug_outputs=debug, average_squared=x3, position_type=position_type)
     orc = oracle.OracleChain(W, H, denoiser, block, use_taa=use_taa, separate_matrices=separate_matrices, raw_f16=raw_f16,
-                             fix_taa_swizzle=fix_taa_swizzle)
+                             fix_taa_swizzle=fix_taa_swizzle, position_type=position_type)
     return pipe, orc
 
 

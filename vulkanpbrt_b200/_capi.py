@@ -129,6 +129,7 @@ _PROTOS = {
     "vkpbrt_bmfr_set_debug_outputs": [H, i32],
     "vkpbrt_bmfr_compile": [H],
     "vkpbrt_bmfr_set_lane": [H, i32],
+    "vkpbrt_bmfr_set_position_type": [H, i32],
     "vkpbrt_bmfr_record": [H, C.POINTER(PushConstants)],
     "vkpbrt_bmfr_set_block_row_range": [H, i32, i32],
     "vkpbrt_bmfr_final_image": [H, PH],

@@ -171,6 +171,7 @@ struct vkpbrt_bmfr_s {
     float* table[2] = {nullptr, nullptr};
     int64_t table_frame[2] = {-1, -1};
     int lane = 0;                 // as vkpbrt_bfr_s::lane
+    int position_type = 0;        // bmfrGeneral.comp:30-31 POSITION_TYPE
     bool tma_enabled = true;      // interior blocks stage their input tiles through TMA (VKPBRT_BMFR_TMA=0 switches it off)
 };
 
@@ -931,6 +932,13 @@ int vkpbrt_bmfr_set_debug_outputs(vkpbrt_bmfr_t b, int enable)
     return VKPBRT_OK;
 }
 
+int vkpbrt_bmfr_set_position_type(vkpbrt_bmfr_t b, int position_type)
+{
+    VK_REQUIRE(b && position_type >= 0 && position_type <= 2, "vkpbrt_bmfr_set_position_type: 0 (depth), 1 (world, normalised depth) or 2 (world)");
+    b->position_type = position_type;
+    return VKPBRT_OK;
+}
+
 int vkpbrt_bmfr_set_lane(vkpbrt_bmfr_t b, int lane)
 {
     VK_REQUIRE(b && lane >= 0 && lane <= vkpbrt_context_s::kLanes, "vkpbrt_bmfr_set_lane: lane must be 0, 1 or 2");
@@ -1013,7 +1021,10 @@ int vkpbrt_bmfr_record(vkpbrt_bmfr_t b, const vkpbrt_push_constants* pc)
     }
     p.table = b->table[slot];
     p.table_next = b->table[slot ^ 1];
-    if (b->tma_enabled) vkpbrt::bmfr_encode_tma(p);     // descriptors follow the planes bound for this frame
+    p.position_type = b->position_type;
+    std::memcpy(p.inv_view, pc->view_inverse, 64);      // camParams.inverseViewMatrix / inverseProjectionMatrix (WORLD modes only)
+    std::memcpy(p.inv_proj, pc->proj_inverse, 64);
+    if (b->tma_enabled && b->position_type == 0) vkpbrt::bmfr_encode_tma(p);     // descriptors follow the planes bound for this frame
     VK_CUDA(vkpbrt::launch_bmfr(p, st));
     VK_CUDA(lane_done(b->ctx, b->lane));
     b->table_frame[slot ^ 1] = (int64_t)(uint32_t)(pc->frame_number + 1u);

@@ -77,6 +77,10 @@ struct BmfrParams {
     // fetch their depth / normal / noisy tiles with three cp.async.bulk.tensor.2d instead of per-thread loads
     int use_tma;
     TmaDesc tma_depth, tma_normal, tma_noisy;
+    // bmfrGeneral.comp:30-31 POSITION_TYPE: 0 POSITION_DEPTH (what the reference's host code runs), 1 POSITION_WORLD_DEPTH_NORM,
+    // 2 POSITION_WORLD; the WORLD modes read the push constants' camera matrices (column-major)
+    int position_type;
+    float inv_view[16], inv_proj[16];
 };
 // encodes the three descriptors for the planes currently in `p` (host; needs the driver's cuTensorMapEncodeTiled).
 // Leaves use_tma = 0 when a plane cannot be described (row pitch not a multiple of 16 bytes, unaligned base, block != 32).

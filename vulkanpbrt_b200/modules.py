@@ -540,6 +540,10 @@ class BMFR(_BlockDenoiser):
         """0: the context's stream; 1, 2: a side lane that runs concurrently with the other denoisers of the frame"""
         capi.call("vkpbrt_bmfr_set_lane", self._h, int(lane))
 
+    def set_position_type(self, position_type: int) -> None:
+        """the shaders' POSITION_TYPE: 0 depth (default), 1 world with normalised depth, 2 world (bmfrGeneral.comp:30-31)"""
+        capi.call("vkpbrt_bmfr_set_position_type", self._h, int(position_type))
+
     def set_block_row_range(self, begin: int, end: int) -> None:
         capi.call("vkpbrt_bmfr_set_block_row_range", self._h, begin, end)
 

@@ -21,7 +21,7 @@ class DenoisePipeline:
                  block_size: DenoisingBlockSize = DenoisingBlockSize.X32, use_taa: bool = False, device: int = 0,
                  stream: Optional[int] = None, separate_matrices: bool = True, raw_f16: bool = False,
                  fix_taa_swizzle: bool = False, bmfr_debug_outputs: bool = False, average_squared: bool = False,
-                 ctx: Optional[Context] = None, external_inputs: bool = False):
+                 ctx: Optional[Context] = None, external_inputs: bool = False, position_type: int = 0):
         self.width, self.height = width, height
         self.ctx = ctx if ctx is not None else Context(device, stream)
         self.separate_matrices = separate_matrices
@@ -71,6 +71,10 @@ class DenoisePipeline:
             self.final, self.modules = add_denoiser_to_commands(
                 denoiser, block_size, self.commands, ctx, width, height, self.push_constants, self.g_buffer,
                 self.illumination_buffer, self.accumulation_buffer, self.average_squared_image)
+        if position_type:
+            for m in self.modules:
+                if isinstance(m, BMFR):
+                    m.set_position_type(position_type)
         self.denoiser_final = self.final
         # :448-456
         self.taa: Optional[Taa] = None
