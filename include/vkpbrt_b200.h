@@ -305,9 +305,34 @@ VKPBRT_API int vkpbrt_taa_compile(vkpbrt_taa_t t);
  * TAA and inherits the denoiser's (App. C-10); here they are passed explicitly. */
 VKPBRT_API int vkpbrt_taa_record(vkpbrt_taa_t t, const vkpbrt_push_constants* pc);
 VKPBRT_API int vkpbrt_taa_set_row_range(vkpbrt_taa_t t, int row_begin, int row_end);
+/* One frame's TAA in several launches over disjoint row ranges (band-sharded runs: the rows that do not need the
+ * neighbour's halo row run while that row is still in flight).  Every part reads the same history; the final -> history
+ * hand-over (Taa.cpp:106) happens with the part that passes last != 0. */
+VKPBRT_API int vkpbrt_taa_record_part(vkpbrt_taa_t t, const vkpbrt_push_constants* pc, int row_begin, int row_end, int last);
 VKPBRT_API int vkpbrt_taa_final_image(vkpbrt_taa_t t, vkpbrt_image_t* out);
 VKPBRT_API int vkpbrt_taa_history_image(vkpbrt_taa_t t, vkpbrt_image_t* out);
 VKPBRT_API int vkpbrt_taa_destroy(vkpbrt_taa_t t);
+
+/* ---------------------------------------------------------------------------------------- */
+/* FormatConverter  (source/renderModules/FormatConverter.hpp:4-21, FormatConverter.cpp:4-93;  */
+/*                   kernel: shaders/formatConverter.comp:1-13)                                 */
+/* The step VulkanPBRT.cpp:476-484 appends when the final image is not B8G8R8A8_UNORM.          */
+/* ---------------------------------------------------------------------------------------- */
+typedef struct vkpbrt_format_converter_s* vkpbrt_format_converter_t;
+/* FormatConverter(src_image, dst_format, work_width = 16, work_height = 16); dst_format must be
+ * VKPBRT_FORMAT_B8G8R8A8_UNORM ("FormatConverter::Unknown format" otherwise, as in the reference) */
+VKPBRT_API int vkpbrt_format_converter_create(vkpbrt_context_t ctx, vkpbrt_image_t src_image, uint32_t dst_format,
+                                              uint32_t work_width, uint32_t work_height, vkpbrt_format_converter_t* out);
+VKPBRT_API int vkpbrt_format_converter_compile_images(vkpbrt_format_converter_t f);
+VKPBRT_API int vkpbrt_format_converter_record(vkpbrt_format_converter_t f);       /* add_dispatch_to_command_graph */
+VKPBRT_API int vkpbrt_format_converter_final_image(vkpbrt_format_converter_t f, vkpbrt_image_t* out);   /* final_image */
+VKPBRT_API int vkpbrt_format_converter_destroy(vkpbrt_format_converter_t f);
+
+/* Producer-side convention (shaders/ptRaygen.rgen:81-88, DEMOD_ILLUMINATION_FLOAT): what a CUDA / OptiX path tracer has
+ * to hand to the Accumulator as IlluminationBufferDemodulatedFloat.  demodulated = min(clamp(radiance, 0, 10) /
+ * (albedo + 1e-6), 1e3) where the primary ray hit something, clamp(radiance, 0, 10) where position_x is infinite. */
+VKPBRT_API int vkpbrt_demodulate_record(vkpbrt_context_t ctx, vkpbrt_image_t radiance, vkpbrt_image_t albedo,
+                                        vkpbrt_image_t position_x, vkpbrt_image_t demodulated);
 
 /* ---------------------------------------------------------------------------------------- */
 /* Vulkan interop (north star: VK_KHR_external_memory_fd / VK_KHR_external_semaphore_fd)      */

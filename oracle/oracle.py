@@ -65,6 +65,8 @@ def lib():
         l.vkpbrt_oracle_bfr_lr.argtypes = [i32]; l.vkpbrt_oracle_bfr_lr.restype = C.c_float
         l.vkpbrt_oracle_bfr_blender.argtypes = [i32, i32, i32] + [vp] * 6; l.vkpbrt_oracle_bfr_blender.restype = None
         l.vkpbrt_oracle_taa.argtypes = [i32, i32, u32, i32] + [vp] * 4; l.vkpbrt_oracle_taa.restype = None
+        l.vkpbrt_oracle_format_converter.argtypes = [i32, i32, i32, vp, vp]; l.vkpbrt_oracle_format_converter.restype = None
+        l.vkpbrt_oracle_demodulate.argtypes = [i32, i32, vp, vp, vp, vp]; l.vkpbrt_oracle_demodulate.restype = None
         l.vkpbrt_oracle_num_threads.argtypes = []; l.vkpbrt_oracle_num_threads.restype = i32
         l.vkpbrt_oracle_set_num_threads.argtypes = [i32]; l.vkpbrt_oracle_set_num_threads.restype = None
         _lib = l
@@ -217,3 +219,20 @@ class OracleChain:
         self.prev_illu[...] = self.illum
         self.prev_view = np.asarray(frame.camera.view, dtype=np.float32).copy()     # VulkanPBRT.cpp:591
         self.prev_cam = frame.camera
+
+
+def format_converter(src: np.ndarray) -> np.ndarray:
+    """formatConverter.comp on a [H][W][4] float32 / float16-bits (uint16) / uint8 image -> [H][W][4] BGRA8"""
+    H, W = src.shape[:2]
+    fmt = {np.dtype(np.float32): 0, np.dtype(np.uint16): 1, np.dtype(np.uint8): 2}[src.dtype]
+    out = np.zeros((H, W, 4), np.uint8)
+    lib().vkpbrt_oracle_format_converter(W, H, fmt, _p(np.ascontiguousarray(src)), _p(out))
+    return out
+
+
+def demodulate(radiance: np.ndarray, albedo: np.ndarray, position_x: np.ndarray) -> np.ndarray:
+    H, W = radiance.shape[:2]
+    out = np.zeros((H, W, 4), np.float32)
+    lib().vkpbrt_oracle_demodulate(W, H, _p(np.ascontiguousarray(radiance, np.float32)), _p(np.ascontiguousarray(albedo, np.float32)),
+                                   _p(np.ascontiguousarray(position_x, np.float32)), _p(out))
+    return out

@@ -151,3 +151,14 @@ class RefChain(O.OracleChain):
         self.prev_illu_squared[...] = self.illum_squared
         self.prev_view = np.asarray(frame.camera.view, dtype=np.float32).copy()
         self.prev_cam = frame.camera
+
+
+def format_converter(src: np.ndarray) -> np.ndarray:
+    """the reference's formatConverter.comp (FormatConverter.cpp:20-35: local size 16 x 16, FORMAT rgba8 on a BGRA8 view)
+    on a [H][W][4] float32 / float16-bits (uint16) / uint8 image"""
+    H, W = src.shape[:2]
+    fmt = {np.dtype(np.float32): F_RGBA32F, np.dtype(np.uint16): F_RGBA16F, np.dtype(np.uint8): F_RGBA8}[src.dtype]
+    out = np.zeros((H, W, 4), np.uint8)
+    dispatch("formatConverter", (16, 16, 0), W, H, 0, None, math.ceil(W / 16), math.ceil(H / 16),
+             {0: (np.ascontiguousarray(src), fmt), 1: (out, F_BGRA8)})
+    return out

@@ -1094,3 +1094,48 @@ ORACLE_API void vkpbrt_oracle_set_num_threads(int n)
     (void)n;
 #endif
 }
+
+/* ------------------------------------------------------------------------------------ */
+/* formatConverter.comp:1-13 (FormatConverter.cpp:4-93): texelFetch(source) -> imageStore */
+/* into an "rgba8" storage image bound to a B8G8R8A8_UNORM view (memory order B,G,R,A).   */
+/* src_format: 0 rgba32f, 1 rgba16f, 2 rgba8 unorm                                        */
+/* ------------------------------------------------------------------------------------ */
+ORACLE_API void vkpbrt_oracle_format_converter(int W, int H, int src_format, const void* src, uint8_t* dst_bgra)
+{
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            size_t pix = (size_t)y * W + x;
+            float v[4];
+            for (int c = 0; c < 4; ++c) {
+                if (src_format == 0) v[c] = ((const float*)src)[4 * pix + c];
+                else if (src_format == 1) v[c] = f16_to_f32(((const uint16_t*)src)[4 * pix + c]);
+                else v[c] = unorm8_to_f32(((const uint8_t*)src)[4 * pix + c]);
+            }
+            dst_bgra[4 * pix + 0] = f32_to_unorm8(v[2]);
+            dst_bgra[4 * pix + 1] = f32_to_unorm8(v[1]);
+            dst_bgra[4 * pix + 2] = f32_to_unorm8(v[0]);
+            dst_bgra[4 * pix + 3] = f32_to_unorm8(v[3]);
+        }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* ptRaygen.rgen:81-88 (DEMOD_ILLUMINATION_FLOAT), constants from ptConstants.glsl:7,10:  */
+/* EPSILON = 1e-6, c_MaxRadiance = 1e1.  PARITY UNPINNED for this function: a ray-generation */
+/* shader cannot go through oracle/glsl_shim; it follows the cited lines only.             */
+/* ------------------------------------------------------------------------------------ */
+ORACLE_API void vkpbrt_oracle_demodulate(int W, int H, const float* radiance, const float* albedo, const float* position_x,
+                                         float* out)
+{
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            size_t pix = (size_t)y * W + x;
+            float c[3];
+            for (int i = 0; i < 3; ++i) c[i] = gl_clamp(radiance[4 * pix + i], 0.0f, 1e1f);            /* :81 */
+            if (!isinf(position_x[pix]))                                                               /* :85 */
+                for (int i = 0; i < 3; ++i) c[i] = gl_min(c[i] / (albedo[4 * pix + i] + 1e-6f), 1e3f);  /* :86 */
+            for (int i = 0; i < 3; ++i) out[4 * pix + i] = c[i];
+            out[4 * pix + 3] = 1.0f;                                                                   /* :88 */
+        }
+}

@@ -157,4 +157,5 @@ void launch(dim3 grid, dim3 block, const std::function<void()>& body)
 #include "../../vulkanpbrt_b200/csrc/taa.cu"
 #include "../../vulkanpbrt_b200/csrc/halo.cu"
 #include "../../vulkanpbrt_b200/csrc/debug.cu"
+#include "../../vulkanpbrt_b200/csrc/convert.cu"
 #include "../../vulkanpbrt_b200/csrc/api.cpp"

@@ -5,7 +5,7 @@ cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
 F=$1; K=$2; WL=$3; shift 3
 CS=vulkanpbrt_b200/csrc
-EXTRA=""; case $F in accumulate.cu|taa.cu) EXTRA="-fmad=false";; esac
+EXTRA=""; case $F in accumulate.cu|taa.cu|convert.cu) EXTRA="-fmad=false";; esac
 for V in "$@"; do
   nvcc -std=c++17 -O3 -lineinfo $EXTRA -ccbin /usr/bin/g++ -Xcompiler -fPIC,-fvisibility=hidden,-ffp-contract=off -gencode arch=compute_100a,code=sm_100a $V -x cu -c $CS/$F -o build/obj/$F.o 2>&1 | grep -E "error"
   nvcc -shared -ccbin /usr/bin/g++ -gencode arch=compute_100a,code=sm_100a -cudart static -o vulkanpbrt_b200/lib/libvkpbrt_b200.so build/obj/*.o

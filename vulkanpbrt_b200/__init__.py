@@ -8,5 +8,6 @@ from .modules import (BFR, BMFR, Accumulator, AccumulationBuffer, BFRBlender, Ca
                       IlluminationBufferDemodulated, IlluminationBufferDemodulatedFloat, IlluminationBufferFinal,
                       IlluminationBufferFinalDemodulated, PushConstants, Taa, add_denoiser_to_commands)
 from .matrix_io import export_matrices, import_matrices  # noqa: F401
+from .modules import FormatConverter, demodulate  # noqa: F401
 from .pipeline import DenoisePipeline  # noqa: F401
 from .render_io import GBufferIO, IlluminationBufferIO, OfflineGBuffer, OfflineIllumination  # noqa: F401

@@ -151,6 +151,13 @@ _PROTOS = {
     "vkpbrt_taa_set_fix_swizzle": [H, i32],
     "vkpbrt_taa_compile": [H],
     "vkpbrt_taa_set_force_scalar": [H, i32],
+    "vkpbrt_taa_record_part": [H, C.c_void_p, i32, i32, i32],
+    "vkpbrt_format_converter_create": [H, H, u32, u32, u32, C.POINTER(H)],
+    "vkpbrt_format_converter_compile_images": [H],
+    "vkpbrt_format_converter_record": [H],
+    "vkpbrt_format_converter_final_image": [H, C.POINTER(H)],
+    "vkpbrt_format_converter_destroy": [H],
+    "vkpbrt_demodulate_record": [H, H, H, H, H],
     "vkpbrt_taa_record": [H, C.POINTER(PushConstants)],
     "vkpbrt_taa_set_row_range": [H, i32, i32],
     "vkpbrt_taa_final_image": [H, PH],
@@ -213,10 +220,20 @@ def call(name: str, *args) -> None:
     check(getattr(lib(), name)(*args))
 
 
+_ZERO16 = (C.c_float * 16)()
+
+
 def mat16(values) -> "C.Array":
-    arr = (C.c_float * 16)()
+    """16 floats as a C array.  The per-frame host path converts ~10 matrices: a float32 ndarray (what the cameras hold) is
+    copied in one call instead of element by element (7 us -> 0.6 us each)."""
+    if isinstance(values, (C.c_float * 16)):
+        return values
+    try:
+        import numpy as np
+        if isinstance(values, np.ndarray) and values.dtype == np.float32 and values.size == 16 and values.flags["C_CONTIGUOUS"]:
+            return (C.c_float * 16).from_buffer_copy(values)
+    except ImportError:     # pragma: no cover
+        pass
     flat = [float(v) for v in values]
     assert len(flat) == 16
-    for i, v in enumerate(flat):
-        arr[i] = v
-    return arr
+    return (C.c_float * 16)(*flat)

@@ -35,6 +35,7 @@ UNITS = {
     "bfr.cu": [],
     "halo.cu": [],
     "debug.cu": [],
+    "convert.cu": ["-fmad=false"],
     "api.cpp": [],
 }
 

@@ -208,6 +208,14 @@ struct vkpbrt_taa_s {
     int row_begin, row_end;
 };
 
+struct vkpbrt_format_converter_s {
+    vkpbrt_context_t ctx;
+    vkpbrt_image_t src;
+    vkpbrt_image_t final_image = nullptr;
+    uint32_t work_width, work_height;
+    bool compiled = false;
+};
+
 struct vkpbrt_external_memory_s {
     vkpbrt_context_t ctx;
     cudaExternalMemory_t mem;
@@ -1288,13 +1296,14 @@ int vkpbrt_taa_set_row_range(vkpbrt_taa_t t, int row_begin, int row_end)
     return VKPBRT_OK;
 }
 
-int vkpbrt_taa_record(vkpbrt_taa_t t, const vkpbrt_push_constants* pc)
+int vkpbrt_taa_record_part(vkpbrt_taa_t t, const vkpbrt_push_constants* pc, int row_begin, int row_end, int last)
 {
     VK_REQUIRE(t && pc, "null argument");
     if (!t->compiled) return fail(VKPBRT_ERR_NOT_COMPILED, "Taa: compile() has not been called");
+    VK_REQUIRE(row_begin >= 0 && row_end <= (int)t->height && row_begin <= row_end, "Taa: row range out of bounds");
     vkpbrt::TaaParams p{};
     p.W = (int)t->width; p.H = (int)t->height;
-    p.row_begin = t->row_begin; p.row_end = t->row_end;
+    p.row_begin = row_begin; p.row_end = row_end;
     p.frame = pc->frame_number;
     p.fix_swizzle = t->fix_swizzle;
     p.motion = (const uint32_t*)t->acc->img[VKPBRT_ACC_MOTION]->data;
@@ -1308,11 +1317,19 @@ int vkpbrt_taa_record(vkpbrt_taa_t t, const vkpbrt_push_constants* pc)
     p.force_scalar = t->force_scalar;
     VK_CUDA(cudaSetDevice(t->ctx->device));
     VK_CUDA(vkpbrt::launch_taa(p, joined(t->ctx)));
-    t->ctx->launches++;
-    // Taa.cpp:106 copy final -> history: both handles now view this frame's output
-    t->final_image->data = outb;
-    t->history->data = outb;
+    if (row_end > row_begin) t->ctx->launches++;
+    if (last) {
+        // Taa.cpp:106 copy final -> history: both handles now view this frame's output
+        t->final_image->data = outb;
+        t->history->data = outb;
+    }
     return VKPBRT_OK;
+}
+
+int vkpbrt_taa_record(vkpbrt_taa_t t, const vkpbrt_push_constants* pc)
+{
+    VK_REQUIRE(t, "null argument");
+    return vkpbrt_taa_record_part(t, pc, t->row_begin, t->row_end, 1);
 }
 
 int vkpbrt_taa_final_image(vkpbrt_taa_t t, vkpbrt_image_t* out)
@@ -1337,6 +1354,86 @@ int vkpbrt_taa_destroy(vkpbrt_taa_t t)
     vkpbrt_image_release(t->final_image);
     vkpbrt_image_release(t->history);
     delete t;
+    return VKPBRT_OK;
+}
+
+// ---- FormatConverter (source/renderModules/FormatConverter.cpp:4-93, shaders/formatConverter.comp) ---
+int vkpbrt_format_converter_create(vkpbrt_context_t ctx, vkpbrt_image_t src_image, uint32_t dst_format, uint32_t work_width,
+                                   uint32_t work_height, vkpbrt_format_converter_t* out)
+{
+    VK_REQUIRE(ctx && src_image && out, "vkpbrt_format_converter_create: null argument");
+    if (dst_format != VKPBRT_FORMAT_B8G8R8A8_UNORM)
+        return fail(VKPBRT_ERR_UNSUPPORTED, "FormatConverter::Unknown format");            // FormatConverter.cpp:13-19
+    if (src_image->format != VKPBRT_FORMAT_R32G32B32A32_SFLOAT && src_image->format != VKPBRT_FORMAT_R16G16B16A16_SFLOAT &&
+        src_image->format != VKPBRT_FORMAT_R8G8B8A8_UNORM)
+        return fail(VKPBRT_ERR_UNSUPPORTED, "FormatConverter: the source must be a four-channel image (rgba32f, rgba16f or rgba8)");
+    auto* f = new vkpbrt_format_converter_s();
+    f->ctx = ctx; f->src = src_image; f->work_width = work_width; f->work_height = work_height;
+    int rc = make_image(ctx, VKPBRT_FORMAT_B8G8R8A8_UNORM, src_image->width, src_image->height, 1, &f->final_image);   // :38-47
+    if (rc) { delete f; return rc; }
+    *out = f;
+    return VKPBRT_OK;
+}
+
+int vkpbrt_format_converter_compile_images(vkpbrt_format_converter_t f)
+{
+    VK_REQUIRE(f, "null format converter");
+    int rc = vkpbrt_image_compile(f->final_image);
+    if (!rc) f->compiled = true;
+    return rc;
+}
+
+int vkpbrt_format_converter_record(vkpbrt_format_converter_t f)
+{
+    VK_REQUIRE(f, "null format converter");
+    if (!f->compiled) return fail(VKPBRT_ERR_NOT_COMPILED, "FormatConverter: compile_images() has not been called");
+    VK_REQUIRE(f->src->data, "FormatConverter: the source image is not compiled");
+    vkpbrt::FormatConvertParams p{};
+    p.W = (int)f->src->width; p.H = (int)f->src->height;
+    p.src_format = f->src->format == VKPBRT_FORMAT_R32G32B32A32_SFLOAT ? 0 : (f->src->format == VKPBRT_FORMAT_R16G16B16A16_SFLOAT ? 1 : 2);
+    p.src = f->src->data;
+    p.dst_bgra = (uint32_t*)f->final_image->data;
+    VK_CUDA(cudaSetDevice(f->ctx->device));
+    VK_CUDA(vkpbrt::launch_format_convert(p, joined(f->ctx)));
+    f->ctx->launches++;
+    return VKPBRT_OK;
+}
+
+int vkpbrt_format_converter_final_image(vkpbrt_format_converter_t f, vkpbrt_image_t* out)
+{
+    VK_REQUIRE(f && out, "null argument");
+    *out = f->final_image;
+    return VKPBRT_OK;
+}
+
+int vkpbrt_format_converter_destroy(vkpbrt_format_converter_t f)
+{
+    if (!f) return VKPBRT_OK;
+    vkpbrt_image_release(f->final_image);
+    delete f;
+    return VKPBRT_OK;
+}
+
+// ---- producer side: demodulated illumination (shaders/ptRaygen.rgen:81-88) ---------------------------
+int vkpbrt_demodulate_record(vkpbrt_context_t ctx, vkpbrt_image_t radiance, vkpbrt_image_t albedo, vkpbrt_image_t position_x,
+                             vkpbrt_image_t demodulated)
+{
+    VK_REQUIRE(ctx && radiance && albedo && position_x && demodulated, "vkpbrt_demodulate_record: null argument");
+    VK_REQUIRE(radiance->format == VKPBRT_FORMAT_R32G32B32A32_SFLOAT && albedo->format == VKPBRT_FORMAT_R32G32B32A32_SFLOAT &&
+               demodulated->format == VKPBRT_FORMAT_R32G32B32A32_SFLOAT && position_x->format == VKPBRT_FORMAT_R32_SFLOAT,
+               "vkpbrt_demodulate_record: radiance / albedo / output are rgba32f, position_x is r32f");
+    VK_REQUIRE(same_extent(albedo, radiance->width, radiance->height) && same_extent(position_x, radiance->width, radiance->height) &&
+               same_extent(demodulated, radiance->width, radiance->height), "vkpbrt_demodulate_record: extent mismatch");
+    VK_REQUIRE(radiance->data && albedo->data && position_x->data && demodulated->data, "vkpbrt_demodulate_record: an image is not compiled");
+    vkpbrt::DemodulateParams p{};
+    p.W = (int)radiance->width; p.H = (int)radiance->height;
+    p.radiance = (const float4*)radiance->data;
+    p.albedo = (const float4*)albedo->data;
+    p.position_x = (const float*)position_x->data;
+    p.out = (float4*)demodulated->data;
+    VK_CUDA(cudaSetDevice(ctx->device));
+    VK_CUDA(vkpbrt::launch_demodulate(p, joined(ctx)));
+    ctx->launches++;
     return VKPBRT_OK;
 }
 

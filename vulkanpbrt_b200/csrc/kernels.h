@@ -76,6 +76,7 @@ struct BmfrParams {
     // TMA descriptors of the stage-1 input planes (32 x 32 texel boxes): blocks whose footprint lies inside the image
     // fetch their depth / normal / noisy tiles with three cp.async.bulk.tensor.2d instead of per-thread loads
     int use_tma;
+    int tma_row0;                 // image row of the descriptors' row 0
     TmaDesc tma_depth, tma_normal, tma_noisy;
     // bmfrGeneral.comp:30-31 POSITION_TYPE: 0 POSITION_DEPTH (what the reference's host code runs), 1 POSITION_WORLD_DEPTH_NORM,
     // 2 POSITION_WORLD; the WORLD modes read the push constants' camera matrices (column-major)
@@ -168,6 +169,23 @@ struct HaloWaitParams {
     unsigned long long* wait_ns;  // statistics
     unsigned long long timeout_ns;
 };
+// ---- convert.cu : shaders/formatConverter.comp, ptRaygen.rgen:81-88 -----------------------------------
+struct FormatConvertParams {
+    int W, H;
+    int src_format;               // 0 rgba32f, 1 rgba16f, 2 rgba8 unorm
+    const void* src;
+    uint32_t* dst_bgra;           // B8G8R8A8_UNORM
+};
+cudaError_t launch_format_convert(const FormatConvertParams& p, cudaStream_t stream);
+struct DemodulateParams {
+    int W, H;
+    const float4* radiance;       // rgba32f: the path tracer's radiance estimate (finalColor before the clamp)
+    const float4* albedo;         // rgba32f: diffuse + specular colour of the primary hit (curAlbedo)
+    const float* position_x;      // r32f: x of the primary hit position, +-inf for a miss (rayPayload.position.x)
+    float4* out;                  // rgba32f demodulated illumination (IlluminationBufferDemodulatedFloat)
+};
+cudaError_t launch_demodulate(const DemodulateParams& p, cudaStream_t stream);
+
 // ---- device-side self checks (debug.cu) ----------------------------------------------------------
 cudaError_t launch_tonemap_sweep(unsigned long long* bad, uint32_t* first_bad, cudaStream_t stream);
 

@@ -400,7 +400,7 @@ class CameraMatrices:
 
     def to_c(self) -> _CCameraMatrices:
         c = _CCameraMatrices()
-        z = [0.0] * 16
+        z = capi._ZERO16
         c.view = capi.mat16(self.view if self.view is not None else z)
         c.inv_view = capi.mat16(self.inv_view if self.inv_view is not None else z)
         c.has_proj = 1 if (self.proj is not None and self.inv_proj is not None) else 0
@@ -660,6 +660,10 @@ class Taa:
         """debug / test switch: the one-pixel-per-thread kernel"""
         capi.call("vkpbrt_taa_set_force_scalar", self._h, 1 if enable else 0)
 
+    def record_part(self, push_constants: "PushConstants", row_begin: int, row_end: int, last: bool) -> None:
+        """one of several launches of a frame's TAA over disjoint row ranges (see vkpbrt_taa_record_part)"""
+        capi.call("vkpbrt_taa_record_part", self._h, C.byref(push_constants.value), int(row_begin), int(row_end), 1 if last else 0)
+
     def add_dispatch_to_command_graph(self, command_graph: Commands) -> None:
         def rec(c: Commands):
             pc = c.bound_push_constants
@@ -677,6 +681,45 @@ class Taa:
             capi.lib().vkpbrt_taa_destroy(self._h)
         except Exception:
             pass
+
+
+class FormatConverter:
+    """source/renderModules/FormatConverter.hpp:4-21: converts the final image to B8G8R8A8_UNORM when no denoiser produced
+    one (VulkanPBRT.cpp:476-484)."""
+
+    def __init__(self, src_image: DescriptorImage, dst_format: int = capi.FORMAT_B8G8R8A8_UNORM, work_width: int = 16,
+                 work_height: int = 16):
+        self.ctx = src_image.ctx
+        self._keep = src_image
+        self._h = C.c_void_p()
+        capi.call("vkpbrt_format_converter_create", self.ctx.handle, src_image.handle, dst_format, work_width, work_height,
+                  C.byref(self._h))
+        self.final_image = _borrow(self.ctx, "vkpbrt_format_converter_final_image", self._h)
+
+    @classmethod
+    def create(cls, *a, **k):
+        return cls(*a, **k)
+
+    def compile_images(self, context: Optional[Context] = None) -> None:
+        capi.call("vkpbrt_format_converter_compile_images", self._h)
+
+    def update_image_layouts(self, context: Optional[Context] = None) -> None:
+        pass
+
+    def add_dispatch_to_command_graph(self, command_graph: Commands) -> None:
+        command_graph.add_child(lambda _c: capi.call("vkpbrt_format_converter_record", self._h))
+
+    def __del__(self):
+        try:
+            capi.lib().vkpbrt_format_converter_destroy(self._h)
+        except Exception:
+            pass
+
+
+def demodulate(ctx: Context, radiance: DescriptorImage, albedo: DescriptorImage, position_x: DescriptorImage,
+               demodulated: DescriptorImage) -> None:
+    """the producer-side convention of shaders/ptRaygen.rgen:81-88 (see vkpbrt_demodulate_record)"""
+    capi.call("vkpbrt_demodulate_record", ctx.handle, radiance.handle, albedo.handle, position_x.handle, demodulated.handle)
 
 
 # ---------------------------------------------------------------------------------------------------

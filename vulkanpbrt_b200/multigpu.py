@@ -619,11 +619,25 @@ class BandedPipeline:
         self._pending_b = None
         self._bmfr_cmd(p.commands)
         if p.taa is not None:
-            if multi:
+            o0, o1 = plan.owned_rows(g, frame)
+            p.taa.set_row_range(o0, o1)
+            if multi and o1 - o0 > 2:
+                # the band's first / last row need one row of the neighbour's tone-mapped output (taa.comp:66-83): the
+                # rows in between run while that row is in flight, the edge rows after it has landed
                 df = self._exchange_desc("F", frame, lambda: {"final": [(p.denoiser_final, None)]}, lambda: plan.final_transfers(frame))
-                self._finish(self._start(df))
-            p.taa.set_row_range(*plan.owned_rows(g, frame))
-            self._taa_cmd(p.commands)
+                pending_f = self._start(df)
+                i0 = o0 + (1 if g > 0 else 0)
+                i1 = o1 - (1 if g < self.world - 1 else 0)
+                p.taa.record_part(p.push_constants, i0, i1, False)
+                self._finish(pending_f)
+                if i0 > o0:
+                    p.taa.record_part(p.push_constants, o0, i0, False)
+                p.taa.record_part(p.push_constants, i1, o1, True)          # (possibly empty) last part: hands final -> history
+            else:
+                if multi:
+                    df = self._exchange_desc("F", frame, lambda: {"final": [(p.denoiser_final, None)]}, lambda: plan.final_transfers(frame))
+                    self._finish(self._start(df))
+                self._taa_cmd(p.commands)
         self._back_cmd(p.commands)
         p.end_frame(cam)
         self._swaps += 1
@@ -680,6 +694,13 @@ def _sha(t) -> str:
     return hashlib.sha256(t.contiguous().cpu().numpy().tobytes()).hexdigest()
 
 
+def _progress(rank: int, what: str) -> None:
+    """phase markers on stderr (rank 0): a crash in a multi-rank run leaves no Python traceback"""
+    import sys
+    if rank == 0:
+        print(f"[bench_multi] {what}", file=sys.stderr, flush=True)
+
+
 def measure_banded(args, name: str, K: int, Wm: int, R: int, rank: int, world: int, local: int, weak: bool, replicas: bool, with_e2e: bool):
     """one workload band-sharded over the ranks.  Returns the result dict on rank 0, None elsewhere."""
     import torch
@@ -690,6 +711,7 @@ def measure_banded(args, name: str, K: int, Wm: int, R: int, rank: int, world: i
     import bench as B     # the repo-root bench.py (constants, sampler)
 
     W, Hband, taa, desc = B.WORKLOADS[name]
+    _progress(rank, f"{name}: start")
     strong = not weak and not replicas
     H = Hband if (strong or replicas) else Hband * world
     prank, pworld = (0, 1) if replicas else (rank, world)
@@ -733,6 +755,7 @@ def measure_banded(args, name: str, K: int, Wm: int, R: int, rank: int, world: i
     t_gen = time.perf_counter() - t_gen
     dseq = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
     torch.cuda.synchronize()
+    _progress(rank, "inputs resident")
     pitch = {"depth": 4 * W, "normal": 8 * W, "albedo": 4 * W, "illum": 16 * W}
 
     def bind(bufs, i):
@@ -751,6 +774,7 @@ def measure_banded(args, name: str, K: int, Wm: int, R: int, rank: int, world: i
     bp.flush()
     torch.cuda.synchronize()
     bp.check()
+    _progress(rank, "set-up frames done")
     # ---- banded == single (every jitter phase has been through the exchange twice by now) -----------------------
     equal = None
     if verify:
@@ -781,6 +805,7 @@ def measure_banded(args, name: str, K: int, Wm: int, R: int, rank: int, world: i
         dfull.clear()
         torch.cuda.empty_cache()
     dist.barrier()
+    _progress(rank, f"verified: {equal}")
     for f in range(PRE, PRE + Wm):
         frame(f)
     torch.cuda.synchronize()
@@ -804,6 +829,7 @@ def measure_banded(args, name: str, K: int, Wm: int, R: int, rank: int, world: i
     bp.check()
     dist.barrier()
     clocks = sampler.stop() if sampler else None
+    _progress(rank, "timed region done")
     # time each rank's streams spent spinning on flag words inside the timed region, per exchange group:
     # [gate of the end-of-frame push, wait in front of the consumer]; rank 0 reports every rank's
     spin = {}
@@ -875,6 +901,7 @@ def measure_banded(args, name: str, K: int, Wm: int, R: int, rank: int, world: i
                "h2d_bytes_per_step": B.INPUT_BYTES * W * rows * world, "d2h_bytes_per_step": 4 * W * H * jobs,
                "ms_per_step": round(e2e_ms / K, 5)}
         del dbuf, out_host
+    _progress(rank, "e2e done")
     halo_bytes = torch.tensor([bp.bytes_exchanged], device=dev, dtype=torch.float64)
     dist.all_reduce(halo_bytes)
     res = None
