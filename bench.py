@@ -487,6 +487,8 @@ def main():
     ap.add_argument("--no-verify", dest="no_verify", action="store_true", help="N > 1: skip the banded == single-GPU comparison")
     ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
                     help="N > 1: halo rows through NVLink peer memory (k_halo_push) or NCCL send/recv groups")
+    ap.add_argument("--host", default="native", choices=["native", "python"],
+                    help="N > 1: the per-frame driver -- vkpbrt::BandedRank (C++, one C-ABI call per frame) or the Python BandedPipeline")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline (0 = skip)")
     ap.add_argument("--no-also", action="store_true", help="skip the secondary workloads nested under 'also'")
     args = ap.parse_args()

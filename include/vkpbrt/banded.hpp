@@ -1,0 +1,375 @@
+// banded.hpp -- one rank of the band-sharded denoising chain, in C++ on top of vkpbrt.hpp.
+//
+// The reference renders on one device; this has no counterpart there.  One process (or thread) per GPU: the frame is
+// cut into horizontal bands of whole block rows of the jittered BMFR grid (BandPlan, band_plan.hpp); blocks are
+// independent, so the only traffic between neighbours is
+//     A  the accumulate planes' history halo (depth history, accumulated illumination, sample counts): pushed right
+//        after k_accumulate, overlaps k_bmfr_block, awaited before the NEXT frame's k_accumulate;
+//     F  one row of the denoiser's tone-mapped output on each side for TAA's 3x3 stencil: pushed after k_bmfr_block,
+//        overlaps the TAA of the band's inner rows, awaited before its two edge rows;
+//     B  the denoised history / TAA history halos and the stale column-0 strip: pushed at the end of the frame,
+//        overlaps the next frame's k_accumulate, awaited before its k_bmfr_block.
+// Every exchange point is ONE k_halo_push launch on a communication stream (rows stored straight into the receivers'
+// HBM over NVLink peer mappings, ordered by flag words, include/vkpbrt_b200.h "Band-sharded multi-GPU runs") and one
+// k_halo_wait in front of the consumer; the descriptors are built once per (group, jitter phase, ping-pong parity).
+//
+// This is the native host of the multi-GPU path: a frame costs one call (run_frame) and ~15 CUDA API calls -- the
+// Python twin (vulkanpbrt_b200/multigpu.py BandedPipeline, kept for the NCCL / gloo transports of the tests) spends
+// more host time per frame than an 8-way sharded 4K frame takes on the GPUs.
+//
+// The transport of the 64-byte IPC handles between the ranks is the caller's: AllGather is a collective every rank
+// calls in the same order (torch.distributed, MPI, a socket; threads of one process in the emulator tests).
+#pragma once
+
+#include <algorithm>
+#include <array>
+#include <functional>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "band_plan.hpp"
+#include "vkpbrt.hpp"
+
+namespace vkpbrt {
+
+// every rank contributes the same number of handles and receives everybody's: result[r] = rank r's list
+using AllGather = std::function<std::vector<std::vector<PeerHandle>>(const std::vector<PeerHandle>&)>;
+
+class BandedRank : public Inherit<BandedRank> {
+public:
+    struct Options {
+        bool use_taa = true;
+        int max_disp_rows = 24;        // reprojection displacement the halo covers (rows); taps beyond it are counted (check())
+        bool external_inputs = false;  // the producer's planes are bound per frame with bind_inputs() (virtual full-frame bases)
+        void* comm_stream = nullptr;   // cudaStream_t of the exchange kernels; nullptr: the context's stream (emulator)
+        uint32_t timeout_ms = 20000;   // a flag wait that lasts longer sets the error word instead of hanging the GPU
+    };
+
+    BandedRank(ref_ptr<Context> ctx, int rank, int world, int width, int height, const Options& opt, AllGather all_gather)
+        : context(ctx), plan(width, height, world, 32, opt.max_disp_rows, opt.use_taa), rank_(rank), world_(world), W(width), H(height), opt_(opt),
+          all_gather_(std::move(all_gather))
+    {
+        make_current(*context);
+        Context& c = *context;
+        if (opt.external_inputs) {
+            const uint32_t fmts[4] = {VKPBRT_FORMAT_R32_SFLOAT, VKPBRT_FORMAT_R32G32_SFLOAT, VKPBRT_FORMAT_R8G8B8A8_UNORM, VKPBRT_FORMAT_R32G32B32A32_SFLOAT};
+            for (int i = 0; i < 4; ++i) {
+                vkpbrt_image_t h;
+                check(vkpbrt_image_wrap(c.handle, fmts[i], (uint32_t)W, (uint32_t)H, 1, nullptr, &h));
+                ext_[i] = DescriptorImage::create(h, true);
+            }
+            g_buffer = GBuffer::create(c, ext_[0], ext_[1], ref_ptr<DescriptorImage>(), ext_[2]);
+            raw_illumination = IlluminationBufferDemodulatedFloat::create(c, std::vector<ref_ptr<DescriptorImage>>{ext_[3]});
+        } else {
+            g_buffer = GBuffer::create(c, (uint32_t)W, (uint32_t)H);
+            raw_illumination = IlluminationBufferDemodulatedFloat::create(c, (uint32_t)W, (uint32_t)H);
+            g_buffer->compile(c);
+            raw_illumination->compile(c);
+        }
+        commands = Commands::create();
+        push_constants = PushConstants::create();
+        accumulator = Accumulator::create(g_buffer, raw_illumination, /*separate_matrices=*/true);
+        accumulator->compile_images(c);
+        accumulator->add_dispatch_to_command_graph(commands);
+        accumulated = accumulator->accumulated_illumination;
+        acc = accumulator->accumulation_buffer;
+        bmfr = BMFR::create((uint32_t)W, (uint32_t)H, 32u, 32u, g_buffer, accumulated, acc);
+        bmfr->compile(c);
+        bmfr->add_dispatch_to_command_graph(commands, push_constants);
+        const Rows br = plan.block_rows(rank_);
+        bmfr->set_block_row_range(br.lo, br.hi);
+        denoiser_final = bmfr->get_final_descriptor_image();
+        final_image = denoiser_final;
+        if (opt.use_taa) {
+            taa = Taa::create((uint32_t)W, (uint32_t)H, 16u, 16u, g_buffer, acc, denoiser_final);
+            taa->compile(c);
+            taa->add_dispatch_to_command_graph(commands);
+            final_image = taa->get_final_descriptor_image();
+            vkpbrt_image_t h;
+            check(vkpbrt_taa_history_image(taa->handle, &h));
+            taa_history = DescriptorImage::create(h, false);
+        }
+        acc->copy_to_back_images(commands, g_buffer, accumulated);
+        vkpbrt_image_t img;
+        check(vkpbrt_accumulation_buffer_image(acc->handle, VKPBRT_ACC_NEXT_DEPTH, &img));
+        next_depth = DescriptorImage::create(img, false);
+        check(vkpbrt_bmfr_image_get(bmfr->handle, VKPBRT_BMFR_IMAGE_DENOISED, &img));
+        denoised = DescriptorImage::create(img, false);
+        if (world_ > 1) {
+            // a rank holds history rows within max_disp_rows (+1) of the rows it computes: taps beyond that are counted, not
+            // silently served from stale rows
+            accumulator->set_max_displacement_rows(opt.max_disp_rows);
+            // flag words: done[group][src] for the groups A, B, F, then ready[dst]
+            flags = DescriptorImage::create(c, (uint32_t)VKPBRT_FORMAT_R32_SFLOAT, (uint32_t)std::max(16, 4 * world), 1u);
+            flags->compile(c);
+            context->waitForCompletion();
+            const auto everyone = all_gather_({peer_export(c, flags->info().data)});
+            flag_base_.resize(world);
+            for (int r = 0; r < world; ++r) flag_base_[r] = r == rank_ ? static_cast<uint8_t*>(flags->info().data) : map(r, everyone[r][0]);
+        }
+    }
+
+    // external inputs: this frame's planes as FULL-FRAME base pointers (a band-local buffer holding rows [lo, hi) of
+    // input_rows() is passed as  buffer - lo * row_pitch; only rows of input_rows() are ever touched)
+    void bind_inputs(void* depth, void* normal, void* albedo, void* illumination)
+    {
+        void* p[4] = {depth, normal, albedo, illumination};
+        for (int i = 0; i < 4; ++i) check(vkpbrt_image_set_data(ext_[i]->handle, p[i]));
+    }
+
+    // cam: view, inv_view, proj, inv_proj (4 x 16 floats, column-major) of this frame (VulkanPBRT.cpp:561-563, :578-591)
+    void run_frame(int frame, const float* cam)
+    {
+        make_current(*context);
+        auto& pc = push_constants->value();
+        CameraMatrices a, b;
+        for (int i = 0; i < 16; ++i) pc.view_inverse.m[i] = a.inv_view.m[i] = cam[16 + i];
+        a.proj = mat4();
+        a.inv_proj = mat4();
+        for (int i = 0; i < 16; ++i) { a.proj->m[i] = cam[32 + i]; a.inv_proj->m[i] = pc.proj_inverse.m[i] = cam[48 + i]; }
+        pc.frame_number = (uint32_t)frame;
+        pc.sample_number = 0;
+        b.view = pc.prev_view;
+        accumulator->set_camera_matrices(frame, a, b);
+        const Rows ar = plan.accumulate_rows(rank_, frame);
+        accumulator->set_row_range(ar.lo, ar.hi);
+        auto& c = commands->children;       // accumulate, bmfr, [taa], copy_to_back
+        const bool multi = world_ > 1;
+
+        finish(pending_a_);
+        c[0](*commands);
+        if (multi) {
+            // A: what k_accumulate just wrote (pre-swap handles) is next frame's history
+            pending_a_ = start(0, frame, [&] { return Images{{"acc", {{next_depth, 0, 0}, {accumulated->illumination_images[0], 0, 0}, {acc->spp, 0, 0}}}}; },
+                               [&] { return filter(plan.history_transfers(frame + 1), true); });
+        }
+        finish(pending_b_);
+        pending_b_ = {};
+        c[1](*commands);
+        if (taa) {
+            const Rows o = plan.owned_rows(rank_, frame);
+            taa->set_row_range(o.lo, o.hi);
+            if (multi && o.hi - o.lo > 2) {
+                // the band's first / last row need one row of the neighbour's tone-mapped output (taa.comp:66-83): the rows in
+                // between run while that row is in flight, the edge rows after it has landed
+                const Pending f = start(2, frame, [&] { return Images{{"final", {{denoiser_final, 0, 0}}}}; }, [&] { return plan.final_transfers(frame); });
+                const int i0 = o.lo + (rank_ > 0 ? 1 : 0), i1 = o.hi - (rank_ < world_ - 1 ? 1 : 0);
+                taa->record_part(*push_constants, i0, i1, false);
+                finish(f);
+                if (i0 > o.lo) taa->record_part(*push_constants, o.lo, i0, false);
+                taa->record_part(*push_constants, i1, o.hi, true);      // (possibly empty) last part: hands final -> history
+            } else {
+                if (multi) finish(start(2, frame, [&] { return Images{{"final", {{denoiser_final, 0, 0}}}}; }, [&] { return plan.final_transfers(frame); }));
+                c[2](*commands);
+            }
+        }
+        c.back()(*commands);
+        for (int i = 0; i < 16; ++i) pc.prev_view.m[i] = cam[i];
+        ++swaps_;
+        if (multi) {
+            // B: denoised / TAA history halos and the stale-column strip
+            const uint32_t layer = (uint32_t)((frame & 1) ^ 1);
+            pending_b_ = start(1, frame,
+                               [&] {
+                                   Images im = {{"denoised", {{denoised, layer, 0}}},
+                                                {"final_col0", {{denoiser_final, 0, 4}}},       // 1 BGRA8 texel
+                                                {"denoised_col0", {{denoised, layer, 8}}}};     // 1 rgba16f texel
+                                   if (taa) im["taa"] = {{taa_history, 0, 0}};
+                                   return im;
+                               },
+                               [&] {
+                                   auto t = filter(plan.history_transfers(frame + 1), false);
+                                   for (const auto& s : plan.stale_column_transfers(frame)) t.push_back(s);
+                                   return t;
+                               });
+        }
+    }
+
+    // stream-side wait for the halos in flight: call before reading planes outside the owned rows
+    void flush()
+    {
+        finish(pending_a_);
+        finish(pending_b_);
+        pending_a_ = pending_b_ = {};
+    }
+
+    // synchronises; throws if a flag wait timed out (a peer died or fell out of step) or a reprojection left the rows this rank holds
+    void check_errors()
+    {
+        context->waitForCompletion();
+        for (auto& kv : cache_) {
+            uint64_t g = 0, w = 0;
+            uint32_t e = 0;
+            check(vkpbrt_halo_exchange_stats(kv.second.exchange->handle, &g, &w, &e));
+            if (e) throw std::runtime_error("halo exchange: a flag wait timed out (peer rank lost or out of step)");
+        }
+        if (world_ > 1) {
+            const uint32_t n = accumulator->displacement_violations();
+            if (n)
+                throw std::runtime_error("band-sharded run: " + std::to_string(n) + " reprojection taps moved more than max_disp_rows = " +
+                                         std::to_string(opt_.max_disp_rows) + " rows; the halo does not cover this camera motion");
+        }
+    }
+
+    // nanoseconds the streams spent spinning on flag words so far, per group (A, B, F): [gate of the push, wait before the consumer]
+    std::array<std::array<uint64_t, 2>, 3> spin_ns()
+    {
+        context->waitForCompletion();
+        std::array<std::array<uint64_t, 2>, 3> out{};
+        for (auto& kv : cache_) {
+            uint64_t g = 0, w = 0;
+            uint32_t e = 0;
+            check(vkpbrt_halo_exchange_stats(kv.second.exchange->handle, &g, &w, &e));
+            out[std::get<0>(kv.first)][0] += g;
+            out[std::get<0>(kv.first)][1] += w;
+        }
+        return out;
+    }
+
+    Rows owned_rows(int frame) const { return plan.owned_rows(rank_, frame); }
+    Rows input_rows() const { return plan.input_rows(rank_); }
+    uint64_t bytes_exchanged() const { return bytes_; }
+
+    ref_ptr<Context> context;
+    BandPlan plan;
+    ref_ptr<GBuffer> g_buffer;
+    ref_ptr<IlluminationBuffer> raw_illumination, accumulated;
+    ref_ptr<DescriptorImage> final_image, denoiser_final, denoised;
+    ref_ptr<Accumulator> accumulator;
+    ref_ptr<BMFR> bmfr;
+    ref_ptr<Taa> taa;
+
+private:
+    struct PlaneRef {            // an image (or one layer of it) that takes part in an exchange, optionally only the first bytes of its rows
+        ref_ptr<DescriptorImage> image;
+        uint32_t layer;
+        uint32_t column_bytes;   // 0: whole rows
+    };
+    using Images = std::map<std::string, std::vector<PlaneRef>>;
+    struct Pending {
+        ref_ptr<HaloExchange> exchange;
+        uint32_t value = 0;
+    };
+    struct Entry {
+        ref_ptr<HaloExchange> exchange;
+        bool active = false;
+        uint64_t bytes = 0;
+    };
+
+    static std::vector<Transfer> filter(const std::vector<Transfer>& in, bool acc_planes)
+    {
+        std::vector<Transfer> out;
+        for (const auto& t : in)
+            if ((t.plane == "acc") == acc_planes) out.push_back(t);
+        return out;
+    }
+
+    // an allocation is opened once; pointers into it differ by the offset their handle carries
+    uint8_t* map(int rank, const PeerHandle& h)
+    {
+        const std::string key = std::to_string(rank) + ":" + std::string(reinterpret_cast<const char*>(h.bytes), sizeof(h.bytes));
+        auto it = mapped_.find(key);
+        if (it == mapped_.end()) it = mapped_.emplace(key, PeerMemory::create(context, h)).first;
+        return static_cast<uint8_t*>(it->second->base()) + h.offset;
+    }
+
+    uint32_t* done_word(int owner, int group, int src) { return reinterpret_cast<uint32_t*>(flag_base_[owner] + 4 * (group * world_ + src)); }
+    uint32_t* ready_word(int owner, int dst) { return reinterpret_cast<uint32_t*>(flag_base_[owner] + 4 * (3 * world_ + dst)); }
+
+    // group: 0 = A, 1 = B, 2 = F
+    template <class ImagesFn, class TransfersFn>
+    Pending start(int group, int frame, ImagesFn images, TransfersFn transfers)
+    {
+        const uint32_t value = ++seq_[group];
+        // buffers alternate with the copy_to_back swaps and the frame parity; row ranges with the jitter phase
+        const auto key = std::make_tuple(group, frame % 16, swaps_ & 1, frame & 1);
+        auto it = cache_.find(key);
+        if (it == cache_.end()) it = cache_.emplace(key, build(group, images(), transfers())).first;
+        if (!it->second.active) return {};
+        bytes_ += it->second.bytes;
+        it->second.exchange->start(opt_.comm_stream, nullptr, value);
+        return {it->second.exchange, value};
+    }
+
+    void finish(const Pending& p)
+    {
+        if (p.exchange) p.exchange->wait(nullptr, p.value);
+    }
+
+    Entry build(int group, const Images& images, const std::vector<Transfer>& transfers)
+    {
+        // every rank exports the images of this exchange point, in the same order, and learns everybody's
+        std::vector<PeerHandle> mine;
+        std::map<std::string, std::vector<size_t>> index;
+        for (const auto& kv : images)
+            for (const auto& p : kv.second) {
+                index[kv.first].push_back(mine.size());
+                mine.push_back(peer_export(*context, p.image->info().data));
+            }
+        const auto everyone = all_gather_(mine);
+        std::vector<vkpbrt_halo_copy> copies;
+        std::vector<int> send_to, recv_from;
+        uint64_t bytes = 0;
+        auto add_unique = [](std::vector<int>& v, int x) { if (std::find(v.begin(), v.end(), x) == v.end()) v.push_back(x); };
+        for (const auto& t : transfers) {
+            if (t.src == t.dst) continue;
+            const auto& planes = images.at(t.plane);
+            for (size_t k = 0; k < planes.size(); ++k) {
+                const auto info = planes[k].image->info();
+                const uint64_t offset = planes[k].layer * info.layer_pitch + (uint64_t)t.rows.lo * info.row_pitch;
+                if (t.src == rank_) {
+                    vkpbrt_halo_copy c{};
+                    c.src = static_cast<uint8_t*>(info.data) + offset;
+                    c.dst = map(t.dst, everyone[t.dst][index.at(t.plane)[k]]) + offset;
+                    c.src_pitch = c.dst_pitch = info.row_pitch;
+                    c.row_bytes = planes[k].column_bytes ? planes[k].column_bytes : (uint32_t)info.row_pitch;
+                    c.rows = (uint32_t)(t.rows.hi - t.rows.lo);
+                    copies.push_back(c);
+                    bytes += (uint64_t)c.row_bytes * c.rows;
+                    add_unique(send_to, t.dst);
+                } else if (t.dst == rank_) {
+                    add_unique(recv_from, t.src);
+                }
+            }
+        }
+        std::sort(send_to.begin(), send_to.end());
+        std::sort(recv_from.begin(), recv_from.end());
+        // the end-of-frame group waits for its receivers' frame to be over (they announce it), as posting a receive would
+        const bool handshake = group == 1;
+        std::vector<uint32_t*> announce, done;
+        std::vector<const uint32_t*> ready, wait;
+        for (int s : recv_from) {
+            if (handshake) announce.push_back(ready_word(s, rank_));
+            wait.push_back(done_word(rank_, group, s));
+        }
+        for (int d : send_to) {
+            if (handshake) ready.push_back(ready_word(rank_, d));
+            done.push_back(done_word(d, group, rank_));
+        }
+        Entry e;
+        e.active = !send_to.empty() || !recv_from.empty();
+        e.bytes = bytes;
+        e.exchange = HaloExchange::create(*context, copies, announce, ready, done, wait, opt_.timeout_ms);
+        return e;
+    }
+
+    const int rank_, world_, W, H;
+    const Options opt_;
+    AllGather all_gather_;
+    ref_ptr<Commands> commands;
+    ref_ptr<PushConstants> push_constants;
+    ref_ptr<AccumulationBuffer> acc;
+    ref_ptr<DescriptorImage> ext_[4], taa_history, next_depth, flags;
+    std::vector<uint8_t*> flag_base_;
+    std::map<std::string, ref_ptr<PeerMemory>> mapped_;
+    std::map<std::tuple<int, int, int, int>, Entry> cache_;
+    uint32_t seq_[3] = {0, 0, 0};
+    int swaps_ = 0;
+    uint64_t bytes_ = 0;
+    Pending pending_a_, pending_b_;
+};
+
+}  // namespace vkpbrt

@@ -53,10 +53,13 @@ struct mat4 {
 class Context : public Inherit<Context> {
 public:
     explicit Context(int device = 0, void* cuda_stream = nullptr) { check(vkpbrt_context_create(device, cuda_stream, &handle)); }
-    ~Context() { vkpbrt_context_destroy(handle); }
+    explicit Context(vkpbrt_context_t borrowed) : handle(borrowed), _owner(false) {}      // a context owned by the C-ABI caller
+    ~Context() { if (_owner) vkpbrt_context_destroy(handle); }
     Context(const Context&) = delete;
     void waitForCompletion() { check(vkpbrt_context_synchronize(handle)); }
     vkpbrt_context_t handle = nullptr;
+private:
+    bool _owner = true;
 };
 
 // vsg::DescriptorImage stand-in: a device image handle
@@ -125,6 +128,16 @@ public:
         depth = member(VKPBRT_GBUFFER_DEPTH); normal = member(VKPBRT_GBUFFER_NORMAL);
         material = member(VKPBRT_GBUFFER_MATERIAL); albedo = member(VKPBRT_GBUFFER_ALBEDO);
     }
+    // caller-provided images (a producer's planes: Vulkan-imported memory, a resident sequence); material may be null
+    GBuffer(Context& ctx, ref_ptr<DescriptorImage> depth_image, ref_ptr<DescriptorImage> normal_image, ref_ptr<DescriptorImage> material_image,
+            ref_ptr<DescriptorImage> albedo_image)
+        : depth(depth_image), normal(normal_image), material(material_image), albedo(albedo_image)
+    {
+        const vkpbrt_image_info i = depth_image->info();
+        width = i.width; height = i.height;
+        check(vkpbrt_gbuffer_create_from_images(ctx.handle, depth_image->handle, normal_image->handle, material_image ? material_image->handle : nullptr,
+                                                albedo_image->handle, &handle));
+    }
     ~GBuffer() { vkpbrt_gbuffer_destroy(handle); }
     void compile(Context&) const { check(vkpbrt_gbuffer_compile(handle)); }
     void update_image_layouts(Context&) const {}   // no image layouts on linear device memory
@@ -150,6 +163,15 @@ protected:
         fill();
     }
     IlluminationBuffer(vkpbrt_illumination_buffer_t borrowed, uint32_t w, uint32_t h) : width(w), height(h), handle(borrowed), _owner(false) { fill(); }
+    IlluminationBuffer(Context& ctx, uint32_t type, const std::vector<ref_ptr<DescriptorImage>>& images) : _owner(true), _wrapped(images)
+    {
+        std::vector<vkpbrt_image_t> h;
+        for (const auto& im : images) h.push_back(im->handle);
+        check(vkpbrt_illumination_buffer_create_from_images(ctx.handle, type, h.data(), (uint32_t)h.size(), &handle));
+        const vkpbrt_image_info i = images.at(0)->info();
+        width = i.width; height = i.height;
+        fill();
+    }
 private:
     void fill()
     {
@@ -158,6 +180,7 @@ private:
         for (uint32_t i = 0; i < n; ++i) { vkpbrt_image_t im; check(vkpbrt_illumination_buffer_image(handle, i, &im)); illumination_images.push_back(DescriptorImage::create(im, false)); }
     }
     bool _owner;
+    std::vector<ref_ptr<DescriptorImage>> _wrapped;      // caller-provided images stay alive with the buffer
 };
 class IlluminationBufferFinal : public IlluminationBuffer, public Inherit<IlluminationBufferFinal> {
 public: IlluminationBufferFinal(Context& c, uint32_t w, uint32_t h) : IlluminationBuffer(c, VKPBRT_ILLUMINATION_FINAL, w, h) {}
@@ -168,7 +191,10 @@ public:
     IlluminationBufferDemodulated(vkpbrt_illumination_buffer_t borrowed, uint32_t w, uint32_t h) : IlluminationBuffer(borrowed, w, h) {}
 };
 class IlluminationBufferDemodulatedFloat : public IlluminationBuffer, public Inherit<IlluminationBufferDemodulatedFloat> {
-public: IlluminationBufferDemodulatedFloat(Context& c, uint32_t w, uint32_t h) : IlluminationBuffer(c, VKPBRT_ILLUMINATION_DEMODULATED_FLOAT, w, h) {}
+public:
+    IlluminationBufferDemodulatedFloat(Context& c, uint32_t w, uint32_t h) : IlluminationBuffer(c, VKPBRT_ILLUMINATION_DEMODULATED_FLOAT, w, h) {}
+    // one caller-provided rgba32f image (the producer's raw 1-spp demodulated illumination)
+    IlluminationBufferDemodulatedFloat(Context& c, const std::vector<ref_ptr<DescriptorImage>>& images) : IlluminationBuffer(c, VKPBRT_ILLUMINATION_DEMODULATED_FLOAT, images) {}
 };
 
 class AccumulationBuffer : public Inherit<AccumulationBuffer> {   // source/buffers/AccumulationBuffer.hpp:13-24

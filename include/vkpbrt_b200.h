@@ -403,6 +403,43 @@ VKPBRT_API int vkpbrt_halo_exchange_wait(vkpbrt_halo_exchange_t x, void* stream,
 VKPBRT_API int vkpbrt_halo_exchange_stats(vkpbrt_halo_exchange_t x, uint64_t* gate_ns, uint64_t* wait_ns, uint32_t* error);
 VKPBRT_API int vkpbrt_halo_exchange_destroy(vkpbrt_halo_exchange_t x);
 
+/* ---------------------------------------------------------------------------------------- */
+/* One rank of the band-sharded chain as ONE object: the native (C++) host of the multi-GPU    */
+/* path, include/vkpbrt/banded.hpp vkpbrt::BandedRank behind the C ABI.  accumulate -> BMFR b=32 */
+/* [-> TAA] on this rank's band of block rows, the three halo exchange points per frame pushed  */
+/* over NVLink peer memory.  A frame is one call.                                               */
+/* ---------------------------------------------------------------------------------------- */
+typedef struct vkpbrt_banded_rank_s* vkpbrt_banded_rank_t;
+/* collective the library calls when an exchange point is first built (every rank, same order): copy `bytes` bytes of
+ * `mine` to slot `rank` of `everyone` (world * bytes) on EVERY rank.  Return 0 on success. */
+typedef int (*vkpbrt_all_gather_fn)(void* user, const void* mine, uint64_t bytes, void* everyone);
+/* a CUDA stream for the exchange kernels (high priority); destroy with vkpbrt_stream_destroy */
+VKPBRT_API int vkpbrt_stream_create(vkpbrt_context_t ctx, int high_priority, void** cuda_stream);
+VKPBRT_API int vkpbrt_stream_destroy(vkpbrt_context_t ctx, void* cuda_stream);
+/* external_inputs != 0: the producer's planes are bound per frame with vkpbrt_banded_rank_bind_inputs.
+ * comm_stream: from vkpbrt_stream_create (NULL: the context's stream).  max_disp_rows: reprojection displacement the
+ * halo covers; taps beyond it make vkpbrt_banded_rank_check fail instead of reading rows this rank never received. */
+VKPBRT_API int vkpbrt_banded_rank_create(vkpbrt_context_t ctx, uint32_t width, uint32_t height, int rank, int world, int use_taa,
+                                         int max_disp_rows, int external_inputs, void* comm_stream, vkpbrt_all_gather_fn all_gather,
+                                         void* user, uint32_t timeout_ms, vkpbrt_banded_rank_t* out);
+/* image rows of the producer's planes this rank ever touches, and the band boundaries in block rows (world + 1 ints) */
+VKPBRT_API int vkpbrt_banded_rank_input_rows(vkpbrt_banded_rank_t r, int* row_begin, int* row_end);
+VKPBRT_API int vkpbrt_banded_rank_block_rows(vkpbrt_banded_rank_t r, int* boundaries);
+/* rows of `frame` this rank's BMFR blocks write (its part of the result) */
+VKPBRT_API int vkpbrt_banded_rank_owned_rows(vkpbrt_banded_rank_t r, uint32_t frame, int* row_begin, int* row_end);
+/* this frame's planes as FULL-FRAME base pointers: a band-local buffer holding rows [lo, hi) of input_rows is passed as
+ * buffer - lo * row_pitch (depth r32f, normal rg32f, albedo rgba8, illumination rgba32f) */
+VKPBRT_API int vkpbrt_banded_rank_bind_inputs(vkpbrt_banded_rank_t r, void* depth, void* normal, void* albedo, void* illumination);
+/* camera: view, inv_view, proj, inv_proj of this frame, 4 x 16 floats, column-major */
+VKPBRT_API int vkpbrt_banded_rank_run_frame(vkpbrt_banded_rank_t r, uint32_t frame, const float* camera);
+VKPBRT_API int vkpbrt_banded_rank_flush(vkpbrt_banded_rank_t r);      /* stream-side wait for the halos in flight */
+VKPBRT_API int vkpbrt_banded_rank_check(vkpbrt_banded_rank_t r);      /* synchronises; fails on a flag timeout / a displacement violation */
+typedef enum { VKPBRT_BANDED_IMAGE_FINAL = 0, VKPBRT_BANDED_IMAGE_DENOISER_FINAL = 1, VKPBRT_BANDED_IMAGE_DENOISED = 2 } vkpbrt_banded_image;
+VKPBRT_API int vkpbrt_banded_rank_image(vkpbrt_banded_rank_t r, uint32_t which, vkpbrt_image_t* out);   /* borrowed */
+/* synchronises; spin_ns[group A,B,F][gate of the push, wait before the consumer], bytes pushed so far */
+VKPBRT_API int vkpbrt_banded_rank_stats(vkpbrt_banded_rank_t r, uint64_t spin_ns[6], uint64_t* bytes_pushed);
+VKPBRT_API int vkpbrt_banded_rank_destroy(vkpbrt_banded_rank_t r);
+
 #ifdef __cplusplus
 }
 #endif

@@ -320,3 +320,70 @@ def test_peer_memory_exchange_protocol_on_the_emulator(world, use_taa, W, H, fra
         import gc
         gc.collect()
         _capi._lib = saved
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("world,use_taa,W,H,frames", [(2, True, 64, 416, 20), (3, True, 64, 480, 18), (3, False, 96, 384, 10)])
+def test_native_banded_rank_on_the_emulator(world, use_taa, W, H, frames):
+    """vkpbrt::BandedRank (include/vkpbrt/banded.hpp) through the C ABI (vkpbrt_banded_rank_*): the C++ host of the
+    band-sharded chain, one call per frame, band-local inputs bound through virtual full-frame base pointers.  Ranks are
+    OS threads over the emulator; the all_gather callback is a thread barrier.  Owned rows must equal the single-rank run
+    bit for bit."""
+    import subprocess
+    import threading
+    subprocess.run(["make", "-C", str(ROOT / "tests" / "hostsim")], check=True, capture_output=True)
+    from vulkanpbrt_b200 import Context, DenoisePipeline, _capi, synth
+    from vulkanpbrt_b200.multigpu import NativeBandedRank
+    saved = _capi._lib
+    _capi._lib = _capi.configure(ctypes.CDLL(str(ROOT / "tests" / "hostsim" / "libvkpbrt_hostsim.so")))
+    try:
+        group = _ThreadGroup(world)
+        results, errors, keep = [None] * world, [], [None] * world
+
+        def rank_main(rank):
+            try:
+                ctx = Context(0)
+                nr = NativeBandedRank(W, H, rank, world, use_taa, ctx, dist=group.rank_view(rank), max_disp_rows=12, external_inputs=True,
+                                      comm_stream=0, timeout_ms=120000)
+                lo, hi = nr.input_rows()
+                out = []
+                for f in range(frames):
+                    fr = synth.render_frame(W, H, f, rows=(lo, hi))
+                    planes = [np.ascontiguousarray(fr.depth[lo:hi]), np.ascontiguousarray(fr.normal[lo:hi]), np.ascontiguousarray(fr.albedo[lo:hi]),
+                              np.ascontiguousarray(fr.illumination[lo:hi])]
+                    pitch = [4 * W, 8 * W, 4 * W, 16 * W]
+                    nr.bind_inputs(*[p.ctypes.data - lo * pt for p, pt in zip(planes, pitch)])
+                    nr.run_frame(f, NativeBandedRank.camera_block(fr.camera))
+                    o = nr.owned_rows(f)
+                    out.append((o, nr.final.download()[o[0]:o[1]].copy(), nr.denoised.download()[(f & 1) ^ 1, o[0]:o[1]].copy()))
+                nr.flush()
+                nr.check()
+                results[rank], keep[rank] = out, (nr, ctx)     # handles stay alive until every rank is done writing into them
+            except BaseException as e:      # noqa: BLE001 -- reported by the main thread
+                import traceback
+                traceback.print_exc()
+                errors.append((rank, e))
+                group.barrier.abort()
+
+        threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        assert not errors, errors
+        pipe = DenoisePipeline(W, H, use_taa=use_taa)
+        for f in range(frames):
+            pipe.run_frame(f, synth.render_frame(W, H, f))
+            full_final = pipe.final.download()
+            full_den = pipe.modules[0].denoised.download()[(f & 1) ^ 1]
+            for r in range(world):
+                (lo, hi), band_f, band_d = results[r][f]
+                np.testing.assert_array_equal(band_f, full_final[lo:hi], err_msg=f"final, frame {f}, rank {r}")
+                np.testing.assert_array_equal(band_d, full_den[lo:hi], err_msg=f"denoised, frame {f}, rank {r}")
+        for k in keep:
+            k[0].close()
+        del pipe, results, keep
+    finally:
+        import gc
+        gc.collect()
+        _capi._lib = saved

@@ -158,6 +158,19 @@ _PROTOS = {
     "vkpbrt_format_converter_final_image": [H, C.POINTER(H)],
     "vkpbrt_format_converter_destroy": [H],
     "vkpbrt_demodulate_record": [H, H, H, H, H],
+    "vkpbrt_stream_create": [H, i32, C.POINTER(C.c_void_p)],
+    "vkpbrt_stream_destroy": [H, C.c_void_p],
+    "vkpbrt_banded_rank_create": [H, u32, u32, i32, i32, i32, i32, i32, C.c_void_p, C.c_void_p, C.c_void_p, u32, C.POINTER(H)],
+    "vkpbrt_banded_rank_input_rows": [H, C.POINTER(i32), C.POINTER(i32)],
+    "vkpbrt_banded_rank_block_rows": [H, C.POINTER(i32)],
+    "vkpbrt_banded_rank_owned_rows": [H, u32, C.POINTER(i32), C.POINTER(i32)],
+    "vkpbrt_banded_rank_bind_inputs": [H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
+    "vkpbrt_banded_rank_run_frame": [H, u32, C.c_void_p],
+    "vkpbrt_banded_rank_flush": [H],
+    "vkpbrt_banded_rank_check": [H],
+    "vkpbrt_banded_rank_image": [H, u32, C.POINTER(H)],
+    "vkpbrt_banded_rank_stats": [H, C.POINTER(u64), C.POINTER(u64)],
+    "vkpbrt_banded_rank_destroy": [H],
     "vkpbrt_taa_record": [H, C.POINTER(PushConstants)],
     "vkpbrt_taa_set_row_range": [H, i32, i32],
     "vkpbrt_taa_final_image": [H, PH],

@@ -1670,3 +1670,168 @@ int vkpbrt_halo_exchange_destroy(vkpbrt_halo_exchange_t x)
 
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// vkpbrt::BandedRank (include/vkpbrt/banded.hpp: the C++ layer, itself written on the C ABI above) behind the C ABI
+// ------------------------------------------------------------------------------------------------
+#include "../../include/vkpbrt/banded.hpp"
+
+struct vkpbrt_banded_rank_s {
+    vkpbrt::ref_ptr<vkpbrt::Context> ctx;
+    vkpbrt::ref_ptr<vkpbrt::BandedRank> rank;
+    int world = 1;
+};
+
+namespace {
+template <class F>
+int guarded(F&& f)
+{
+    try {
+        f();
+        return VKPBRT_OK;
+    } catch (const std::exception& e) {
+        // errors of nested C-ABI calls arrive as "vkpbrt: <last error>": keep the message, report a generic code
+        return fail(VKPBRT_ERR_INVALID_ARGUMENT, e.what());
+    }
+}
+}  // namespace
+
+extern "C" {
+
+int vkpbrt_stream_create(vkpbrt_context_t ctx, int high_priority, void** cuda_stream)
+{
+    VK_REQUIRE(ctx && cuda_stream, "vkpbrt_stream_create: null argument");
+    VK_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = nullptr;
+#ifndef VKPBRT_HOSTSIM
+    int lo = 0, hi = 0;
+    VK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    VK_CUDA(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, high_priority ? hi : lo));
+#else
+    (void)high_priority;
+    VK_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+#endif
+    *cuda_stream = s;
+    return VKPBRT_OK;
+}
+
+int vkpbrt_stream_destroy(vkpbrt_context_t ctx, void* cuda_stream)
+{
+    VK_REQUIRE(ctx, "null context");
+    if (cuda_stream) cudaStreamDestroy((cudaStream_t)cuda_stream);
+    return VKPBRT_OK;
+}
+
+int vkpbrt_banded_rank_create(vkpbrt_context_t ctx, uint32_t width, uint32_t height, int rank, int world, int use_taa, int max_disp_rows,
+                              int external_inputs, void* comm_stream, vkpbrt_all_gather_fn all_gather, void* user, uint32_t timeout_ms,
+                              vkpbrt_banded_rank_t* out)
+{
+    VK_REQUIRE(ctx && out && world >= 1 && rank >= 0 && rank < world, "vkpbrt_banded_rank_create: bad argument");
+    VK_REQUIRE(world == 1 || all_gather, "vkpbrt_banded_rank_create: more than one rank needs an all_gather callback");
+    VK_REQUIRE(world <= VKPBRT_HALO_MAX_PEERS, "vkpbrt_banded_rank_create: at most VKPBRT_HALO_MAX_PEERS ranks per node");
+    auto* r = new vkpbrt_banded_rank_s();
+    r->world = world;
+    const int rc = guarded([&] {
+        r->ctx = std::make_shared<vkpbrt::Context>(ctx);
+        vkpbrt::BandedRank::Options opt;
+        opt.use_taa = use_taa != 0;
+        opt.max_disp_rows = max_disp_rows;
+        opt.external_inputs = external_inputs != 0;
+        opt.comm_stream = comm_stream;
+        opt.timeout_ms = timeout_ms;
+        vkpbrt::AllGather ag = [all_gather, user, world, rank](const std::vector<vkpbrt::PeerHandle>& mine) {
+            std::vector<std::vector<vkpbrt::PeerHandle>> everyone((size_t)world, std::vector<vkpbrt::PeerHandle>(mine.size()));
+            if (world == 1) { everyone[0] = mine; return everyone; }
+            const uint64_t bytes = mine.size() * sizeof(vkpbrt::PeerHandle);
+            std::vector<unsigned char> flat((size_t)world * bytes);
+            if (all_gather(user, mine.data(), bytes, flat.data()) != 0) throw std::runtime_error("all_gather callback failed");
+            for (int g = 0; g < world; ++g) std::memcpy(everyone[g].data(), flat.data() + (size_t)g * bytes, bytes);
+            return everyone;
+        };
+        r->rank = vkpbrt::BandedRank::create(r->ctx, rank, world, (int)width, (int)height, opt, ag);
+    });
+    if (rc) { delete r; return rc; }
+    *out = r;
+    return VKPBRT_OK;
+}
+
+int vkpbrt_banded_rank_input_rows(vkpbrt_banded_rank_t r, int* row_begin, int* row_end)
+{
+    VK_REQUIRE(r && row_begin && row_end, "null argument");
+    const vkpbrt::Rows rows = r->rank->input_rows();
+    *row_begin = rows.lo; *row_end = rows.hi;
+    return VKPBRT_OK;
+}
+
+int vkpbrt_banded_rank_block_rows(vkpbrt_banded_rank_t r, int* boundaries)
+{
+    VK_REQUIRE(r && boundaries, "null argument");
+    for (int g = 0; g < r->world; ++g) boundaries[g] = r->rank->plan.block_rows(g).lo;
+    boundaries[r->world] = r->rank->plan.block_rows(r->world - 1).hi;
+    return VKPBRT_OK;
+}
+
+int vkpbrt_banded_rank_owned_rows(vkpbrt_banded_rank_t r, uint32_t frame, int* row_begin, int* row_end)
+{
+    VK_REQUIRE(r && row_begin && row_end, "null argument");
+    const vkpbrt::Rows rows = r->rank->owned_rows((int)frame);
+    *row_begin = rows.lo; *row_end = rows.hi;
+    return VKPBRT_OK;
+}
+
+int vkpbrt_banded_rank_bind_inputs(vkpbrt_banded_rank_t r, void* depth, void* normal, void* albedo, void* illumination)
+{
+    VK_REQUIRE(r, "null argument");
+    return guarded([&] { r->rank->bind_inputs(depth, normal, albedo, illumination); });
+}
+
+int vkpbrt_banded_rank_run_frame(vkpbrt_banded_rank_t r, uint32_t frame, const float* camera)
+{
+    VK_REQUIRE(r && camera, "null argument");
+    return guarded([&] { r->rank->run_frame((int)frame, camera); });
+}
+
+int vkpbrt_banded_rank_flush(vkpbrt_banded_rank_t r)
+{
+    VK_REQUIRE(r, "null argument");
+    return guarded([&] { r->rank->flush(); });
+}
+
+int vkpbrt_banded_rank_check(vkpbrt_banded_rank_t r)
+{
+    VK_REQUIRE(r, "null argument");
+    return guarded([&] { r->rank->check_errors(); });
+}
+
+int vkpbrt_banded_rank_image(vkpbrt_banded_rank_t r, uint32_t which, vkpbrt_image_t* out)
+{
+    VK_REQUIRE(r && out, "null argument");
+    switch (which) {
+    case VKPBRT_BANDED_IMAGE_FINAL: *out = r->rank->final_image->handle; break;
+    case VKPBRT_BANDED_IMAGE_DENOISER_FINAL: *out = r->rank->denoiser_final->handle; break;
+    case VKPBRT_BANDED_IMAGE_DENOISED: *out = r->rank->denoised->handle; break;
+    default: return fail(VKPBRT_ERR_INVALID_ARGUMENT, "vkpbrt_banded_rank_image: unknown image");
+    }
+    return VKPBRT_OK;
+}
+
+int vkpbrt_banded_rank_stats(vkpbrt_banded_rank_t r, uint64_t spin_ns[6], uint64_t* bytes_pushed)
+{
+    VK_REQUIRE(r && spin_ns && bytes_pushed, "null argument");
+    return guarded([&] {
+        const auto s = r->rank->spin_ns();
+        for (int g = 0; g < 3; ++g) { spin_ns[2 * g] = s[g][0]; spin_ns[2 * g + 1] = s[g][1]; }
+        *bytes_pushed = r->rank->bytes_exchanged();
+    });
+}
+
+int vkpbrt_banded_rank_destroy(vkpbrt_banded_rank_t r)
+{
+    if (!r) return VKPBRT_OK;
+    r->rank.reset();
+    r->ctx.reset();
+    delete r;
+    return VKPBRT_OK;
+}
+
+}  // extern "C"

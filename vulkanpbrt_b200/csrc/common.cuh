@@ -143,11 +143,16 @@ VK_DEVICE void vk_sincos(float x, float& sn, float& cs)
     float pc = mul_rn(mul_rn(add_rn(mul_rn(add_rn(mul_rn(2.443315711809948e-5f, z), -1.388731625493765e-3f), z), 4.166664568298827e-2f), z), z);
     pc = sub_rn(pc, mul_rn(0.5f, z));
     pc = add_rn(pc, 1.0f);
+    // quadrant q: (s, c) = (ps, pc), (pc, -ps), (-ps, -pc), (-pc, ps).  One select per output and the signs as xors of the
+    // sign bit (exactly the unary minus): the four-way select chains compiled to three-way branches per call
     const uint32_t q = (j >> 1) & 3u;
-    const float s = (q == 0u) ? ps : ((q == 1u) ? pc : ((q == 2u) ? -ps : -pc));
-    const float c = (q == 0u) ? pc : ((q == 1u) ? -ps : ((q == 2u) ? -pc : ps));
+    const bool odd = (q & 1u) != 0u;
+    const uint32_t s_sign = ((q & 2u) << 30) ^ (x < 0.0f ? 0x80000000u : 0u);       // sin: q = 2, 3; odd function
+    const uint32_t c_sign = ((q + 1u) & 2u) << 30;                                  // cos: q = 1, 2
+    const float s = __uint_as_float(__float_as_uint(odd ? pc : ps) ^ s_sign);
+    const float c = __uint_as_float(__float_as_uint(odd ? ps : pc) ^ c_sign);
     const float nan = __uint_as_float(0x7fc00000u);
-    sn = in_range ? ((x < 0.0f) ? -s : s) : nan;
+    sn = in_range ? s : nan;
     cs = in_range ? c : nan;
 }
 

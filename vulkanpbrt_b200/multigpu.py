@@ -19,6 +19,7 @@ BandPlan is pure integer geometry (tested on CPU); BandedPipeline drives one ran
 """
 from __future__ import annotations
 
+import os
 import time
 from dataclasses import dataclass
 from typing import Callable, Dict, List, Tuple
@@ -677,6 +678,100 @@ class BandedPipeline:
         return self.plan.owned_rows(self.rank, frame)
 
 
+class NativeBandedRank:
+    """vkpbrt::BandedRank (include/vkpbrt/banded.hpp) through the C ABI: the native host of the band-sharded chain.  One
+    C call per frame instead of ~15 ctypes calls and their Python glue -- at N = 8 the Python driver above spends more
+    host time per frame (0.13 ms) than a rank's share of a 4K frame takes on its GPU (0.09 ms).
+    dist: anything with all_gather_object (torch.distributed on GPUs, a thread group in the emulator tests)."""
+
+    def __init__(self, width: int, height: int, rank: int, world: int, use_taa: bool, ctx, dist=None, max_disp_rows: int = 24,
+                 external_inputs: bool = True, comm_stream: int = None, timeout_ms: int = 20000):
+        import ctypes as C
+        self.C, self.ctx, self.rank, self.world, self.dist = C, ctx, rank, world, dist
+        self.width, self.height = width, height
+        self._own_stream = None
+        if comm_stream is None and world > 1:
+            s = C.c_void_p()
+            capi.call("vkpbrt_stream_create", ctx.handle, 1, C.byref(s))
+            self._own_stream = comm_stream = s.value
+
+        def all_gather(_user, mine, nbytes, everyone):
+            try:
+                out = [None] * world
+                dist.all_gather_object(out, C.string_at(mine, nbytes))
+                C.memmove(everyone, b"".join(out), nbytes * world)
+                return 0
+            except Exception:       # noqa: BLE001 -- reported as a C-ABI error by the library
+                import traceback
+                traceback.print_exc()
+                return 1
+        self._cb = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p)(all_gather)
+        self._h = C.c_void_p()
+        capi.call("vkpbrt_banded_rank_create", ctx.handle, width, height, rank, world, 1 if use_taa else 0, int(max_disp_rows),
+                  1 if external_inputs else 0, C.c_void_p(comm_stream or 0), C.cast(self._cb, C.c_void_p) if world > 1 else None, None,
+                  int(timeout_ms), C.byref(self._h))
+        lib = capi.lib()
+        self._run, self._bind = lib.vkpbrt_banded_rank_run_frame, lib.vkpbrt_banded_rank_bind_inputs
+        from .modules import DescriptorImage
+        img = lambda which: (lambda h: (capi.call("vkpbrt_banded_rank_image", self._h, which, C.byref(h)), DescriptorImage(ctx, h, False))[1])(C.c_void_p())
+        self.final, self.denoiser_final, self.denoised = img(0), img(1), img(2)
+        b = (C.c_int * (world + 1))()
+        capi.call("vkpbrt_banded_rank_block_rows", self._h, b)
+        self.brow = list(b)
+        self.max_disp_rows = max_disp_rows
+
+    def input_rows(self) -> Rows:
+        lo, hi = self.C.c_int(), self.C.c_int()
+        capi.call("vkpbrt_banded_rank_input_rows", self._h, self.C.byref(lo), self.C.byref(hi))
+        return (lo.value, hi.value)
+
+    def owned_rows(self, frame: int) -> Rows:
+        lo, hi = self.C.c_int(), self.C.c_int()
+        capi.call("vkpbrt_banded_rank_owned_rows", self._h, frame, self.C.byref(lo), self.C.byref(hi))
+        return (lo.value, hi.value)
+
+    def bind_inputs(self, depth_ptr: int, normal_ptr: int, albedo_ptr: int, illumination_ptr: int) -> None:
+        rc = self._bind(self._h, depth_ptr, normal_ptr, albedo_ptr, illumination_ptr)
+        if rc:
+            capi.check(rc)
+
+    @staticmethod
+    def camera_block(cam):
+        """view, inv_view, proj, inv_proj as one contiguous float32[64] (build once per camera, reuse every frame)"""
+        return np.ascontiguousarray(np.concatenate([np.asarray(m, np.float32).reshape(16) for m in (cam.view, cam.inv_view, cam.proj, cam.inv_proj)]))
+
+    def run_frame(self, frame: int, cam_block: np.ndarray) -> None:
+        rc = self._run(self._h, frame, cam_block.ctypes.data)
+        if rc:
+            capi.check(rc)
+
+    def flush(self) -> None:
+        capi.call("vkpbrt_banded_rank_flush", self._h)
+
+    def check(self) -> None:
+        capi.call("vkpbrt_banded_rank_check", self._h)
+
+    def stats(self):
+        """synchronises; ({group: [gate ms, wait ms]}, bytes pushed)"""
+        s, b = (self.C.c_uint64 * 6)(), self.C.c_uint64()
+        capi.call("vkpbrt_banded_rank_stats", self._h, s, self.C.byref(b))
+        return {k: [s[2 * i] * 1e-6, s[2 * i + 1] * 1e-6] for i, k in enumerate(("A", "B", "F"))}, int(b.value)
+
+    def close(self) -> None:
+        if self._h:
+            capi.call("vkpbrt_banded_rank_destroy", self._h)
+            self._h = None
+        if self._own_stream:
+            capi.call("vkpbrt_stream_destroy", self.ctx.handle, self.C.c_void_p(self._own_stream))
+            self._own_stream = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def cuda_view(device):
     """view(image) for CUDA ranks: zero-copy uint8 tensor over the image's current device buffer"""
     import torch
@@ -701,6 +796,79 @@ def _progress(rank: int, what: str) -> None:
         print(f"[bench_multi] {what}", file=sys.stderr, flush=True)
 
 
+class _PythonAdapter:
+    """BandedPipeline behind the small interface bench_multi drives"""
+
+    def __init__(self, bp: "BandedPipeline"):
+        self.bp = bp
+
+    final = property(lambda self: self.bp.pipe.final)
+    denoised = property(lambda self: self.bp.bmfr.denoised)
+
+    def prepare_camera(self, cam):
+        return cam
+
+    def bind_inputs(self, *ptrs):
+        self.bp.pipe.bind_inputs(*ptrs)
+
+    def run_frame(self, f, cam):
+        self.bp.run_frame(f, cam)
+
+    def flush(self):
+        self.bp.flush()
+
+    def check(self):
+        self.bp.check()
+
+    def owned_rows(self, f):
+        return self.bp.owned_rows(f)
+
+    def spin_stats(self):
+        return dict(self.bp.peer.stats()[0]) if self.bp.peer is not None else {}
+
+    def bytes_exchanged(self):
+        return self.bp.bytes_exchanged
+
+    def close(self):
+        if self.bp.peer is not None:
+            self.bp.peer.close()
+
+
+class _NativeAdapter:
+    """NativeBandedRank behind the same interface"""
+
+    def __init__(self, nr: "NativeBandedRank"):
+        self.nr = nr
+        self.final, self.denoised = nr.final, nr.denoised
+
+    def prepare_camera(self, cam):
+        return NativeBandedRank.camera_block(cam)
+
+    def bind_inputs(self, *ptrs):
+        self.nr.bind_inputs(*ptrs)
+
+    def run_frame(self, f, cam):
+        self.nr.run_frame(f, cam)
+
+    def flush(self):
+        self.nr.flush()
+
+    def check(self):
+        self.nr.check()
+
+    def owned_rows(self, f):
+        return self.nr.owned_rows(f)
+
+    def spin_stats(self):
+        return self.nr.stats()[0] if self.nr.world > 1 else {}
+
+    def bytes_exchanged(self):
+        return self.nr.stats()[1]
+
+    def close(self):
+        self.nr.close()
+
+
 def measure_banded(args, name: str, K: int, Wm: int, R: int, rank: int, world: int, local: int, weak: bool, replicas: bool, with_e2e: bool):
     """one workload band-sharded over the ranks.  Returns the result dict on rank 0, None elsewhere."""
     import torch
@@ -722,12 +890,22 @@ def measure_banded(args, name: str, K: int, Wm: int, R: int, rank: int, world: i
     assert ctx.stream == stream.cuda_stream
     view = cuda_view(dev)
     halo = getattr(args, "halo", "peer")
+    host = getattr(args, "host", "native")
     # reprojection displacement grows with the resolution: 24 rows per 1080 rows of image height
     max_disp = max(24, -(-24 * Hband // 1080))
-    bp = BandedPipeline(W, H, prank, pworld, taa, ctx, view, max_disp_rows=max_disp, dist=dist,
-                        nccl=NcclDirect(dist, rank, world, dev) if (halo == "nccl" and not replicas) else None,
-                        peer=PeerDirect(dist, rank, world, dev, ctx) if (halo == "peer" and not replicas) else None)
-    lo, hi = bp.plan.input_rows(prank)
+    plan = BandPlan(W, H, pworld, 32, max_disp, taa)
+    native = host == "native" and halo == "peer"
+    if native:
+        # the C++ driver (include/vkpbrt/banded.hpp) through the C ABI: one call per frame
+        nr = NativeBandedRank(W, H, prank, pworld, taa, ctx, dist=dist, max_disp_rows=max_disp, external_inputs=True)
+        rank_obj = _NativeAdapter(nr)
+    else:
+        bp = BandedPipeline(W, H, prank, pworld, taa, ctx, view, max_disp_rows=max_disp, dist=dist,
+                            nccl=NcclDirect(dist, rank, world, dev) if (halo == "nccl" and not replicas) else None,
+                            peer=PeerDirect(dist, rank, world, dev, ctx) if (halo == "peer" and not replicas) else None)
+        rank_obj = _PythonAdapter(bp)
+    bp = rank_obj
+    lo, hi = plan.input_rows(prank)
     rows = hi - lo
     # Parity evidence that travels with the number: rank 0 ALSO runs the same frames through a plain single-GPU pipeline
     # (outside every timed region) and the ranks' owned rows are compared with it after the set-up frames.
@@ -758,13 +936,15 @@ def measure_banded(args, name: str, K: int, Wm: int, R: int, rank: int, world: i
     _progress(rank, "inputs resident")
     pitch = {"depth": 4 * W, "normal": 8 * W, "albedo": 4 * W, "illum": 16 * W}
 
+    cam_arg = [bp.prepare_camera(c) for c in cams]
+
     def bind(bufs, i):
-        bp.pipe.bind_inputs(*[bufs[k][i].data_ptr() - lo * pitch[k] for k in ("depth", "normal", "albedo", "illum")])
+        bp.bind_inputs(*[bufs[k][i].data_ptr() - lo * pitch[k] for k in ("depth", "normal", "albedo", "illum")])
 
     def frame(f):
         i = B.seq_index(f, R)
         bind(dseq, i)
-        bp.run_frame(f, cams[i])
+        bp.run_frame(f, cam_arg[i])
 
     # set-up, not warm-up: the exchange descriptors (row ranges x ping-pong buffers: period 32 frames) are built
     # -- and for the peer path the neighbours' allocations mapped -- the first time each one is needed
@@ -780,8 +960,8 @@ def measure_banded(args, name: str, K: int, Wm: int, R: int, rank: int, world: i
     if verify:
         layer = ((PRE - 1) & 1) ^ 1
         mine = bp.owned_rows(PRE - 1)
-        fin = view(bp.pipe.final)                       # [H][W*4]
-        den = view(bp.bmfr.denoised)                    # [2][H][W*8]
+        fin = view(bp.final)                            # [H][W*4]
+        den = view(bp.denoised)                         # [2][H][W*8]
         my_hash = (_sha(fin[mine[0]:mine[1]]), _sha(den[layer, mine[0]:mine[1]]))
         hashes = [None] * world
         dist.all_gather_object(hashes, my_hash)
@@ -799,7 +979,7 @@ def measure_banded(args, name: str, K: int, Wm: int, R: int, rank: int, world: i
             sfin, sden = view(sp.final), view(sp.modules[0].denoised)
             equal = True
             for g in range(world):
-                o = bp.plan.owned_rows(g, PRE - 1)
+                o = plan.owned_rows(g, PRE - 1)
                 equal = equal and hashes[g] == (_sha(sfin[o[0]:o[1]]), _sha(sden[layer, o[0]:o[1]]))
             del sp, sfin, sden
         dfull.clear()
@@ -809,7 +989,7 @@ def measure_banded(args, name: str, K: int, Wm: int, R: int, rank: int, world: i
     for f in range(PRE, PRE + Wm):
         frame(f)
     torch.cuda.synchronize()
-    stats0 = bp.peer.stats()[0] if bp.peer is not None else {}
+    stats0 = bp.spin_stats()
     # rank 0's GPU is the one whose clocks are reported.  NVML is initialised BEFORE the barrier: a rank that enters
     # the timed region late makes its neighbours' clocks run while they wait for its halos
     sampler = B.ClockSampler(local) if rank == 0 else None
@@ -818,13 +998,28 @@ def measure_banded(args, name: str, K: int, Wm: int, R: int, rank: int, world: i
         sampler.start()
     launches0 = ctx.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    prof = None
+    if rank == 0 and os.environ.get("VKPBRT_PROFILE_HOST"):
+        import cProfile
+        prof = cProfile.Profile()
     e0.record(stream)
     t_host = time.perf_counter()
+    if prof:
+        prof.enable()
     for f in range(PRE + Wm, PRE + Wm + K):
         frame(f)
+    if prof:
+        prof.disable()
     bp.flush()
     e1.record(stream)
     t_host = (time.perf_counter() - t_host) / K * 1e3      # host time to ENQUEUE one frame (no sync inside)
+    if prof:
+        import io
+        import pstats
+        import sys
+        buf = io.StringIO()
+        pstats.Stats(prof, stream=buf).sort_stats("tottime").print_stats(22)
+        print(buf.getvalue(), file=sys.stderr, flush=True)
     torch.cuda.synchronize()
     bp.check()
     dist.barrier()
@@ -833,10 +1028,9 @@ def measure_banded(args, name: str, K: int, Wm: int, R: int, rank: int, world: i
     # time each rank's streams spent spinning on flag words inside the timed region, per exchange group:
     # [gate of the end-of-frame push, wait in front of the consumer]; rank 0 reports every rank's
     spin = {}
-    if bp.peer is not None:
-        for kind, (g_ms, w_ms) in bp.peer.stats()[0].items():
-            g0, w0 = stats0.get(kind, (0.0, 0.0))
-            spin[kind] = [round((g_ms - g0) / K, 4), round((w_ms - w0) / K, 4)]
+    for kind, (g_ms, w_ms) in bp.spin_stats().items():
+        g0, w0 = stats0.get(kind, (0.0, 0.0))
+        spin[kind] = [round((g_ms - g0) / K, 4), round((w_ms - w0) / K, 4)]
     spins = [None] * world
     dist.all_gather_object(spins, spin)
     t = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -869,11 +1063,11 @@ def measure_banded(args, name: str, K: int, Wm: int, R: int, rank: int, world: i
         def frame_e2e(f):
             s = f % 2
             stream.wait_event(copied[s])
-            bp.pipe.bind_inputs(*[dbuf[s][k].data_ptr() - lo * pitch[k] for k in ("depth", "normal", "albedo", "illum")])
-            bp.run_frame(f, cams[B.seq_index(f, R)])
+            bp.bind_inputs(*[dbuf[s][k].data_ptr() - lo * pitch[k] for k in ("depth", "normal", "albedo", "illum")])
+            bp.run_frame(f, cam_arg[B.seq_index(f, R)])
             consumed[s].record(stream)
             o = bp.owned_rows(f)
-            out_host[o[0]:o[1]].copy_(view(bp.pipe.final)[o[0]:o[1]], non_blocking=True)     # [H][W*4] bytes
+            out_host[o[0]:o[1]].copy_(view(bp.final)[o[0]:o[1]], non_blocking=True)     # [H][W*4] bytes
 
         for s in range(2):
             consumed[s].record(stream)
@@ -902,7 +1096,7 @@ def measure_banded(args, name: str, K: int, Wm: int, R: int, rank: int, world: i
                "ms_per_step": round(e2e_ms / K, 5)}
         del dbuf, out_host
     _progress(rank, "e2e done")
-    halo_bytes = torch.tensor([bp.bytes_exchanged], device=dev, dtype=torch.float64)
+    halo_bytes = torch.tensor([bp.bytes_exchanged()], device=dev, dtype=torch.float64)
     dist.all_reduce(halo_bytes)
     res = None
     if rank == 0:
@@ -916,8 +1110,10 @@ def measure_banded(args, name: str, K: int, Wm: int, R: int, rank: int, world: i
                             "description": (f"{world} independent sequences, one per GPU, no communication" if replicas
                                             else f"frame {W}x{H} cut into {world} horizontal block bands"
                                             + ("" if strong else f" (weak scaling: one {W}x{Hband} band per GPU)")),
-                            "band_block_rows": bp.plan.brow,
-                            "halo": f"history rows +-{bp.plan.D + 1} (+ REPEAT wrap row) per boundary, "
+                            "band_block_rows": plan.brow,
+                            "host": ("C++ (vkpbrt::BandedRank through the C ABI, one call per frame)" if native
+                                     else "Python (BandedPipeline: one ctypes call per kernel / exchange point)"),
+                            "halo": f"history rows +-{plan.D + 1} (+ REPEAT wrap row) per boundary, "
                                     + ("stored into the neighbours' HBM over NVLink peer mappings by k_halo_push, flag words for ordering"
                                        if halo == "peer" else "NCCL send/recv groups per frame"),
                             "resident_band_frames": R, "sequence_generation_s": round(t_gen, 1)},
@@ -932,9 +1128,8 @@ def measure_banded(args, name: str, K: int, Wm: int, R: int, rank: int, world: i
                "halo_bytes_per_step": float(halo_bytes.item()) / nframes, "host_enqueue_ms_per_step": round(t_host, 4),
                "halo_spin_ms_per_step_by_rank": spins, "ms_per_step_by_rank": per_rank_ms}
     dist.barrier()
-    if bp.peer is not None:
-        bp.peer.close()
-    del bp, dseq, host
+    bp.close()
+    del bp, rank_obj, dseq, host
     torch.cuda.synchronize()
     torch.cuda.empty_cache()
     return res
