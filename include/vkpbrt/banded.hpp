@@ -5,10 +5,17 @@
 // independent, so the only traffic between neighbours is
 //     A  the accumulate planes' history halo (depth history, accumulated illumination, sample counts): pushed right
 //        after k_accumulate, overlaps k_bmfr_block, awaited before the NEXT frame's k_accumulate;
-//     F  one row of the denoiser's tone-mapped output on each side for TAA's 3x3 stencil: pushed after k_bmfr_block,
-//        overlaps the TAA of the band's inner rows, awaited before its two edge rows;
-//     B  the denoised history / TAA history halos and the stale column-0 strip: pushed at the end of the frame,
-//        overlaps the next frame's k_accumulate, awaited before its k_bmfr_block.
+//     B  everything k_bmfr_block produced that a neighbour reads: the denoised-history halo, the stale column-0 strips
+//        and one row of the tone-mapped output on each side for TAA's 3x3 stencil.  Pushed right after k_bmfr_block,
+//        overlaps the TAA of the band's inner rows, awaited before its two edge rows (which also covers the next frame's
+//        k_bmfr_block);
+//     C  the TAA history halo: pushed after TAA, overlaps the next frame's k_accumulate + k_bmfr_block, awaited before
+//        its TAA.
+// No rendezvous: that a push may overwrite the receiver's rows follows from what the sender has already waited for
+// (a sender at frame f has seen its neighbours' frame f-1 pushes, which they issued after their last read of the
+// buffers it writes), with one exception -- B overwrites the stencil row the receiver's TAA of the PREVIOUS frame
+// reads, and B is issued before this rank's own TAA -- which is closed by gating B's copies, on the communication
+// stream, on the arrival of the receiver's previous C (issued after that TAA).
 // Every exchange point is ONE k_halo_push launch on a communication stream (rows stored straight into the receivers'
 // HBM over NVLink peer mappings, ordered by flag words, include/vkpbrt_b200.h "Band-sharded multi-GPU runs") and one
 // k_halo_wait in front of the consumer; the descriptors are built once per (group, jitter phase, ping-pong parity).
@@ -23,6 +30,8 @@
 
 #include <algorithm>
 #include <array>
+#include <cstdio>
+#include <cstdlib>
 #include <functional>
 #include <map>
 #include <stdexcept>
@@ -102,7 +111,7 @@ public:
             // a rank holds history rows within max_disp_rows (+1) of the rows it computes: taps beyond that are counted, not
             // silently served from stale rows
             accumulator->set_max_displacement_rows(opt.max_disp_rows);
-            // flag words: done[group][src] for the groups A, B, F, then ready[dst]
+            // flag words: done[group][src] for the groups A, B, C
             flags = DescriptorImage::create(c, (uint32_t)VKPBRT_FORMAT_R32_SFLOAT, (uint32_t)std::max(16, 4 * world), 1u);
             flags->compile(c);
             context->waitForCompletion();
@@ -143,48 +152,58 @@ public:
         c[0](*commands);
         if (multi) {
             // A: what k_accumulate just wrote (pre-swap handles) is next frame's history
-            pending_a_ = start(0, frame, [&] { return Images{{"acc", {{next_depth, 0, 0}, {accumulated->illumination_images[0], 0, 0}, {acc->spp, 0, 0}}}}; },
-                               [&] { return filter(plan.history_transfers(frame + 1), true); });
+            pending_a_ = start(0, frame, 0, [&] { return Images{{"acc", {{next_depth, 0, 0}, {accumulated->illumination_images[0], 0, 0}, {acc->spp, 0, 0}}}}; },
+                               [&] { return filter(plan.history_transfers(frame + 1), "acc"); });
         }
         finish(pending_b_);
         pending_b_ = {};
         c[1](*commands);
+        Pending pb;
+        if (multi) {
+            const uint32_t layer = (uint32_t)((frame & 1) ^ 1);
+            // gate: the receivers' previous C has arrived here, i.e. their previous TAA no longer reads the stencil row
+            pb = start(1, frame, taa ? seq_[2] : 0,
+                      [&] {
+                          Images im = {{"denoised", {{denoised, layer, 0}}},
+                                       {"final_col0", {{denoiser_final, 0, 4}}},       // 1 BGRA8 texel
+                                       {"denoised_col0", {{denoised, layer, 8}}}};     // 1 rgba16f texel
+                          if (taa) im["final"] = {{denoiser_final, 0, 0}};
+                          return im;
+                      },
+                      [&] {
+                          auto t = filter(plan.history_transfers(frame + 1), "denoised");
+                          for (const auto& s : plan.stale_column_transfers(frame)) t.push_back(s);
+                          if (taa)
+                              for (const auto& s : plan.final_transfers(frame)) t.push_back(s);
+                          return t;
+                      });
+        }
         if (taa) {
             const Rows o = plan.owned_rows(rank_, frame);
             taa->set_row_range(o.lo, o.hi);
+            finish(pending_c_);           // the neighbours' TAA history rows of the previous frame
+            pending_c_ = {};
             if (multi && o.hi - o.lo > 2) {
                 // the band's first / last row need one row of the neighbour's tone-mapped output (taa.comp:66-83): the rows in
                 // between run while that row is in flight, the edge rows after it has landed
-                const Pending f = start(2, frame, [&] { return Images{{"final", {{denoiser_final, 0, 0}}}}; }, [&] { return plan.final_transfers(frame); });
                 const int i0 = o.lo + (rank_ > 0 ? 1 : 0), i1 = o.hi - (rank_ < world_ - 1 ? 1 : 0);
                 taa->record_part(*push_constants, i0, i1, false);
-                finish(f);
+                finish(pb);
                 if (i0 > o.lo) taa->record_part(*push_constants, o.lo, i0, false);
                 taa->record_part(*push_constants, i1, o.hi, true);      // (possibly empty) last part: hands final -> history
             } else {
-                if (multi) finish(start(2, frame, [&] { return Images{{"final", {{denoiser_final, 0, 0}}}}; }, [&] { return plan.final_transfers(frame); }));
+                finish(pb);
                 c[2](*commands);
             }
+        } else {
+            pending_b_ = pb;              // awaited before the next frame's k_bmfr_block
         }
         c.back()(*commands);
         for (int i = 0; i < 16; ++i) pc.prev_view.m[i] = cam[i];
         ++swaps_;
-        if (multi) {
-            // B: denoised / TAA history halos and the stale-column strip
-            const uint32_t layer = (uint32_t)((frame & 1) ^ 1);
-            pending_b_ = start(1, frame,
-                               [&] {
-                                   Images im = {{"denoised", {{denoised, layer, 0}}},
-                                                {"final_col0", {{denoiser_final, 0, 4}}},       // 1 BGRA8 texel
-                                                {"denoised_col0", {{denoised, layer, 8}}}};     // 1 rgba16f texel
-                                   if (taa) im["taa"] = {{taa_history, 0, 0}};
-                                   return im;
-                               },
-                               [&] {
-                                   auto t = filter(plan.history_transfers(frame + 1), false);
-                                   for (const auto& s : plan.stale_column_transfers(frame)) t.push_back(s);
-                                   return t;
-                               });
+        if (multi && taa) {
+            pending_c_ = start(2, frame, 0, [&] { return Images{{"taa", {{taa_history, 0, 0}}}}; },
+                               [&] { return filter(plan.history_transfers(frame + 1), "taa"); });
         }
     }
 
@@ -193,7 +212,8 @@ public:
     {
         finish(pending_a_);
         finish(pending_b_);
-        pending_a_ = pending_b_ = {};
+        finish(pending_c_);
+        pending_a_ = pending_b_ = pending_c_ = {};
     }
 
     // synchronises; throws if a flag wait timed out (a peer died or fell out of step) or a reprojection left the rows this rank holds
@@ -214,7 +234,7 @@ public:
         }
     }
 
-    // nanoseconds the streams spent spinning on flag words so far, per group (A, B, F): [gate of the push, wait before the consumer]
+    // nanoseconds the streams spent spinning on flag words so far, per group (A, B, C): [gate of the push, wait before the consumer]
     std::array<std::array<uint64_t, 2>, 3> spin_ns()
     {
         context->waitForCompletion();
@@ -259,11 +279,11 @@ private:
         uint64_t bytes = 0;
     };
 
-    static std::vector<Transfer> filter(const std::vector<Transfer>& in, bool acc_planes)
+    static std::vector<Transfer> filter(const std::vector<Transfer>& in, const char* plane)
     {
         std::vector<Transfer> out;
         for (const auto& t : in)
-            if ((t.plane == "acc") == acc_planes) out.push_back(t);
+            if (t.plane == plane) out.push_back(t);
         return out;
     }
 
@@ -277,29 +297,38 @@ private:
     }
 
     uint32_t* done_word(int owner, int group, int src) { return reinterpret_cast<uint32_t*>(flag_base_[owner] + 4 * (group * world_ + src)); }
-    uint32_t* ready_word(int owner, int dst) { return reinterpret_cast<uint32_t*>(flag_base_[owner] + 4 * (3 * world_ + dst)); }
 
-    // group: 0 = A, 1 = B, 2 = F
+    // group: 0 = A, 1 = B, 2 = C.  gate_value: see the header comment (0 = no gate)
     template <class ImagesFn, class TransfersFn>
-    Pending start(int group, int frame, ImagesFn images, TransfersFn transfers)
+    Pending start(int group, int frame, uint32_t gate_value, ImagesFn images, TransfersFn transfers)
     {
         const uint32_t value = ++seq_[group];
+        trace("start", group, frame, value, gate_value);
         // buffers alternate with the copy_to_back swaps and the frame parity; row ranges with the jitter phase
         const auto key = std::make_tuple(group, frame % 16, swaps_ & 1, frame & 1);
         auto it = cache_.find(key);
-        if (it == cache_.end()) it = cache_.emplace(key, build(group, images(), transfers())).first;
+        if (it == cache_.end()) it = cache_.emplace(key, build(group, frame, images(), transfers())).first;
         if (!it->second.active) return {};
         bytes_ += it->second.bytes;
-        it->second.exchange->start(opt_.comm_stream, nullptr, value);
+        it->second.exchange->start_gated(opt_.comm_stream, nullptr, value, gate_value);
         return {it->second.exchange, value};
     }
 
     void finish(const Pending& p)
     {
-        if (p.exchange) p.exchange->wait(nullptr, p.value);
+        if (p.exchange) {
+            trace("wait", -1, -1, p.value, 0);
+            p.exchange->wait(nullptr, p.value);
+            trace("waited", -1, -1, p.value, 0);
+        }
+    }
+    void trace(const char* what, int group, int frame, uint32_t value, uint32_t gate) const
+    {
+        static const bool on = std::getenv("VKPBRT_BANDED_TRACE") != nullptr;
+        if (on) std::fprintf(stderr, "[rank %d] %s group %d frame %d value %u gate %u\n", rank_, what, group, frame, value, gate);
     }
 
-    Entry build(int group, const Images& images, const std::vector<Transfer>& transfers)
+    Entry build(int group, int /*frame*/, const Images& images, const std::vector<Transfer>& transfers)
     {
         // every rank exports the images of this exchange point, in the same order, and learns everybody's
         std::vector<PeerHandle> mine;
@@ -337,18 +366,24 @@ private:
         }
         std::sort(send_to.begin(), send_to.end());
         std::sort(recv_from.begin(), recv_from.end());
-        // the end-of-frame group waits for its receivers' frame to be over (they announce it), as posting a receive would
-        const bool handshake = group == 1;
+        // C always signals both adjacent ranks, rows to copy or not: B's gate (below) counts on one C word per frame
+        if (group == 2) {
+            for (int d : {rank_ - 1, rank_ + 1})
+                if (d >= 0 && d < world_) { add_unique(send_to, d); add_unique(recv_from, d); }
+            std::sort(send_to.begin(), send_to.end());
+            std::sort(recv_from.begin(), recv_from.end());
+        }
+        // B's copies are gated on the C words of the ranks whose TAA stencil row it overwrites: the adjacent ranks (local
+        // words, set by THEIR C pushes into this rank)
         std::vector<uint32_t*> announce, done;
         std::vector<const uint32_t*> ready, wait;
-        for (int s : recv_from) {
-            if (handshake) announce.push_back(ready_word(s, rank_));
-            wait.push_back(done_word(rank_, group, s));
-        }
-        for (int d : send_to) {
-            if (handshake) ready.push_back(ready_word(rank_, d));
-            done.push_back(done_word(d, group, rank_));
-        }
+        for (int s : recv_from) wait.push_back(done_word(rank_, group, s));
+        std::vector<int> gate_on;
+        if (group == 1 && opt_.use_taa)
+            for (const auto& t : transfers)
+                if (t.plane == "final" && t.src == rank_ && (t.dst == rank_ - 1 || t.dst == rank_ + 1)) add_unique(gate_on, t.dst);
+        for (int d : gate_on) ready.push_back(done_word(rank_, 2, d));
+        for (int d : send_to) done.push_back(done_word(d, group, rank_));
         Entry e;
         e.active = !send_to.empty() || !recv_from.empty();
         e.bytes = bytes;
@@ -369,7 +404,7 @@ private:
     uint32_t seq_[3] = {0, 0, 0};
     int swaps_ = 0;
     uint64_t bytes_ = 0;
-    Pending pending_a_, pending_b_;
+    Pending pending_a_, pending_b_, pending_c_;
 };
 
 }  // namespace vkpbrt

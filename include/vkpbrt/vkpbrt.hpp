@@ -499,6 +499,8 @@ public:
     HaloExchange(const HaloExchange&) = delete;
     // one launch on comm_stream, ordered after the work already enqueued on after_stream (cudaStream_t; nullptr = the context's)
     void start(void* comm_stream, void* after_stream, uint32_t value) { check(vkpbrt_halo_exchange_start(handle, comm_stream, after_stream, value)); }
+    // the push's gate (its ready flags) opens at gate_value instead of value
+    void start_gated(void* comm_stream, void* after_stream, uint32_t value, uint32_t gate_value) { check(vkpbrt_halo_exchange_start_gated(handle, comm_stream, after_stream, value, gate_value)); }
     // in front of the consuming kernel
     void wait(void* stream, uint32_t value) { check(vkpbrt_halo_exchange_wait(handle, stream, value)); }
     vkpbrt_halo_exchange_t handle = nullptr;

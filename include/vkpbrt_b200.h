@@ -398,6 +398,11 @@ typedef struct vkpbrt_halo_exchange_desc {
 VKPBRT_API int vkpbrt_halo_exchange_create(vkpbrt_context_t ctx, const vkpbrt_halo_exchange_desc* desc, uint32_t timeout_ms,
                                            vkpbrt_halo_exchange_t* out);
 VKPBRT_API int vkpbrt_halo_exchange_start(vkpbrt_halo_exchange_t x, void* comm_stream, void* after_stream, uint32_t value);
+/* as vkpbrt_halo_exchange_start, but the push's gate (its ready_flags, local words) opens at gate_value instead of value:
+ * "do not overwrite the receivers' rows before THEIR exchange number gate_value has reached me" -- orders a push after
+ * work of the receivers that a later exchange of theirs follows, without a rendezvous on the main stream */
+VKPBRT_API int vkpbrt_halo_exchange_start_gated(vkpbrt_halo_exchange_t x, void* comm_stream, void* after_stream, uint32_t value,
+                                                uint32_t gate_value);
 VKPBRT_API int vkpbrt_halo_exchange_wait(vkpbrt_halo_exchange_t x, void* stream, uint32_t value);
 /* synchronises the device; nanoseconds spent spinning in step 2 and in `wait` since creation, and the error word */
 VKPBRT_API int vkpbrt_halo_exchange_stats(vkpbrt_halo_exchange_t x, uint64_t* gate_ns, uint64_t* wait_ns, uint32_t* error);

@@ -187,6 +187,7 @@ _PROTOS = {
     "vkpbrt_peer_close": [H, C.c_void_p],
     "vkpbrt_halo_exchange_create": [H, C.c_void_p, u32, PH],
     "vkpbrt_halo_exchange_start": [H, C.c_void_p, C.c_void_p, u32],
+    "vkpbrt_halo_exchange_start_gated": [H, C.c_void_p, C.c_void_p, u32, u32],
     "vkpbrt_halo_exchange_wait": [H, C.c_void_p, u32],
     "vkpbrt_halo_exchange_stats": [H, C.POINTER(u64), C.POINTER(u64), C.POINTER(u32)],
     "vkpbrt_halo_exchange_destroy": [H],

@@ -61,7 +61,8 @@ def _stale(target: Path, deps) -> bool:
 def build_cuda(force=False, verbose=False) -> Path:
     LIB.mkdir(parents=True, exist_ok=True)
     OBJ.mkdir(parents=True, exist_ok=True)
-    headers = list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [ROOT / "include" / "vkpbrt_b200.h"]
+    headers = (list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + list(CSRC.glob("*.inc")) + [ROOT / "include" / "vkpbrt_b200.h"]
+               + list((ROOT / "include" / "vkpbrt").glob("*.hpp")))       # api.cpp includes the C++ layer (vkpbrt::BandedRank)
     objs = []
     for name, extra in UNITS.items():
         src = CSRC / name

@@ -1617,7 +1617,7 @@ int vkpbrt_halo_exchange_create(vkpbrt_context_t ctx, const vkpbrt_halo_exchange
     return VKPBRT_OK;
 }
 
-int vkpbrt_halo_exchange_start(vkpbrt_halo_exchange_t x, void* comm_stream, void* after_stream, uint32_t value)
+int vkpbrt_halo_exchange_start_gated(vkpbrt_halo_exchange_t x, void* comm_stream, void* after_stream, uint32_t value, uint32_t gate_value)
 {
     VK_REQUIRE(x, "null exchange");
     if (!x->has_start) return VKPBRT_OK;
@@ -1628,10 +1628,16 @@ int vkpbrt_halo_exchange_start(vkpbrt_halo_exchange_t x, void* comm_stream, void
         VK_CUDA(cudaStreamWaitEvent(comm, x->ordered, 0));
     }
     x->push.value = value;
+    x->push.gate_value = gate_value;
     // 16 CTAs x 256 threads x 16 B x 4 in flight = 256 KB per sweep of one block of rows
     VK_CUDA(vkpbrt::launch_halo_push(x->push, x->push.n_copies ? 16 : 1, comm));
     x->ctx->launches++;
     return VKPBRT_OK;
+}
+
+int vkpbrt_halo_exchange_start(vkpbrt_halo_exchange_t x, void* comm_stream, void* after_stream, uint32_t value)
+{
+    return vkpbrt_halo_exchange_start_gated(x, comm_stream, after_stream, value, value);
 }
 
 int vkpbrt_halo_exchange_wait(vkpbrt_halo_exchange_t x, void* stream, uint32_t value)

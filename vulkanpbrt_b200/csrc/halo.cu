@@ -4,7 +4,7 @@
 // (accumulator.comp:75-98 history taps, bmfrPost.comp:103-118 / taa.comp:44-60 neighbourhoods),
 // see vulkanpbrt_b200/multigpu.py BandPlan.
 //
-//   k_halo_push   [announce "ready" to the senders] -> [gate on the receivers' "ready" flags] -> copy every block of rows of the table
+//   k_halo_push   [announce "ready" to the senders] -> [gate: spin until the local "ready" words reach gate_value] -> copy every block of rows of the table
 //                 with 16-byte peer stores -> the last CTA publishes `value` to the receivers'
 //                 "done" flags (release at system scope).  One launch per exchange point.
 //   k_halo_wait   one warp; lane i spins (acquire at system scope) until flag i >= value.
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(256) k_halo_push(const HaloPushParams p)
     if (blockIdx.x == 0 && blockIdx.y == 0 && (int)threadIdx.x < p.n_announce) st_release_sys(p.announce_flags[threadIdx.x], p.value);
     if (p.n_ready > 0) {
         if ((int)threadIdx.x < p.n_ready) {
-            const unsigned long long ns = spin_until(p.ready_flags[threadIdx.x], p.value, p.timeout_ns, p.error);
+            const unsigned long long ns = spin_until(p.ready_flags[threadIdx.x], p.gate_value, p.timeout_ns, p.error);
             if (ns && blockIdx.x == 0 && blockIdx.y == 0) atomicMax(p.gate_ns + 1, ns), atomicAdd(p.gate_ns, ns);
         }
         __syncthreads();

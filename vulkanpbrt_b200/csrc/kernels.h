@@ -156,6 +156,7 @@ struct HaloPushParams {
     const uint32_t* ready_flags[kHaloMaxPeers];   // local words the receivers set when their halo rows may be overwritten
     uint32_t* done_flags[kHaloMaxPeers];          // receivers' words (peer mapped), set to `value` once every copy has landed
     uint32_t value;
+    uint32_t gate_value;          // what the ready flags must have reached before any copy starts
     uint32_t* counter;            // last-CTA detection, left at 0
     uint32_t* error;              // set to 1 when a spin timed out
     unsigned long long* gate_ns;  // statistics: time CTA 0 spent in the gate
