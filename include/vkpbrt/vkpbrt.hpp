@@ -139,6 +139,13 @@ public:
                                                 albedo_image->handle, &handle));
     }
     ~GBuffer() { vkpbrt_gbuffer_destroy(handle); }
+    // offline sequences: GBufferIO's import conversions (RenderIO.cpp:101-120, :160-195) on the device; planes are rgba32f
+    // DescriptorImages of this size, any of them may be null.  inv_view: the frame's (combined) inverse view matrix.
+    void import_planes(ref_ptr<DescriptorImage> position, const mat4* inv_view, ref_ptr<DescriptorImage> normal_plane, ref_ptr<DescriptorImage> albedo_plane)
+    {
+        check(vkpbrt_gbuffer_import_record(handle, position ? position->handle : nullptr, inv_view ? inv_view->m : nullptr,
+                                           normal_plane ? normal_plane->handle : nullptr, albedo_plane ? albedo_plane->handle : nullptr));
+    }
     void compile(Context&) const { check(vkpbrt_gbuffer_compile(handle)); }
     void update_image_layouts(Context&) const {}   // no image layouts on linear device memory
     uint32_t width, height;

@@ -328,6 +328,14 @@ VKPBRT_API int vkpbrt_format_converter_record(vkpbrt_format_converter_t f);     
 VKPBRT_API int vkpbrt_format_converter_final_image(vkpbrt_format_converter_t f, vkpbrt_image_t* out);   /* final_image */
 VKPBRT_API int vkpbrt_format_converter_destroy(vkpbrt_format_converter_t f);
 
+/* Offline sequences (source/io/RenderIO.cpp:71-158): the conversions GBufferIO::import_g_buffer_position runs on the host
+ * between what the files hold and what the G-buffer holds, as ONE launch on the device: world position -> Euclidean
+ * distance to the eye (:101-120; eye = column 2 of inv_view divided by its w, the convention of the offline, combined
+ * matrices), cartesian normal -> (acos(n.z), atan2(n.y, n.x)) (:160-178), float albedo * 255 -> rgba8, truncating
+ * (:180-195).  The planes are compiled rgba32f images of the g-buffer's size; any of them may be NULL (left alone). */
+VKPBRT_API int vkpbrt_gbuffer_import_record(vkpbrt_gbuffer_t g, vkpbrt_image_t position, const float* inv_view,
+                                            vkpbrt_image_t normal, vkpbrt_image_t albedo);
+
 /* Producer-side convention (shaders/ptRaygen.rgen:81-88, DEMOD_ILLUMINATION_FLOAT): what a CUDA / OptiX path tracer has
  * to hand to the Accumulator as IlluminationBufferDemodulatedFloat.  demodulated = min(clamp(radiance, 0, 10) /
  * (albedo + 1e-6), 1e3) where the primary ray hit something, clamp(radiance, 0, 10) where position_x is infinite. */
@@ -441,7 +449,7 @@ VKPBRT_API int vkpbrt_banded_rank_flush(vkpbrt_banded_rank_t r);      /* stream-
 VKPBRT_API int vkpbrt_banded_rank_check(vkpbrt_banded_rank_t r);      /* synchronises; fails on a flag timeout / a displacement violation */
 typedef enum { VKPBRT_BANDED_IMAGE_FINAL = 0, VKPBRT_BANDED_IMAGE_DENOISER_FINAL = 1, VKPBRT_BANDED_IMAGE_DENOISED = 2 } vkpbrt_banded_image;
 VKPBRT_API int vkpbrt_banded_rank_image(vkpbrt_banded_rank_t r, uint32_t which, vkpbrt_image_t* out);   /* borrowed */
-/* synchronises; spin_ns[group A,B,F][gate of the push, wait before the consumer], bytes pushed so far */
+/* synchronises; spin_ns[group A,B,C][gate of the push, wait before the consumer], bytes pushed so far */
 VKPBRT_API int vkpbrt_banded_rank_stats(vkpbrt_banded_rank_t r, uint64_t spin_ns[6], uint64_t* bytes_pushed);
 VKPBRT_API int vkpbrt_banded_rank_destroy(vkpbrt_banded_rank_t r);
 

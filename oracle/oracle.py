@@ -66,6 +66,7 @@ def lib():
         l.vkpbrt_oracle_bfr_blender.argtypes = [i32, i32, i32] + [vp] * 6; l.vkpbrt_oracle_bfr_blender.restype = None
         l.vkpbrt_oracle_taa.argtypes = [i32, i32, u32, i32] + [vp] * 4; l.vkpbrt_oracle_taa.restype = None
         l.vkpbrt_oracle_format_converter.argtypes = [i32, i32, i32, vp, vp]; l.vkpbrt_oracle_format_converter.restype = None
+        l.vkpbrt_oracle_gbuffer_import.argtypes = [i32, i32] + [vp] * 7; l.vkpbrt_oracle_gbuffer_import.restype = None
         l.vkpbrt_oracle_demodulate.argtypes = [i32, i32, vp, vp, vp, vp]; l.vkpbrt_oracle_demodulate.restype = None
         l.vkpbrt_oracle_num_threads.argtypes = []; l.vkpbrt_oracle_num_threads.restype = i32
         l.vkpbrt_oracle_set_num_threads.argtypes = [i32]; l.vkpbrt_oracle_set_num_threads.restype = None
@@ -236,3 +237,18 @@ def demodulate(radiance: np.ndarray, albedo: np.ndarray, position_x: np.ndarray)
     lib().vkpbrt_oracle_demodulate(W, H, _p(np.ascontiguousarray(radiance, np.float32)), _p(np.ascontiguousarray(albedo, np.float32)),
                                    _p(np.ascontiguousarray(position_x, np.float32)), _p(out))
     return out
+
+
+def gbuffer_import(inv_view, position=None, normal=None, albedo=None):
+    """GBufferIO::import_g_buffer_position's conversions; returns (depth, normal (theta, phi), albedo rgba8), None where no input"""
+    ref = next(a for a in (position, normal, albedo) if a is not None)
+    H, W = ref.shape[:2]
+    c = lambda a: None if a is None else np.ascontiguousarray(a, np.float32)
+    position, normal, albedo = c(position), c(normal), c(albedo)
+    d = np.zeros((H, W), np.float32) if position is not None else None
+    n = np.zeros((H, W, 2), np.float32) if normal is not None else None
+    a = np.zeros((H, W, 4), np.uint8) if albedo is not None else None
+    iv = np.ascontiguousarray(inv_view, np.float32) if inv_view is not None else None
+    q = lambda x: None if x is None else _p(x)
+    lib().vkpbrt_oracle_gbuffer_import(W, H, q(iv), q(position), q(normal), q(albedo), q(d), q(n), q(a))
+    return d, n, a

@@ -1139,3 +1139,31 @@ ORACLE_API void vkpbrt_oracle_demodulate(int W, int H, const float* radiance, co
             out[4 * pix + 3] = 1.0f;                                                                   /* :88 */
         }
 }
+
+/* ------------------------------------------------------------------------------------ */
+/* GBufferIO::import_g_buffer_position conversions (source/io/RenderIO.cpp:101-120,       */
+/* :160-178, :180-195).  Inputs rgba32f [H][W][4] or NULL.  camera = inv_view[2] / w.      */
+/* ------------------------------------------------------------------------------------ */
+ORACLE_API void vkpbrt_oracle_gbuffer_import(int W, int H, const float* inv_view, const float* position, const float* normal,
+                                             const float* albedo, float* depth_out, float* normal_out, uint8_t* albedo_out)
+{
+    float cam[3] = {0, 0, 0};
+    if (position)
+        for (int i = 0; i < 3; ++i) cam[i] = inv_view[8 + i] / inv_view[11];                 /* :109-110 */
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < W * H; ++i) {
+        if (position) {
+            float dx = cam[0] - position[4 * i], dy = cam[1] - position[4 * i + 1], dz = cam[2] - position[4 * i + 2];
+            depth_out[i] = sqrtf((dx * dx + dy * dy) + dz * dz);                             /* :116 length() */
+        }
+        if (normal) {
+            normal_out[2 * i] = acosf(normal[4 * i + 2]);                                    /* :174 */
+            normal_out[2 * i + 1] = atan2f(normal[4 * i + 1], normal[4 * i]);                /* :175 */
+        }
+        if (albedo)
+            for (int c = 0; c < 4; ++c) {
+                float s = albedo[4 * i + c] * 255.0f;                                        /* :187, truncating conversion */
+                albedo_out[4 * i + c] = (uint8_t)(s > 0.0f ? (s < 255.0f ? s : 255.0f) : 0.0f);
+            }
+    }
+}

@@ -68,7 +68,7 @@ def test_position_round_trip_recovers_depth(tmp_path):
     assert GBufferIO.depth_to_position(fr.depth, CameraMatrices(view=c.view, inv_view=c.inv_view)) is None
 
 
-@pytest.mark.parametrize("backend", backend_params()[:1], indirect=True)      # host-side I/O: the emulator backend is enough
+@pytest.mark.parametrize("backend", backend_params(), indirect=True)
 def test_exported_sequence_imports_and_drives_the_modules(tmp_path, backend, oracle, capsys):
     """export a synthetic sequence the way the reference stores it (EXR: depth, cartesian normals, float albedo, 1-spp
     illumination), import it back and denoise it: every plane equals the oracle fed with the same imported planes"""
@@ -99,3 +99,33 @@ def test_exported_sequence_imports_and_drives_the_modules(tmp_path, backend, ora
     # a missing frame is reported like the reference does, and leaves that frame empty
     short = GBufferIO.import_g_buffer_depth(d + "/depth_%d.exr", d + "/normal_%d.exr", "", d + "/albedo_%d.exr", frames + 1)
     assert short[frames].depth is None and "Failed to load image" in capsys.readouterr().out
+
+
+@pytest.mark.parametrize("backend", backend_params(), indirect=True)
+def test_import_conversions_on_the_device(backend, oracle):
+    """vkpbrt_gbuffer_import_record (k_gbuffer_import): GBufferIO's host conversions (RenderIO.cpp:101-120, :160-195) as one
+    launch into a compiled GBuffer, against the oracle's restatement: depth and albedo bit for bit; the spherical normals
+    within 1e-6 rad (acos / atan2 are the platform's libm in the reference, CUDA's on the device: a couple of ulps apart)"""
+    from vulkanpbrt_b200 import Context
+    from vulkanpbrt_b200.modules import GBuffer
+    W, H = 70, 37
+    fr = synth.render_frame(W, H, 2)
+    c = fr.camera
+    pos = GBufferIO.depth_to_position(fr.depth, CameraMatrices(view=c.view, inv_view=c.inv_view, proj=c.proj, inv_proj=c.inv_proj))
+    v = np.asarray(c.view, np.float64).reshape(4, 4).T
+    p = np.asarray(c.proj, np.float64).reshape(4, 4).T
+    ivp = np.linalg.inv(p @ v).T.astype(np.float32).reshape(-1)          # combined inverse: the offline convention
+    cart = GBufferIO.spherical_to_cartesian(fr.normal)
+    alb = (fr.albedo.astype(np.float32) / np.float32(255.0) * np.float32(1.003)).astype(np.float32)      # some values above 1: the clamp
+    ctx = Context(0)
+    g = GBuffer.create(ctx, W, H)
+    g.compile(ctx)
+    GBufferIO.import_to_device(g, pos, CameraMatrices(view=None, inv_view=ivp), cart, alb)
+    want_d, want_n, want_a = oracle.gbuffer_import(ivp, pos, cart, alb)
+    np.testing.assert_array_equal(g.depth.download().view(np.uint32), want_d.view(np.uint32))
+    np.testing.assert_array_equal(g.albedo.download(), want_a)
+    np.testing.assert_allclose(g.normal.download(), want_n, atol=1e-6, rtol=0)
+    # and the oracle's restatement is the host path the reference runs (numpy float32 == libm to the same tolerance)
+    np.testing.assert_array_equal(want_d, GBufferIO.position_to_depth(pos, CameraMatrices(view=None, inv_view=ivp)))
+    np.testing.assert_allclose(want_n, GBufferIO.convert_normal_to_spherical(cart), atol=1e-6, rtol=0)
+    np.testing.assert_array_equal(want_a, GBufferIO.compress_albedo(alb))

@@ -158,6 +158,7 @@ _PROTOS = {
     "vkpbrt_format_converter_final_image": [H, C.POINTER(H)],
     "vkpbrt_format_converter_destroy": [H],
     "vkpbrt_demodulate_record": [H, H, H, H, H],
+    "vkpbrt_gbuffer_import_record": [H, H, C.c_void_p, H, H],
     "vkpbrt_stream_create": [H, i32, C.POINTER(C.c_void_p)],
     "vkpbrt_stream_destroy": [H, C.c_void_p],
     "vkpbrt_banded_rank_create": [H, u32, u32, i32, i32, i32, i32, i32, C.c_void_p, C.c_void_p, C.c_void_p, u32, C.POINTER(H)],

@@ -559,9 +559,9 @@ int vkpbrt_illumination_buffer_create(vkpbrt_context_t ctx, uint32_t type, uint3
     switch (type) {
     case VKPBRT_ILLUMINATION_DEMODULATED: fmts = {VKPBRT_FORMAT_R16G16B16A16_SFLOAT, VKPBRT_FORMAT_R16G16B16A16_SFLOAT}; break;
     case VKPBRT_ILLUMINATION_DEMODULATED_FLOAT: fmts = {VKPBRT_FORMAT_R32G32B32A32_SFLOAT}; break;
-    case VKPBRT_ILLUMINATION_FINAL: fmts = {VKPBRT_FORMAT_R8G8B8A8_UNORM}; break;
-    case VKPBRT_ILLUMINATION_FINAL_DEMODULATED:
-        fmts = {VKPBRT_FORMAT_R8G8B8A8_UNORM, VKPBRT_FORMAT_R16G16B16A16_SFLOAT, VKPBRT_FORMAT_R16G16B16A16_SFLOAT};
+    case VKPBRT_ILLUMINATION_FINAL: fmts = {VKPBRT_FORMAT_B8G8R8A8_UNORM}; break;              // IlluminationBuffer.cpp:84
+    case VKPBRT_ILLUMINATION_FINAL_DEMODULATED:                                                   // IlluminationBuffer.cpp:174
+        fmts = {VKPBRT_FORMAT_B8G8R8A8_UNORM, VKPBRT_FORMAT_R16G16B16A16_SFLOAT, VKPBRT_FORMAT_R16G16B16A16_SFLOAT};
         break;
     default: delete b; return fail(VKPBRT_ERR_INVALID_ARGUMENT, "unknown illumination buffer type");
     }
@@ -1411,6 +1411,39 @@ int vkpbrt_format_converter_destroy(vkpbrt_format_converter_t f)
     if (!f) return VKPBRT_OK;
     vkpbrt_image_release(f->final_image);
     delete f;
+    return VKPBRT_OK;
+}
+
+// ---- offline sequences: the import conversions of GBufferIO on the device (source/io/RenderIO.cpp:101-120, :160-195) ----
+int vkpbrt_gbuffer_import_record(vkpbrt_gbuffer_t g, vkpbrt_image_t position, const float* inv_view, vkpbrt_image_t normal,
+                                 vkpbrt_image_t albedo)
+{
+    VK_REQUIRE(g, "vkpbrt_gbuffer_import_record: null g-buffer");
+    VK_REQUIRE(!position || inv_view, "vkpbrt_gbuffer_import_record: a position plane needs the frame's inverse view matrix");
+    for (vkpbrt_image_t i : {position, normal, albedo})
+        VK_REQUIRE(!i || (i->format == VKPBRT_FORMAT_R32G32B32A32_SFLOAT && same_extent(i, g->width, g->height) && i->data),
+                   "vkpbrt_gbuffer_import_record: planes are compiled rgba32f images of the g-buffer's size");
+    vkpbrt::GBufferImportParams p{};
+    p.W = (int)g->width; p.H = (int)g->height;
+    if (position) {
+        for (int i = 0; i < 3; ++i) p.camera[i] = inv_view[8 + i] / inv_view[11];        // RenderIO.cpp:109-110: inv_view[2] / w
+        p.position = (const float4*)position->data;
+        p.depth = (float*)g->img[VKPBRT_GBUFFER_DEPTH]->data;
+        VK_REQUIRE(p.depth, "vkpbrt_gbuffer_import_record: the g-buffer is not compiled");
+    }
+    if (normal) {
+        p.normal = (const float4*)normal->data;
+        p.normal_out = (float2*)g->img[VKPBRT_GBUFFER_NORMAL]->data;
+        VK_REQUIRE(p.normal_out, "vkpbrt_gbuffer_import_record: the g-buffer is not compiled");
+    }
+    if (albedo) {
+        p.albedo = (const float4*)albedo->data;
+        p.albedo_out = (uint32_t*)g->img[VKPBRT_GBUFFER_ALBEDO]->data;
+        VK_REQUIRE(p.albedo_out, "vkpbrt_gbuffer_import_record: the g-buffer is not compiled");
+    }
+    VK_CUDA(cudaSetDevice(g->ctx->device));
+    VK_CUDA(vkpbrt::launch_gbuffer_import(p, joined(g->ctx)));
+    g->ctx->launches++;
     return VKPBRT_OK;
 }
 

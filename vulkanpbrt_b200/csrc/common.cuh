@@ -261,6 +261,24 @@ VK_DEVICE Bilin bilin_setup(float u, float v, int W, int H)
     return b;
 }
 
+// bilin_setup for coordinates that did not come from k_accumulate (a caller-supplied motion plane, stale rows): the
+// reference samples with a REPEAT sampler, which is defined for ANY uv.  Same weights; the integer taps are wrapped with
+// a true modulo when they fall outside the cheap wrap's range, and a non-finite coordinate samples texel (0, 0) with
+// NaN weights (what a sampler returns for NaN coordinates is undefined) instead of reading out of bounds.
+VK_DEVICE Bilin bilin_setup_repeat(float u, float v, int W, int H)
+{
+    Bilin b = bilin_setup(u, v, W, H);
+    const bool cheap_ok = ((unsigned)b.x0 < (unsigned)W) & ((unsigned)b.x1 < (unsigned)W) & ((unsigned)b.y0 < (unsigned)H) & ((unsigned)b.y1 < (unsigned)H);
+    if (!cheap_ok) {
+        const float x = sub_rn(mul_rn(u, (float)W), 0.5f), y = sub_rn(mul_rn(v, (float)H), 0.5f);
+        const bool finite = (fabsf(x) < 1.0e9f) & (fabsf(y) < 1.0e9f);
+        const int ix = finite ? (int)floorf(x) : 0, iy = finite ? (int)floorf(y) : 0;
+        b.x0 = wrapi(ix, W); b.x1 = wrapi(ix + 1, W);
+        b.y0 = wrapi(iy, H); b.y1 = wrapi(iy + 1, H);
+    }
+    return b;
+}
+
 VK_DEVICE float bilin_mix(const Bilin& b, float t00, float t10, float t01, float t11)
 {
     return add_rn(add_rn(add_rn(mul_rn(b.w00, t00), mul_rn(b.w10, t10)), mul_rn(b.w01, t01)), mul_rn(b.w11, t11));
@@ -341,7 +359,7 @@ VK_DEVICE void denoise_epilogue(float cr, float cg, float cb, uint32_t frame, si
     float pixel_spp = mul_rn(unorm8_to_f32(spp_code), 256.0f);
     float pr = 0.0f, pg = 0.0f, pb = 0.0f, blend = 1.0f;
     if (frame > 0 && accept) {
-        Bilin bl = bilin_setup(uvx, uvy, W, H);
+        Bilin bl = bilin_setup_repeat(uvx, uvy, W, H);
         sample_rgb16f(denoised_prev, bl, W, pr, pg, pb);
         blend = gl_max(__frcp_rn(pixel_spp), 0.1f);
     }

@@ -55,6 +55,39 @@ __global__ void __launch_bounds__(256) k_demodulate(const DemodulateParams p)
     p.out[pix] = make_float4(c[0], c[1], c[2], 1.0f);                                                     // :88
 }
 
+// source/io/RenderIO.cpp:101-120 (world position -> distance to the eye), :160-178 (cartesian normal -> (acos(n.z),
+// atan2(n.y, n.x))), :180-195 (vec4 albedo * 255.0F -> ubvec4, which TRUNCATES).  acos / atan2 are the platform's libm in
+// the reference (its host code); here they are CUDA's (<= 2 ulp): the two agree to ~1e-6 rad, the tolerance of the test.
+__global__ void __launch_bounds__(256) k_gbuffer_import(const GBufferImportParams p)
+{
+    const int gx = blockIdx.x * 32 + threadIdx.x, gy = blockIdx.y * 8 + threadIdx.y;
+    if (gx >= p.W || gy >= p.H) return;
+    const size_t pix = (size_t)gy * p.W + gx;
+    if (p.position) {
+        const float4 q = __ldg(p.position + pix);
+        const float dx = sub_rn(p.camera[0], q.x), dy = sub_rn(p.camera[1], q.y), dz = sub_rn(p.camera[2], q.z);      // :116
+        p.depth[pix] = sqrt_rn(add_rn(add_rn(mul_rn(dx, dx), mul_rn(dy, dy)), mul_rn(dz, dz)));
+    }
+    if (p.normal) {
+        const float4 n = __ldg(p.normal + pix);
+        p.normal_out[pix] = make_float2(acosf(n.z), atan2f(n.y, n.x));                                                // :174-175
+    }
+    if (p.albedo) {
+        const float4 a = __ldg(p.albedo + pix);
+        // float -> unsigned char conversion of an out-of-range value is undefined in C++; clamped here
+        auto q8 = [](float v) { const float s = mul_rn(v, 255.0f); return (uint32_t)(s > 0.0f ? (s < 255.0f ? s : 255.0f) : 0.0f); };
+        p.albedo_out[pix] = q8(a.x) | (q8(a.y) << 8) | (q8(a.z) << 16) | (q8(a.w) << 24);                                // :187
+    }
+}
+
+cudaError_t launch_gbuffer_import(const GBufferImportParams& p, cudaStream_t stream)
+{
+    if (p.W <= 0 || p.H <= 0) return cudaSuccess;
+    dim3 block(32, 8, 1), grid((p.W + 31) / 32, (p.H + 7) / 8, 1);
+    VKPBRT_LAUNCH(k_gbuffer_import, grid, block, 0, stream, p);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_format_convert(const FormatConvertParams& p, cudaStream_t stream)
 {
     if (p.W <= 0 || p.H <= 0) return cudaSuccess;

@@ -187,6 +187,19 @@ struct DemodulateParams {
 };
 cudaError_t launch_demodulate(const DemodulateParams& p, cudaStream_t stream);
 
+// offline-sequence import conversions (source/io/RenderIO.cpp:101-120, :160-195); any of the three inputs may be null
+struct GBufferImportParams {
+    int W, H;
+    float camera[3];              // eye point: column 2 of the (combined) inverse view matrix divided by its w (:109-110)
+    const float4* position;       // rgba32f world position  -> depth
+    const float4* normal;         // rgba32f cartesian normal -> (theta, phi)
+    const float4* albedo;         // rgba32f albedo           -> rgba8 (truncating)
+    float* depth;
+    float2* normal_out;
+    uint32_t* albedo_out;
+};
+cudaError_t launch_gbuffer_import(const GBufferImportParams& p, cudaStream_t stream);
+
 // ---- device-side self checks (debug.cu) ----------------------------------------------------------
 cudaError_t launch_tonemap_sweep(unsigned long long* bad, uint32_t* first_bad, cudaStream_t stream);
 

@@ -755,7 +755,7 @@ class NativeBandedRank:
         """synchronises; ({group: [gate ms, wait ms]}, bytes pushed)"""
         s, b = (self.C.c_uint64 * 6)(), self.C.c_uint64()
         capi.call("vkpbrt_banded_rank_stats", self._h, s, self.C.byref(b))
-        return {k: [s[2 * i] * 1e-6, s[2 * i + 1] * 1e-6] for i, k in enumerate(("A", "B", "F"))}, int(b.value)
+        return {k: [s[2 * i] * 1e-6, s[2 * i + 1] * 1e-6] for i, k in enumerate(("A", "B", "C"))}, int(b.value)
 
     def close(self) -> None:
         if self._h:

@@ -142,6 +142,33 @@ class GBufferIO:
         out[..., :3] = iv[3][:3][None, None, :] + direction
         return out
 
+    # ---- on the device ---------------------------------------------------------------------------------------------
+    @staticmethod
+    def import_to_device(g_buffer, position: Optional[np.ndarray], matrices: Optional[CameraMatrices], normal: Optional[np.ndarray],
+                         albedo: Optional[np.ndarray]) -> None:
+        """position_to_depth + convert_normal_to_spherical + compress_albedo of one frame as ONE device launch straight into
+        a compiled GBuffer (vkpbrt_gbuffer_import_record): the decoded rgba32f planes are uploaded as they come out of the
+        files and converted where the denoiser reads them.  Any plane may be None (that member is left alone)."""
+        import ctypes as C
+
+        from . import _capi as capi
+        from .modules import DescriptorImage
+        ctx = g_buffer.ctx
+        imgs = []
+        for plane in (position, normal, albedo):
+            if plane is None:
+                imgs.append(None)
+                continue
+            a = np.ascontiguousarray(_rgba(np.asarray(plane, np.float32)))
+            im = DescriptorImage.create(ctx, capi.FORMAT_R32G32B32A32_SFLOAT, a.shape[1], a.shape[0])
+            im.compile()
+            im.upload(a)
+            imgs.append(im)
+        iv = capi.mat16(np.asarray(matrices.inv_view, np.float32)) if (position is not None and matrices is not None) else None
+        h = lambda im: im.handle if im is not None else None
+        capi.call("vkpbrt_gbuffer_import_record", g_buffer.handle, h(imgs[0]), C.cast(iv, C.c_void_p) if iv is not None else None, h(imgs[1]), h(imgs[2]))
+        ctx.synchronize()        # the staging images die with this call
+
     # ---- files -----------------------------------------------------------------------------------------------------
     @staticmethod
     def import_g_buffer_depth(depth_format: str, normal_format: str, material_format: str, albedo_format: str, num_frames: int,
