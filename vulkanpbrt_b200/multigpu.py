@@ -992,7 +992,7 @@ def measure_banded(args, name: str, K: int, Wm: int, R: int, rank: int, world: i
     stats0 = bp.spin_stats()
     # rank 0's GPU is the one whose clocks are reported.  NVML is initialised BEFORE the barrier: a rank that enters
     # the timed region late makes its neighbours' clocks run while they wait for its halos
-    sampler = B.ClockSampler(local) if rank == 0 else None
+    sampler = B.ClockSampler(local) if (rank == 0 and not os.environ.get("VKPBRT_NO_CLOCK_SAMPLER")) else None
     dist.barrier()
     if sampler:
         sampler.start()
