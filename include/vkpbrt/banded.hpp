@@ -5,10 +5,13 @@
 // independent, so the only traffic between neighbours is
 //     A  the accumulate planes' history halo (depth history, accumulated illumination, sample counts): pushed right
 //        after k_accumulate, overlaps k_bmfr_block, awaited before the NEXT frame's k_accumulate;
-//     B  everything k_bmfr_block produced that a neighbour reads: the denoised-history halo, the stale column-0 strips
-//        and one row of the tone-mapped output on each side for TAA's 3x3 stencil.  Pushed right after k_bmfr_block,
-//        overlaps the TAA of the band's inner rows, awaited before its two edge rows (which also covers the next frame's
-//        k_bmfr_block);
+//     B  what k_bmfr_block produced and a neighbour reads THIS frame: one row of the tone-mapped output on each side for
+//        TAA's 3x3 stencil and column 0 of the rows around the boundary -- a few KB, so that its flag follows the kernel
+//        by one launch latency.  Pushed right after k_bmfr_block, overlaps the TAA of the band's inner rows, awaited
+//        before its two edge rows;
+//     D  what they read NEXT frame: the denoised-history halo (megabytes).  Behind B on the communication stream,
+//        awaited before the next frame's k_bmfr_block.  (With both in one push the edge rows waited ~35 us after
+//        k_bmfr_block for 3 MB they did not need -- measured at N = 8, 4K.)
 //     C  the TAA history halo: pushed after TAA, overlaps the next frame's k_accumulate + k_bmfr_block, awaited before
 //        its TAA.
 // No rendezvous: that a push may overwrite the receiver's rows follows from what the sender has already waited for
@@ -111,7 +114,7 @@ public:
             // a rank holds history rows within max_disp_rows (+1) of the rows it computes: taps beyond that are counted, not
             // silently served from stale rows
             accumulator->set_max_displacement_rows(opt.max_disp_rows);
-            // flag words: done[group][src] for the groups A, B, C
+            // flag words: done[group][src] for the groups A, B, C, D
             flags = DescriptorImage::create(c, (uint32_t)VKPBRT_FORMAT_R32_SFLOAT, (uint32_t)std::max(16, 4 * world), 1u);
             flags->compile(c);
             context->waitForCompletion();
@@ -155,28 +158,40 @@ public:
             pending_a_ = start(0, frame, 0, [&] { return Images{{"acc", {{next_depth, 0, 0}, {accumulated->illumination_images[0], 0, 0}, {acc->spp, 0, 0}}}}; },
                                [&] { return filter(plan.history_transfers(frame + 1), "acc"); });
         }
-        finish(pending_b_);
-        pending_b_ = {};
+        finish(pending_d_);              // the neighbours' denoised history rows of the previous frame (bmfrPost.comp:111)
+        finish(pending_b_);              // without TAA nothing else waits for B
+        pending_b_ = pending_d_ = {};
         c[1](*commands);
         Pending pb;
         if (multi) {
             const uint32_t layer = (uint32_t)((frame & 1) ^ 1);
-            // gate: the receivers' previous C has arrived here, i.e. their previous TAA no longer reads the stencil row
+            // B: what a neighbour reads THIS frame -- the TAA stencil row and column 0 of the tone-mapped image: a few KB,
+            // so its flag follows k_bmfr_block by one launch latency.  Gate: the receivers' previous C has arrived here,
+            // i.e. their previous TAA no longer reads the stencil row.
             pb = start(1, frame, taa ? seq_[2] : 0,
-                      [&] {
-                          Images im = {{"denoised", {{denoised, layer, 0}}},
-                                       {"final_col0", {{denoiser_final, 0, 4}}},       // 1 BGRA8 texel
-                                       {"denoised_col0", {{denoised, layer, 8}}}};     // 1 rgba16f texel
-                          if (taa) im["final"] = {{denoiser_final, 0, 0}};
-                          return im;
-                      },
-                      [&] {
-                          auto t = filter(plan.history_transfers(frame + 1), "denoised");
-                          for (const auto& s : plan.stale_column_transfers(frame)) t.push_back(s);
-                          if (taa)
-                              for (const auto& s : plan.final_transfers(frame)) t.push_back(s);
-                          return t;
-                      });
+                       [&] {
+                           Images im = {{"final_col0", {{denoiser_final, 0, 4}}}};       // 1 BGRA8 texel
+                           if (taa) im["final"] = {{denoiser_final, 0, 0}};
+                           return im;
+                       },
+                       [&] {
+                           auto t = filter(plan.stale_column_transfers(frame), "final_col0");
+                           if (taa)
+                               for (const auto& x : plan.final_transfers(frame)) t.push_back(x);
+                           return t;
+                       });
+            // D: what they read NEXT frame -- the denoised history rows (megabytes): behind B on the communication stream,
+            // awaited before the next k_bmfr_block.  No gate: this rank's k_bmfr_block ran after the receivers' previous D
+            // arrived, i.e. after their previous k_bmfr_block, the last reader of the layer D overwrites.
+            pending_d_ = start(3, frame, 0,
+                               [&] {
+                                   return Images{{"denoised", {{denoised, layer, 0}}}, {"denoised_col0", {{denoised, layer, 8}}}};     // 1 rgba16f texel
+                               },
+                               [&] {
+                                   auto t = filter(plan.history_transfers(frame + 1), "denoised");
+                                   for (const auto& x : filter(plan.stale_column_transfers(frame), "denoised_col0")) t.push_back(x);
+                                   return t;
+                               });
         }
         if (taa) {
             const Rows o = plan.owned_rows(rank_, frame);
@@ -189,8 +204,7 @@ public:
                 const int i0 = o.lo + (rank_ > 0 ? 1 : 0), i1 = o.hi - (rank_ < world_ - 1 ? 1 : 0);
                 taa->record_part(*push_constants, i0, i1, false);
                 finish(pb);
-                if (i0 > o.lo) taa->record_part(*push_constants, o.lo, i0, false);
-                taa->record_part(*push_constants, i1, o.hi, true);      // (possibly empty) last part: hands final -> history
+                taa->record_parts(*push_constants, o.lo, i0, i1, o.hi, true);   // both edge rows, one launch (either may be empty): hands final -> history
             } else {
                 finish(pb);
                 c[2](*commands);
@@ -213,7 +227,8 @@ public:
         finish(pending_a_);
         finish(pending_b_);
         finish(pending_c_);
-        pending_a_ = pending_b_ = pending_c_ = {};
+        finish(pending_d_);
+        pending_a_ = pending_b_ = pending_c_ = pending_d_ = {};
     }
 
     // synchronises; throws if a flag wait timed out (a peer died or fell out of step) or a reprojection left the rows this rank holds
@@ -234,11 +249,11 @@ public:
         }
     }
 
-    // nanoseconds the streams spent spinning on flag words so far, per group (A, B, C): [gate of the push, wait before the consumer]
-    std::array<std::array<uint64_t, 2>, 3> spin_ns()
+    // nanoseconds the streams spent spinning on flag words so far, per group (A, B, C, D): [gate of the push, wait before the consumer]
+    std::array<std::array<uint64_t, 2>, 4> spin_ns()
     {
         context->waitForCompletion();
-        std::array<std::array<uint64_t, 2>, 3> out{};
+        std::array<std::array<uint64_t, 2>, 4> out{};
         for (auto& kv : cache_) {
             uint64_t g = 0, w = 0;
             uint32_t e = 0;
@@ -298,7 +313,7 @@ private:
 
     uint32_t* done_word(int owner, int group, int src) { return reinterpret_cast<uint32_t*>(flag_base_[owner] + 4 * (group * world_ + src)); }
 
-    // group: 0 = A, 1 = B, 2 = C.  gate_value: see the header comment (0 = no gate)
+    // group: 0 = A, 1 = B, 2 = C, 3 = D.  gate_value: see the header comment (0 = no gate)
     template <class ImagesFn, class TransfersFn>
     Pending start(int group, int frame, uint32_t gate_value, ImagesFn images, TransfersFn transfers)
     {
@@ -401,10 +416,10 @@ private:
     std::vector<uint8_t*> flag_base_;
     std::map<std::string, ref_ptr<PeerMemory>> mapped_;
     std::map<std::tuple<int, int, int, int>, Entry> cache_;
-    uint32_t seq_[3] = {0, 0, 0};
+    uint32_t seq_[4] = {0, 0, 0, 0};
     int swaps_ = 0;
     uint64_t bytes_ = 0;
-    Pending pending_a_, pending_b_, pending_c_;
+    Pending pending_a_, pending_b_, pending_c_, pending_d_;
 };
 
 }  // namespace vkpbrt

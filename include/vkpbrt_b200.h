@@ -300,6 +300,9 @@ VKPBRT_API int vkpbrt_taa_create(vkpbrt_context_t ctx, uint32_t width, uint32_t 
 VKPBRT_API int vkpbrt_taa_set_fix_swizzle(vkpbrt_taa_t t, int fix);
 /* debug / test switch: the one-pixel-per-thread kernel (bit-identical to the default two-column kernel) */
 VKPBRT_API int vkpbrt_taa_set_force_scalar(vkpbrt_taa_t t, int enable);
+/* debug / test switch: rows a warp of the two-column kernel walks per launch (0 = automatic: 16, less when the launch would
+ * otherwise leave most of the GPU's warp slots empty).  Results do not depend on it. */
+VKPBRT_API int vkpbrt_taa_set_strip_rows(vkpbrt_taa_t t, int rows);
 VKPBRT_API int vkpbrt_taa_compile(vkpbrt_taa_t t);
 /* dispatch + final->history hand-over (Taa.cpp:99-107).  The reference never pushes constants for
  * TAA and inherits the denoiser's (App. C-10); here they are passed explicitly. */
@@ -309,6 +312,9 @@ VKPBRT_API int vkpbrt_taa_set_row_range(vkpbrt_taa_t t, int row_begin, int row_e
  * neighbour's halo row run while that row is still in flight).  Every part reads the same history; the final -> history
  * hand-over (Taa.cpp:106) happens with the part that passes last != 0. */
 VKPBRT_API int vkpbrt_taa_record_part(vkpbrt_taa_t t, const vkpbrt_push_constants* pc, int row_begin, int row_end, int last);
+/* the same with two disjoint row ranges in ONE launch (either may be empty): the first and the last row of a band */
+VKPBRT_API int vkpbrt_taa_record_parts(vkpbrt_taa_t t, const vkpbrt_push_constants* pc, int row_begin, int row_end, int row_begin2,
+                                       int row_end2, int last);
 VKPBRT_API int vkpbrt_taa_final_image(vkpbrt_taa_t t, vkpbrt_image_t* out);
 VKPBRT_API int vkpbrt_taa_history_image(vkpbrt_taa_t t, vkpbrt_image_t* out);
 VKPBRT_API int vkpbrt_taa_destroy(vkpbrt_taa_t t);
@@ -449,8 +455,8 @@ VKPBRT_API int vkpbrt_banded_rank_flush(vkpbrt_banded_rank_t r);      /* stream-
 VKPBRT_API int vkpbrt_banded_rank_check(vkpbrt_banded_rank_t r);      /* synchronises; fails on a flag timeout / a displacement violation */
 typedef enum { VKPBRT_BANDED_IMAGE_FINAL = 0, VKPBRT_BANDED_IMAGE_DENOISER_FINAL = 1, VKPBRT_BANDED_IMAGE_DENOISED = 2 } vkpbrt_banded_image;
 VKPBRT_API int vkpbrt_banded_rank_image(vkpbrt_banded_rank_t r, uint32_t which, vkpbrt_image_t* out);   /* borrowed */
-/* synchronises; spin_ns[group A,B,C][gate of the push, wait before the consumer], bytes pushed so far */
-VKPBRT_API int vkpbrt_banded_rank_stats(vkpbrt_banded_rank_t r, uint64_t spin_ns[6], uint64_t* bytes_pushed);
+/* synchronises; spin_ns[group A,B,C,D][gate of the push, wait before the consumer], bytes pushed so far */
+VKPBRT_API int vkpbrt_banded_rank_stats(vkpbrt_banded_rank_t r, uint64_t spin_ns[8], uint64_t* bytes_pushed);
 VKPBRT_API int vkpbrt_banded_rank_destroy(vkpbrt_banded_rank_t r);
 
 #ifdef __cplusplus

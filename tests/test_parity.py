@@ -102,6 +102,34 @@ def test_one_pixel_per_thread_kernels(backend, oracle):
     run_sequence(oracle, 161, 97, 3, first=8, denoiser="bmfr", block=32, use_taa=True)
 
 
+@pytest.mark.parametrize("strip_rows", [1, 2, 3, 7, 16, 40])
+def test_taa_strip_heights_and_split_launches(backend, oracle, strip_rows):
+    """k_taa walks strips of rows whose height follows the size of the launch (and two row ranges can share a launch: the
+    first and the last row of a band); every height, and the frame's TAA cut into inner rows + both edge rows as the
+    band-sharded driver issues it (include/vkpbrt/banded.hpp), gives the oracle's image bit for bit"""
+    W, H = 180, 101
+    pipe, orc = make_pair(oracle, W, H, denoiser="bmfr", block=32, use_taa=True)
+    pipe.taa.set_strip_rows(strip_rows)
+    c = pipe.commands.children          # accumulate, bmfr, taa, copy_to_back
+    from vulkanpbrt_b200 import synth
+    for f in range(4):
+        fr = synth.render_frame(W, H, f)
+        pipe.upload_frame(fr)
+        pipe.set_frame_constants(f, fr.camera)
+        c[0](pipe.commands)
+        c[1](pipe.commands)
+        if f % 2 == 0:
+            c[2](pipe.commands)
+        else:
+            pipe.taa.record_part(pipe.push_constants, 1, H - 1, False)
+            pipe.taa.record_parts(pipe.push_constants, 0, 1, H - 1, H, True)
+        c[3](pipe.commands)
+        pipe.end_frame(fr.camera)
+        pipe.ctx.synchronize()
+        orc.run_frame(f, fr)
+        assert_frame_equal(pipe, orc, f)
+
+
 def test_bfr_l1_branch_after_ten_samples(backend, oracle):
     """after ~10 accumulated frames pixel_spp >= SPP_THRESH switches residuals to sign() (bfr.comp:267-268)"""
     W, H = 96, 64

@@ -151,7 +151,9 @@ _PROTOS = {
     "vkpbrt_taa_set_fix_swizzle": [H, i32],
     "vkpbrt_taa_compile": [H],
     "vkpbrt_taa_set_force_scalar": [H, i32],
+    "vkpbrt_taa_set_strip_rows": [H, i32],
     "vkpbrt_taa_record_part": [H, C.c_void_p, i32, i32, i32],
+    "vkpbrt_taa_record_parts": [H, C.c_void_p, i32, i32, i32, i32, i32],
     "vkpbrt_format_converter_create": [H, H, u32, u32, u32, C.POINTER(H)],
     "vkpbrt_format_converter_compile_images": [H],
     "vkpbrt_format_converter_record": [H],

@@ -202,6 +202,7 @@ struct vkpbrt_taa_s {
     vkpbrt_image_t denoised;
     vkpbrt_image_t final_image = nullptr, history = nullptr;   // handles; data flips between buf[0..1]
     void* buf[2] = {nullptr, nullptr};
+    int strip_rows = 0;           // test switch: strip height of the pair kernel (0 = chosen per launch)
     int fix_swizzle = 0;
     int force_scalar = 0;
     bool compiled = false;
@@ -1272,6 +1273,13 @@ int vkpbrt_taa_set_force_scalar(vkpbrt_taa_t t, int enable)
     return VKPBRT_OK;
 }
 
+int vkpbrt_taa_set_strip_rows(vkpbrt_taa_t t, int rows)
+{
+    VK_REQUIRE(t && rows >= 0 && rows <= 4096, "vkpbrt_taa_set_strip_rows: 0 (automatic) or a strip height in rows");
+    t->strip_rows = rows;
+    return VKPBRT_OK;
+}
+
 int vkpbrt_taa_compile(vkpbrt_taa_t t)
 {
     VK_REQUIRE(t, "null taa");
@@ -1296,14 +1304,17 @@ int vkpbrt_taa_set_row_range(vkpbrt_taa_t t, int row_begin, int row_end)
     return VKPBRT_OK;
 }
 
-int vkpbrt_taa_record_part(vkpbrt_taa_t t, const vkpbrt_push_constants* pc, int row_begin, int row_end, int last)
+int vkpbrt_taa_record_parts(vkpbrt_taa_t t, const vkpbrt_push_constants* pc, int row_begin, int row_end, int row_begin2, int row_end2, int last)
 {
     VK_REQUIRE(t && pc, "null argument");
     if (!t->compiled) return fail(VKPBRT_ERR_NOT_COMPILED, "Taa: compile() has not been called");
     VK_REQUIRE(row_begin >= 0 && row_end <= (int)t->height && row_begin <= row_end, "Taa: row range out of bounds");
+    VK_REQUIRE(row_begin2 >= 0 && row_end2 <= (int)t->height && row_begin2 <= row_end2, "Taa: second row range out of bounds");
+    VK_REQUIRE(row_end2 == row_begin2 || row_end == row_begin || row_end <= row_begin2 || row_end2 <= row_begin, "Taa: the two row ranges overlap");
     vkpbrt::TaaParams p{};
     p.W = (int)t->width; p.H = (int)t->height;
     p.row_begin = row_begin; p.row_end = row_end;
+    p.row_begin2 = row_begin2; p.row_end2 = row_end2;
     p.frame = pc->frame_number;
     p.fix_swizzle = t->fix_swizzle;
     p.motion = (const uint32_t*)t->acc->img[VKPBRT_ACC_MOTION]->data;
@@ -1315,15 +1326,21 @@ int vkpbrt_taa_record_part(vkpbrt_taa_t t, const vkpbrt_push_constants* pc, int 
     VK_REQUIRE(p.motion && p.denoised, "Taa: an input image is not compiled");
     p.one = 1.0f; p.neg_one = -1.0f;
     p.force_scalar = t->force_scalar;
+    p.rows_per_warp = t->strip_rows;
     VK_CUDA(cudaSetDevice(t->ctx->device));
     VK_CUDA(vkpbrt::launch_taa(p, joined(t->ctx)));
-    if (row_end > row_begin) t->ctx->launches++;
+    if (row_end > row_begin || row_end2 > row_begin2) t->ctx->launches++;
     if (last) {
         // Taa.cpp:106 copy final -> history: both handles now view this frame's output
         t->final_image->data = outb;
         t->history->data = outb;
     }
     return VKPBRT_OK;
+}
+
+int vkpbrt_taa_record_part(vkpbrt_taa_t t, const vkpbrt_push_constants* pc, int row_begin, int row_end, int last)
+{
+    return vkpbrt_taa_record_parts(t, pc, row_begin, row_end, 0, 0, last);
 }
 
 int vkpbrt_taa_record(vkpbrt_taa_t t, const vkpbrt_push_constants* pc)
@@ -1854,12 +1871,12 @@ int vkpbrt_banded_rank_image(vkpbrt_banded_rank_t r, uint32_t which, vkpbrt_imag
     return VKPBRT_OK;
 }
 
-int vkpbrt_banded_rank_stats(vkpbrt_banded_rank_t r, uint64_t spin_ns[6], uint64_t* bytes_pushed)
+int vkpbrt_banded_rank_stats(vkpbrt_banded_rank_t r, uint64_t spin_ns[8], uint64_t* bytes_pushed)
 {
     VK_REQUIRE(r && spin_ns && bytes_pushed, "null argument");
     return guarded([&] {
         const auto s = r->rank->spin_ns();
-        for (int g = 0; g < 3; ++g) { spin_ns[2 * g] = s[g][0]; spin_ns[2 * g + 1] = s[g][1]; }
+        for (int g = 0; g < 4; ++g) { spin_ns[2 * g] = s[g][0]; spin_ns[2 * g + 1] = s[g][1]; }
         *bytes_pushed = r->rank->bytes_exchanged();
     });
 }

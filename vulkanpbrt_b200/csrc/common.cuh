@@ -45,8 +45,9 @@ VK_DEVICE float sqrt_rn(float a) { return __fsqrt_rn(a); }
 // a / b == RN(a / b) from a correctly rounded reciprocal rb = RN(1 / b) (Markstein): q0 = RN(a*rb),
 // e = a - b*q0 (exact in one FMA), q = RN(q0 + e*rb).  Bit-identical to IEEE division whenever no
 // intermediate leaves the normal range; callers guarantee that with the range predicates below
-// (2^-40 <= |b| <= 2^40, |a| == 0 or 2^-60 <= |a| <= 2^60; validated against a / b on 4e8 random and
-// adversarial operand pairs, tools/markstein_check.c).  3 instructions instead of the ~12 + branch of
+// (2^-40 <= |b| <= 2^40, |a| == 0 or 2^-84 <= |a| <= 2^84: the quotient stays normal and the residual e is a multiple of
+// 2^-149; validated against a / b on 4e8 random and adversarial operand pairs, tools/markstein_check.c -- the same
+// program reports mismatches from 2^90 on).  3 instructions instead of the ~12 + branch of
 // the generic IEEE sequence.
 VK_DEVICE float div_by_rcp(float a, float b, float rb)
 {
@@ -67,18 +68,22 @@ VK_DEVICE bool in_pow2_range(float x, uint32_t lo_bits, uint32_t hi_bits)   // l
     return ((__float_as_uint(x) & 0x7fffffffu) - lo_bits) <= (hi_bits - lo_bits);
 }
 VK_DEVICE bool safe_divisor(float b) { return in_pow2_range(b, 0x2b800000u, 0x53800000u); }        // 2^-40 .. 2^40
-VK_DEVICE bool safe_factor(float x)                                                               // 0 or 2^-30 .. 2^30
+// One factor of a numerator that is the product of two: 0 or 2^-42 .. 2^42, so the product lies in div_by_rcp's range.
+// (The first version used 2^-30: chance cancellations -- a dot product or a column entry of some 1e-10 in a block whose columns
+// are at the 1e-4 noise level -- sent ~8 blocks of a 4K frame through the slow generic fit, which is what a band's
+// kernel then waits for when such a block runs in its last wave.)
+VK_DEVICE bool safe_factor(float x)
 {
     // '|' on purpose: a short-circuit '||' (and '&&' chains of these tests in the callers) compiles to a branch inside a
     // convergence-barrier region per test, which costs far more in the unrolled Householder stream than the test itself
     const uint32_t a = __float_as_uint(x) & 0x7fffffffu;
-    return (a == 0u) | ((a - 0x30800000u) <= (0x4e800000u - 0x30800000u));
+    return (a == 0u) | ((a - 0x2a800000u) <= (0x54800000u - 0x2a800000u));
 }
 // a / b for a divisor whose reciprocal is reused: exact fast path when both operands are in range
 VK_DEVICE float div_guarded(float a, float b, float rb, bool b_safe)
 {
     const uint32_t ia = __float_as_uint(a) & 0x7fffffffu;
-    const bool ok = b_safe & ((ia == 0u) | ((ia - 0x21800000u) <= (0x5d800000u - 0x21800000u)));     // 0 or 2^-60 .. 2^60; one branch
+    const bool ok = b_safe & ((ia == 0u) | ((ia - 0x15800000u) <= (0x69800000u - 0x15800000u)));     // 0 or 2^-84 .. 2^84; one branch
     if (ok) return div_by_rcp(a, b, rb);
     return div_rn_cold(a, b);
 }

@@ -137,6 +137,9 @@ struct TaaParams {
     uint32_t* final_bgra;         // this frame's TAA final == next frame's history (ping-pong)
     float one, neg_one;           // 1.0f / -1.0f as run-time values (common.cuh: packed pairs)
     int force_scalar;             // debug: the one-pixel-per-thread kernel
+    int row_begin2, row_end2;     // optional second row range of the same launch (empty when row_end2 <= row_begin2)
+    int rows_per_warp;            // strip height of the pair kernel; <= 0: launch_taa chooses it from the size of the launch
+    int strips;                   // set by launch_taa: number of strips of the first range
 };
 cudaError_t launch_taa(const TaaParams& p, cudaStream_t stream);
 

@@ -11,6 +11,8 @@
 // separably from it.  Algorithmic traffic per pixel: denoised 4 + motion 4 + history 4 read,
 // final 4 written = 16 B.
 // All arithmetic is non-contracted IEEE so the BGRA8 output is bit-exact against the oracle.
+#include <atomic>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -235,8 +237,12 @@ __global__ void __launch_bounds__(TAA_WARPS * 32, TAA_MIN_CTAS) k_taa(const TaaP
     const int wx = blockIdx.x * TAA_WARPS + warp;
     if (wx * TAA_COLS >= t.W) return;                                     // whole warp
     t.xa = wx * TAA_COLS - 2 + 2 * t.lane;                                // this thread's columns xa, xa + 1 (W is even)
-    t.y0 = p.row_begin + blockIdx.y * TAA_ROWS;
-    t.y1 = (t.y0 + TAA_ROWS < p.row_end) ? t.y0 + TAA_ROWS : p.row_end;
+    // grid rows: the strips of [row_begin, row_end), then those of the optional second range (band-sharded runs: both edge
+    // rows of a band in one launch)
+    int strip = (int)blockIdx.y, rb = p.row_begin, re = p.row_end;
+    if (strip >= p.strips) { strip -= p.strips; rb = p.row_begin2; re = p.row_end2; }
+    t.y0 = rb + strip * p.rows_per_warp;
+    t.y1 = (t.y0 + p.rows_per_warp < re) ? t.y0 + p.rows_per_warp : re;
     // Out-of-image neighbours are skipped by the shader (taa.comp:70); clamping the coordinate instead re-reads a texel
     // that is already in the same box / cross set, so min and max are unchanged.  A pair left of the image is texel 0
     // twice, a pair right of it texel W-1 twice.
@@ -343,19 +349,56 @@ __global__ void __launch_bounds__(TAA_BX* TAA_BY) k_taa_scalar(const TaaParams p
                         ((uint32_t)f32_to_unorm8(res[0]) << 16) | 0xff000000u;
 }
 
-cudaError_t launch_taa(const TaaParams& p, cudaStream_t stream)
+// strip height of the pair kernel.  A warp walks its strip row by row with dependent gathers (~1.4 us per row on B200), so
+// a launch lasts at least strip-height steps: TAA_ROWS amortises the two lead-in rows when the grid fills the GPU several
+// times over, but a band of a sharded frame (or a small image) would leave most warp slots empty for that long.  Then the
+// strips shrink until the launch fills the resident warp slots about once.
+static int taa_strip_rows(int rows, int warps_x)
 {
-    const int rows = p.row_end - p.row_begin;
-    if (rows <= 0) return cudaSuccess;
+    int sms = 148;
+#ifndef VKPBRT_HOSTSIM
+    static std::atomic<int> cached{0};
+    sms = cached.load(std::memory_order_relaxed);
+    if (sms == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached.store(sms = n, std::memory_order_relaxed);
+    }
+#endif
+    const int slots = sms * TAA_MIN_CTAS * TAA_WARPS;                       // resident warps (register-limited)
+    const int ctas_x = (warps_x + TAA_WARPS - 1) / TAA_WARPS;
+    const int strips_that_fit = slots / (ctas_x * TAA_WARPS);              // per launch, one resident round
+    if ((rows + TAA_ROWS - 1) / TAA_ROWS >= strips_that_fit || strips_that_fit <= 0) return TAA_ROWS;
+    const int h = (rows + strips_that_fit - 1) / strips_that_fit;          // < TAA_ROWS
+    return h < 1 ? 1 : h;
+}
+
+cudaError_t launch_taa(const TaaParams& p_in, cudaStream_t stream)
+{
+    TaaParams p = p_in;
+    if (p.row_end < p.row_begin) p.row_end = p.row_begin;
+    if (p.row_end2 < p.row_begin2) p.row_end2 = p.row_begin2;
+    const int rows1 = p.row_end - p.row_begin, rows2 = p.row_end2 - p.row_begin2;
+    if (rows1 + rows2 <= 0) return cudaSuccess;
     if (p.one != 1.0f || p.neg_one != -1.0f) return cudaErrorInvalidValue;
     const uintptr_t al = (uintptr_t)p.denoised | (uintptr_t)p.motion | (uintptr_t)p.final_bgra;
     if (p.W % 2 == 0 && p.W >= 2 && al % 8 == 0 && !p.force_scalar) {
         const int warps_x = (p.W + TAA_COLS - 1) / TAA_COLS;
-        dim3 block(TAA_WARPS * 32, 1, 1), grid((warps_x + TAA_WARPS - 1) / TAA_WARPS, (rows + TAA_ROWS - 1) / TAA_ROWS, 1);
+        if (p.rows_per_warp <= 0) p.rows_per_warp = taa_strip_rows(rows1 + rows2, warps_x);      // > 0: the caller's (tests)
+        p.strips = (rows1 + p.rows_per_warp - 1) / p.rows_per_warp;
+        const int strips2 = (rows2 + p.rows_per_warp - 1) / p.rows_per_warp;
+        dim3 block(TAA_WARPS * 32, 1, 1), grid((warps_x + TAA_WARPS - 1) / TAA_WARPS, p.strips + strips2, 1);
         VKPBRT_LAUNCH(k_taa, grid, block, 0, stream, p);
     } else {
-        dim3 block(TAA_BX, TAA_BY, 1), grid((p.W + TAA_BX - 1) / TAA_BX, (rows + TAA_BY - 1) / TAA_BY, 1);
-        VKPBRT_LAUNCH(k_taa_scalar, grid, block, 0, stream, p);
+        // one pixel per thread: one launch per range
+        for (int part = 0; part < 2; ++part) {
+            TaaParams q = p;
+            if (part == 1) { q.row_begin = p.row_begin2; q.row_end = p.row_end2; }
+            const int rows = q.row_end - q.row_begin;
+            if (rows <= 0) continue;
+            dim3 block(TAA_BX, TAA_BY, 1), grid((p.W + TAA_BX - 1) / TAA_BX, (rows + TAA_BY - 1) / TAA_BY, 1);
+            VKPBRT_LAUNCH(k_taa_scalar, grid, block, 0, stream, q);
+        }
     }
     return cudaGetLastError();
 }

@@ -660,9 +660,18 @@ class Taa:
         """debug / test switch: the one-pixel-per-thread kernel"""
         capi.call("vkpbrt_taa_set_force_scalar", self._h, 1 if enable else 0)
 
+    def set_strip_rows(self, rows: int) -> None:
+        """test switch: rows per warp and launch of the two-column kernel (0 = automatic); results do not depend on it"""
+        capi.call("vkpbrt_taa_set_strip_rows", self._h, int(rows))
+
     def record_part(self, push_constants: "PushConstants", row_begin: int, row_end: int, last: bool) -> None:
         """one of several launches of a frame's TAA over disjoint row ranges (see vkpbrt_taa_record_part)"""
         capi.call("vkpbrt_taa_record_part", self._h, C.byref(push_constants.value), int(row_begin), int(row_end), 1 if last else 0)
+
+    def record_parts(self, push_constants: "PushConstants", row_begin: int, row_end: int, row_begin2: int, row_end2: int, last: bool) -> None:
+        """two disjoint row ranges in ONE launch (either may be empty): the first and the last row of a band"""
+        capi.call("vkpbrt_taa_record_parts", self._h, C.byref(push_constants.value), int(row_begin), int(row_end), int(row_begin2),
+                  int(row_end2), 1 if last else 0)
 
     def add_dispatch_to_command_graph(self, command_graph: Commands) -> None:
         def rec(c: Commands):

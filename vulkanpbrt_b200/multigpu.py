@@ -631,9 +631,7 @@ class BandedPipeline:
                 i1 = o1 - (1 if g < self.world - 1 else 0)
                 p.taa.record_part(p.push_constants, i0, i1, False)
                 self._finish(pending_f)
-                if i0 > o0:
-                    p.taa.record_part(p.push_constants, o0, i0, False)
-                p.taa.record_part(p.push_constants, i1, o1, True)          # (possibly empty) last part: hands final -> history
+                p.taa.record_parts(p.push_constants, o0, i0, i1, o1, True)     # both edge rows, one launch (either may be empty): hands final -> history
             else:
                 if multi:
                     df = self._exchange_desc("F", frame, lambda: {"final": [(p.denoiser_final, None)]}, lambda: plan.final_transfers(frame))
@@ -753,9 +751,9 @@ class NativeBandedRank:
 
     def stats(self):
         """synchronises; ({group: [gate ms, wait ms]}, bytes pushed)"""
-        s, b = (self.C.c_uint64 * 6)(), self.C.c_uint64()
+        s, b = (self.C.c_uint64 * 8)(), self.C.c_uint64()
         capi.call("vkpbrt_banded_rank_stats", self._h, s, self.C.byref(b))
-        return {k: [s[2 * i] * 1e-6, s[2 * i + 1] * 1e-6] for i, k in enumerate(("A", "B", "C"))}, int(b.value)
+        return {k: [s[2 * i] * 1e-6, s[2 * i + 1] * 1e-6] for i, k in enumerate(("A", "B", "C", "D"))}, int(b.value)
 
     def close(self) -> None:
         if self._h:
