@@ -394,6 +394,7 @@ public:
     // band-sharded runs (not in the reference)
     void set_row_range(int row_begin, int row_end) { check(vkpbrt_taa_set_row_range(handle, row_begin, row_end)); }
     void set_force_scalar(bool enable) { check(vkpbrt_taa_set_force_scalar(handle, enable ? 1 : 0)); }
+    void set_strip_rows(int rows) { check(vkpbrt_taa_set_strip_rows(handle, rows)); }      // test switch; 0 = automatic
     void record_part(const PushConstants& pc, int row_begin, int row_end, bool last) { check(vkpbrt_taa_record_part(handle, pc.c(), row_begin, row_end, last ? 1 : 0)); }
     // two disjoint row ranges in one launch (either may be empty)
     void record_parts(const PushConstants& pc, int row_begin, int row_end, int row_begin2, int row_end2, bool last)

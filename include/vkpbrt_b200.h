@@ -19,6 +19,11 @@
  *     the reference's COMPUTE->COMPUTE pipeline barriers (denoisers/BMFR.cpp:203-230).  The
  *     C++ layer keeps the reference's record-once / replay-per-frame command list on top.
  *   - there is no CPU fallback: every *_record call launches sm_100a kernels or fails.
+ *   - lifetimes: images are reference counted (vkpbrt_image_retain / _release); a buffer bundle (g-buffer, illumination,
+ *     accumulation buffer) retains its images.  A MODULE (accumulator, bmfr, bfr, blender, taa, converter) borrows the
+ *     bundles and the context it was created from: they must outlive it, and modules are destroyed before the context.
+ *     The C++ classes of include/vkpbrt/ hold the references that guarantee this (ref_ptr members, and the recorded
+ *     command closures keep their module alive, as the reference's command graph does).
  */
 #ifndef VKPBRT_B200_H
 #define VKPBRT_B200_H
