@@ -361,6 +361,11 @@ public:
         auto h = handle;
         command_graph->addChild([h, keep = keep_alive()](Commands&) { check(vkpbrt_bfr_blender_record(h)); });
     }
+    // BFRBlender.hpp:17, BFRBlender.cpp:91-124: appends a copy of the final image into dst_image (same extent, 4-byte texels)
+    void copy_final_image(ref_ptr<Commands> commands, ref_ptr<DescriptorImage> dst_image)
+    {
+        commands->addChild([src = _final, dst_image, keep = keep_alive()](Commands&) { check(vkpbrt_image_copy_record(src->handle, dst_image->handle)); });
+    }
     ref_ptr<DescriptorImage> get_final_descriptor_image() const { return _final; }
     vkpbrt_bfr_blender_t handle = nullptr;
 private:
@@ -389,6 +394,12 @@ public:
             if (!c.bound_push_constants) throw std::runtime_error("Taa: no push constants bound; record a denoiser first (Taa.cpp:99-107)");
             check(vkpbrt_taa_record(h, c.bound_push_constants->c()));
         });
+    }
+    // Taa.hpp:23, Taa.cpp:108-141: appends a copy of the final image into dst_image.  (The reference also uses it for
+    // its own final -> history copy, Taa.cpp:106; here the ping-pong pair replaces that one.)
+    void copy_final_image(ref_ptr<Commands> commands, ref_ptr<DescriptorImage> dst_image)
+    {
+        commands->addChild([src = _final, dst_image, keep = keep_alive()](Commands&) { check(vkpbrt_image_copy_record(src->handle, dst_image->handle)); });
     }
     ref_ptr<DescriptorImage> get_final_descriptor_image() const { return _final; }
     // band-sharded runs (not in the reference)

@@ -71,6 +71,11 @@ VKPBRT_API int vkpbrt_context_synchronize(vkpbrt_context_t ctx);
 VKPBRT_API int vkpbrt_context_stream(vkpbrt_context_t ctx, void** cuda_stream);
 /* number of kernels this context has launched so far (bench.py's gpu_launches)               */
 VKPBRT_API int vkpbrt_context_launch_count(vkpbrt_context_t ctx, uint64_t* out);
+/* CUDA devices of this process and their 16-byte UUIDs: a Vulkan host picks the CUDA device whose UUID equals
+ * VkPhysicalDeviceIDProperties::deviceUUID of the VkPhysicalDevice it renders on (include/vkpbrt/vk_interop.hpp);
+ * external memory can only be imported on the device that exported it. */
+VKPBRT_API int vkpbrt_device_count(int* count);
+VKPBRT_API int vkpbrt_device_uuid(int device, uint8_t uuid[16]);
 /* Device-side self check (tests): evaluates the tone-map quantiser of bmfrPost.comp:121-123 / bfr.comp:306-308 for
  * EVERY non-negative binary32 input both ways -- the kernels' threshold search and the pow form -- and returns the
  * number of inputs on which they differ (must be 0) and the smallest such bit pattern. */
@@ -119,6 +124,11 @@ VKPBRT_API int vkpbrt_image_info_get(vkpbrt_image_t img, vkpbrt_image_info* out)
 VKPBRT_API int vkpbrt_image_upload(vkpbrt_image_t img, const void* host, uint64_t bytes);
 VKPBRT_API int vkpbrt_image_download(vkpbrt_image_t img, void* host, uint64_t bytes);
 VKPBRT_API int vkpbrt_image_clear(vkpbrt_image_t img);
+/* device-to-device copy of a whole image on the context stream: BFRBlender::copy_final_image / Taa::copy_final_image
+ * (denoisers/BFRBlender.cpp:91-124, Taa.cpp:108-141: vkCmdCopyImage between two images of equal extent and texel
+ * size; the pipeline barriers around it are stream order here).  Formats must have the same texel size, extents and
+ * layer counts must match. */
+VKPBRT_API int vkpbrt_image_copy_record(vkpbrt_image_t src, vkpbrt_image_t dst);
 VKPBRT_API int vkpbrt_image_retain(vkpbrt_image_t img);
 VKPBRT_API int vkpbrt_image_release(vkpbrt_image_t img);
 
@@ -362,6 +372,10 @@ typedef struct vkpbrt_external_semaphore_s* vkpbrt_external_semaphore_t;
  * [offset, offset+size) as a linear device pointer usable with vkpbrt_image_wrap */
 VKPBRT_API int vkpbrt_import_external_memory_fd(vkpbrt_context_t ctx, int fd, uint64_t allocation_size, uint64_t offset,
                                                 uint64_t size, vkpbrt_external_memory_t* out, void** device_ptr);
+/* as above; dedicated != 0 when the VkDeviceMemory is a dedicated allocation (VkMemoryDedicatedAllocateInfo:
+ * cudaExternalMemoryDedicated has to be passed for those, and some drivers export buffers only that way) */
+VKPBRT_API int vkpbrt_import_external_memory_fd_ex(vkpbrt_context_t ctx, int fd, uint64_t allocation_size, uint64_t offset,
+                                                   uint64_t size, int dedicated, vkpbrt_external_memory_t* out, void** device_ptr);
 VKPBRT_API int vkpbrt_external_memory_destroy(vkpbrt_external_memory_t m);
 VKPBRT_API int vkpbrt_import_external_semaphore_fd(vkpbrt_context_t ctx, int fd, int timeline, vkpbrt_external_semaphore_t* out);
 VKPBRT_API int vkpbrt_external_semaphore_wait(vkpbrt_external_semaphore_t s, uint64_t value);   /* on ctx stream */

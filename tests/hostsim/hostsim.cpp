@@ -3,6 +3,10 @@
 #include "hostsim.h"
 
 #include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <mutex>
 
 asm(R"(
 .text
@@ -149,6 +153,108 @@ void launch(dim3 grid, dim3 block, const std::function<void()>& body)
 }
 
 }  // namespace hostsim
+
+// ---- external memory / semaphores (the Vulkan side is tests/vkmock) -------------------------------------
+// Memory: the fd is a memfd of the allocation's size, mapped shared.  Semaphore: a memfd of one page that starts
+// with {magic, payload, timeline?}; both sides use atomics on the payload.
+struct hostsim_external_memory_s { void* base; size_t size; };
+struct hostsim_semaphore_page { uint64_t magic; uint64_t payload; uint32_t timeline; };
+struct hostsim_external_semaphore_s { hostsim_semaphore_page* page; bool timeline; };
+static const uint64_t kSemaphoreMagic = 0x564b4d4f434b5345ull;   // "VKMOCKSE"
+static std::mutex g_ext_mutex;
+static std::vector<hostsim_external_memory_s*> g_ext_mappings;
+
+bool hostsim_is_external_mapping(const void* p)
+{
+    std::lock_guard<std::mutex> lock(g_ext_mutex);
+    for (auto* m : g_ext_mappings)
+        if ((const char*)p >= (const char*)m->base && (const char*)p < (const char*)m->base + m->size) return true;
+    return false;
+}
+
+cudaError_t cudaImportExternalMemory(cudaExternalMemory_t* out, const cudaExternalMemoryHandleDesc* d)
+{
+    if (!out || !d || d->type != cudaExternalMemoryHandleTypeOpaqueFd) return cudaErrorInvalidValue;
+    struct stat st;
+    if (fstat(d->handle.fd, &st) != 0 || (unsigned long long)st.st_size < d->size || d->size == 0) return cudaErrorInvalidValue;
+    void* base = mmap(nullptr, d->size, PROT_READ | PROT_WRITE, MAP_SHARED, d->handle.fd, 0);
+    if (base == MAP_FAILED) return cudaErrorInvalidValue;
+    close(d->handle.fd);                                   // ownership of the fd passes to the importer
+    auto* m = new hostsim_external_memory_s{base, (size_t)d->size};
+    { std::lock_guard<std::mutex> lock(g_ext_mutex); g_ext_mappings.push_back(m); }
+    *out = m;
+    return cudaSuccess;
+}
+
+cudaError_t cudaExternalMemoryGetMappedBuffer(void** ptr, cudaExternalMemory_t m, const cudaExternalMemoryBufferDesc* d)
+{
+    if (!ptr || !m || !d || d->offset + d->size > m->size) return cudaErrorInvalidValue;
+    *ptr = (char*)m->base + d->offset;
+    return cudaSuccess;
+}
+
+cudaError_t cudaDestroyExternalMemory(cudaExternalMemory_t m)
+{
+    if (!m) return cudaSuccess;
+    {
+        std::lock_guard<std::mutex> lock(g_ext_mutex);
+        for (size_t i = 0; i < g_ext_mappings.size(); ++i)
+            if (g_ext_mappings[i] == m) { g_ext_mappings.erase(g_ext_mappings.begin() + i); break; }
+    }
+    munmap(m->base, m->size);
+    delete m;
+    return cudaSuccess;
+}
+
+cudaError_t cudaImportExternalSemaphore(cudaExternalSemaphore_t* out, const cudaExternalSemaphoreHandleDesc* d)
+{
+    if (!out || !d) return cudaErrorInvalidValue;
+    const bool timeline = d->type == cudaExternalSemaphoreHandleTypeTimelineSemaphoreFd;
+    if (!timeline && d->type != cudaExternalSemaphoreHandleTypeOpaqueFd) return cudaErrorInvalidValue;
+    void* base = mmap(nullptr, 4096, PROT_READ | PROT_WRITE, MAP_SHARED, d->handle.fd, 0);
+    if (base == MAP_FAILED) return cudaErrorInvalidValue;
+    auto* page = (hostsim_semaphore_page*)base;
+    if (page->magic != kSemaphoreMagic || (page->timeline != 0) != timeline) { munmap(base, 4096); return cudaErrorInvalidValue; }
+    close(d->handle.fd);
+    *out = new hostsim_external_semaphore_s{page, timeline};
+    return cudaSuccess;
+}
+
+cudaError_t cudaWaitExternalSemaphoresAsync(cudaExternalSemaphore_t* sems, const cudaExternalSemaphoreWaitParams* params, unsigned n, cudaStream_t)
+{
+    for (unsigned i = 0; i < n; ++i) {
+        hostsim_external_semaphore_s* s = sems[i];
+        const uint64_t want = s->timeline ? params[i].params.fence.value : 1;
+        timespec t0; clock_gettime(CLOCK_MONOTONIC, &t0);
+        while (__atomic_load_n(&s->page->payload, __ATOMIC_ACQUIRE) < want) {
+            sched_yield();
+            timespec t1; clock_gettime(CLOCK_MONOTONIC, &t1);
+            if (t1.tv_sec - t0.tv_sec > 20) return cudaErrorNotSupported;     // a deadlock in a test must not hang the suite
+        }
+        if (!s->timeline) __atomic_store_n(&s->page->payload, 0, __ATOMIC_RELEASE);   // a binary semaphore is reset by its wait
+    }
+    return cudaSuccess;
+}
+
+cudaError_t cudaSignalExternalSemaphoresAsync(cudaExternalSemaphore_t* sems, const cudaExternalSemaphoreSignalParams* params, unsigned n, cudaStream_t)
+{
+    for (unsigned i = 0; i < n; ++i) {
+        hostsim_external_semaphore_s* s = sems[i];
+        if (!s->timeline) { __atomic_store_n(&s->page->payload, 1, __ATOMIC_RELEASE); continue; }
+        const uint64_t v = params[i].params.fence.value;
+        if (v <= __atomic_load_n(&s->page->payload, __ATOMIC_ACQUIRE)) return cudaErrorInvalidValue;   // timeline values must increase
+        __atomic_store_n(&s->page->payload, v, __ATOMIC_RELEASE);
+    }
+    return cudaSuccess;
+}
+
+cudaError_t cudaDestroyExternalSemaphore(cudaExternalSemaphore_t s)
+{
+    if (!s) return cudaSuccess;
+    munmap(s->page, 4096);
+    delete s;
+    return cudaSuccess;
+}
 
 // ---- the library under test -------------------------------------------------------------------------
 #include "../../vulkanpbrt_b200/csrc/accumulate.cu"

@@ -54,12 +54,13 @@ enum { cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorNotSupported = 801 }
 typedef struct hostsim_stream_s* cudaStream_t;
 enum { cudaStreamNonBlocking = 1 };
 enum cudaMemcpyKind { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
-struct cudaDeviceProp { char name[64]; int major, minor; };
+struct cudaUUID_t { char bytes[16]; };
+struct cudaDeviceProp { char name[64]; cudaUUID_t uuid; int major, minor; };
 
 inline const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "hostsim error"; }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
-inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { strcpy(p->name, "HOSTSIM (CPU test emulator)"); p->major = 10; p->minor = 0; return cudaSuccess; }
+inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { strcpy(p->name, "HOSTSIM (CPU test emulator)"); memcpy(p->uuid.bytes, "HOSTSIM-DEVICE-0", 16); p->major = 10; p->minor = 0; return cudaSuccess; }
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 template <typename F>
@@ -68,7 +69,8 @@ inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = n
 inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaMalloc(void** p, size_t n) { *p = aligned_alloc(256, (n + 255) / 256 * 256); return *p ? cudaSuccess : cudaErrorInvalidValue; }
-inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+bool hostsim_is_external_mapping(const void* p);       // hostsim.cpp: pointers handed out by cudaExternalMemoryGetMappedBuffer
+inline cudaError_t cudaFree(void* p) { if (!hostsim_is_external_mapping(p)) free(p); return cudaSuccess; }
 inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
 inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return cudaSuccess; }
@@ -105,22 +107,27 @@ inline unsigned long long atomicMax(unsigned long long* p, unsigned long long v)
 }
 inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline void __nanosleep(unsigned) { sched_yield(); }
-// external memory / semaphores are not emulated
-typedef void* cudaExternalMemory_t;
-typedef void* cudaExternalSemaphore_t;
+// external memory / semaphores (tests/vkmock plays the Vulkan side): an exported "VkDeviceMemory" is a memfd that is
+// mapped shared, an exported semaphore a memfd holding one 64-bit payload.  As with CUDA, a successful import takes
+// ownership of the file descriptor.  Launches are synchronous, so a wait spins (bounded) until the payload arrives.
+struct hostsim_external_memory_s;
+struct hostsim_external_semaphore_s;
+typedef hostsim_external_memory_s* cudaExternalMemory_t;
+typedef hostsim_external_semaphore_s* cudaExternalSemaphore_t;
 enum { cudaExternalMemoryHandleTypeOpaqueFd = 1, cudaExternalSemaphoreHandleTypeOpaqueFd = 1, cudaExternalSemaphoreHandleTypeTimelineSemaphoreFd = 9 };
-struct cudaExternalMemoryHandleDesc { int type; struct { int fd; } handle; unsigned long long size; };
-struct cudaExternalMemoryBufferDesc { unsigned long long offset, size; };
-struct cudaExternalSemaphoreHandleDesc { int type; struct { int fd; } handle; };
-struct cudaExternalSemaphoreWaitParams { struct { struct { unsigned long long value; } fence; } params; };
-struct cudaExternalSemaphoreSignalParams { struct { struct { unsigned long long value; } fence; } params; };
-inline cudaError_t cudaImportExternalMemory(cudaExternalMemory_t*, const cudaExternalMemoryHandleDesc*) { return cudaErrorNotSupported; }
-inline cudaError_t cudaExternalMemoryGetMappedBuffer(void**, cudaExternalMemory_t, const cudaExternalMemoryBufferDesc*) { return cudaErrorNotSupported; }
-inline cudaError_t cudaDestroyExternalMemory(cudaExternalMemory_t) { return cudaSuccess; }
-inline cudaError_t cudaImportExternalSemaphore(cudaExternalSemaphore_t*, const cudaExternalSemaphoreHandleDesc*) { return cudaErrorNotSupported; }
-inline cudaError_t cudaWaitExternalSemaphoresAsync(cudaExternalSemaphore_t*, const cudaExternalSemaphoreWaitParams*, unsigned, cudaStream_t) { return cudaErrorNotSupported; }
-inline cudaError_t cudaSignalExternalSemaphoresAsync(cudaExternalSemaphore_t*, const cudaExternalSemaphoreSignalParams*, unsigned, cudaStream_t) { return cudaErrorNotSupported; }
-inline cudaError_t cudaDestroyExternalSemaphore(cudaExternalSemaphore_t) { return cudaSuccess; }
+enum { cudaExternalMemoryDedicated = 1 };
+struct cudaExternalMemoryHandleDesc { int type; struct { int fd; } handle; unsigned long long size; unsigned flags; };
+struct cudaExternalMemoryBufferDesc { unsigned long long offset, size; unsigned flags; };
+struct cudaExternalSemaphoreHandleDesc { int type; struct { int fd; } handle; unsigned flags; };
+struct cudaExternalSemaphoreWaitParams { struct { struct { unsigned long long value; } fence; } params; unsigned flags; };
+struct cudaExternalSemaphoreSignalParams { struct { struct { unsigned long long value; } fence; } params; unsigned flags; };
+cudaError_t cudaImportExternalMemory(cudaExternalMemory_t*, const cudaExternalMemoryHandleDesc*);
+cudaError_t cudaExternalMemoryGetMappedBuffer(void**, cudaExternalMemory_t, const cudaExternalMemoryBufferDesc*);
+cudaError_t cudaDestroyExternalMemory(cudaExternalMemory_t);
+cudaError_t cudaImportExternalSemaphore(cudaExternalSemaphore_t*, const cudaExternalSemaphoreHandleDesc*);
+cudaError_t cudaWaitExternalSemaphoresAsync(cudaExternalSemaphore_t*, const cudaExternalSemaphoreWaitParams*, unsigned, cudaStream_t);
+cudaError_t cudaSignalExternalSemaphoresAsync(cudaExternalSemaphore_t*, const cudaExternalSemaphoreSignalParams*, unsigned, cudaStream_t);
+cudaError_t cudaDestroyExternalSemaphore(cudaExternalSemaphore_t);
 
 // ---- fibers -----------------------------------------------------------------------------------------
 extern "C" void hostsim_switch(void** save_sp, void* load_sp);

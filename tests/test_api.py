@@ -77,6 +77,32 @@ class TestHostBehaviour:
         i = img.info()
         assert (i.width, i.height, i.layers, i.row_pitch, i.size_bytes) == (37, 19, 2, 37 * 8, 2 * 19 * 37 * 8)
 
+    def test_copy_final_image_and_device_uuid(self, backend):
+        """Taa.hpp:23 / BFRBlender.hpp:17 copy_final_image: a recorded whole-image copy between size-compatible formats;
+        vkpbrt_device_uuid: what a Vulkan host matches VkPhysicalDeviceIDProperties::deviceUUID against"""
+        from vulkanpbrt_b200 import Commands, Context, DenoisePipeline, DenoisingType, DescriptorImage, VkpbrtError, _capi, synth
+        n = ctypes.c_int(0)
+        _capi.call("vkpbrt_device_count", ctypes.byref(n))
+        assert n.value >= 1
+        uuid = (ctypes.c_uint8 * 16)()
+        _capi.call("vkpbrt_device_uuid", 0, uuid)
+        assert any(uuid)
+        assert _capi.lib().vkpbrt_device_uuid(n.value, uuid) == _capi.ERR_INVALID_ARGUMENT
+        W, H = 64, 64
+        pipe = DenoisePipeline(W, H, DenoisingType.BMFR, use_taa=True)
+        dst = DescriptorImage.create(pipe.ctx, _capi.FORMAT_R8G8B8A8_UNORM, W, H)       # 4-byte texels like the BGRA8 final
+        dst.compile()
+        pipe.taa.copy_final_image(pipe.commands, dst)
+        for f in range(2):
+            pipe.run_frame(f, synth.render_frame(W, H, f))
+            pipe.ctx.synchronize()
+            np.testing.assert_array_equal(dst.download(), pipe.final.download())
+        small = DescriptorImage.create(pipe.ctx, _capi.FORMAT_R8G8B8A8_UNORM, W, H - 1)
+        small.compile()
+        with pytest.raises(VkpbrtError) as e:
+            _capi.call("vkpbrt_image_copy_record", pipe.final.handle, small.handle)
+        assert e.value.code == _capi.ERR_INVALID_ARGUMENT
+
     def test_wrong_illumination_buffer_type_is_rejected(self, backend):
         """denoisers/BMFR.cpp:17-22 / BFR.cpp:15-20 print and return a half-built object; we reject"""
         from vulkanpbrt_b200 import (BFR, BMFR, AccumulationBuffer, Context, GBuffer, IlluminationBufferFinal, VkpbrtError,

@@ -96,6 +96,9 @@ _PROTOS = {
     "vkpbrt_image_upload": [H, C.c_void_p, u64],
     "vkpbrt_image_download": [H, C.c_void_p, u64],
     "vkpbrt_image_clear": [H],
+    "vkpbrt_image_copy_record": [H, H],
+    "vkpbrt_device_count": [C.POINTER(i32)],
+    "vkpbrt_device_uuid": [i32, C.c_void_p],
     "vkpbrt_image_retain": [H],
     "vkpbrt_image_release": [H],
     "vkpbrt_gbuffer_create": [H, u32, u32, PH],
@@ -180,6 +183,7 @@ _PROTOS = {
     "vkpbrt_taa_history_image": [H, PH],
     "vkpbrt_taa_destroy": [H],
     "vkpbrt_import_external_memory_fd": [H, i32, u64, u64, u64, PH, PH],
+    "vkpbrt_import_external_memory_fd_ex": [H, i32, u64, u64, u64, i32, PH, PH],
     "vkpbrt_external_memory_destroy": [H],
     "vkpbrt_import_external_semaphore_fd": [H, i32, i32, PH],
     "vkpbrt_external_semaphore_wait": [H, u64],

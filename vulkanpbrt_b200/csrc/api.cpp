@@ -361,6 +361,29 @@ int vkpbrt_context_launch_count(vkpbrt_context_t ctx, uint64_t* out)
     return VKPBRT_OK;
 }
 
+int vkpbrt_device_count(int* count)
+{
+    VK_REQUIRE(count, "vkpbrt_device_count: null argument");
+    *count = 0;
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) { *count = 0; return fail(VKPBRT_ERR_NO_DEVICE, std::string("vkpbrt_device_count: ") + cudaGetErrorString(e)); }
+    return VKPBRT_OK;
+}
+
+int vkpbrt_device_uuid(int device, uint8_t uuid[16])
+{
+    VK_REQUIRE(uuid, "vkpbrt_device_uuid: null argument");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) return fail(VKPBRT_ERR_NO_DEVICE, std::string("vkpbrt_device_uuid: no CUDA device (") + cudaGetErrorString(e) + ")");
+    VK_REQUIRE(device >= 0 && device < count, "vkpbrt_device_uuid: device index out of range");
+    cudaDeviceProp prop;
+    VK_CUDA(cudaGetDeviceProperties(&prop, device));
+    static_assert(sizeof(prop.uuid.bytes) == 16, "CUDA device UUIDs are 16 bytes, like VkPhysicalDeviceIDProperties::deviceUUID");
+    memcpy(uuid, prop.uuid.bytes, 16);
+    return VKPBRT_OK;
+}
+
 // ---- device-side self checks ---------------------------------------------------------------------
 int vkpbrt_debug_tonemap_sweep(vkpbrt_context_t ctx, uint64_t* mismatches, uint32_t* first_mismatch)
 {
@@ -469,6 +492,21 @@ int vkpbrt_image_clear(vkpbrt_image_t img)
 {
     VK_REQUIRE(img && img->data, "vkpbrt_image_clear: image not compiled");
     VK_CUDA(cudaMemsetAsync(img->data, 0, img->size_bytes(), joined(img->ctx)));
+    return VKPBRT_OK;
+}
+
+int vkpbrt_image_copy_record(vkpbrt_image_t src, vkpbrt_image_t dst)
+{
+    VK_REQUIRE(src && dst, "vkpbrt_image_copy_record: null image");
+    VK_REQUIRE(src->data && dst->data, "vkpbrt_image_copy_record: image not compiled");
+    VK_REQUIRE(src->ctx == dst->ctx, "vkpbrt_image_copy_record: images of different contexts");
+    VK_REQUIRE(src->width == dst->width && src->height == dst->height && src->layers == dst->layers,
+               "vkpbrt_image_copy_record: extents differ");
+    VK_REQUIRE(vkpbrt_format_texel_size(src->format) == vkpbrt_format_texel_size(dst->format),
+               "vkpbrt_image_copy_record: texel sizes differ (vkCmdCopyImage requires size-compatible formats)");
+    if (src->data == dst->data) return VKPBRT_OK;
+    VK_CUDA(cudaSetDevice(src->ctx->device));
+    VK_CUDA(cudaMemcpyAsync(dst->data, src->data, src->size_bytes(), cudaMemcpyDeviceToDevice, joined(src->ctx)));
     return VKPBRT_OK;
 }
 
@@ -1488,18 +1526,20 @@ int vkpbrt_demodulate_record(vkpbrt_context_t ctx, vkpbrt_image_t radiance, vkpb
 }
 
 // ---- Vulkan interop --------------------------------------------------------------------------------
-int vkpbrt_import_external_memory_fd(vkpbrt_context_t ctx, int fd, uint64_t allocation_size, uint64_t offset, uint64_t size,
-                                     vkpbrt_external_memory_t* out, void** device_ptr)
+int vkpbrt_import_external_memory_fd_ex(vkpbrt_context_t ctx, int fd, uint64_t allocation_size, uint64_t offset, uint64_t size,
+                                        int dedicated, vkpbrt_external_memory_t* out, void** device_ptr)
 {
     VK_REQUIRE(ctx && out && device_ptr, "null argument");
-    VK_REQUIRE(offset + size <= allocation_size, "mapped range exceeds the allocation");
+    VK_REQUIRE(fd >= 0, "vkpbrt_import_external_memory_fd: invalid file descriptor");
+    VK_REQUIRE(size > 0 && offset <= allocation_size && size <= allocation_size - offset, "mapped range exceeds the allocation");
     VK_CUDA(cudaSetDevice(ctx->device));
     cudaExternalMemoryHandleDesc hd{};
     hd.type = cudaExternalMemoryHandleTypeOpaqueFd;
     hd.handle.fd = fd;
     hd.size = allocation_size;
+    hd.flags = dedicated ? cudaExternalMemoryDedicated : 0;
     cudaExternalMemory_t mem;
-    VK_CUDA(cudaImportExternalMemory(&mem, &hd));
+    VK_CUDA(cudaImportExternalMemory(&mem, &hd));      // on success the fd belongs to CUDA (the caller must not close it)
     cudaExternalMemoryBufferDesc bd{};
     bd.offset = offset;
     bd.size = size;
@@ -1509,6 +1549,12 @@ int vkpbrt_import_external_memory_fd(vkpbrt_context_t ctx, int fd, uint64_t allo
     *out = new vkpbrt_external_memory_s{ctx, mem, ptr};
     *device_ptr = ptr;
     return VKPBRT_OK;
+}
+
+int vkpbrt_import_external_memory_fd(vkpbrt_context_t ctx, int fd, uint64_t allocation_size, uint64_t offset, uint64_t size,
+                                     vkpbrt_external_memory_t* out, void** device_ptr)
+{
+    return vkpbrt_import_external_memory_fd_ex(ctx, fd, allocation_size, offset, size, 0, out, device_ptr);
 }
 
 int vkpbrt_external_memory_destroy(vkpbrt_external_memory_t m)

@@ -618,6 +618,11 @@ class BFRBlender:
     def add_dispatch_to_command_graph(self, command_graph: Commands) -> None:
         command_graph.add_child(lambda _c: capi.call("vkpbrt_bfr_blender_record", self._h))
 
+    def copy_final_image(self, commands: Commands, dst_image: DescriptorImage) -> None:
+        """BFRBlender.hpp:17 / BFRBlender.cpp:91-124: appends a copy of the final image into ``dst_image``."""
+        src = self._final
+        commands.add_child(lambda _c: capi.call("vkpbrt_image_copy_record", src.handle, dst_image.handle))
+
     def get_final_descriptor_image(self) -> DescriptorImage:
         return self._final
 
@@ -681,6 +686,12 @@ class Taa:
                                   "Taa: no push constants bound; record a denoiser before Taa (Taa.cpp:99-107)")
             capi.call("vkpbrt_taa_record", self._h, C.byref(pc.value))
         command_graph.add_child(rec)
+
+    def copy_final_image(self, commands: Commands, dst_image: DescriptorImage) -> None:
+        """Taa.hpp:23 / Taa.cpp:108-141: appends a copy of the final image into ``dst_image`` (the reference uses it for
+        its own final -> history copy, which the ping-pong pair replaces here, and exposes it publicly)."""
+        src = self._final
+        commands.add_child(lambda _c: capi.call("vkpbrt_image_copy_record", src.handle, dst_image.handle))
 
     def get_final_descriptor_image(self) -> DescriptorImage:
         return self._final
