@@ -37,6 +37,15 @@ def test_bmfr_negative_jitter_frames_leave_pixels_unwritten(backend, oracle):
     run_sequence(oracle, 250, 130, 5, first=6, denoiser="bmfr", block=32, use_taa=True)
 
 
+def test_bmfr_image_narrower_than_two_blocks(backend, oracle):
+    """W < 64 with b = 32: the block grid is 3 wide, so the launch's extra grid row has too few threads to produce the
+    next frame's block-invariant table and every frame builds its own (found by fuzzing sizes: frames >= 1 used a
+    partly stale table); also the smallest legal image, one block"""
+    run_sequence(oracle, 54, 64, 4, denoiser="bmfr", block=32, use_taa=True, debug=True)
+    if backend == "hostsim":        # (not yet confirmed on a GPU: added after the round's last GPU visit)
+        run_sequence(oracle, 32, 32, 3, first=7, denoiser="bmfr", block=32, use_taa=True)
+
+
 @pytest.mark.parametrize("block,W,H", [(16, 208, 144), (8, 200, 136)])
 def test_bmfr_other_block_sizes(backend, oracle, block, W, H):
     """BMFR::create(w, h, 16, 16, ...) and (8, 8, ..., fitting_kernel = 64) (DenoiserUtils.cpp:78-95)"""

@@ -1067,14 +1067,18 @@ int vkpbrt_bmfr_record(vkpbrt_bmfr_t b, const vkpbrt_push_constants* pc)
         b->table_frame[slot] = (int64_t)pc->frame_number;
     }
     p.table = b->table[slot];
-    p.table_next = b->table[slot ^ 1];
+    // The launch's extra grid row (blocks_x CTAs of fitting_kernel threads) writes the next frame's table, one element
+    // per thread: that covers the work x work elements unless the image is narrower than two 32-blocks (blocks_x < 4),
+    // and there is no extra row when the launch is empty.  Then the next frame builds its table itself.
+    const bool builds_next = p.block_row_end > p.block_row_begin && (uint64_t)p.blocks_x * b->fitting_kernel >= (uint64_t)b->work * b->work;
+    p.table_next = builds_next ? b->table[slot ^ 1] : nullptr;
     p.position_type = b->position_type;
     std::memcpy(p.inv_view, pc->view_inverse, 64);      // camParams.inverseViewMatrix / inverseProjectionMatrix (WORLD modes only)
     std::memcpy(p.inv_proj, pc->proj_inverse, 64);
     if (b->tma_enabled && b->position_type == 0) vkpbrt::bmfr_encode_tma(p);     // descriptors follow the planes bound for this frame
     VK_CUDA(vkpbrt::launch_bmfr(p, st));
     VK_CUDA(lane_done(b->ctx, b->lane));
-    b->table_frame[slot ^ 1] = (int64_t)(uint32_t)(pc->frame_number + 1u);
+    if (builds_next) b->table_frame[slot ^ 1] = (int64_t)(uint32_t)(pc->frame_number + 1u);
     b->ctx->launches++;
     return VKPBRT_OK;
 }
