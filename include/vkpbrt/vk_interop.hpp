@@ -22,7 +22,8 @@
 // VKPBRT_VULKAN_HEADER to the header to use (e.g. <vulkan/vulkan.h>) if it is not <vulkan/vulkan_core.h>.
 // Requires Vulkan 1.2 (timeline semaphores, external memory / semaphore capabilities in core), which is what the
 // reference requests (VulkanPBRT.cpp:176), plus the two *_fd device extensions of required_device_extensions(),
-// to be appended to window_traits->deviceExtensionNames (VulkanPBRT.cpp:171-175).
+// to be appended to window_traits->deviceExtensionNames (VulkanPBRT.cpp:171-175), and the timelineSemaphore feature
+// (next to the other VkPhysicalDeviceVulkan12Features the reference enables, VulkanPBRT.cpp:185-192).
 //
 // tests/test_vk_interop.py compiles examples/cpp_vulkan_interop.cpp (a raw-Vulkan host written against this
 // header) and runs it against tests/vkmock, a mock Vulkan implementation whose exported memory and semaphores are
