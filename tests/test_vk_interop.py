@@ -37,7 +37,7 @@ def built(tmp_path_factory):
     subprocess.run(["make", "-C", str(HOSTSIM)], check=True, capture_output=True)
     mock = out / "libvkmock.so"
     r = subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-fPIC", "-shared", "-fvisibility=hidden", "-I", str(inc),
-                        str(ROOT / "tests" / "vkmock" / "vkmock.cpp"), "-o", str(mock)], capture_output=True, text=True)
+                        str(ROOT / "tests" / "vkmock" / "vkmock.cpp"), "-o", str(mock), "-ldl"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     exes = {}
     for name, src in (("cpp_vulkan_interop", ROOT / "examples" / "cpp_vulkan_interop.cpp"), ("interop_checks", ROOT / "tests" / "vkmock" / "interop_checks.cpp")):

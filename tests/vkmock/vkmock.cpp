@@ -1,8 +1,8 @@
 // vkmock.cpp -- TEST-ONLY mock of the Vulkan entry points the interop layer (include/vkpbrt/vk_interop.hpp) and its
 // example host (examples/cpp_vulkan_interop.cpp) use.  Neither machine of this project has a Vulkan loader, driver or
 // lavapipe, so this plays "the Vulkan implementation" for tests/test_vk_interop.py, with the CUDA side on the test
-// emulator (tests/hostsim).  It is not a Vulkan implementation: no shaders, no pipelines, one queue that executes a
-// submission synchronously inside vkQueueSubmit.
+// emulator (tests/hostsim), and for tools/vk_oracle (tests/test_vk_oracle.py).  It is not a Vulkan implementation: one
+// queue that executes a submission synchronously inside vkQueueSubmit, and "compute" that does not run SPIR-V (below).
 //
 // What it does model, because the interop depends on it:
 //   * device memory is a memfd; vkGetMemoryFdKHR hands out a dup() of it (the importer maps the same pages), and only
@@ -15,9 +15,15 @@
 //     SharedPlane::cmd_copy_* are checked that way);
 //   * entry points of an extension / feature that was not enabled at vkCreateDevice are not returned by
 //     vkGetDeviceProcAddr.
+//   * compute: a "shader module" is not SPIR-V but a text blob "VKMOCK-SHADER:<name>" naming one of the reference's
+//     shaders; vkCmdDispatch gathers the bound descriptors, specialisation and push constants and runs that shader's
+//     SOURCE TEXT as compiled by oracle/glsl_shim (oracle/_ref/libref.so, dlopen'ed from $VKMOCK_LIBREF) -- so a raw-Vulkan
+//     host (tools/vk_oracle) is checked for the reference's binding numbers, descriptor types, formats, specialisation
+//     constants, push-constant blocks and dispatch sizes by the result it produces.  Real SPIR-V is refused.
 // The only exported symbol is vkGetInstanceProcAddr, as with a real loader used through vk::open_loader().
 #include <vulkan/vulkan_core.h>
 
+#include <dlfcn.h>
 #include <fcntl.h>
 #include <sched.h>
 #include <sys/mman.h>
@@ -29,6 +35,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -43,10 +50,27 @@ struct VkQueue_T { int dummy; };
 struct VkDevice_T { bool ext_memory_fd = false, ext_semaphore_fd = false, timeline = false; VkQueue_T queue; };
 struct VkDeviceMemory_T { int fd; size_t size; char* map; uint32_t type; bool exportable; bool dedicated; };
 struct VkBuffer_T { VkDeviceSize size; VkBufferUsageFlags usage; bool external; VkDeviceMemory_T* mem; VkDeviceSize offset; };
-struct VkImage_T { VkFormat format; uint32_t w, h, texel; size_t pitch; VkImageLayout layout; VkImageUsageFlags usage; VkDeviceMemory_T* mem; VkDeviceSize offset; };
+struct VkImage_T {
+    VkFormat format; uint32_t w, h, texel; size_t pitch; VkImageLayout layout; VkImageUsageFlags usage; VkDeviceMemory_T* mem; VkDeviceSize offset;
+    uint32_t layers = 1;
+    size_t layer_stride() const { return pitch * h; }
+    char* row(uint32_t layer, uint32_t y) const { return mem->map + offset + layer * layer_stride() + y * pitch; }
+};
+struct VkImageView_T { VkImage_T* image; VkImageViewType type; VkFormat format; uint32_t base_layer, layer_count; };
+struct VkSampler_T { VkFilter mag, min; VkSamplerAddressMode u, v; VkBool32 unnormalized; };
+struct VkShaderModule_T { std::string name; };
+struct VkDescriptorSetLayout_T { std::map<uint32_t, VkDescriptorType> bindings; };
+struct VkPipelineLayout_T { std::vector<VkDescriptorSetLayout_T*> sets; uint32_t push_size; };
+struct VkPipeline_T { std::string shader; std::map<uint32_t, int32_t> spec; VkPipelineLayout_T* layout; };
+struct VkDescriptorPool_T { int dummy; };
+struct Descriptor { VkDescriptorType type; VkImageView_T* view; VkSampler_T* sampler; VkImageLayout layout; };
+struct VkDescriptorSet_T { VkDescriptorSetLayout_T* layout; std::map<uint32_t, Descriptor> bound; };
 struct VkSemaphore_T { bool timeline; bool exportable; int fd; SemaphorePage* page; };
 struct VkCommandPool_T { int dummy; };
-struct VkCommandBuffer_T { std::vector<std::function<void()>> cmds; bool recording = false; };
+struct VkCommandBuffer_T {
+    std::vector<std::function<void()>> cmds; bool recording = false;
+    VkPipeline_T* pipeline = nullptr; VkDescriptorSet_T* set = nullptr; std::vector<unsigned char> push;     // state while recording
+};
 
 static VkInstance_T g_instance;
 static VkPhysicalDevice_T g_physical_device;
@@ -212,19 +236,20 @@ static VKAPI_ATTR void VKAPI_CALL mock_GetBufferMemoryRequirements(VkDevice, VkB
 }
 static VKAPI_ATTR VkResult VKAPI_CALL mock_CreateImage(VkDevice, const VkImageCreateInfo* ci, const VkAllocationCallbacks*, VkImage* out)
 {
-    if (!ci || ci->sType != VK_STRUCTURE_TYPE_IMAGE_CREATE_INFO || ci->imageType != VK_IMAGE_TYPE_2D || ci->extent.depth != 1 || ci->mipLevels != 1 || ci->arrayLayers != 1)
-        MOCK_FAIL("vkCreateImage: only single-level 2-D images");
+    if (!ci || ci->sType != VK_STRUCTURE_TYPE_IMAGE_CREATE_INFO || ci->imageType != VK_IMAGE_TYPE_2D || ci->extent.depth != 1 || ci->mipLevels != 1 || ci->arrayLayers < 1)
+        MOCK_FAIL("vkCreateImage: only single-level 2-D (array) images");
     const uint32_t texel = texel_size(ci->format);
     if (!texel) MOCK_FAIL("vkCreateImage: format %d is not modelled", (int)ci->format);
     size_t pitch = (size_t)ci->extent.width * texel;
     if (ci->tiling == VK_IMAGE_TILING_OPTIMAL) pitch = (pitch + 63) / 64 * 64 + 64;     // "opaque" layout: rows are not where a linear view expects them
     *out = new VkImage_T{ci->format, ci->extent.width, ci->extent.height, texel, pitch, ci->initialLayout, ci->usage, nullptr, 0};
+    (*out)->layers = ci->arrayLayers;
     return VK_SUCCESS;
 }
 static VKAPI_ATTR void VKAPI_CALL mock_DestroyImage(VkDevice, VkImage i, const VkAllocationCallbacks*) { delete i; }
 static VKAPI_ATTR void VKAPI_CALL mock_GetImageMemoryRequirements(VkDevice, VkImage i, VkMemoryRequirements* r)
 {
-    r->size = (i->pitch * i->h + 4095) / 4096 * 4096;
+    r->size = (i->layer_stride() * i->layers + 4095) / 4096 * 4096;
     r->alignment = 1024;
     r->memoryTypeBits = 0x2;                            // device-local only: images cannot be mapped
 }
@@ -259,7 +284,7 @@ static VKAPI_ATTR VkResult VKAPI_CALL mock_BindBufferMemory(VkDevice, VkBuffer b
 }
 static VKAPI_ATTR VkResult VKAPI_CALL mock_BindImageMemory(VkDevice, VkImage i, VkDeviceMemory m, VkDeviceSize offset)
 {
-    if (offset % 1024 || offset + i->pitch * i->h > m->size) MOCK_FAIL("vkBindImageMemory: bad offset / size");
+    if (offset % 1024 || offset + i->layer_stride() * i->layers > m->size) MOCK_FAIL("vkBindImageMemory: bad offset / size");
     if (m->type != 1) MOCK_FAIL("vkBindImageMemory: images live in device-local memory");
     i->mem = m; i->offset = offset;
     return VK_SUCCESS;
@@ -365,7 +390,7 @@ static VKAPI_ATTR void VKAPI_CALL mock_CmdPipelineBarrier(VkCommandBuffer cb, Vk
         for (const auto& b : copy) {
             if (b.oldLayout != VK_IMAGE_LAYOUT_UNDEFINED && b.oldLayout != b.image->layout)
                 MOCK_FAIL("image barrier: oldLayout %d but the image is in layout %d", (int)b.oldLayout, (int)b.image->layout);
-            if (b.oldLayout == VK_IMAGE_LAYOUT_UNDEFINED && b.image->mem) memset(b.image->mem->map + b.image->offset, 0xEE, b.image->pitch * b.image->h);   // contents discarded
+            if (b.oldLayout == VK_IMAGE_LAYOUT_UNDEFINED && b.image->mem) memset(b.image->mem->map + b.image->offset, 0xEE, b.image->layer_stride() * b.image->layers);   // contents discarded
             b.image->layout = b.newLayout;
         }
     });
@@ -374,9 +399,10 @@ static void check_region(const VkBufferImageCopy& r, const VkBuffer_T* b, const 
 {
     if (r.imageOffset.x || r.imageOffset.y || r.imageOffset.z || r.imageExtent.width != i->w || r.imageExtent.height != i->h || r.imageExtent.depth != 1)
         MOCK_FAIL("%s: only whole-image regions are modelled", who);
-    if (r.imageSubresource.aspectMask != VK_IMAGE_ASPECT_COLOR_BIT || r.imageSubresource.layerCount != 1) MOCK_FAIL("%s: bad subresource", who);
+    if (r.imageSubresource.aspectMask != VK_IMAGE_ASPECT_COLOR_BIT || r.imageSubresource.layerCount < 1 || r.imageSubresource.mipLevel != 0 ||
+        r.imageSubresource.baseArrayLayer + r.imageSubresource.layerCount > i->layers) MOCK_FAIL("%s: bad subresource", who);
     const size_t row = (r.bufferRowLength ? r.bufferRowLength : i->w) * (size_t)i->texel;
-    if (r.bufferOffset + row * i->h > b->size) MOCK_FAIL("%s: the region does not fit the buffer (%zu > %llu)", who, (size_t)r.bufferOffset + row * i->h, (unsigned long long)b->size);
+    if (r.bufferOffset + row * i->h * r.imageSubresource.layerCount > b->size) MOCK_FAIL("%s: the region does not fit the buffer (%zu > %llu)", who, (size_t)r.bufferOffset + row * i->h, (unsigned long long)b->size);
     if (!b->mem || !i->mem) MOCK_FAIL("%s: unbound resource", who);
 }
 static VKAPI_ATTR void VKAPI_CALL mock_CmdCopyImageToBuffer(VkCommandBuffer cb, VkImage src, VkImageLayout layout, VkBuffer dst, uint32_t n, const VkBufferImageCopy* regions)
@@ -386,10 +412,11 @@ static VKAPI_ATTR void VKAPI_CALL mock_CmdCopyImageToBuffer(VkCommandBuffer cb, 
     const VkBufferImageCopy r = regions[0];
     cb->cmds.push_back([=] {
         check_region(r, dst, src, "vkCmdCopyImageToBuffer");
-        if (src->layout != layout || layout != VK_IMAGE_LAYOUT_TRANSFER_SRC_OPTIMAL) MOCK_FAIL("vkCmdCopyImageToBuffer: image is in layout %d, command says %d", (int)src->layout, (int)layout);
+        if (src->layout != layout || (layout != VK_IMAGE_LAYOUT_TRANSFER_SRC_OPTIMAL && layout != VK_IMAGE_LAYOUT_GENERAL)) MOCK_FAIL("vkCmdCopyImageToBuffer: image is in layout %d, command says %d", (int)src->layout, (int)layout);
         const size_t row = (r.bufferRowLength ? r.bufferRowLength : src->w) * (size_t)src->texel;
-        for (uint32_t y = 0; y < src->h; ++y)
-            memcpy(dst->mem->map + dst->offset + r.bufferOffset + y * row, src->mem->map + src->offset + y * src->pitch, (size_t)src->w * src->texel);
+        for (uint32_t l = 0; l < r.imageSubresource.layerCount; ++l)
+            for (uint32_t y = 0; y < src->h; ++y)
+                memcpy(dst->mem->map + dst->offset + r.bufferOffset + ((size_t)l * src->h + y) * row, src->row(r.imageSubresource.baseArrayLayer + l, y), (size_t)src->w * src->texel);
     });
 }
 static VKAPI_ATTR void VKAPI_CALL mock_CmdCopyBufferToImage(VkCommandBuffer cb, VkBuffer src, VkImage dst, VkImageLayout layout, uint32_t n, const VkBufferImageCopy* regions)
@@ -399,10 +426,11 @@ static VKAPI_ATTR void VKAPI_CALL mock_CmdCopyBufferToImage(VkCommandBuffer cb, 
     const VkBufferImageCopy r = regions[0];
     cb->cmds.push_back([=] {
         check_region(r, src, dst, "vkCmdCopyBufferToImage");
-        if (dst->layout != layout || layout != VK_IMAGE_LAYOUT_TRANSFER_DST_OPTIMAL) MOCK_FAIL("vkCmdCopyBufferToImage: image is in layout %d, command says %d", (int)dst->layout, (int)layout);
+        if (dst->layout != layout || (layout != VK_IMAGE_LAYOUT_TRANSFER_DST_OPTIMAL && layout != VK_IMAGE_LAYOUT_GENERAL)) MOCK_FAIL("vkCmdCopyBufferToImage: image is in layout %d, command says %d", (int)dst->layout, (int)layout);
         const size_t row = (r.bufferRowLength ? r.bufferRowLength : dst->w) * (size_t)dst->texel;
-        for (uint32_t y = 0; y < dst->h; ++y)
-            memcpy(dst->mem->map + dst->offset + y * dst->pitch, src->mem->map + src->offset + r.bufferOffset + y * row, (size_t)dst->w * dst->texel);
+        for (uint32_t l = 0; l < r.imageSubresource.layerCount; ++l)
+            for (uint32_t y = 0; y < dst->h; ++y)
+                memcpy(dst->row(r.imageSubresource.baseArrayLayer + l, y), src->mem->map + src->offset + r.bufferOffset + ((size_t)l * dst->h + y) * row, (size_t)dst->w * dst->texel);
     });
 }
 static VKAPI_ATTR VkResult VKAPI_CALL mock_QueueSubmit(VkQueue, uint32_t n, const VkSubmitInfo* submits, VkFence fence)
@@ -442,6 +470,235 @@ static VKAPI_ATTR VkResult VKAPI_CALL mock_QueueSubmit(VkQueue, uint32_t n, cons
     return VK_SUCCESS;
 }
 
+
+// ---- compute: pipelines whose "SPIR-V" names a shader of oracle/_ref/libref.so -----------------------------------------------
+struct RefBinding { void* data; int width, height, layers, format; };
+typedef int (*ref_dispatch_fn)(const char*, int, int, int, int, int, int, const void*, int, int, int, const RefBinding*, int);
+static ref_dispatch_fn ref_dispatch()
+{
+    static ref_dispatch_fn fn = nullptr;
+    if (!fn) {
+        const char* path = getenv("VKMOCK_LIBREF");
+        void* lib = path ? dlopen(path, RTLD_NOW | RTLD_LOCAL) : nullptr;
+        if (!lib) MOCK_FAIL("compute needs VKMOCK_LIBREF=<oracle/_ref/libref.so> (%s)", path ? dlerror() : "not set");
+        fn = (ref_dispatch_fn)dlsym(lib, "ref_dispatch");
+        if (!fn) MOCK_FAIL("libref.so has no ref_dispatch");
+    }
+    return fn;
+}
+static int shim_format(VkFormat f)      // oracle/ref.py: F_R32F .. F_R16F
+{
+    switch (f) {
+    case VK_FORMAT_R32_SFLOAT: return 1; case VK_FORMAT_R32G32_SFLOAT: return 2; case VK_FORMAT_R8G8B8A8_UNORM: return 3;
+    case VK_FORMAT_B8G8R8A8_UNORM: return 4; case VK_FORMAT_R16G16_SFLOAT: return 5; case VK_FORMAT_R8_UNORM: return 6;
+    case VK_FORMAT_R16G16B16A16_SFLOAT: return 7; case VK_FORMAT_R32G32B32A32_SFLOAT: return 8; case VK_FORMAT_R16_SFLOAT: return 9;
+    default: return 0;
+    }
+}
+static VKAPI_ATTR VkResult VKAPI_CALL mock_CreateImageView(VkDevice, const VkImageViewCreateInfo* ci, const VkAllocationCallbacks*, VkImageView* out)
+{
+    if (!ci || ci->sType != VK_STRUCTURE_TYPE_IMAGE_VIEW_CREATE_INFO) MOCK_FAIL("vkCreateImageView: bad create info");
+    const VkImageSubresourceRange& r = ci->subresourceRange;
+    if (r.aspectMask != VK_IMAGE_ASPECT_COLOR_BIT || r.baseMipLevel != 0 || r.levelCount != 1 || r.baseArrayLayer + r.layerCount > ci->image->layers)
+        MOCK_FAIL("vkCreateImageView: bad subresource range");
+    if (ci->viewType == VK_IMAGE_VIEW_TYPE_2D && r.layerCount != 1) MOCK_FAIL("vkCreateImageView: a 2D view has one layer");
+    if (ci->viewType != VK_IMAGE_VIEW_TYPE_2D && ci->viewType != VK_IMAGE_VIEW_TYPE_2D_ARRAY) MOCK_FAIL("vkCreateImageView: view type not modelled");
+    if (texel_size(ci->format) != ci->image->texel) MOCK_FAIL("vkCreateImageView: view format is not size-compatible with the image");
+    *out = new VkImageView_T{ci->image, ci->viewType, ci->format, r.baseArrayLayer, r.layerCount};
+    return VK_SUCCESS;
+}
+static VKAPI_ATTR void VKAPI_CALL mock_DestroyImageView(VkDevice, VkImageView v, const VkAllocationCallbacks*) { delete v; }
+static VKAPI_ATTR VkResult VKAPI_CALL mock_CreateSampler(VkDevice, const VkSamplerCreateInfo* ci, const VkAllocationCallbacks*, VkSampler* out)
+{
+    *out = new VkSampler_T{ci->magFilter, ci->minFilter, ci->addressModeU, ci->addressModeV, ci->unnormalizedCoordinates};
+    return VK_SUCCESS;
+}
+static VKAPI_ATTR void VKAPI_CALL mock_DestroySampler(VkDevice, VkSampler s, const VkAllocationCallbacks*) { delete s; }
+static VKAPI_ATTR VkResult VKAPI_CALL mock_CreateShaderModule(VkDevice, const VkShaderModuleCreateInfo* ci, const VkAllocationCallbacks*, VkShaderModule* out)
+{
+    static const char tag[] = "VKMOCK-SHADER:";
+    if (!ci || ci->codeSize % 4 || ci->codeSize < sizeof(tag)) MOCK_FAIL("vkCreateShaderModule: bad code size");
+    if (ci->pCode[0] == 0x07230203u) MOCK_FAIL("vkCreateShaderModule: this is real SPIR-V; the mock only runs 'VKMOCK-SHADER:<name>' stand-ins");
+    std::string text((const char*)ci->pCode, ci->codeSize);
+    if (text.compare(0, sizeof(tag) - 1, tag) != 0) MOCK_FAIL("vkCreateShaderModule: neither SPIR-V nor a mock shader");
+    text = text.substr(sizeof(tag) - 1);
+    text = text.substr(0, text.find_first_of("\n \0", 0, 3));
+    *out = new VkShaderModule_T{text};
+    return VK_SUCCESS;
+}
+static VKAPI_ATTR void VKAPI_CALL mock_DestroyShaderModule(VkDevice, VkShaderModule m, const VkAllocationCallbacks*) { delete m; }
+static VKAPI_ATTR VkResult VKAPI_CALL mock_CreateDescriptorSetLayout(VkDevice, const VkDescriptorSetLayoutCreateInfo* ci, const VkAllocationCallbacks*, VkDescriptorSetLayout* out)
+{
+    auto* l = new VkDescriptorSetLayout_T();
+    for (uint32_t i = 0; i < ci->bindingCount; ++i) {
+        const VkDescriptorSetLayoutBinding& b = ci->pBindings[i];
+        if (b.descriptorCount != 1 || !(b.stageFlags & VK_SHADER_STAGE_COMPUTE_BIT)) MOCK_FAIL("vkCreateDescriptorSetLayout: binding %u: one compute-visible descriptor expected", b.binding);
+        if (b.descriptorType != VK_DESCRIPTOR_TYPE_STORAGE_IMAGE && b.descriptorType != VK_DESCRIPTOR_TYPE_COMBINED_IMAGE_SAMPLER) MOCK_FAIL("descriptor type not modelled");
+        l->bindings[b.binding] = b.descriptorType;
+    }
+    *out = l;
+    return VK_SUCCESS;
+}
+static VKAPI_ATTR void VKAPI_CALL mock_DestroyDescriptorSetLayout(VkDevice, VkDescriptorSetLayout l, const VkAllocationCallbacks*) { delete l; }
+static VKAPI_ATTR VkResult VKAPI_CALL mock_CreatePipelineLayout(VkDevice, const VkPipelineLayoutCreateInfo* ci, const VkAllocationCallbacks*, VkPipelineLayout* out)
+{
+    auto* l = new VkPipelineLayout_T();
+    for (uint32_t i = 0; i < ci->setLayoutCount; ++i) l->sets.push_back(ci->pSetLayouts[i]);
+    l->push_size = 0;
+    for (uint32_t i = 0; i < ci->pushConstantRangeCount; ++i) {
+        if (ci->pPushConstantRanges[i].offset != 0 || !(ci->pPushConstantRanges[i].stageFlags & VK_SHADER_STAGE_COMPUTE_BIT)) MOCK_FAIL("push constant range not modelled");
+        l->push_size = ci->pPushConstantRanges[i].size;
+    }
+    if (l->push_size > 256) MOCK_FAIL("push constants larger than 256 bytes");
+    *out = l;
+    return VK_SUCCESS;
+}
+static VKAPI_ATTR void VKAPI_CALL mock_DestroyPipelineLayout(VkDevice, VkPipelineLayout l, const VkAllocationCallbacks*) { delete l; }
+static VKAPI_ATTR VkResult VKAPI_CALL mock_CreateComputePipelines(VkDevice, VkPipelineCache, uint32_t n, const VkComputePipelineCreateInfo* cis, const VkAllocationCallbacks*, VkPipeline* out)
+{
+    for (uint32_t i = 0; i < n; ++i) {
+        const VkPipelineShaderStageCreateInfo& st = cis[i].stage;
+        if (st.stage != VK_SHADER_STAGE_COMPUTE_BIT || strcmp(st.pName, "main")) MOCK_FAIL("vkCreateComputePipelines: compute stage 'main' expected");
+        auto* p = new VkPipeline_T{st.module->name, {}, cis[i].layout};
+        if (st.pSpecializationInfo)
+            for (uint32_t e = 0; e < st.pSpecializationInfo->mapEntryCount; ++e) {
+                const VkSpecializationMapEntry& m = st.pSpecializationInfo->pMapEntries[e];
+                if (m.size != 4 || m.offset + 4 > st.pSpecializationInfo->dataSize) MOCK_FAIL("specialisation constants are 32-bit here");
+                int32_t v; memcpy(&v, (const char*)st.pSpecializationInfo->pData + m.offset, 4);
+                p->spec[m.constantID] = v;
+            }
+        out[i] = p;
+    }
+    return VK_SUCCESS;
+}
+static VKAPI_ATTR void VKAPI_CALL mock_DestroyPipeline(VkDevice, VkPipeline p, const VkAllocationCallbacks*) { delete p; }
+static VKAPI_ATTR VkResult VKAPI_CALL mock_CreateDescriptorPool(VkDevice, const VkDescriptorPoolCreateInfo*, const VkAllocationCallbacks*, VkDescriptorPool* out) { *out = new VkDescriptorPool_T{0}; return VK_SUCCESS; }
+static VKAPI_ATTR void VKAPI_CALL mock_DestroyDescriptorPool(VkDevice, VkDescriptorPool p, const VkAllocationCallbacks*) { delete p; }
+static VKAPI_ATTR VkResult VKAPI_CALL mock_AllocateDescriptorSets(VkDevice, const VkDescriptorSetAllocateInfo* ai, VkDescriptorSet* out)
+{
+    for (uint32_t i = 0; i < ai->descriptorSetCount; ++i) out[i] = new VkDescriptorSet_T{ai->pSetLayouts[i], {}};     // (leaked with the pool: test process)
+    return VK_SUCCESS;
+}
+static VKAPI_ATTR void VKAPI_CALL mock_UpdateDescriptorSets(VkDevice, uint32_t n, const VkWriteDescriptorSet* writes, uint32_t ncopies, const VkCopyDescriptorSet*)
+{
+    if (ncopies) MOCK_FAIL("vkUpdateDescriptorSets: copies not modelled");
+    for (uint32_t i = 0; i < n; ++i) {
+        const VkWriteDescriptorSet& w = writes[i];
+        if (w.descriptorCount != 1 || w.dstArrayElement != 0 || !w.pImageInfo) MOCK_FAIL("vkUpdateDescriptorSets: one image descriptor per write expected");
+        auto it = w.dstSet->layout->bindings.find(w.dstBinding);
+        if (it == w.dstSet->layout->bindings.end()) MOCK_FAIL("vkUpdateDescriptorSets: binding %u is not in the set layout", w.dstBinding);
+        if (it->second != w.descriptorType) MOCK_FAIL("vkUpdateDescriptorSets: binding %u: descriptor type %d, layout says %d", w.dstBinding, (int)w.descriptorType, (int)it->second);
+        if (w.descriptorType == VK_DESCRIPTOR_TYPE_COMBINED_IMAGE_SAMPLER && !w.pImageInfo->sampler) MOCK_FAIL("binding %u: combined image sampler without a sampler", w.dstBinding);
+        w.dstSet->bound[w.dstBinding] = Descriptor{w.descriptorType, w.pImageInfo->imageView, w.pImageInfo->sampler, w.pImageInfo->imageLayout};
+    }
+}
+static VKAPI_ATTR void VKAPI_CALL mock_CmdBindPipeline(VkCommandBuffer cb, VkPipelineBindPoint bp, VkPipeline p)
+{
+    if (bp != VK_PIPELINE_BIND_POINT_COMPUTE) MOCK_FAIL("only compute pipelines");
+    cb->pipeline = p;
+}
+static VKAPI_ATTR void VKAPI_CALL mock_CmdBindDescriptorSets(VkCommandBuffer cb, VkPipelineBindPoint bp, VkPipelineLayout, uint32_t first, uint32_t n, const VkDescriptorSet* sets, uint32_t ndyn, const uint32_t*)
+{
+    if (bp != VK_PIPELINE_BIND_POINT_COMPUTE || first != 0 || n != 1 || ndyn) MOCK_FAIL("vkCmdBindDescriptorSets: one compute set at index 0 expected");
+    cb->set = sets[0];
+}
+static VKAPI_ATTR void VKAPI_CALL mock_CmdPushConstants(VkCommandBuffer cb, VkPipelineLayout layout, VkShaderStageFlags stages, uint32_t offset, uint32_t size, const void* data)
+{
+    if (!(stages & VK_SHADER_STAGE_COMPUTE_BIT) || offset + size > layout->push_size) MOCK_FAIL("vkCmdPushConstants: outside the layout's range (%u + %u > %u)", offset, size, layout->push_size);
+    if (cb->push.size() < offset + size) cb->push.resize(offset + size);
+    memcpy(cb->push.data() + offset, data, size);
+}
+static VKAPI_ATTR void VKAPI_CALL mock_CmdDispatch(VkCommandBuffer cb, uint32_t gx, uint32_t gy, uint32_t gz)
+{
+    if (!cb->recording || !cb->pipeline || !cb->set || gz != 1) MOCK_FAIL("vkCmdDispatch: needs a bound pipeline and descriptor set, z = 1");
+    VkPipeline_T* pipe = cb->pipeline;
+    VkDescriptorSet_T* set = cb->set;
+    if (pipe->layout->sets.size() != 1 || pipe->layout->sets[0] != set->layout) MOCK_FAIL("vkCmdDispatch: the bound set's layout is not the pipeline layout's");
+    std::vector<unsigned char> push = cb->push;
+    if (push.size() < pipe->layout->push_size) MOCK_FAIL("vkCmdDispatch: %zu bytes of push constants pushed, the layout declares %u", push.size(), pipe->layout->push_size);
+    cb->cmds.push_back([=] {
+        auto spec = [&](uint32_t id) { auto it = pipe->spec.find(id); if (it == pipe->spec.end()) MOCK_FAIL("shader %s: specialisation constant %u not set", pipe->shader.c_str(), id); return (int)it->second; };
+        std::string name = pipe->shader;
+        int k0, k1, k2 = 0, W = 0, H = 0, radius = 0;
+        const bool acc = name.rfind("accumulator", 0) == 0, conv = name == "formatConverter";
+        if (acc || conv) { k0 = spec(0); k1 = spec(1); }
+        else {
+            W = spec(0); H = spec(1); k0 = spec(2); k1 = spec(3);
+            if (name.rfind("bmfr", 0) == 0) k2 = spec(4);
+            if (name == "bfrBlender") radius = spec(4);
+            if ((name == "bmfrPre" || name == "bmfrPost") && pipe->spec.count(5) && pipe->spec.at(5)) name += pipe->spec.at(5) == 1 ? "_w1" : "_w2";
+        }
+        RefBinding arr[32];
+        memset(arr, 0, sizeof arr);
+        std::vector<std::vector<char>> tight(32);
+        int nb = 0;
+        for (auto& kv : set->layout->bindings) {
+            const uint32_t b = kv.first;
+            if (b >= 32) MOCK_FAIL("binding %u too large", b);
+            auto it = set->bound.find(b);
+            if (it == set->bound.end()) MOCK_FAIL("shader %s: binding %u was never written", name.c_str(), b);
+            const Descriptor& d = it->second;
+            VkImage_T* img = d.view->image;
+            if (img->layout != VK_IMAGE_LAYOUT_GENERAL || d.layout != VK_IMAGE_LAYOUT_GENERAL) MOCK_FAIL("shader %s: binding %u: image must be in GENERAL layout", name.c_str(), b);
+            if (d.type == VK_DESCRIPTOR_TYPE_STORAGE_IMAGE && !(img->usage & VK_IMAGE_USAGE_STORAGE_BIT)) MOCK_FAIL("binding %u: image lacks STORAGE usage", b);
+            if (d.type == VK_DESCRIPTOR_TYPE_COMBINED_IMAGE_SAMPLER) {
+                if (!(img->usage & VK_IMAGE_USAGE_SAMPLED_BIT)) MOCK_FAIL("binding %u: image lacks SAMPLED usage", b);
+                // vsg::Sampler defaults (external/vsg/include/vsg/state/Sampler.h:29-43), which is what the shim's texture() implements
+                if (d.sampler->mag != VK_FILTER_LINEAR || d.sampler->min != VK_FILTER_LINEAR || d.sampler->u != VK_SAMPLER_ADDRESS_MODE_REPEAT ||
+                    d.sampler->v != VK_SAMPLER_ADDRESS_MODE_REPEAT || d.sampler->unnormalized) MOCK_FAIL("binding %u: sampler is not LINEAR / REPEAT / normalised", b);
+            }
+            const size_t row = (size_t)img->w * img->texel;
+            tight[b].resize(row * img->h * d.view->layer_count);
+            for (uint32_t l = 0; l < d.view->layer_count; ++l)
+                for (uint32_t y = 0; y < img->h; ++y) memcpy(tight[b].data() + ((size_t)l * img->h + y) * row, img->row(d.view->base_layer + l, y), row);
+            arr[b] = RefBinding{tight[b].data(), (int)img->w, (int)img->h, (int)d.view->layer_count, shim_format(d.view->format)};
+            if ((int)b + 1 > nb) nb = (int)b + 1;
+            if (acc && b == 1) { W = (int)img->w; H = (int)img->h; }
+            if (conv && b == 0) { W = (int)img->w; H = (int)img->h; }
+        }
+        const int rc = ref_dispatch()(name.c_str(), k0, k1, k2, W, H, radius, push.empty() ? nullptr : push.data(), (int)pipe->layout->push_size, (int)gx, (int)gy, arr, nb);
+        if (rc) MOCK_FAIL("shader %s with key (%d, %d, %d) is not in libref.so (rc %d)", name.c_str(), k0, k1, k2, rc);
+        for (auto& kv : set->bound) {                 // storage images may have been written
+            const Descriptor& d = kv.second;
+            if (d.type != VK_DESCRIPTOR_TYPE_STORAGE_IMAGE) continue;
+            VkImage_T* img = d.view->image;
+            const size_t row = (size_t)img->w * img->texel;
+            for (uint32_t l = 0; l < d.view->layer_count; ++l)
+                for (uint32_t y = 0; y < img->h; ++y) memcpy(img->row(d.view->base_layer + l, y), tight[kv.first].data() + ((size_t)l * img->h + y) * row, row);
+        }
+    });
+}
+static VKAPI_ATTR void VKAPI_CALL mock_CmdCopyImage(VkCommandBuffer cb, VkImage src, VkImageLayout sl, VkImage dst, VkImageLayout dl, uint32_t n, const VkImageCopy* regions)
+{
+    if (!cb->recording || n != 1) MOCK_FAIL("vkCmdCopyImage: not recording / one region expected");
+    if (!(src->usage & VK_IMAGE_USAGE_TRANSFER_SRC_BIT) || !(dst->usage & VK_IMAGE_USAGE_TRANSFER_DST_BIT)) MOCK_FAIL("vkCmdCopyImage: missing TRANSFER usage");
+    const VkImageCopy r = regions[0];
+    cb->cmds.push_back([=] {
+        if (src->texel != dst->texel) MOCK_FAIL("vkCmdCopyImage: formats are not size-compatible");
+        if (src->layout != sl || dst->layout != dl) MOCK_FAIL("vkCmdCopyImage: layouts (%d, %d), command says (%d, %d)", (int)src->layout, (int)dst->layout, (int)sl, (int)dl);
+        if ((sl != VK_IMAGE_LAYOUT_TRANSFER_SRC_OPTIMAL && sl != VK_IMAGE_LAYOUT_GENERAL) || (dl != VK_IMAGE_LAYOUT_TRANSFER_DST_OPTIMAL && dl != VK_IMAGE_LAYOUT_GENERAL)) MOCK_FAIL("vkCmdCopyImage: bad layouts");
+        if (r.extent.width != src->w || r.extent.height != src->h || r.extent.width != dst->w || r.extent.height != dst->h || r.srcOffset.x || r.srcOffset.y || r.dstOffset.x || r.dstOffset.y)
+            MOCK_FAIL("vkCmdCopyImage: only whole-image copies are modelled");
+        if (r.srcSubresource.layerCount != r.dstSubresource.layerCount || r.srcSubresource.baseArrayLayer + r.srcSubresource.layerCount > src->layers ||
+            r.dstSubresource.baseArrayLayer + r.dstSubresource.layerCount > dst->layers) MOCK_FAIL("vkCmdCopyImage: bad layers");
+        for (uint32_t l = 0; l < r.srcSubresource.layerCount; ++l)
+            for (uint32_t y = 0; y < src->h; ++y) memcpy(dst->row(r.dstSubresource.baseArrayLayer + l, y), src->row(r.srcSubresource.baseArrayLayer + l, y), (size_t)src->w * src->texel);
+    });
+}
+static VKAPI_ATTR void VKAPI_CALL mock_CmdClearColorImage(VkCommandBuffer cb, VkImage img, VkImageLayout layout, const VkClearColorValue* color, uint32_t n, const VkImageSubresourceRange* ranges)
+{
+    if (!cb->recording || n != 1) MOCK_FAIL("vkCmdClearColorImage: not recording / one range expected");
+    const VkClearColorValue c = *color;
+    const VkImageSubresourceRange r = ranges[0];
+    cb->cmds.push_back([=] {
+        if (img->layout != layout || (layout != VK_IMAGE_LAYOUT_GENERAL && layout != VK_IMAGE_LAYOUT_TRANSFER_DST_OPTIMAL)) MOCK_FAIL("vkCmdClearColorImage: bad layout");
+        if (c.uint32[0] || c.uint32[1] || c.uint32[2] || c.uint32[3]) MOCK_FAIL("vkCmdClearColorImage: only clears to zero are modelled");
+        const uint32_t layers = r.layerCount == VK_REMAINING_ARRAY_LAYERS ? img->layers - r.baseArrayLayer : r.layerCount;
+        for (uint32_t l = 0; l < layers; ++l)
+            for (uint32_t y = 0; y < img->h; ++y) memset(img->row(r.baseArrayLayer + l, y), 0, (size_t)img->w * img->texel);
+    });
+}
+
 // ---- dispatch -------------------------------------------------------------------------------------------------------
 static VKAPI_ATTR PFN_vkVoidFunction VKAPI_CALL mock_GetDeviceProcAddr(VkDevice d, const char* name);
 extern "C" __attribute__((visibility("default"))) VKAPI_ATTR PFN_vkVoidFunction VKAPI_CALL vkGetInstanceProcAddr(VkInstance instance, const char* name);
@@ -458,6 +715,11 @@ static const Entry kEntries[] = {
     E(CreateSemaphore, 0), E(DestroySemaphore, 0), E(GetSemaphoreFdKHR, 2), E(SignalSemaphore, 3), E(WaitSemaphores, 3), E(GetSemaphoreCounterValue, 3),
     E(CreateCommandPool, 0), E(DestroyCommandPool, 0), E(AllocateCommandBuffers, 0), E(FreeCommandBuffers, 0), E(BeginCommandBuffer, 0), E(EndCommandBuffer, 0),
     E(CmdPipelineBarrier, 0), E(CmdCopyImageToBuffer, 0), E(CmdCopyBufferToImage, 0),
+    E(CreateImageView, 0), E(DestroyImageView, 0), E(CreateSampler, 0), E(DestroySampler, 0), E(CreateShaderModule, 0), E(DestroyShaderModule, 0),
+    E(CreateDescriptorSetLayout, 0), E(DestroyDescriptorSetLayout, 0), E(CreatePipelineLayout, 0), E(DestroyPipelineLayout, 0),
+    E(CreateComputePipelines, 0), E(DestroyPipeline, 0), E(CreateDescriptorPool, 0), E(DestroyDescriptorPool, 0), E(AllocateDescriptorSets, 0),
+    E(UpdateDescriptorSets, 0), E(CmdBindPipeline, 0), E(CmdBindDescriptorSets, 0), E(CmdPushConstants, 0), E(CmdDispatch, 0), E(CmdCopyImage, 0),
+    E(CmdClearColorImage, 0),
 };
 #undef E
 
