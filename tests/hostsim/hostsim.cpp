@@ -154,6 +154,54 @@ void launch(dim3 grid, dim3 block, const std::function<void()>& body)
 
 }  // namespace hostsim
 
+// ---- device memory ---------------------------------------------------------------------------------------------------
+// Default: aligned_alloc, like cudaMalloc's 256-byte alignment.  Guard modes (environment HOSTSIM_GUARD, read once):
+//   end    the allocation (rounded up to 16 bytes, the widest vector access) ends at an inaccessible page
+//   start  the allocation starts on a page that follows an inaccessible one
+// so out-of-bounds accesses of the kernels fault (SIGSEGV) instead of reading a neighbour's bytes -- the emulator's
+// stand-in for compute-sanitizer memcheck, used with the size fuzz.
+bool hostsim_is_external_mapping(const void* p);
+struct GuardedAllocation { void* region; size_t length; };
+static std::mutex g_alloc_mutex;
+static std::vector<std::pair<void*, GuardedAllocation>> g_guarded;
+static int guard_mode()
+{
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("HOSTSIM_GUARD");
+        mode = !e ? 0 : !strcmp(e, "end") ? 1 : !strcmp(e, "start") ? 2 : 0;
+    }
+    return mode;
+}
+
+cudaError_t cudaMalloc(void** p, size_t n)
+{
+    const int mode = guard_mode();
+    if (!mode) { *p = aligned_alloc(256, (n + 255) / 256 * 256); return *p ? cudaSuccess : cudaErrorInvalidValue; }
+    const size_t page = 4096, bytes = (n + 15) / 16 * 16, body = (bytes + page - 1) / page * page, length = body + 2 * page;
+    char* region = (char*)mmap(nullptr, length, PROT_NONE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (region == MAP_FAILED) return cudaErrorInvalidValue;
+    if (mprotect(region + page, body, PROT_READ | PROT_WRITE) != 0) { munmap(region, length); return cudaErrorInvalidValue; }
+    *p = mode == 1 ? region + page + body - bytes : region + page;
+    std::lock_guard<std::mutex> lock(g_alloc_mutex);
+    g_guarded.push_back({*p, GuardedAllocation{region, length}});
+    return cudaSuccess;
+}
+
+cudaError_t cudaFree(void* p)
+{
+    if (!p || hostsim_is_external_mapping(p)) return cudaSuccess;
+    if (!guard_mode()) { free(p); return cudaSuccess; }
+    std::lock_guard<std::mutex> lock(g_alloc_mutex);
+    for (size_t i = 0; i < g_guarded.size(); ++i)
+        if (g_guarded[i].first == p) {
+            munmap(g_guarded[i].second.region, g_guarded[i].second.length);
+            g_guarded.erase(g_guarded.begin() + i);
+            return cudaSuccess;
+        }
+    return cudaErrorInvalidValue;
+}
+
 // ---- external memory / semaphores (the Vulkan side is tests/vkmock) -------------------------------------
 // Memory: the fd is a memfd of the allocation's size, mapped shared.  Semaphore: a memfd of one page that starts
 // with {magic, payload, timeline?}; both sides use atomics on the payload.

@@ -68,9 +68,10 @@ inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = nullptr; return cudaSuccess; }
 inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
-inline cudaError_t cudaMalloc(void** p, size_t n) { *p = aligned_alloc(256, (n + 255) / 256 * 256); return *p ? cudaSuccess : cudaErrorInvalidValue; }
-bool hostsim_is_external_mapping(const void* p);       // hostsim.cpp: pointers handed out by cudaExternalMemoryGetMappedBuffer
-inline cudaError_t cudaFree(void* p) { if (!hostsim_is_external_mapping(p)) free(p); return cudaSuccess; }
+// hostsim.cpp.  HOSTSIM_GUARD=end|start places every allocation against an inaccessible page (its end, 16-byte granular,
+// or its start): a kernel that reads or writes outside a plane faults instead of touching a neighbouring allocation.
+cudaError_t cudaMalloc(void** p, size_t n);
+cudaError_t cudaFree(void* p);
 inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
 inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return cudaSuccess; }
