@@ -174,14 +174,25 @@ static int guard_mode()
     return mode;
 }
 
+static long g_live_allocations = 0;
+// test hook (emulator library only): device allocations that have not been freed
+extern "C" __attribute__((visibility("default"))) long hostsim_live_allocations() { return __atomic_load_n(&g_live_allocations, __ATOMIC_SEQ_CST); }
+
 cudaError_t cudaMalloc(void** p, size_t n)
 {
     const int mode = guard_mode();
-    if (!mode) { *p = aligned_alloc(256, (n + 255) / 256 * 256); return *p ? cudaSuccess : cudaErrorInvalidValue; }
+    __atomic_fetch_add(&g_live_allocations, 1, __ATOMIC_SEQ_CST);
+    // fresh device memory is not zero: poison it, so that nothing can depend on an allocation it never initialised
+    if (!mode) {
+        *p = aligned_alloc(256, (n + 255) / 256 * 256);
+        if (*p) memset(*p, 0xCB, (n + 255) / 256 * 256);
+        return *p ? cudaSuccess : cudaErrorInvalidValue;
+    }
     const size_t page = 4096, bytes = (n + 15) / 16 * 16, body = (bytes + page - 1) / page * page, length = body + 2 * page;
     char* region = (char*)mmap(nullptr, length, PROT_NONE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
     if (region == MAP_FAILED) return cudaErrorInvalidValue;
     if (mprotect(region + page, body, PROT_READ | PROT_WRITE) != 0) { munmap(region, length); return cudaErrorInvalidValue; }
+    memset(region + page, 0xCB, body);
     *p = mode == 1 ? region + page + body - bytes : region + page;
     std::lock_guard<std::mutex> lock(g_alloc_mutex);
     g_guarded.push_back({*p, GuardedAllocation{region, length}});
@@ -191,6 +202,7 @@ cudaError_t cudaMalloc(void** p, size_t n)
 cudaError_t cudaFree(void* p)
 {
     if (!p || hostsim_is_external_mapping(p)) return cudaSuccess;
+    __atomic_fetch_sub(&g_live_allocations, 1, __ATOMIC_SEQ_CST);
     if (!guard_mode()) { free(p); return cudaSuccess; }
     std::lock_guard<std::mutex> lock(g_alloc_mutex);
     for (size_t i = 0; i < g_guarded.size(); ++i)

@@ -190,3 +190,34 @@ class TestHostBehaviour:
             np.testing.assert_array_equal(band.denoiser_final.download(), full.denoiser_final.download())
             np.testing.assert_array_equal(band.modules[0].denoised.download(), full.modules[0].denoised.download())
             np.testing.assert_array_equal(band.accumulation_buffer.motion.download(), full.accumulation_buffer.motion.download())
+
+
+def test_destroying_the_modules_frees_every_device_allocation():
+    """emulator-only: the emulator counts device allocations; after the pipelines of every wiring (incl. the debug images,
+    the per-frame tables, the side lanes) are destroyed none is left"""
+    import gc
+    import subprocess
+    from tests.conftest import HOSTSIM_DIR, HOSTSIM_LIB
+    from vulkanpbrt_b200 import DenoisePipeline, DenoisingBlockSize, DenoisingType, _capi, synth
+    subprocess.run(["make", "-C", str(HOSTSIM_DIR)], check=True, capture_output=True)
+    gc.collect()
+    saved = _capi._lib
+    lib = ctypes.CDLL(str(HOSTSIM_LIB))
+    lib.hostsim_live_allocations.restype = ctypes.c_long
+    _capi._lib = _capi.configure(lib)
+    try:
+        before = lib.hostsim_live_allocations()
+        for den, bs, taa in [(DenoisingType.BMFR, DenoisingBlockSize.X32, True), (DenoisingType.BFR, DenoisingBlockSize.X16, False),
+                             (DenoisingType.BFR, DenoisingBlockSize.X8X16X32, True), (DenoisingType.BMFR, DenoisingBlockSize.X8X16X32, True)]:
+            x3 = bs == DenoisingBlockSize.X8X16X32
+            pipe = DenoisePipeline(64, 64, den, bs, use_taa=taa, average_squared=x3, bmfr_debug_outputs=True)
+            for f in range(2):
+                pipe.run_frame(f, synth.render_frame(64, 64, f))
+            pipe.ctx.synchronize()
+            assert lib.hostsim_live_allocations() > before
+            del pipe
+            gc.collect()
+            assert lib.hostsim_live_allocations() == before
+    finally:
+        gc.collect()
+        _capi._lib = saved
