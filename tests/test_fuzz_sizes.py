@@ -57,3 +57,20 @@ def test_images_smaller_than_one_block_are_rejected(backend):
                 cls.create(w, h, 32, 32, g, acc.accumulated_illumination, acc.accumulation_buffer)
             assert e.value.code == _capi.ERR_INVALID_ARGUMENT and "smaller than one block" in str(e.value)
             cls.create(w, h, 16, 16, g, acc.accumulated_illumination, acc.accumulation_buffer)      # fine with a smaller block
+
+
+@pytest.mark.parametrize("backend", [backend_params()[0]], indirect=True)
+@pytest.mark.parametrize("den,block,start", [("bmfr", 32, 2**32 - 3), ("bmfr", 8, 2**31 - 2), ("bfr", 16, 2**32 - 3), ("bmfr", 16, 65534)])
+def test_frame_numbers_up_to_the_uint32_wrap(backend, oracle, den, block, start):
+    """frameNumber is a uint (PipelineStructs.hpp:12): the noise seed (bmfrGeneral.comp:115-116), the jitter phase, the
+    ping-pong layer and the per-frame table's frame + 1 all wrap with it; 2^32 - 1 is followed by frame 0 (no history)"""
+    from vulkanpbrt_b200 import synth
+    W, H = 64, 40
+    pipe, orc = make_pair(oracle, W, H, denoiser=den, block=block, use_taa=True)
+    for k in range(5):
+        f = (start + k) % 2**32
+        fr = synth.render_frame(W, H, k)
+        pipe.run_frame(f, fr)
+        pipe.ctx.synchronize()
+        orc.run_frame(f, fr)
+        assert_frame_equal(pipe, orc, f)

@@ -12,10 +12,11 @@ import numpy as np
 import pytest
 
 from tests.test_vk_interop import _vulkan_include
+from tests.util import second_moment_plane
 from vulkanpbrt_b200 import synth
 
 ROOT = Path(__file__).resolve().parents[1]
-SHADERS = ["accumulator_sep", "bmfrPre", "bmfrFit", "bmfrPost", "bfr", "taa"]
+SHADERS = ["accumulator_sep", "bmfrPre", "bmfrFit", "bmfrPost", "bfr", "bfrBlender", "taa"]
 
 
 @pytest.fixture(scope="module")
@@ -42,35 +43,43 @@ def built(tmp_path_factory):
     return mock, exe, spv
 
 
-def _compare(tmp, orc, block, W, H, f):
-    got = dict(final=np.fromfile(tmp / f"final_{f}.bgra", np.uint8).reshape(H, W, 4),
-               denoised=np.fromfile(tmp / f"denoised_{f}.rgba16f", np.uint16).reshape(2, H, W, 4),
-               motion=np.fromfile(tmp / f"motion_{f}.rg16f", np.uint16).reshape(H, W, 2),
-               spp=np.fromfile(tmp / f"spp_{f}.r8", np.uint8).reshape(H, W),
-               illum=np.fromfile(tmp / f"illum_{f}.rgba16f", np.uint16).reshape(H, W, 4))
-    want = dict(final=orc.final(), denoised=orc.denoised[block], motion=orc.motion, spp=orc.spp, illum=orc.illum)
-    for k in got:
-        np.testing.assert_array_equal(got[k], want[k], err_msg=f"{k}, frame {f}")
-
-
 @pytest.mark.parametrize("W,H,first,frames,den,block,taa", [(160, 128, 0, 3, "bmfr", 32, True), (168, 104, 7, 3, "bfr", 16, False),
-                                                            (136, 72, 7, 3, "bmfr", 8, True)])
+                                                            (136, 72, 7, 3, "bmfr", 8, True), (96, 72, 0, 3, "bfrx3", 32, True),
+                                                            (96, 72, 7, 2, "bmfrx3", 32, False)])
 def test_raw_vulkan_host_replays_the_reference_frame(tmp_path, oracle, built, W, H, first, frames, den, block, taa):
     mock, exe, spv = built
+    env = dict(os.environ, VK_ORACLE_LOADER=str(mock), VKMOCK_LIBREF=str(ROOT / "oracle" / "_ref" / "libref.so"))
+    x3 = den.endswith("x3")
     orc = oracle.OracleChain(W, H, den, block, use_taa=taa)
+    frames_data = []
     for f in range(first, first + frames):
         fr = synth.render_frame(W, H, f)
         base = tmp_path / f"frame_{f}"
         fr.depth.tofile(str(base) + ".depth"); fr.normal.tofile(str(base) + ".normal")
         fr.albedo.tofile(str(base) + ".albedo"); fr.illumination.tofile(str(base) + ".illum")
         np.concatenate([fr.camera.view, fr.camera.inv_view, fr.camera.proj, fr.camera.inv_proj]).astype(np.float32).tofile(str(base) + ".cam")
-    env = dict(os.environ, VK_ORACLE_LOADER=str(mock), VKMOCK_LIBREF=str(ROOT / "oracle" / "_ref" / "libref.so"))
+        if x3:
+            # a defined averageSquared plane for the blender, derived from the history the oracle holds
+            # BEFORE this frame -- so the oracle has to advance frame by frame while the files are written
+            sq = second_moment_plane(oracle, orc)
+            sq.tofile(str(base) + ".avgsq")
+            orc.average_squared[...] = sq
+        orc.run_frame(f, fr)
+        frames_data.append({k: np.copy(v) for k, v in dict(final=orc.final(), motion=orc.motion, spp=orc.spp, illum=orc.illum).items()}
+                           | {f"denoised{b}": orc.denoised[b].copy() for b in orc.blocks})
     r = subprocess.run([str(exe), str(spv), str(tmp_path), str(tmp_path), str(W), str(H), str(first), str(frames), den, str(block), "1" if taa else "0"],
                        capture_output=True, text=True, env=env, timeout=900)
     assert r.returncode == 0, r.stdout + r.stderr
-    for f in range(first, first + frames):
-        orc.run_frame(f, synth.render_frame(W, H, f))
-        _compare(tmp_path, orc, block, W, H, f)
+    for i, f in enumerate(range(first, first + frames)):
+        want = frames_data[i]
+        got = dict(final=np.fromfile(tmp_path / f"final_{f}.bgra", np.uint8).reshape(H, W, 4),
+                   motion=np.fromfile(tmp_path / f"motion_{f}.rg16f", np.uint16).reshape(H, W, 2),
+                   spp=np.fromfile(tmp_path / f"spp_{f}.r8", np.uint8).reshape(H, W),
+                   illum=np.fromfile(tmp_path / f"illum_{f}.rgba16f", np.uint16).reshape(H, W, 4))
+        for b in orc.blocks:
+            got[f"denoised{b}"] = np.fromfile(tmp_path / f"denoised{b}_{f}.rgba16f", np.uint16).reshape(2, H, W, 4)
+        for k in got:
+            np.testing.assert_array_equal(got[k], want[k], err_msg=f"{k}, frame {f}")
 
 
 def test_real_spirv_is_refused_by_the_mock(tmp_path, built):

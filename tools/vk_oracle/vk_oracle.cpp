@@ -8,16 +8,20 @@
 //                           denoisers/BMFR.cpp:56-133, BFR.cpp:33-80, Taa.cpp:21-60
 //   samplers                vsg::Sampler defaults (external/vsg/include/vsg/state/Sampler.h:29-43): LINEAR, REPEAT, normalised
 //   descriptor bindings     shaders/accumulator.comp:5-18, bmfrGeneral.comp:3-14 (BMFR.hpp:28-30), bfr.comp:5-14, taa.comp:8-11
-//   specialisation          Accumulator.cpp:21-24, BMFR.cpp:32-54, BFR.cpp:26-31, Taa.cpp:14-19
+//   specialisation          Accumulator.cpp:21-24, BMFR.cpp:32-54, BFR.cpp:26-31, BFRBlender.cpp:13-19, Taa.cpp:14-19
 //   push constants          Accumulator.hpp:28-33 + Accumulator.cpp:85-117 (separate matrices), PipelineStructs.hpp:6-13 +
 //                           VulkanPBRT.cpp:561-563, :591
-//   dispatch sizes / order  Accumulator.cpp:72-83, BMFR.cpp:203-230, BFR.cpp:128-138, Taa.cpp:99-107, VulkanPBRT.cpp:551-618
+//   dispatch sizes / order  Accumulator.cpp:72-83, BMFR.cpp:203-230, BFR.cpp:128-138, BFRBlender.cpp:80-90, Taa.cpp:99-107,
+//                           util/DenoiserUtils.cpp:8-130, VulkanPBRT.cpp:551-618
 //   end-of-frame copies     Taa.cpp:106 (final -> accumulation), AccumulationBuffer.cpp:72-244
 //
-//   vk_oracle <spv_dir> <frames_dir> <out_dir> <width> <height> <first_frame> <frames> <bmfr|bfr> <block> <taa 0|1>
-//     <spv_dir>/{accumulator_sep,bmfrPre,bmfrFit,bmfrPost,bfr,taa}.comp.spv      (README.md: how to build them with glslc)
+//   vk_oracle <spv_dir> <frames_dir> <out_dir> <width> <height> <first_frame> <frames> <bmfr|bfr|bmfrx3|bfrx3> <block> <taa 0|1>
+//     <spv_dir>/{accumulator_sep,bmfrPre,bmfrFit,bmfrPost,bfr,bfrBlender,taa}.comp.spv   (README.md: how to build them with glslc)
 //     <frames_dir>/frame_%d.{depth,normal,albedo,illum,cam}                      (same raw files as examples/cpp_frame_loop.cpp)
-//     -> <out_dir>/{final_%d.bgra, denoised_%d.rgba16f (2 layers), motion_%d.rg16f, spp_%d.r8, illum_%d.rgba16f}
+//     <frames_dir>/frame_%d.avgsq   optional rgba16f plane loaded into illuminationSquared before the denoisers: no shader ever
+//                                   writes that image (accumulator.comp:104), and the blender of the x3 wirings reads it
+//     -> <out_dir>/{final_%d.bgra, denoised<b>_%d.rgba16f (2 layers, per block size), motion_%d.rg16f, spp_%d.r8, illum_%d.rgba16f}
+//   x3 = DenoisingBlockSize::X8X16X32: three denoisers (b = 8, 16, 32) + BFRBlender (util/DenoiserUtils.cpp:48-70, :106-124)
 //   VK_ORACLE_LOADER: Vulkan loader to dlopen (default libvulkan.so.1).
 //
 // Status: neither machine of this project has a Vulkan loader, an ICD or glslc, so this program has never met a real
@@ -35,6 +39,7 @@
 #include <cstring>
 #include <fstream>
 #include <iostream>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -373,14 +378,15 @@ static VkBufferImageCopy whole(const Image& im, VkDeviceSize offset)
 int main(int argc, char** argv)
 {
     if (argc < 11) {
-        std::cerr << "usage: vk_oracle spv_dir frames_dir out_dir width height first_frame frames bmfr|bfr block taa\n";
+        std::cerr << "usage: vk_oracle spv_dir frames_dir out_dir width height first_frame frames bmfr|bfr|bmfrx3|bfrx3 block taa\n";
         return 2;
     }
     const std::string spv = argv[1], in = argv[2], out = argv[3];
     const uint32_t W = atoi(argv[4]), H = atoi(argv[5]);
     const int first = atoi(argv[6]), frames = atoi(argv[7]);
-    const bool bmfr = std::string(argv[8]) == "bmfr";
-    const uint32_t B = atoi(argv[9]);
+    const std::string kind = argv[8];
+    const bool bmfr = kind.rfind("bmfr", 0) == 0, x3 = kind.size() > 2 && kind.compare(kind.size() - 2, 2, "x3") == 0;
+    const std::vector<uint32_t> blocks = x3 ? std::vector<uint32_t>{8, 16, 32} : std::vector<uint32_t>{(uint32_t)atoi(argv[9])};
     const bool use_taa = atoi(argv[10]) != 0;
     try {
         Vk vk;
@@ -394,14 +400,28 @@ int main(int argc, char** argv)
               prev_depth = make_image(vk, VK_FORMAT_R32_SFLOAT, W, H), prev_normal = make_image(vk, VK_FORMAT_R32G32_SFLOAT, W, H),  // :277, :290
               motion = make_image(vk, VK_FORMAT_R16G16_SFLOAT, W, H),                                                              // :303
               prev_illu = make_image(vk, VK_FORMAT_R16G16B16A16_SFLOAT, W, H), prev_illu_sq = make_image(vk, VK_FORMAT_R16G16B16A16_SFLOAT, W, H);   // :316, :329
-        const uint32_t bx = W / B + 2, by = H / B + 2;                                                                             // BMFR.cpp:12-13, BFR.cpp:134
-        Image denoised = make_image(vk, VK_FORMAT_R16G16B16A16_SFLOAT, W, H, 2, true);                                             // BMFR.cpp:56-75
-        Image final_image = make_image(vk, VK_FORMAT_B8G8R8A8_UNORM, W, H);                                                        // BMFR.cpp:78-93
-        Image features = make_image(vk, VK_FORMAT_R16_SFLOAT, bx * B, by * B, 13, true);                                           // BMFR.cpp:96-113
-        Image weights = make_image(vk, VK_FORMAT_R32_SFLOAT, bx, by, 30, true);                                                    // BMFR.cpp:116-133
+        struct Denoiser {
+            uint32_t B, bx, by;
+            Image denoised, final_image, features, weights;
+            Stage stage;
+            VkPipeline pre = VK_NULL_HANDLE, fit = VK_NULL_HANDLE, post = VK_NULL_HANDLE, bfr = VK_NULL_HANDLE;
+        };
+        std::vector<std::unique_ptr<Denoiser>> dens;
+        for (uint32_t B : blocks) {
+            auto d = std::make_unique<Denoiser>();
+            d->B = B; d->bx = W / B + 2; d->by = H / B + 2;                                                                        // BMFR.cpp:12-13, BFR.cpp:134
+            d->denoised = make_image(vk, VK_FORMAT_R16G16B16A16_SFLOAT, W, H, 2, true);                                            // BMFR.cpp:56-75
+            d->final_image = make_image(vk, VK_FORMAT_B8G8R8A8_UNORM, W, H);                                                       // BMFR.cpp:78-93
+            d->features = make_image(vk, VK_FORMAT_R16_SFLOAT, d->bx * B, d->by * B, 13, true);                                    // BMFR.cpp:96-113
+            d->weights = make_image(vk, VK_FORMAT_R32_SFLOAT, d->bx, d->by, 30, true);                                             // BMFR.cpp:116-133
+            dens.push_back(std::move(d));
+        }
+        Image blend_final = make_image(vk, VK_FORMAT_B8G8R8A8_UNORM, W, H);                                                        // BFRBlender.cpp:21-37
         Image taa_final = make_image(vk, VK_FORMAT_B8G8R8A8_UNORM, W, H), taa_accumulation = make_image(vk, VK_FORMAT_R8G8B8A8_UNORM, W, H);   // Taa.cpp:42, :24
         std::vector<Image*> all = {&depth, &normal, &material, &albedo, &raw, &illum, &illum_sq, &spp, &prev_spp, &prev_depth, &prev_normal, &motion,
-                                   &prev_illu, &prev_illu_sq, &denoised, &final_image, &features, &weights, &taa_final, &taa_accumulation};
+                                   &prev_illu, &prev_illu_sq, &blend_final, &taa_final, &taa_accumulation};
+        for (auto& d : dens) { all.push_back(&d->denoised); all.push_back(&d->final_image); all.push_back(&d->features); all.push_back(&d->weights); }
+        const Image& denoiser_final = x3 ? blend_final : dens[0]->final_image;
 
         VkSamplerCreateInfo sci{};                            // vsg::Sampler::create() defaults
         sci.sType = VK_STRUCTURE_TYPE_SAMPLER_CREATE_INFO;
@@ -413,10 +433,10 @@ int main(int argc, char** argv)
         VkSampler sampler;
         vk_check(vk.CreateSampler(vk.device, &sci, nullptr, &sampler), "vkCreateSampler");
 
-        VkDescriptorPoolSize sizes[2] = {{VK_DESCRIPTOR_TYPE_STORAGE_IMAGE, 64}, {VK_DESCRIPTOR_TYPE_COMBINED_IMAGE_SAMPLER, 32}};
+        VkDescriptorPoolSize sizes[2] = {{VK_DESCRIPTOR_TYPE_STORAGE_IMAGE, 128}, {VK_DESCRIPTOR_TYPE_COMBINED_IMAGE_SAMPLER, 64}};
         VkDescriptorPoolCreateInfo dpi{};
         dpi.sType = VK_STRUCTURE_TYPE_DESCRIPTOR_POOL_CREATE_INFO;
-        dpi.maxSets = 8;
+        dpi.maxSets = 16;
         dpi.poolSizeCount = 2;
         dpi.pPoolSizes = sizes;
         VkDescriptorPool pool;
@@ -430,33 +450,44 @@ int main(int argc, char** argv)
                                                    {11, SI, &illum}, {12, CIS, &prev_illu_sq}, {13, SI, &illum_sq}}, sizeof(AccumulatorPush));
         const VkPipeline p_acc = add_pipeline(vk, acc, spv + "/accumulator_sep.comp.spv", {16, 16});                 // Accumulator.cpp:21-24, work size 16 x 16 (Accumulator.hpp:17)
         // bmfrGeneral.comp:3-14 / bfr.comp:5-14
-        std::vector<Binding> den_bindings = {{0, SI, &depth}, {1, SI, &normal}, {2, SI, &material}, {3, SI, &albedo}, {4, SI, &motion}, {5, SI, &spp},
-                                             {6, CIS, &denoised}, {7, SI, &final_image}, {8, CIS, &illum}, {9, SI, &denoised}};
-        if (bmfr) { den_bindings.push_back({10, SI, &features}); den_bindings.push_back({11, SI, &weights}); }
-        Stage den = make_stage(vk, pool, sampler, den_bindings, sizeof(RayTracingPush));
-        VkPipeline p_pre = VK_NULL_HANDLE, p_fit = VK_NULL_HANDLE, p_post = VK_NULL_HANDLE, p_bfr = VK_NULL_HANDLE;
-        if (bmfr) {
-            const int32_t T = B == 8 ? 64 : 256;                                                                      // DenoiserUtils.cpp:78-95 (fitting_kernel)
-            p_pre = add_pipeline(vk, den, spv + "/bmfrPre.comp.spv", {(int32_t)W, (int32_t)H, (int32_t)B, (int32_t)B, (int32_t)B});      // BMFR.cpp:32-38
-            p_fit = add_pipeline(vk, den, spv + "/bmfrFit.comp.spv", {(int32_t)W, (int32_t)H, T, 1, (int32_t)B});                         // :40-46
-            p_post = add_pipeline(vk, den, spv + "/bmfrPost.comp.spv", {(int32_t)W, (int32_t)H, (int32_t)B, (int32_t)B, (int32_t)B});    // :48-54
-        } else {
-            p_bfr = add_pipeline(vk, den, spv + "/bfr.comp.spv", {(int32_t)W, (int32_t)H, (int32_t)B, (int32_t)B});                       // BFR.cpp:26-31
+        for (auto& d : dens) {
+            const int32_t B = (int32_t)d->B;
+            std::vector<Binding> b = {{0, SI, &depth}, {1, SI, &normal}, {2, SI, &material}, {3, SI, &albedo}, {4, SI, &motion}, {5, SI, &spp},
+                                      {6, CIS, &d->denoised}, {7, SI, &d->final_image}, {8, CIS, &illum}, {9, SI, &d->denoised}};
+            if (bmfr) { b.push_back({10, SI, &d->features}); b.push_back({11, SI, &d->weights}); }
+            d->stage = make_stage(vk, pool, sampler, b, sizeof(RayTracingPush));
+            if (bmfr) {
+                const int32_t T = B == 8 ? 64 : 256;                                                                  // DenoiserUtils.cpp:78-95 (fitting_kernel)
+                d->pre = add_pipeline(vk, d->stage, spv + "/bmfrPre.comp.spv", {(int32_t)W, (int32_t)H, B, B, B});    // BMFR.cpp:32-38
+                d->fit = add_pipeline(vk, d->stage, spv + "/bmfrFit.comp.spv", {(int32_t)W, (int32_t)H, T, 1, B});    // :40-46
+                d->post = add_pipeline(vk, d->stage, spv + "/bmfrPost.comp.spv", {(int32_t)W, (int32_t)H, B, B, B});  // :48-54
+            } else {
+                d->bfr = add_pipeline(vk, d->stage, spv + "/bfr.comp.spv", {(int32_t)W, (int32_t)H, B, B});           // BFR.cpp:26-31
+            }
+        }
+        // bfrBlender.comp:4-9; BFRBlender(width, height, illumination_images[0], [1], den8, den16, den32) (DenoiserUtils.cpp:53-55)
+        Stage blend;
+        VkPipeline p_blend = VK_NULL_HANDLE;
+        if (x3) {
+            blend = make_stage(vk, pool, sampler, {{0, SI, &illum}, {1, SI, &illum_sq}, {2, SI, &dens[0]->final_image}, {3, SI, &dens[1]->final_image},
+                                                   {4, SI, &dens[2]->final_image}, {5, SI, &blend_final}}, 0);
+            p_blend = add_pipeline(vk, blend, spv + "/bfrBlender.comp.spv", {(int32_t)W, (int32_t)H, 16, 16, 2});     // BFRBlender.cpp:13-19 (work_height, work_width, radius)
         }
         // taa.comp:8-11
         Stage taa;
         VkPipeline p_taa = VK_NULL_HANDLE;
         if (use_taa) {
-            taa = make_stage(vk, pool, sampler, {{0, SI, &motion}, {1, CIS, &final_image}, {2, SI, &taa_final}, {3, CIS, &taa_accumulation}}, sizeof(RayTracingPush));
+            taa = make_stage(vk, pool, sampler, {{0, SI, &motion}, {1, CIS, &denoiser_final}, {2, SI, &taa_final}, {3, CIS, &taa_accumulation}}, sizeof(RayTracingPush));
             p_taa = add_pipeline(vk, taa, spv + "/taa.comp.spv", {(int32_t)W, (int32_t)H, 16, 16});                   // Taa.cpp:14-19, VulkanPBRT.cpp:450
         }
 
         // ---- staging, command buffer ----
         const VkDeviceSize px = (VkDeviceSize)W * H;
-        const VkDeviceSize up_depth = 0, up_normal = up_depth + px * 4, up_albedo = up_normal + px * 8, up_illum = up_albedo + px * 4, up_end = up_illum + px * 16;
+        const VkDeviceSize up_depth = 0, up_normal = up_depth + px * 4, up_albedo = up_normal + px * 8, up_illum = up_albedo + px * 4, up_avgsq = up_illum + px * 16, up_end = up_avgsq + px * 8;
         HostBuffer upload = make_host_buffer(vk, up_end);
-        const Image& shown = use_taa ? taa_final : final_image;
-        const VkDeviceSize rb_final = 0, rb_den = rb_final + px * 4, rb_motion = rb_den + denoised.bytes(), rb_spp = rb_motion + px * 4, rb_illum = rb_spp + px,
+        const Image& shown = use_taa ? taa_final : denoiser_final;
+        const VkDeviceSize den_bytes = dens[0]->denoised.bytes();
+        const VkDeviceSize rb_final = 0, rb_den = rb_final + px * 4, rb_motion = rb_den + den_bytes * dens.size(), rb_spp = rb_motion + px * 4, rb_illum = rb_spp + px,
                            rb_end = rb_illum + px * 8;
         HostBuffer readback = make_host_buffer(vk, (rb_end + 15) / 16 * 16);
         VkCommandPoolCreateInfo cpi{};
@@ -538,6 +569,15 @@ int main(int argc, char** argv)
                 const VkBufferImageCopy r = whole(*u.im, u.off);
                 vk.CmdCopyBufferToImage(cb, upload.buffer, u.im->image, VK_IMAGE_LAYOUT_GENERAL, 1, &r);
             }
+            {
+                std::ifstream sq(base + ".avgsq", std::ios::binary);
+                if (sq) {
+                    sq.read(upload.map + up_avgsq, (std::streamsize)(px * 8));
+                    if ((VkDeviceSize)sq.gcount() != px * 8) throw std::runtime_error("bad size: " + base + ".avgsq");
+                    const VkBufferImageCopy r = whole(illum_sq, up_avgsq);
+                    vk.CmdCopyBufferToImage(cb, upload.buffer, illum_sq.image, VK_IMAGE_LAYOUT_GENERAL, 1, &r);
+                }
+            }
             barrier(vk, cb, TRANSFER, COMPUTE);
             // Accumulator::add_dispatch_to_command_graph (Accumulator.cpp:72-83)
             vk.CmdBindPipeline(cb, VK_PIPELINE_BIND_POINT_COMPUTE, p_acc);
@@ -545,19 +585,27 @@ int main(int argc, char** argv)
             vk.CmdPushConstants(cb, acc.layout, VK_SHADER_STAGE_COMPUTE_BIT, 0, sizeof(apc), &apc);
             vk.CmdDispatch(cb, (uint32_t)std::ceil((float)W / 16.f), (uint32_t)std::ceil((float)H / 16.f), 1);
             barrier(vk, cb, COMPUTE, COMPUTE);
-            if (bmfr) {                                                   // BMFR.cpp:203-230: pre, fit, post with W_padded / b groups
-                for (VkPipeline p : {p_pre, p_fit, p_post}) {
-                    vk.CmdBindPipeline(cb, VK_PIPELINE_BIND_POINT_COMPUTE, p);
-                    vk.CmdBindDescriptorSets(cb, VK_PIPELINE_BIND_POINT_COMPUTE, den.layout, 0, 1, &den.set, 0, nullptr);
-                    vk.CmdPushConstants(cb, den.layout, VK_SHADER_STAGE_COMPUTE_BIT, 0, sizeof(rpc), &rpc);
-                    vk.CmdDispatch(cb, bx, by, 1);
+            for (auto& d : dens) {
+                if (bmfr) {                                               // BMFR.cpp:203-230: pre, fit, post with W_padded / b groups
+                    for (VkPipeline p : {d->pre, d->fit, d->post}) {
+                        vk.CmdBindPipeline(cb, VK_PIPELINE_BIND_POINT_COMPUTE, p);
+                        vk.CmdBindDescriptorSets(cb, VK_PIPELINE_BIND_POINT_COMPUTE, d->stage.layout, 0, 1, &d->stage.set, 0, nullptr);
+                        vk.CmdPushConstants(cb, d->stage.layout, VK_SHADER_STAGE_COMPUTE_BIT, 0, sizeof(rpc), &rpc);
+                        vk.CmdDispatch(cb, d->bx, d->by, 1);
+                        barrier(vk, cb, COMPUTE, COMPUTE);
+                    }
+                } else {                                                  // BFR.cpp:128-138
+                    vk.CmdBindPipeline(cb, VK_PIPELINE_BIND_POINT_COMPUTE, d->bfr);
+                    vk.CmdBindDescriptorSets(cb, VK_PIPELINE_BIND_POINT_COMPUTE, d->stage.layout, 0, 1, &d->stage.set, 0, nullptr);
+                    vk.CmdPushConstants(cb, d->stage.layout, VK_SHADER_STAGE_COMPUTE_BIT, 0, sizeof(rpc), &rpc);
+                    vk.CmdDispatch(cb, d->bx, d->by, 1);
                     barrier(vk, cb, COMPUTE, COMPUTE);
                 }
-            } else {                                                      // BFR.cpp:128-138
-                vk.CmdBindPipeline(cb, VK_PIPELINE_BIND_POINT_COMPUTE, p_bfr);
-                vk.CmdBindDescriptorSets(cb, VK_PIPELINE_BIND_POINT_COMPUTE, den.layout, 0, 1, &den.set, 0, nullptr);
-                vk.CmdPushConstants(cb, den.layout, VK_SHADER_STAGE_COMPUTE_BIT, 0, sizeof(rpc), &rpc);
-                vk.CmdDispatch(cb, bx, by, 1);
+            }
+            if (x3) {                                                     // BFRBlender.cpp:80-90
+                vk.CmdBindPipeline(cb, VK_PIPELINE_BIND_POINT_COMPUTE, p_blend);
+                vk.CmdBindDescriptorSets(cb, VK_PIPELINE_BIND_POINT_COMPUTE, blend.layout, 0, 1, &blend.set, 0, nullptr);
+                vk.CmdDispatch(cb, (uint32_t)std::ceil((float)W / 16.f), (uint32_t)std::ceil((float)H / 16.f), 1);
                 barrier(vk, cb, COMPUTE, COMPUTE);
             }
             if (use_taa) {
@@ -578,8 +626,10 @@ int main(int argc, char** argv)
             {
                 VkBufferImageCopy r = whole(shown, rb_final);
                 vk.CmdCopyImageToBuffer(cb, shown.image, VK_IMAGE_LAYOUT_GENERAL, readback.buffer, 1, &r);
-                r = whole(denoised, rb_den);
-                vk.CmdCopyImageToBuffer(cb, denoised.image, VK_IMAGE_LAYOUT_GENERAL, readback.buffer, 1, &r);
+                for (size_t i = 0; i < dens.size(); ++i) {
+                    r = whole(dens[i]->denoised, rb_den + den_bytes * i);
+                    vk.CmdCopyImageToBuffer(cb, dens[i]->denoised.image, VK_IMAGE_LAYOUT_GENERAL, readback.buffer, 1, &r);
+                }
                 r = whole(motion, rb_motion);
                 vk.CmdCopyImageToBuffer(cb, motion.image, VK_IMAGE_LAYOUT_GENERAL, readback.buffer, 1, &r);
                 r = whole(spp, rb_spp);
@@ -604,14 +654,16 @@ int main(int argc, char** argv)
                 std::ofstream(out + "/" + name + "_" + std::to_string(f) + "." + ext, std::ios::binary).write(readback.map + off, (std::streamsize)bytes);
             };
             dump("final", "bgra", rb_final, px * 4);
-            dump("denoised", "rgba16f", rb_den, denoised.bytes());
+            for (size_t i = 0; i < dens.size(); ++i) dump(("denoised" + std::to_string(dens[i]->B)).c_str(), "rgba16f", rb_den + den_bytes * i, den_bytes);
             dump("motion", "rg16f", rb_motion, px * 4);
             dump("spp", "r8", rb_spp, px);
             dump("illum", "rgba16f", rb_illum, px * 8);
         }
 
         // ---- teardown ----
-        for (Stage* s : {&acc, &den, &taa}) {
+        std::vector<Stage*> stages = {&acc, &blend, &taa};
+        for (auto& d : dens) stages.push_back(&d->stage);
+        for (Stage* s : stages) {
             for (VkPipeline p : s->pipelines) vk.DestroyPipeline(vk.device, p, nullptr);
             for (VkShaderModule m : s->modules) vk.DestroyShaderModule(vk.device, m, nullptr);
             if (s->layout) vk.DestroyPipelineLayout(vk.device, s->layout, nullptr);
