@@ -129,3 +129,135 @@ def test_import_conversions_on_the_device(backend, oracle):
     np.testing.assert_array_equal(want_d, GBufferIO.position_to_depth(pos, CameraMatrices(view=None, inv_view=ivp)))
     np.testing.assert_allclose(want_n, GBufferIO.convert_normal_to_spherical(cart), atol=1e-6, rtol=0)
     np.testing.assert_array_equal(want_a, GBufferIO.compress_albedo(alb))
+
+
+def _cxx_offline(tmp_path, backend):
+    """examples/cpp_offline_sequence.cpp built against the product library (cuda) or the emulator (hostsim)"""
+    import subprocess
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    libdir, lib = (root / "tests" / "hostsim", "vkpbrt_hostsim") if backend == "hostsim" else (root / "vulkanpbrt_b200" / "lib", "vkpbrt_b200")
+    exe = tmp_path / "cpp_offline_sequence"
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-I", str(root / "include"), str(root / "examples" / "cpp_offline_sequence.cpp"), "-o", str(exe),
+                        f"-L{libdir}", f"-l{lib}", f"-Wl,-rpath,{libdir}", "-lz"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+@pytest.mark.parametrize("backend", backend_params(), indirect=True)
+@pytest.mark.parametrize("source", ["position", "depth"])
+def test_cxx_offline_sequence_import(tmp_path, backend, source):
+    """include/vkpbrt/io.hpp (MatrixIO, GBufferIO, IlluminationBufferIO, the EXR reader) in the reference's offline
+    frame loop (examples/cpp_offline_sequence.cpp): a sequence exported by the Python layer (OpenCV's OpenEXR, ZIP, and
+    the reference's matrix JSON) is imported by the C++ layer and denoised; the imported G-buffer and every final image
+    equal the Python layer's import of the same files bit for bit (both run the conversions on the device)"""
+    import subprocess
+    from vulkanpbrt_b200 import DenoisePipeline, _capi as capi
+    from vulkanpbrt_b200.matrix_io import export_matrices, import_matrices
+    W, H, frames = 96, 64, 3
+    seq = _sequence(W, H, frames)
+    d = str(tmp_path)
+    g = [OfflineGBuffer(depth=fr.depth, normal=fr.normal, material=fr.material, albedo=fr.albedo) for fr in seq]
+    mats = [CameraMatrices(view=fr.camera.view, inv_view=fr.camera.inv_view, proj=fr.camera.proj, inv_proj=fr.camera.inv_proj) for fr in seq]
+    assert GBufferIO.export_g_buffer(d + "/pos_%d.exr", d + "/depth_%d.exr", d + "/normal_%d.exr", "", d + "/albedo_%d.exr", frames, g, mats)
+    assert IlluminationBufferIO.export_illumination(d + "/illu_%d.exr", frames, [OfflineIllumination(noisy=fr.illumination) for fr in seq])
+    assert export_matrices(d + "/matrices.json", mats)
+    exe = _cxx_offline(tmp_path, backend)
+    r = subprocess.run([str(exe), d, str(frames), source], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    # the same import through the Python layer
+    loaded = import_matrices(d + "/matrices.json")
+    pipe = DenoisePipeline(W, H, use_taa=True, separate_matrices=True)
+    for f in range(frames):
+        pos = read_exr(d + f"/pos_{f}.exr") if source == "position" else None
+        GBufferIO.import_to_device(pipe.g_buffer, pos, loaded[f] if pos is not None else None, read_exr(d + f"/normal_{f}.exr"), read_exr(d + f"/albedo_{f}.exr"))
+        if source == "depth":
+            pipe.g_buffer.depth.upload(read_exr(d + f"/depth_{f}.exr").reshape(H, W))
+        pipe.raw_illumination.illumination_images[0].upload(np.ascontiguousarray(read_exr(d + f"/illu_{f}.exr")))
+        np.testing.assert_array_equal(np.fromfile(tmp_path / f"gbuffer_{f}.depth", np.uint32).reshape(H, W), pipe.g_buffer.depth.download().view(np.uint32), err_msg=f"depth {f}")
+        np.testing.assert_array_equal(np.fromfile(tmp_path / f"gbuffer_{f}.normal", np.uint32).reshape(H, W, 2), pipe.g_buffer.normal.download().view(np.uint32), err_msg=f"normal {f}")
+        np.testing.assert_array_equal(np.fromfile(tmp_path / f"gbuffer_{f}.albedo", np.uint8).reshape(H, W, 4), pipe.g_buffer.albedo.download(), err_msg=f"albedo {f}")
+        cur, prev = loaded[f], loaded[f - 1] if f > 0 else loaded[f]
+        pc = pipe.push_constants.value
+        pc.view_inverse = capi.mat16(cur.inv_view)
+        pc.proj_inverse = capi.mat16(cur.inv_proj)
+        pc.frame_number, pc.sample_number = f, 0
+        pipe.accumulator.set_camera_matrices(f, cur, prev)
+        pipe.record()
+        pc.prev_view = capi.mat16(cur.view)
+        pipe.ctx.synchronize()
+        np.testing.assert_array_equal(np.fromfile(tmp_path / f"final_{f}.bgra", np.uint8).reshape(H, W, 4), pipe.final.download(), err_msg=f"final {f}")
+    # with positions the planes are what the source frames held (up to the stored precision), not merely self-consistent
+    assert np.abs(pipe.g_buffer.albedo.download().astype(int) - seq[-1].albedo.astype(int)).max() <= 1
+
+
+def test_cxx_exr_reader_and_matrix_files(tmp_path):
+    """io.hpp on its own (no device): EXR files written by OpenCV in float / half, 1 / 3 / 4 channels, ZIP (default), and its
+    own uncompressed files read back by OpenCV; the matrix JSON and the BMFR-dataset text layout against the Python reader"""
+    import subprocess
+    from pathlib import Path
+    from vulkanpbrt_b200.matrix_io import export_matrices, import_matrices
+    root = Path(__file__).resolve().parents[1]
+    src = tmp_path / "io_probe.cpp"
+    src.write_text(r'''
+#include <vkpbrt/io.hpp>
+using namespace vkpbrt;
+int main(int argc, char** argv) {
+    const std::string dir = argv[1];
+    for (const char* name : {"rgba_f32", "rgb_f32", "gray_f32", "rgba_f16", "big_zip"}) {
+        exr::Image im;
+        if (!exr::read(dir + "/" + name + ".exr", im)) return 1;
+        std::ofstream(dir + "/" + name + ".raw", std::ios::binary).write((const char*)im.data.data(), im.data.size() * 4);
+        std::ofstream(dir + "/" + name + ".dims") << im.width << " " << im.height << " " << im.channels;
+        if (!exr::write(dir + "/" + name + "_back.exr", im.data.data(), im.width, im.height, im.channels)) return 2;
+    }
+    exr::Image none;
+    if (exr::read(dir + "/missing.exr", none) || exr::read(dir + "/garbage.exr", none)) return 3;
+    auto m = MatrixIO::import_matrices(dir + "/m.json");
+    if (!MatrixIO::export_matrices(dir + "/m_back.json", m)) return 4;
+    auto t = MatrixIO::import_matrices(dir + "/cams.txt");
+    if (!MatrixIO::export_matrices(dir + "/t_back.json", t)) return 5;
+    if (!MatrixIO::import_matrices(dir + "/nope.json").empty()) return 6;
+    return 0;
+}
+''')
+    exe = tmp_path / "io_probe"
+    libdir = root / "tests" / "hostsim"
+    subprocess.run(["make", "-C", str(libdir)], check=True, capture_output=True)
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-I", str(root / "include"), str(src), "-o", str(exe), f"-L{libdir}", "-lvkpbrt_hostsim",
+                        f"-Wl,-rpath,{libdir}", "-lz"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    rng = np.random.default_rng(11)
+    planes = {"rgba_f32": rng.standard_normal((9, 13, 4)).astype(np.float32), "rgb_f32": rng.standard_normal((7, 5, 3)).astype(np.float32),
+              "gray_f32": rng.standard_normal((33, 17)).astype(np.float32), "big_zip": np.tile(rng.standard_normal((1, 70, 4)).astype(np.float32), (50, 1, 1))}
+    for name, a in planes.items():
+        assert write_exr(tmp_path / f"{name}.exr", a)
+    half = rng.standard_normal((6, 10, 4)).astype(np.float16)
+    b = np.ascontiguousarray(half.astype(np.float32)[..., [2, 1, 0, 3]])
+    assert cv2.imwrite(str(tmp_path / "rgba_f16.exr"), b, [cv2.IMWRITE_EXR_TYPE, cv2.IMWRITE_EXR_TYPE_HALF])
+    planes["rgba_f16"] = half.astype(np.float32)
+    (tmp_path / "garbage.exr").write_bytes(b"not an exr file at all")
+    seq = _sequence(32, 32, 2)
+    mats = [CameraMatrices(view=fr.camera.view, inv_view=fr.camera.inv_view, proj=fr.camera.proj, inv_proj=fr.camera.inv_proj) for fr in seq]
+    mats.append(CameraMatrices(view=seq[0].camera.view, inv_view=seq[0].camera.inv_view))           # one combined-matrix entry
+    assert export_matrices(tmp_path / "m.json", mats)
+    (tmp_path / "cams.txt").write_text("{" + ", ".join(f"{v:.9g}" for v in seq[0].camera.view) + "},\n{" + " ".join(f"{v:.9g}," for v in seq[1].camera.proj) + "}\n")
+    r = subprocess.run([str(exe), str(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert "missing.exr" not in r.stderr and "garbage.exr" in r.stderr
+    for name, a in planes.items():
+        w, h, c = map(int, (tmp_path / f"{name}.dims").read_text().split())
+        assert (h, w) == a.shape[:2] and c == (a.shape[2] if a.ndim == 3 else 1)
+        got = np.fromfile(tmp_path / f"{name}.raw", np.float32).reshape(a.shape)
+        np.testing.assert_array_equal(got.view(np.uint32), a.view(np.uint32), err_msg=name)
+        back = read_exr(tmp_path / f"{name}_back.exr")                                              # io.hpp's writer -> OpenCV's reader
+        np.testing.assert_array_equal(back.reshape(a.shape).view(np.uint32), a.view(np.uint32), err_msg=name + " (written by io.hpp)")
+    for back, want in (("m_back.json", mats), ("t_back.json", import_matrices(tmp_path / "cams.txt"))):
+        got = import_matrices(tmp_path / back)
+        assert len(got) == len(want) and len(want) >= 2
+        for x, y in zip(got, want):
+            np.testing.assert_array_equal(np.asarray(x.view, np.float32), np.asarray(y.view, np.float32))
+            np.testing.assert_array_equal(np.asarray(x.inv_view, np.float32), np.asarray(y.inv_view, np.float32))
+            assert (x.proj is None) == (y.proj is None)
+            if y.proj is not None:
+                np.testing.assert_array_equal(np.asarray(x.inv_proj, np.float32), np.asarray(y.inv_proj, np.float32))
