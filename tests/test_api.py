@@ -88,7 +88,7 @@ class TestHostBehaviour:
         _capi.call("vkpbrt_device_uuid", 0, uuid)
         assert any(uuid)
         assert _capi.lib().vkpbrt_device_uuid(n.value, uuid) == _capi.ERR_INVALID_ARGUMENT
-        W, H = 64, 64
+        W, H = 192, 128
         pipe = DenoisePipeline(W, H, DenoisingType.BMFR, use_taa=True)
         dst = DescriptorImage.create(pipe.ctx, _capi.FORMAT_R8G8B8A8_UNORM, W, H)       # 4-byte texels like the BGRA8 final
         dst.compile()

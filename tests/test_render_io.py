@@ -154,7 +154,7 @@ def test_cxx_offline_sequence_import(tmp_path, backend, source):
     import subprocess
     from vulkanpbrt_b200 import DenoisePipeline, _capi as capi
     from vulkanpbrt_b200.matrix_io import export_matrices, import_matrices
-    W, H, frames = 96, 64, 3
+    W, H, frames = 192, 128, 3
     seq = _sequence(W, H, frames)
     d = str(tmp_path)
     g = [OfflineGBuffer(depth=fr.depth, normal=fr.normal, material=fr.material, albedo=fr.albedo) for fr in seq]
