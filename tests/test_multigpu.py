@@ -9,6 +9,8 @@ from pathlib import Path
 import numpy as np
 import pytest
 
+from tests.conftest import backend_params
+
 ROOT = Path(__file__).resolve().parents[1]
 
 
@@ -383,6 +385,105 @@ def test_native_banded_rank_on_the_emulator(world, use_taa, W, H, frames):
         for k in keep:
             k[0].close()
         del pipe, results, keep
+    finally:
+        import gc
+        gc.collect()
+        _capi._lib = saved
+
+
+def _pitched(camera, angle):
+    """the camera turned about its own x axis: the image content moves vertically by ~ angle / fov_y * H rows"""
+    import copy
+    c = copy.copy(camera)
+    V = np.asarray(camera.view, np.float64).reshape(4, 4).T
+    R = np.eye(4)
+    R[1:3, 1:3] = [[np.cos(angle), -np.sin(angle)], [np.sin(angle), np.cos(angle)]]
+    V2 = R @ V
+    c.view = V2.T.astype(np.float32).reshape(-1).copy()
+    c.inv_view = np.linalg.inv(V2).T.astype(np.float32).reshape(-1).copy()
+    return c
+
+
+@pytest.mark.parametrize("backend", backend_params(), indirect=True)
+def test_reprojection_beyond_the_halo_is_counted(backend):
+    """the guard behind band sharding's one assumption (a rank holds history rows only within max_disp_rows of the rows it
+    computes): k_accumulate counts every reprojection tap that lands further away, instead of serving stale rows.  The
+    synthetic sequence's own motion stays inside 12 rows; a camera that pitches by 0.3 rad between two frames does not."""
+    from vulkanpbrt_b200 import DenoisePipeline, synth
+    W, H = 160, 256
+    pipe = DenoisePipeline(W, H, use_taa=False)
+    pipe.accumulator.set_max_displacement_rows(12)
+    for f in range(3):
+        pipe.run_frame(f, synth.render_frame(W, H, f))
+    pipe.ctx.synchronize()
+    assert pipe.accumulator.displacement_violations() == 0
+    fr = synth.render_frame(W, H, 3)
+    fr.camera = _pitched(fr.camera, 0.3)
+    pipe.run_frame(3, fr)
+    pipe.ctx.synchronize()
+    n = pipe.accumulator.displacement_violations()
+    assert n > W * H // 8, n                      # most pixels whose reprojection stays on screen
+    pipe.accumulator.set_max_displacement_rows(0)             # off: nothing is counted
+    fr = synth.render_frame(W, H, 4)
+    fr.camera = _pitched(fr.camera, -0.3)
+    pipe.run_frame(4, fr)
+    pipe.ctx.synchronize()
+    assert pipe.accumulator.displacement_violations() in (0, n)
+
+
+@pytest.mark.timeout(600)
+def test_native_banded_rank_fails_loudly_when_the_camera_outruns_the_halo():
+    """vkpbrt_banded_rank_check after a camera jump: every rank reports the violation (VKPBRT error with the count and
+    the remedy) instead of returning frames built from stale history rows"""
+    import subprocess
+    import threading
+    subprocess.run(["make", "-C", str(ROOT / "tests" / "hostsim")], check=True, capture_output=True)
+    from vulkanpbrt_b200 import Context, VkpbrtError, _capi, synth
+    from vulkanpbrt_b200.multigpu import NativeBandedRank
+    saved = _capi._lib
+    _capi._lib = _capi.configure(ctypes.CDLL(str(ROOT / "tests" / "hostsim" / "libvkpbrt_hostsim.so")))
+    W, H, world = 64, 416, 2
+    try:
+        group = _ThreadGroup(world)
+        messages, errors, keep = [None] * world, [], [None] * world
+
+        def rank_main(rank):
+            try:
+                ctx = Context(0)
+                nr = NativeBandedRank(W, H, rank, world, True, ctx, dist=group.rank_view(rank), max_disp_rows=12, external_inputs=True,
+                                      comm_stream=0, timeout_ms=120000)
+                lo, hi = nr.input_rows()
+                for f in range(4):
+                    fr = synth.render_frame(W, H, f, rows=(lo, hi))
+                    cam = fr.camera if f < 3 else _pitched(fr.camera, 0.3)
+                    planes = [np.ascontiguousarray(fr.depth[lo:hi]), np.ascontiguousarray(fr.normal[lo:hi]), np.ascontiguousarray(fr.albedo[lo:hi]),
+                              np.ascontiguousarray(fr.illumination[lo:hi])]
+                    nr.bind_inputs(*[p.ctypes.data - lo * pt for p, pt in zip(planes, [4 * W, 8 * W, 4 * W, 16 * W])])
+                    nr.run_frame(f, NativeBandedRank.camera_block(cam))
+                    if f == 2:
+                        nr.flush()
+                        nr.check()                     # the sequence's own motion is covered
+                nr.flush()
+                try:
+                    nr.check()
+                except VkpbrtError as e:
+                    messages[rank] = str(e)
+                keep[rank] = (nr, ctx)
+            except BaseException as e:      # noqa: BLE001 -- reported by the main thread
+                errors.append((rank, e))
+                group.barrier.abort()
+
+        threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        assert not errors, errors
+        for m in messages:
+            assert m is not None and "max_disp_rows" in m, m
+        for k in keep:
+            k[0].close()
+        del keep
     finally:
         import gc
         gc.collect()
