@@ -176,7 +176,9 @@ class OracleChain:
     def denoiser_final(self) -> np.ndarray:
         return self.blend_final if self.denoiser.endswith("x3") else self.finals[self.block]
 
-    def run_frame(self, frame_index: int, frame, keep_debug: bool = False) -> None:
+    def run_frame(self, frame_index: int, frame, keep_debug: bool = False, motion_override=None) -> None:
+        """motion_override: a motion plane (rg16f bits) that replaces the accumulator's before the denoisers run -- what a
+        caller that uploads its own motion vectors does (the image is public: AccumulationBuffer::motion)"""
         L, W, H = lib(), self.W, self.H
         self._set_camera_matrices(frame_index, frame.camera)
         if self.raw_f16:
@@ -189,6 +191,8 @@ class OracleChain:
         L.vkpbrt_oracle_accumulator(W, H, 1 if self.separate else 0, C.byref(self.pc), _p(src), 1 if self.raw_f16 else 0,
                                     _p(depth), _p(self.prev_depth), _p(self.prev_illu), _p(self.prev_spp),
                                     _p(self.motion), _p(self.spp), _p(self.illum))
+        if motion_override is not None:
+            self.motion[...] = motion_override
         for b in self.blocks:
             if self.denoiser.startswith("bmfr"):
                 T = 64 if b == 8 else 256

@@ -224,3 +224,34 @@ def test_tonemap_threshold_search_equals_pow_for_every_input(backend, oracle):
     bad, first = C.c_uint64(0), C.c_uint32(0)
     _capi.call("vkpbrt_debug_tonemap_sweep", ctx.handle, C.byref(bad), C.byref(first))
     assert bad.value == 0, f"{bad.value} inputs differ, first bit pattern 0x{first.value:08x}"
+
+
+@pytest.mark.parametrize("den,block", [("bmfr", 32), ("bfr", 16)])
+def test_caller_supplied_motion_outside_the_unit_square(backend, oracle, den, block):
+    """the history fetch of bmfrPost.comp:108-113 / bfr.comp:293-298 samples with a REPEAT sampler at whatever the motion
+    image holds, and accepts any uv.x >= 0; the accumulator only ever writes uv in [0,1]^2 or -1, but the image is public
+    (AccumulationBuffer::motion) and a host may upload its own vectors.  Coordinates beyond 1 must wrap like the sampler
+    does instead of reading out of bounds (round 1 review: the cheap wrap assumed [0,1])"""
+    from vulkanpbrt_b200 import synth
+    W, H = 96, 72
+    pipe, orc = make_pair(oracle, W, H, denoiser=den, block=block, use_taa=True)
+    rng = np.random.default_rng(17)
+    for f in range(3):
+        fr = synth.render_frame(W, H, f)
+        pipe.upload_frame(fr)
+        pipe.set_frame_constants(f, fr.camera)
+        pipe.commands.children[0](pipe.commands)                     # accumulate
+        pipe.ctx.synchronize()
+        motion = pipe.accumulation_buffer.motion.download()
+        if f > 0:
+            uv = rng.choice(np.array([1.0, 1.25, 2.5, 37.75, 1000.5, 0.0, 0.999, 3.0], np.float16), size=(H, W, 2))
+            pick = rng.random((H, W)) < 0.3
+            motion = motion.copy()
+            motion[pick] = uv.view(np.uint16)[pick]
+            pipe.accumulation_buffer.motion.upload(motion)
+        for child in pipe.commands.children[1:]:
+            child(pipe.commands)
+        pipe.end_frame(fr.camera)
+        pipe.ctx.synchronize()
+        orc.run_frame(f, fr, motion_override=motion)
+        assert_frame_equal(pipe, orc, f)
