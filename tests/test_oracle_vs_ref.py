@@ -81,3 +81,42 @@ def test_world_position_modes(oracle, ref, ptype, block, W, H):
     a2 = oracle.OracleChain(W, H, "bmfr", block, use_taa=False, position_type=ptype)
     a2.run_frame(7, synth.render_frame(W, H, 7), keep_debug=True)
     assert not np.array_equal(a2.features[4:7], c.features[4:7])
+
+
+@pytest.mark.parametrize("den,block", [("bmfr", 32), ("bfr", 16)])
+def test_history_sampling_with_motion_outside_the_unit_square(oracle, ref, den, block, monkeypatch):
+    """texture() with REPEAT addressing at uv beyond [0,1] (a caller-supplied motion plane): the oracle's sampler against
+    the shim's, through bmfrPost.comp:108-113 / bfr.comp:293-298; the CUDA side of this case is
+    tests/test_parity.py::test_caller_supplied_motion_outside_the_unit_square"""
+    import copy
+    W, H = 96, 72
+    a = oracle.OracleChain(W, H, den, block, use_taa=True)
+    b = ref.RefChain(W, H, den, block, use_taa=True)
+    rng = np.random.default_rng(17)
+    real_dispatch = ref.dispatch
+    for f in range(3):
+        fr = synth.render_frame(W, H, f)
+        probe = copy.deepcopy(a)
+        probe.run_frame(f, fr)
+        motion = probe.motion.copy()                       # what the accumulator writes this frame ...
+        if f > 0:                                          # ... with a third of the vectors replaced
+            uv = rng.choice(np.array([1.0, 1.25, 2.5, 37.75, 1000.5, 0.0, 0.999, 3.0], np.float16), size=(H, W, 2))
+            pick = rng.random((H, W)) < 0.3
+            motion[pick] = uv.view(np.uint16)[pick]
+        injected = []
+
+        def dispatch(shader, *args, **kw):
+            if not shader.startswith("accumulator") and not injected:
+                b.motion[...] = motion
+                injected.append(shader)
+            return real_dispatch(shader, *args, **kw)
+
+        monkeypatch.setattr(ref, "dispatch", dispatch)
+        a.run_frame(f, fr, motion_override=motion)
+        b.run_frame(f, fr)
+        monkeypatch.setattr(ref, "dispatch", real_dispatch)
+        assert injected
+        for name in ("motion", "spp", "illum", "taa_final"):
+            np.testing.assert_array_equal(getattr(a, name), getattr(b, name), err_msg=f"{name}, frame {f}")
+        np.testing.assert_array_equal(a.denoised[block], b.denoised[block], err_msg=f"denoised, frame {f}")
+        np.testing.assert_array_equal(a.finals[block], b.finals[block], err_msg=f"final, frame {f}")
