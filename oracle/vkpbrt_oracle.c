@@ -885,7 +885,14 @@ ORACLE_API void vkpbrt_oracle_bfr(int W, int H, int b, uint32_t frame, const uin
                 memset(m, 0, sizeof m);
                 memset(v, 0, sizeof v);
                 /* :260-278; GRADIENT_THRESH == 0 so the loop runs all 40 iterations unless the
-                 * gradient sum turns NaN (NaN >= 0 is false) */
+                 * gradient sum turns NaN (NaN >= 0 is false).  WHICH gradients are in that sum follows from the
+                 * shader's thread numbering: ID = x * size.y + y (:75), so the 7 threads with id < ALPHA_SIZE sit in
+                 * column 0, rows 0..6 -- invocation indices id * b, i.e. spread over subgroups of 32 / b ids each --
+                 * and `subgroupAdd(abs(delta))` (:136) runs per subgroup; thread id == 0 publishes ITS subgroup's
+                 * sum (:137).  gradient_left therefore covers features j < 32 / b only (4, 2, 1 for b = 8, 16, 32):
+                 * a NaN in a later feature's gradient does not end the loop.  (Found by fuzzing the oracle against
+                 * the reference's shader source with non-finite inputs; invisible with finite data.) */
+                const int grad_feats = 32 / b > 0 ? 32 / b : 1;
                 float gradient_rest = 0.0f;
                 for (int it = 0; gradient_rest >= 0.0f && it < 40; ++it) {
                     const int t = it + 1;
@@ -922,7 +929,7 @@ ORACLE_API void vkpbrt_oracle_bfr(int W, int H, int b, uint32_t frame, const uin
                             m[j][c] = beta1 * m[j][c] + (1 - .3f) * d;
                             v[j][c] = beta2 * v[j][c] + (1 - .7314f) * (fabsf(d) * fabsf(d));
                             alpha[j][c] += lr * (m[j][c] / (sqrtf(v[j][c]) + 1e-8f));
-                            gsum[c] += fabsf(d);
+                            if (j < grad_feats) gsum[c] += fabsf(d);
                         }
                     gradient_rest = gsum[0] + gsum[1] + gsum[2];
                 }

@@ -120,3 +120,103 @@ def test_history_sampling_with_motion_outside_the_unit_square(oracle, ref, den, 
             np.testing.assert_array_equal(getattr(a, name), getattr(b, name), err_msg=f"{name}, frame {f}")
         np.testing.assert_array_equal(a.denoised[block], b.denoised[block], err_msg=f"denoised, frame {f}")
         np.testing.assert_array_equal(a.finals[block], b.finals[block], err_msg=f"final, frame {f}")
+
+
+def _canon_nan(a):
+    a = np.asarray(a)
+    if a.dtype == np.uint16:            # fp16 bits: NaN payload / sign are not defined by IEEE 754
+        a = a.copy()
+        a[(a & 0x7FFF) > 0x7C00] = 0x7E00
+    return a
+
+
+@pytest.mark.parametrize("block,W,H,px", [(8, 64, 48, (7, 0)), (16, 64, 48, (7, 0)), (32, 96, 64, (10, 34))])
+def test_bfr_descent_stops_on_the_gradients_the_shader_actually_sums(oracle, ref, block, W, H, px):
+    """bfr.comp:260 leaves the descent when gradient_rest turns NaN.  gradient_left (:136-137) is a subgroupAdd over the
+    threads with id < 7 that share thread 0's SUBGROUP, and ID = x * size.y + y (:75) spreads those threads over
+    subgroups of 32 / b features: only features j < 32 / b (4, 2, 1) can end the loop.  An infinite history value at a sky
+    pixel next to the horizon (normal (0, 0, 1): features 4 and 5 are exactly 0, 0 * inf = NaN there and +-inf in the
+    others) separates the two readings: summing all seven gradients stops after one iteration, the shader runs on and
+    the FINITE channels of that block end up different.  Found by fuzzing the oracle against the shader source."""
+    a = oracle.OracleChain(W, H, "bfr", block)
+    b = ref.RefChain(W, H, "bfr", block)
+    fr7, fr8 = synth.render_frame(W, H, 7), synth.render_frame(W, H, 8)
+    assert fr8.depth[px] > 1e9                      # a sky pixel
+    a.run_frame(7, fr7)
+    b.run_frame(7, fr7)
+    for ch in (a, b):
+        ch.prev_illu[px[0], px[1], 0] = 0x7C00      # +inf in the red channel of the accumulated history
+    a.run_frame(8, fr8)
+    b.run_frame(8, fr8)
+    assert a.illum[px[0], px[1], 0] == 0x7C00        # it reached the denoiser's input
+    for name in ("motion", "spp", "illum"):
+        np.testing.assert_array_equal(_canon_nan(getattr(a, name)), _canon_nan(getattr(b, name)), err_msg=name)
+    np.testing.assert_array_equal(_canon_nan(a.denoised[block]), _canon_nan(b.denoised[block]), err_msg="denoised")
+    np.testing.assert_array_equal(a.finals[block], b.finals[block], err_msg="final")
+    red_nan = (a.denoised[block][1, ..., 0] & 0x7FFF) > 0x7C00
+    assert red_nan.any() and not ((a.denoised[block][1, ..., 1] & 0x7FFF) > 0x7C00).any()     # red is lost in that block, green is not
+
+
+def _fuzz_configs(seed, n):
+    import random
+    from tests.test_fuzz_data import MODES
+    rng = random.Random(seed)
+    out = []
+    for i in range(n):
+        den = rng.choice(["bmfr", "bmfr", "bfr", "bfrx3", "bmfrx3"])
+        block = rng.choice([8, 16, 32])
+        big = 32 if den.endswith("x3") else block
+        W = max(big, rng.choice([1, 8, 17, 31, 32, 33, 40, 54, 63, 64, 65, 70, 97]) if rng.random() < 0.6 else rng.randint(1, 110))
+        H = max(big, rng.choice([1, 8, 17, 31, 32, 33, 40, 63, 64, 65, 70]) if rng.random() < 0.6 else rng.randint(1, 110))
+        first = rng.choice([0, 0, 7, 14])
+        frames = rng.randint(2, 3)
+        out.append(dict(W=W, H=H, den=den, block=block, taa=rng.random() < 0.7, first=first, frames=frames, sep=True if first else rng.random() < 0.7,
+                        f16=rng.random() < 0.2, pos=rng.choice([0, 0, 1, 2]) if den == "bmfr" and block in (16, 32) else 0,
+                        modes=[rng.choice(MODES + ["none", "none"]) for _ in range(frames)], seed=seed * 1000 + i))
+    return out
+
+
+@pytest.mark.parametrize("cfg", _fuzz_configs(5, 14), ids=lambda c: f"{c['den']}{c['block']}-{c['W']}x{c['H']}-f{c['first']}-{'-'.join(c['modes'])}")
+def test_seeded_fuzz_against_the_shader_source(oracle, ref, cfg):
+    """the oracle against the reference's shader source over random sizes (down to one block), wirings, modes AND extreme
+    data (tests/test_fuzz_data.py's perturbations): every plane, NaN payloads canonicalised; feature buffer and weights
+    for the blocks that hold at least one image pixel (for the others the reference's single-reflection mirror() reads
+    out of bounds and the two sides differ, with no effect on any output).  tools/fuzz/fuzz_oracle_vs_ref.py is the
+    unbounded version; it found the descent-exit discrepancy fixed above."""
+    from tests.test_fuzz_data import _perturb
+    from tests.util import second_moment_plane
+    W, H, den, block = cfg["W"], cfg["H"], cfg["den"], cfg["block"]
+    kw = dict(use_taa=cfg["taa"], separate_matrices=cfg["sep"], raw_f16=cfg["f16"], position_type=cfg["pos"])
+    a, b = oracle.OracleChain(W, H, den, block, **kw), ref.RefChain(W, H, den, block, **kw)
+    rng = np.random.default_rng(cfg["seed"])
+
+    def canon(x):
+        x = _canon_nan(x)
+        if x.dtype == np.float32:
+            x = x.copy()
+            x[np.isnan(x)] = np.float32(np.nan)
+            return x.view(np.uint32)
+        return x
+
+    for k, f in enumerate(range(cfg["first"], cfg["first"] + cfg["frames"])):
+        with np.errstate(over="ignore"):
+            fr = _perturb(synth.render_frame(W, H, f), rng, cfg["modes"][k])
+            if den.endswith("x3"):
+                sq = second_moment_plane(oracle, a)
+                a.average_squared[...] = sq
+                b.average_squared[...] = sq
+            a.run_frame(f, fr, keep_debug=True)
+            b.run_frame(f, fr, keep_debug=True)
+        for name in ("motion", "spp", "illum", "prev_depth", "blend_final", "taa_final", "taa_history"):
+            np.testing.assert_array_equal(canon(getattr(a, name)), canon(getattr(b, name)), err_msg=f"{name}, frame {f}")
+        for blk in a.blocks:
+            np.testing.assert_array_equal(canon(a.denoised[blk]), canon(b.denoised[blk]), err_msg=f"denoised b={blk}, frame {f}")
+            np.testing.assert_array_equal(a.finals[blk], b.finals[blk], err_msg=f"final b={blk}, frame {f}")
+        if den == "bmfr":
+            ox, oy = oracle.bmfr_block_offset(block, f)
+            Hb, Wb = a.weights.shape[1:]
+            inside = np.array([[bx * block - ox < W and bx * block - ox + block > 0 and by * block - oy < H and by * block - oy + block > 0
+                                for bx in range(Wb)] for by in range(Hb)])
+            np.testing.assert_array_equal(canon(a.weights)[:, inside], canon(b.weights)[:, inside], err_msg=f"weights, frame {f}")
+            big = np.repeat(np.repeat(inside, block, 0), block, 1)
+            np.testing.assert_array_equal(canon(a.features)[:, big], canon(b.features)[:, big], err_msg=f"feature buffer, frame {f}")

@@ -255,3 +255,31 @@ def test_caller_supplied_motion_outside_the_unit_square(backend, oracle, den, bl
         pipe.ctx.synchronize()
         orc.run_frame(f, fr, motion_override=motion)
         assert_frame_equal(pipe, orc, f)
+
+
+@pytest.mark.parametrize("block,W,H,px", [(8, 64, 48, (7, 0)), (16, 64, 48, (7, 0)), (32, 96, 64, (10, 34))])
+def test_bfr_descent_with_a_non_finite_gradient(backend, oracle, block, W, H, px, monkeypatch):
+    """the CUDA side of tests/test_oracle_vs_ref.py::test_bfr_descent_stops_on_the_gradients_the_shader_actually_sums: an
+    infinite history value makes some gradients NaN; which of them end the descent (features j < 32 / b only) decides
+    what the finite channels of that block become"""
+    from vulkanpbrt_b200 import synth
+    exact = np.testing.assert_array_equal
+
+    def canon(a):
+        a = np.asarray(a)
+        if a.dtype == np.uint16:
+            a = a.copy()
+            a[(a & 0x7FFF) > 0x7C00] = 0x7E00
+        return a
+
+    monkeypatch.setattr(np.testing, "assert_array_equal", lambda a, b, err_msg="": exact(canon(a), canon(b), err_msg=err_msg))
+    pipe, orc = make_pair(oracle, W, H, denoiser="bfr", block=block)
+    step_both(oracle, pipe, orc, W, H, 7)
+    assert_frame_equal(pipe, orc, 7)
+    hist = orc.prev_illu.copy()
+    hist[px[0], px[1], 0] = 0x7C00
+    orc.prev_illu[...] = hist
+    pipe.accumulation_buffer.prev_illu.upload(hist)
+    step_both(oracle, pipe, orc, W, H, 8)
+    assert orc.illum[px[0], px[1], 0] == 0x7C00
+    assert_frame_equal(pipe, orc, 8)

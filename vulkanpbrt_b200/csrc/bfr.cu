@@ -213,7 +213,10 @@ __global__ void __launch_bounds__(T, (T == 256 ? BFR_CTAS_B32 : (T == 64 ? BFR_C
             v = add_rn(mul_rn(beta2, v), mul_rn((1.0f - .7314f), mul_rn(fabsf(delta), fabsf(delta))));
             const float step = div_rn(mul_rn(mul_rn(a, p.lr_exp[it]), p.lr_sqrt[it]), p.lr_den[it]);
             sm.alpha[t] = add_rn(sm.alpha[t], mul_rn(step, div_rn(m, add_rn(sqrt_rn(v), 1e-8f))));
-            if (isnan(delta)) sm.stop = 1;       // gradient_rest turns NaN -> the loop condition fails (:260)
+            // gradient_rest turns NaN -> the loop condition fails (:260).  gradient_left is the subgroupAdd of |delta| over
+            // the threads with id < 7 that share thread id 0's subgroup (:136-137): with ID = x * size.y + y (:75) those are
+            // the features j < 32 / B, so only their gradients can end the loop (oracle/vkpbrt_oracle.c, same place)
+            if (t < 3 * (32 / B) && isnan(delta)) sm.stop = 1;
         }
         __syncthreads();
         if (sm.stop) break;
