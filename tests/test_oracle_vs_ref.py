@@ -219,4 +219,7 @@ def test_seeded_fuzz_against_the_shader_source(oracle, ref, cfg):
                                 for bx in range(Wb)] for by in range(Hb)])
             np.testing.assert_array_equal(canon(a.weights)[:, inside], canon(b.weights)[:, inside], err_msg=f"weights, frame {f}")
             big = np.repeat(np.repeat(inside, block, 0), block, 1)
-            np.testing.assert_array_equal(canon(a.features)[:, big], canon(b.features)[:, big], err_msg=f"feature buffer, frame {f}")
+            fa, fb = canon(a.features).copy(), canon(b.features).copy()
+            for x in (fa, fb):
+                x[x == 0x8000] = 0      # a block holding both +0 and -0 depths: which zero a min / max reduction returns depends on its order
+            np.testing.assert_array_equal(fa[:, big], fb[:, big], err_msg=f"feature buffer, frame {f}")

@@ -65,6 +65,7 @@ for it in range(n):
                 assert np.array_equal(wa[:, inside], wb[:, inside]), ("weights", f)
                 big = np.repeat(np.repeat(inside, block, 0), block, 1)
                 fa, fb = canon(a.features), canon(b.features)
+                for x in (fa, fb): x[x == 0x8000] = 0      # -0 / +0 depths in one block: which zero a min / max reduction returns depends on its order
                 assert np.array_equal(fa[:, big], fb[:, big]), ("features", f)
         print("ok", cfg, flush=True)
     except AssertionError as e:
