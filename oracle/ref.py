@@ -162,3 +162,15 @@ def format_converter(src: np.ndarray) -> np.ndarray:
     dispatch("formatConverter", (16, 16, 0), W, H, 0, None, math.ceil(W / 16), math.ceil(H / 16),
              {0: (np.ascontiguousarray(src), fmt), 1: (out, F_BGRA8)})
     return out
+
+
+def demodulate(radiance: np.ndarray, albedo: np.ndarray, position_x: np.ndarray) -> np.ndarray:
+    """the radiance clamp and the DEMOD_ILLUMINATION_FLOAT block of the reference's ray-generation shader
+    (ptRaygen.rgen:81-88), cut out of its text and wrapped in a compute main() by glsl_shim/extract_rgen.py, on
+    [H][W][4] float32 radiance / albedo planes and a [H][W] plane of the primary hit's position.x (infinite for misses)"""
+    H, W = radiance.shape[:2]
+    out = np.zeros((H, W, 4), np.float32)
+    dispatch("demodRgen", (16, 16, 0), W, H, 0, None, math.ceil(W / 16), math.ceil(H / 16),
+             {0: (np.ascontiguousarray(radiance, np.float32), F_RGBA32F), 1: (np.ascontiguousarray(albedo, np.float32), F_RGBA32F),
+              2: (np.ascontiguousarray(position_x, np.float32), F_R32F), 3: (out, F_RGBA32F)})
+    return out

@@ -1128,8 +1128,9 @@ ORACLE_API void vkpbrt_oracle_format_converter(int W, int H, int src_format, con
 
 /* ------------------------------------------------------------------------------------ */
 /* ptRaygen.rgen:81-88 (DEMOD_ILLUMINATION_FLOAT), constants from ptConstants.glsl:7,10:  */
-/* EPSILON = 1e-6, c_MaxRadiance = 1e1.  PARITY UNPINNED for this function: a ray-generation */
-/* shader cannot go through oracle/glsl_shim; it follows the cited lines only.             */
+/* EPSILON = 1e-6, c_MaxRadiance = 1e1.  Pinned: oracle/glsl_shim/extract_rgen.py cuts those */
+/* statements out of the ray-generation shader's text and wraps them in a compute main()   */
+/* (tests/test_convert.py::test_demodulate_oracle_equals_reference_statements).            */
 /* ------------------------------------------------------------------------------------ */
 ORACLE_API void vkpbrt_oracle_demodulate(int W, int H, const float* radiance, const float* albedo, const float* position_x,
                                          float* out)

@@ -53,6 +53,34 @@ def test_format_converter_module(backend, oracle, dtype):
         FormatConverter.create(img, capi.FORMAT_R8G8B8A8_UNORM)
 
 
+def _demod_inputs(H, W, seed):
+    rng = np.random.default_rng(seed)
+    L = rng.uniform(-1, 14, (H, W, 4)).astype(np.float32)
+    alb = rng.uniform(0, 1, (H, W, 4)).astype(np.float32)
+    alb[2, :10, :3] = 0.0                                      # black albedo: the 1e3 cap
+    px = rng.uniform(-50, 50, (H, W)).astype(np.float32)
+    px[5:9, 20:40] = np.inf                                    # misses
+    px[10, 3] = -np.inf
+    sp = rng.random((H, W, 4)) < 0.05                          # zeros, denormals, huge values, infinities
+    L[sp] = rng.choice(np.array([0.0, -0.0, 1e-40, 1e-6, 9.999999, 10.0, 10.000001, 3e38, np.inf, -np.inf], np.float32), size=int(sp.sum()))
+    sp = rng.random((H, W, 4)) < 0.05
+    alb[sp] = rng.choice(np.array([0.0, 1e-7, 1e-6, 1e-3, 0.01, 1.0], np.float32), size=int(sp.sum()))
+    return L, alb, px
+
+
+@pytest.mark.parametrize("H,W", [(33, 70), (1, 1), (16, 17)])
+def test_demodulate_oracle_equals_reference_statements(oracle, H, W):
+    """pins vkpbrt_oracle_demodulate: the reference's own statements (ptRaygen.rgen:81-88 -- the radiance clamp and the
+    DEMOD_ILLUMINATION_FLOAT block, cut out of the shader's text and wrapped in a compute main() by
+    oracle/glsl_shim/extract_rgen.py) against the oracle, bit for bit"""
+    from oracle import ref as R
+    if not R.build():
+        pytest.skip("oracle/_ref is not built and /root/reference is not mounted")
+    L, alb, px = _demod_inputs(max(H, 12), max(W, 41), 5)
+    L, alb, px = np.ascontiguousarray(L[:H, :W]), np.ascontiguousarray(alb[:H, :W]), np.ascontiguousarray(px[:H, :W])
+    np.testing.assert_array_equal(oracle.demodulate(L, alb, px).view(np.uint32), R.demodulate(L, alb, px).view(np.uint32))
+
+
 @pytest.mark.parametrize("backend", backend_params(), indirect=True)
 def test_demodulate(backend, oracle):
     """min(clamp(L, 0, 10) / (albedo + 1e-6), 1e3) for hits, the clamped radiance for misses (ptRaygen.rgen:81-88)"""
@@ -75,3 +103,19 @@ def test_demodulate(backend, oracle):
     np.testing.assert_array_equal(out.download().view(np.uint32), want.view(np.uint32))
     assert want[2, 0, 0] in (1e3, np.float32(1e3)) or L[2, 0, 0] <= 0
     np.testing.assert_array_equal(want[6, 25, :3], np.clip(L[6, 25, :3], 0, 10))
+
+
+@pytest.mark.parametrize("backend", [backend_params()[0]], indirect=True)
+def test_demodulate_special_values(backend, oracle):
+    """zeros, denormals, values at the clamp, huge values and infinities in radiance / albedo (emulator only: added after
+    the round's last GPU visit)"""
+    H, W = 33, 70
+    L, alb, px = _demod_inputs(H, W, 9)
+    ctx = Context(0)
+    mk = lambda fmt, a: (lambda im: (im.compile(), im.upload(np.ascontiguousarray(a)), im)[2])(DescriptorImage.create(ctx, fmt, W, H))
+    iL, ia, ip = mk(capi.FORMAT_R32G32B32A32_SFLOAT, L), mk(capi.FORMAT_R32G32B32A32_SFLOAT, alb), mk(capi.FORMAT_R32_SFLOAT, px)
+    out = DescriptorImage.create(ctx, capi.FORMAT_R32G32B32A32_SFLOAT, W, H)
+    out.compile()
+    demodulate(ctx, iL, ia, ip, out)
+    ctx.synchronize()
+    np.testing.assert_array_equal(out.download().view(np.uint32), oracle.demodulate(L, alb, px).view(np.uint32))
