@@ -174,3 +174,44 @@ def demodulate(radiance: np.ndarray, albedo: np.ndarray, position_x: np.ndarray)
              {0: (np.ascontiguousarray(radiance, np.float32), F_RGBA32F), 1: (np.ascontiguousarray(albedo, np.float32), F_RGBA32F),
               2: (np.ascontiguousarray(position_x, np.float32), F_R32F), 3: (out, F_RGBA32F)})
     return out
+
+
+# ---- the reference's HOST conversion code (source/io/RenderIO.cpp), oracle/host_shim ---------------------------------
+_HOST_LIB = _DIR / "_ref" / "libhostref.so"
+_host = None
+
+
+def build_host(reference: str = "/root/reference") -> bool:
+    if Path(reference, "source", "io", "RenderIO.cpp").exists():
+        r = subprocess.run(["make", "-C", str(_DIR / "host_shim"), f"REF={reference}"], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("oracle/_ref host build failed:\n" + r.stdout[-3000:] + r.stderr[-3000:])
+    return _HOST_LIB.exists()
+
+
+def gbuffer_import(inv_view, position=None, normal=None, albedo=None):
+    """GBufferIO::convert_normal_to_spherical, GBufferIO::compress_albedo and the position -> depth block of
+    import_g_buffer_position (RenderIO.cpp:101-120, :160-211) as the reference's own C++ text, compiled against vsg's
+    maths headers; same interface as oracle.gbuffer_import"""
+    global _host
+    if _host is None:
+        _host = C.CDLL(str(_HOST_LIB))
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    d = n = a = None
+    if position is not None:
+        position = np.ascontiguousarray(position, np.float32)
+        H, W = position.shape[:2]
+        d = np.zeros((H, W), np.float32)
+        iv = np.ascontiguousarray(inv_view, np.float32)
+        assert _host.hostref_depth(p(position), W, H, p(iv), p(d)) == 0
+    if normal is not None:
+        normal = np.ascontiguousarray(normal, np.float32)
+        H, W = normal.shape[:2]
+        n = np.zeros((H, W, 2), np.float32)
+        assert _host.hostref_normals(p(normal), W, H, p(n)) == 0
+    if albedo is not None:
+        albedo = np.ascontiguousarray(albedo, np.float32)
+        H, W = albedo.shape[:2]
+        a = np.zeros((H, W, 4), np.uint8)
+        assert _host.hostref_albedo(p(albedo), W, H, p(a)) == 0
+    return d, n, a

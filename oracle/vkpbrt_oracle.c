@@ -1151,13 +1151,18 @@ ORACLE_API void vkpbrt_oracle_demodulate(int W, int H, const float* radiance, co
 /* ------------------------------------------------------------------------------------ */
 /* GBufferIO::import_g_buffer_position conversions (source/io/RenderIO.cpp:101-120,       */
 /* :160-178, :180-195).  Inputs rgba32f [H][W][4] or NULL.  camera = inv_view[2] / w.      */
+/* Pinned against that C++ text itself (oracle/host_shim, tests/test_render_io.py).        */
 /* ------------------------------------------------------------------------------------ */
 ORACLE_API void vkpbrt_oracle_gbuffer_import(int W, int H, const float* inv_view, const float* position, const float* normal,
                                              const float* albedo, float* depth_out, float* normal_out, uint8_t* albedo_out)
 {
     float cam[3] = {0, 0, 0};
-    if (position)
-        for (int i = 0; i < 3; ++i) cam[i] = inv_view[8 + i] / inv_view[11];                 /* :109-110 */
+    if (position) {
+        /* :109-110 `camera_pos /= camera_pos.w`: vsg's t_vec4::operator/= multiplies by the reciprocal
+         * (external/vsg/include/vsg/maths/vec4.h:131-140), which rounds differently from a division */
+        const float inv = 1.0f / inv_view[11];
+        for (int i = 0; i < 3; ++i) cam[i] = inv_view[8 + i] * inv;
+    }
 #pragma omp parallel for schedule(static)
     for (int i = 0; i < W * H; ++i) {
         if (position) {

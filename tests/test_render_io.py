@@ -261,3 +261,33 @@ int main(int argc, char** argv) {
             assert (x.proj is None) == (y.proj is None)
             if y.proj is not None:
                 np.testing.assert_array_equal(np.asarray(x.inv_proj, np.float32), np.asarray(y.inv_proj, np.float32))
+
+
+def test_import_oracle_equals_the_reference_host_code(oracle):
+    """pins vkpbrt_oracle_gbuffer_import: the reference's own C++ (GBufferIO::convert_normal_to_spherical,
+    GBufferIO::compress_albedo and the position -> depth block of import_g_buffer_position, cut out of
+    source/io/RenderIO.cpp by oracle/host_shim/extract_host.py and compiled against vsg's maths headers) against the
+    oracle: depth and albedo bit for bit -- this is what showed that `camera_pos /= camera_pos.w` multiplies by the
+    reciprocal in vsg -- and the spherical normals within one ulp (acos / atan2 resolve to the double or the float libm
+    routine depending on the headers in scope)"""
+    from oracle import ref as R
+    if not R.build_host():
+        pytest.skip("oracle/_ref host library is not built and /root/reference is not mounted")
+    rng = np.random.default_rng(3)
+    for (H, W) in ((37, 50), (1, 1), (16, 129)):
+        pos = rng.uniform(-50, 50, (H, W, 4)).astype(np.float32)
+        v = rng.standard_normal((H, W, 3))
+        v /= np.linalg.norm(v, axis=-1, keepdims=True)
+        nrm = np.concatenate([v, np.ones((H, W, 1))], -1).astype(np.float32)
+        special = np.array([[0, 0, 1, 1], [0, 0, -1, 1], [1, 0, 0, 1], [0, -1, 0, 1], [-1, 0, 0, 1], [0.6, 0.8, 0, 1]], np.float32)
+        nrm.reshape(-1, 4)[:min(len(special), H * W)] = special[:H * W]
+        alb = rng.uniform(0, 1, (H, W, 4)).astype(np.float32)
+        edge = np.array([0, 0.5, 1.0, 0.999, 0.0039, 0.25, 1 / 255, 254.5 / 255], np.float32)
+        alb.reshape(-1)[:min(len(edge), alb.size)] = edge[:alb.size]
+        for trial in range(4):
+            iv = rng.uniform(-2, 2, 16).astype(np.float32)
+            iv[11] = np.float32([0.37, 3.0, -1.7, 1.0][trial])           # the w the eye point is divided by
+            a, b = oracle.gbuffer_import(iv, pos, nrm, alb), R.gbuffer_import(iv, pos, nrm, alb)
+            np.testing.assert_array_equal(a[0].view(np.uint32), b[0].view(np.uint32), err_msg="depth")
+            np.testing.assert_array_equal(a[2], b[2], err_msg="albedo")
+            np.testing.assert_array_max_ulp(a[1], b[1], maxulp=1)

@@ -1485,7 +1485,10 @@ int vkpbrt_gbuffer_import_record(vkpbrt_gbuffer_t g, vkpbrt_image_t position, co
     vkpbrt::GBufferImportParams p{};
     p.W = (int)g->width; p.H = (int)g->height;
     if (position) {
-        for (int i = 0; i < 3; ++i) p.camera[i] = inv_view[8 + i] / inv_view[11];        // RenderIO.cpp:109-110: inv_view[2] / w
+        // RenderIO.cpp:109-110 `camera_pos = inv_view[2]; camera_pos /= camera_pos.w`: vsg's vec4 /= multiplies by the
+        // reciprocal (vsg/maths/vec4.h:131-140) -- not the same rounding as a division
+        const float inv_w = 1.0f / inv_view[11];
+        for (int i = 0; i < 3; ++i) p.camera[i] = inv_view[8 + i] * inv_w;
         p.position = (const float4*)position->data;
         p.depth = (float*)g->img[VKPBRT_GBUFFER_DEPTH]->data;
         VK_REQUIRE(p.depth, "vkpbrt_gbuffer_import_record: the g-buffer is not compiled");

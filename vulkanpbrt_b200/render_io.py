@@ -117,7 +117,7 @@ class GBufferIO:
         offline matrices are combined view-projections, for which that column of the inverse is the eye point"""
         iv = np.asarray(matrices.inv_view, dtype=np.float32).reshape(4, 4)      # [col][row]
         with np.errstate(divide="ignore", invalid="ignore"):
-            cam = (iv[2] / iv[2][3])[:3].astype(np.float32)
+            cam = (iv[2] * (np.float32(1.0) / iv[2][3]))[:3].astype(np.float32)      # vsg's vec4 /= multiplies by the reciprocal
         d = cam[None, None, :] - _rgba(position)[..., :3].astype(np.float32)
         return np.sqrt((d * d).sum(axis=-1, dtype=np.float32)).astype(np.float32)
 
