@@ -198,27 +198,9 @@ public:
         f << "\n    ]\n}\n";
         return (bool)f;
     }
-    // 4x4 inverse by cofactors in binary32, column-major in and out: vsg's inverse_4x4 evaluation order -- the same one the
-    // library's set_camera_matrices and the oracle use, so a matrix loaded from a text file gets the inverse the
-    // accumulator would get
-    static void inverse(const float* m, float* inv)
-    {
-        const float a00 = m[0], a01 = m[1], a02 = m[2], a03 = m[3], a10 = m[4], a11 = m[5], a12 = m[6], a13 = m[7];
-        const float a20 = m[8], a21 = m[9], a22 = m[10], a23 = m[11], a30 = m[12], a31 = m[13], a32 = m[14], a33 = m[15];
-        const float b00 = a00 * a11 - a01 * a10, b01 = a00 * a12 - a02 * a10, b02 = a00 * a13 - a03 * a10, b03 = a01 * a12 - a02 * a11;
-        const float b04 = a01 * a13 - a03 * a11, b05 = a02 * a13 - a03 * a12, b06 = a20 * a31 - a21 * a30, b07 = a20 * a32 - a22 * a30;
-        const float b08 = a20 * a33 - a23 * a30, b09 = a21 * a32 - a22 * a31, b10 = a21 * a33 - a23 * a31, b11 = a22 * a33 - a23 * a32;
-        const float det = ((((b00 * b11 - b01 * b10) + b02 * b09) + b03 * b08) - b04 * b07) + b05 * b06;
-        const float id = 1.0f / det;
-        inv[0] = ((a11 * b11 - a12 * b10) + a13 * b09) * id;  inv[1] = ((a02 * b10 - a01 * b11) - a03 * b09) * id;
-        inv[2] = ((a31 * b05 - a32 * b04) + a33 * b03) * id;  inv[3] = ((a22 * b04 - a21 * b05) - a23 * b03) * id;
-        inv[4] = ((a12 * b08 - a10 * b11) - a13 * b07) * id;  inv[5] = ((a00 * b11 - a02 * b08) + a03 * b07) * id;
-        inv[6] = ((a32 * b02 - a30 * b05) - a33 * b01) * id;  inv[7] = ((a20 * b05 - a22 * b02) + a23 * b01) * id;
-        inv[8] = ((a10 * b10 - a11 * b08) + a13 * b06) * id;  inv[9] = ((a01 * b08 - a00 * b10) - a03 * b06) * id;
-        inv[10] = ((a30 * b04 - a31 * b02) + a33 * b00) * id; inv[11] = ((a21 * b02 - a20 * b04) - a23 * b00) * id;
-        inv[12] = ((a11 * b07 - a10 * b09) - a12 * b06) * id; inv[13] = ((a00 * b09 - a01 * b07) + a02 * b06) * id;
-        inv[14] = ((a31 * b01 - a30 * b03) - a32 * b00) * id; inv[15] = ((a20 * b03 - a21 * b01) + a22 * b00) * id;
-    }
+    // vsg::inverse(mat4), what the reference's import calls (RenderIO.cpp:659): the library's restatement of it
+    // (vkpbrt_mat4_inverse; external/vsg/src/vsg/maths/maths_transform.cpp:36-156)
+    static void inverse(const float* m, float* inv) { check(vkpbrt_mat4_inverse(m, inv)); }
 private:
     static mat4 to_mat(const json::Value& v)
     {

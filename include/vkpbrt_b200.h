@@ -71,6 +71,11 @@ VKPBRT_API int vkpbrt_context_synchronize(vkpbrt_context_t ctx);
 VKPBRT_API int vkpbrt_context_stream(vkpbrt_context_t ctx, void** cuda_stream);
 /* number of kernels this context has launched so far (bench.py's gpu_launches)               */
 VKPBRT_API int vkpbrt_context_launch_count(vkpbrt_context_t ctx, uint64_t* out);
+/* vsg::inverse(const mat4&) as the reference's host code uses it (Accumulator.cpp:100, the BMFR-dataset matrix import
+ * RenderIO.cpp:639-664; external/vsg/src/vsg/maths/maths_transform.cpp:36-156): column-major 4x4, binary32, the same
+ * operations in the same order, so a host that lets this library invert its matrices feeds the modules the bits the
+ * reference would.  Pure host code: needs no device.  m and inverse may alias. */
+VKPBRT_API int vkpbrt_mat4_inverse(const float m[16], float inverse[16]);
 /* CUDA devices of this process and their 16-byte UUIDs: a Vulkan host picks the CUDA device whose UUID equals
  * VkPhysicalDeviceIDProperties::deviceUUID of the VkPhysicalDevice it renders on (include/vkpbrt/vk_interop.hpp);
  * external memory can only be imported on the device that exported it. */

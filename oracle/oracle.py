@@ -48,6 +48,7 @@ def lib():
         l.vkpbrt_oracle_f16_to_f32.argtypes = [C.c_uint16]; l.vkpbrt_oracle_f16_to_f32.restype = C.c_float
         l.vkpbrt_oracle_f32_to_unorm8.argtypes = [C.c_float]; l.vkpbrt_oracle_f32_to_unorm8.restype = C.c_uint8
         l.vkpbrt_oracle_mat_inverse.argtypes = [vp, vp]; l.vkpbrt_oracle_mat_inverse.restype = None
+        l.vkpbrt_oracle_vsg_inverse.argtypes = [vp, vp]; l.vkpbrt_oracle_vsg_inverse.restype = None
         l.vkpbrt_oracle_mat_mul.argtypes = [vp, vp, vp]; l.vkpbrt_oracle_mat_mul.restype = None
         l.vkpbrt_oracle_accumulator.argtypes = [i32, i32, i32, C.POINTER(AccPush), vp, i32, vp, vp, vp, vp, vp, vp, vp]
         l.vkpbrt_oracle_accumulator.restype = None
@@ -92,6 +93,14 @@ def mat_inverse(m) -> np.ndarray:
     a = np.ascontiguousarray(m, dtype=np.float32).reshape(16)
     out = np.empty(16, np.float32)
     lib().vkpbrt_oracle_mat_inverse(_p(a), _p(out))
+    return out
+
+
+def vsg_inverse(m) -> np.ndarray:
+    """vsg::inverse(mat4) as the reference's HOST code calls it (not the shader's inverse(): that is mat_inverse)"""
+    a = np.ascontiguousarray(m, dtype=np.float32).reshape(16)
+    out = np.empty(16, np.float32)
+    lib().vkpbrt_oracle_vsg_inverse(_p(a), _p(out))
     return out
 
 
@@ -152,7 +161,7 @@ class OracleChain:
             put(pc.inv_view, cam.inv_view)
             if frame_index != 0:
                 put(pc.prev_view, self.prev_view)
-                inv = mat_inverse(self.prev_view)
+                inv = vsg_inverse(self.prev_view)               # :100 inverse(prev.view)[3]: vsg's host-side inverse
                 put(pc.prev_origin, [inv[12], inv[13], inv[14], 1.0])
         else:
             from vulkanpbrt_b200.pipeline import _combined   # host-side matrix prep shared with the pipeline helper
@@ -162,8 +171,8 @@ class OracleChain:
             if frame_index != 0:
                 pvp, pivp = _combined(self.prev_cam)
                 put(pc.prev_view, pvp)
-                w = np.float32(pivp[11])
-                put(pc.prev_origin, [np.float32(pivp[8 + i]) / w for i in range(4)])
+                inv_w = np.float32(1.0) / np.float32(pivp[11])     # :110-111 vsg's vec4 /= multiplies by the reciprocal
+                put(pc.prev_origin, [np.float32(pivp[8 + i]) * inv_w for i in range(4)])
         pc.frame_number = frame_index
 
     def final(self) -> np.ndarray:

@@ -262,6 +262,76 @@ static void mat_inverse(const float* m, float* inv)
 }
 
 ORACLE_API void vkpbrt_oracle_mat_inverse(const float* m, float* inv) { mat_inverse(m, inv); }
+
+/* vsg::inverse(const mat4&) as the reference's HOST code calls it (Accumulator.cpp:100 `inverse(prev.view)[3]`, the
+ * BMFR-dataset matrix import RenderIO.cpp:639-664): external/vsg/src/vsg/maths/maths_transform.cpp:36-156 -- an affine
+ * matrix (last row 0 0 0 1) takes t_inverse_4x3, everything else t_inverse_4x4; a zero determinant yields NaN on the
+ * diagonal.  Expressions in the source's order (a - b + c is (a - b) + c).  Pinned against that source text itself
+ * (oracle/host_shim, tests/test_matrix_io.py).  NOT the shader's inverse(): that one is mat_inverse above. */
+#define M_(c, r) m[4 * (c) + (r)]
+static void vsg_inverse(const float* m, float* o)
+{
+    const float nan = NAN;
+    if (M_(0, 3) == 0.0f && M_(1, 3) == 0.0f && M_(2, 3) == 0.0f && M_(3, 3) == 1.0f) {
+        const float det = (M_(0, 0) * (M_(1, 1) * M_(2, 2) - M_(1, 2) * M_(2, 1)) - M_(0, 1) * (M_(1, 0) * M_(2, 2) - M_(1, 2) * M_(2, 0))) +
+                          M_(0, 2) * (M_(1, 0) * M_(2, 1) - M_(1, 1) * M_(2, 0));
+        if (det == 0.0f) { for (int i = 0; i < 16; ++i) o[i] = (i % 5 == 0) ? nan : 0.0f; return; }
+        const float A1223 = M_(2, 1) * M_(3, 2) - M_(2, 2) * M_(3, 1), A0223 = M_(2, 0) * M_(3, 2) - M_(2, 2) * M_(3, 0);
+        const float A0123 = M_(2, 0) * M_(3, 1) - M_(2, 1) * M_(3, 0), A1213 = M_(1, 1) * M_(3, 2) - M_(1, 2) * M_(3, 1);
+        const float A0213 = M_(1, 0) * M_(3, 2) - M_(1, 2) * M_(3, 0), A0113 = M_(1, 0) * M_(3, 1) - M_(1, 1) * M_(3, 0);
+        const float id = 1.0f / det;
+        o[0] = id * (M_(1, 1) * M_(2, 2) - M_(1, 2) * M_(2, 1));
+        o[1] = id * (M_(0, 2) * M_(2, 1) - M_(0, 1) * M_(2, 2));
+        o[2] = id * (M_(0, 1) * M_(1, 2) - M_(0, 2) * M_(1, 1));
+        o[3] = 0.0f;
+        o[4] = id * (M_(1, 2) * M_(2, 0) - M_(1, 0) * M_(2, 2));
+        o[5] = id * (M_(0, 0) * M_(2, 2) - M_(0, 2) * M_(2, 0));
+        o[6] = id * (M_(0, 2) * M_(1, 0) - M_(0, 0) * M_(1, 2));
+        o[7] = 0.0f;
+        o[8] = id * (M_(1, 0) * M_(2, 1) - M_(1, 1) * M_(2, 0));
+        o[9] = id * (M_(0, 1) * M_(2, 0) - M_(0, 0) * M_(2, 1));
+        o[10] = id * (M_(0, 0) * M_(1, 1) - M_(0, 1) * M_(1, 0));
+        o[11] = 0.0f;
+        o[12] = id * ((M_(1, 1) * A0223 - M_(1, 2) * A0123) - M_(1, 0) * A1223);
+        o[13] = id * ((M_(0, 0) * A1223 - M_(0, 1) * A0223) + M_(0, 2) * A0123);
+        o[14] = id * ((M_(0, 1) * A0213 - M_(0, 2) * A0113) - M_(0, 0) * A1213);
+        o[15] = 1.0f;
+        return;
+    }
+    const float A2323 = M_(2, 2) * M_(3, 3) - M_(2, 3) * M_(3, 2), A1323 = M_(2, 1) * M_(3, 3) - M_(2, 3) * M_(3, 1);
+    const float A1223 = M_(2, 1) * M_(3, 2) - M_(2, 2) * M_(3, 1), A0323 = M_(2, 0) * M_(3, 3) - M_(2, 3) * M_(3, 0);
+    const float A0223 = M_(2, 0) * M_(3, 2) - M_(2, 2) * M_(3, 0), A0123 = M_(2, 0) * M_(3, 1) - M_(2, 1) * M_(3, 0);
+    const float A2313 = M_(1, 2) * M_(3, 3) - M_(1, 3) * M_(3, 2), A1313 = M_(1, 1) * M_(3, 3) - M_(1, 3) * M_(3, 1);
+    const float A1213 = M_(1, 1) * M_(3, 2) - M_(1, 2) * M_(3, 1), A2312 = M_(1, 2) * M_(2, 3) - M_(1, 3) * M_(2, 2);
+    const float A1312 = M_(1, 1) * M_(2, 3) - M_(1, 3) * M_(2, 1), A1212 = M_(1, 1) * M_(2, 2) - M_(1, 2) * M_(2, 1);
+    const float A0313 = M_(1, 0) * M_(3, 3) - M_(1, 3) * M_(3, 0), A0213 = M_(1, 0) * M_(3, 2) - M_(1, 2) * M_(3, 0);
+    const float A0312 = M_(1, 0) * M_(2, 3) - M_(1, 3) * M_(2, 0), A0212 = M_(1, 0) * M_(2, 2) - M_(1, 2) * M_(2, 0);
+    const float A0113 = M_(1, 0) * M_(3, 1) - M_(1, 1) * M_(3, 0), A0112 = M_(1, 0) * M_(2, 1) - M_(1, 1) * M_(2, 0);
+    const float det = ((M_(0, 0) * ((M_(1, 1) * A2323 - M_(1, 2) * A1323) + M_(1, 3) * A1223) - M_(0, 1) * ((M_(1, 0) * A2323 - M_(1, 2) * A0323) + M_(1, 3) * A0223)) +
+                       M_(0, 2) * ((M_(1, 0) * A1323 - M_(1, 1) * A0323) + M_(1, 3) * A0123)) -
+                      M_(0, 3) * ((M_(1, 0) * A1223 - M_(1, 1) * A0223) + M_(1, 2) * A0123);
+    if (det == 0.0f) { for (int i = 0; i < 16; ++i) o[i] = (i % 5 == 0) ? nan : 0.0f; return; }
+    const float id = 1.0f / det;
+    o[0] = id * ((M_(1, 1) * A2323 - M_(1, 2) * A1323) + M_(1, 3) * A1223);
+    o[1] = id * -((M_(0, 1) * A2323 - M_(0, 2) * A1323) + M_(0, 3) * A1223);
+    o[2] = id * ((M_(0, 1) * A2313 - M_(0, 2) * A1313) + M_(0, 3) * A1213);
+    o[3] = id * -((M_(0, 1) * A2312 - M_(0, 2) * A1312) + M_(0, 3) * A1212);
+    o[4] = id * -((M_(1, 0) * A2323 - M_(1, 2) * A0323) + M_(1, 3) * A0223);
+    o[5] = id * ((M_(0, 0) * A2323 - M_(0, 2) * A0323) + M_(0, 3) * A0223);
+    o[6] = id * -((M_(0, 0) * A2313 - M_(0, 2) * A0313) + M_(0, 3) * A0213);
+    o[7] = id * ((M_(0, 0) * A2312 - M_(0, 2) * A0312) + M_(0, 3) * A0212);
+    o[8] = id * ((M_(1, 0) * A1323 - M_(1, 1) * A0323) + M_(1, 3) * A0123);
+    o[9] = id * -((M_(0, 0) * A1323 - M_(0, 1) * A0323) + M_(0, 3) * A0123);
+    o[10] = id * ((M_(0, 0) * A1313 - M_(0, 1) * A0313) + M_(0, 3) * A0113);
+    o[11] = id * -((M_(0, 0) * A1312 - M_(0, 1) * A0312) + M_(0, 3) * A0112);
+    o[12] = id * -((M_(1, 0) * A1223 - M_(1, 1) * A0223) + M_(1, 2) * A0123);
+    o[13] = id * ((M_(0, 0) * A1223 - M_(0, 1) * A0223) + M_(0, 2) * A0123);
+    o[14] = id * -((M_(0, 0) * A1213 - M_(0, 1) * A0213) + M_(0, 2) * A0113);
+    o[15] = id * ((M_(0, 0) * A1212 - M_(0, 1) * A0212) + M_(0, 2) * A0112);
+}
+#undef M_
+ORACLE_API void vkpbrt_oracle_vsg_inverse(const float* m, float* inv) { vsg_inverse(m, inv); }
+
 ORACLE_API void vkpbrt_oracle_mat_mul(const float* a, const float* b, float* r) { mat_mul(a, b, r); }
 
 /* ------------------------------------------------------------------------------------ */

@@ -56,19 +56,106 @@ def test_bmfr_dataset_text_format(tmp_path, oracle):
     for c, m in zip(cams, got):
         np.testing.assert_array_equal(m.view, c.view.astype(np.float32))
         want = (C.c_float * 16)()
-        L.vkpbrt_oracle_mat_inverse((C.c_float * 16)(*[float(x) for x in c.view]), want)
+        L.vkpbrt_oracle_vsg_inverse((C.c_float * 16)(*[float(x) for x in c.view]), want)      # RenderIO.cpp:659 inverse(tmp) is vsg's
         np.testing.assert_array_equal(m.inv_view.view(np.uint32), np.array(list(want), np.float32).view(np.uint32))
         assert m.proj is None
 
 
+def _matrices(n, seed):
+    """affine, general and singular matrices, plus the synthetic sequence's own"""
+    rng = np.random.default_rng(seed)
+    out = []
+    for f in range(12):
+        cam = synth.camera(160, 128, f)
+        v = np.asarray(cam.view, np.float64).reshape(4, 4).T
+        p = np.asarray(cam.proj, np.float64).reshape(4, 4).T
+        out += [cam.view, cam.proj, cam.inv_view, cam.inv_proj, (p @ v).T.astype(np.float32).reshape(-1)]
+    for _ in range(n):
+        m = rng.uniform(-3, 3, 16).astype(np.float32)
+        if rng.random() < 0.5:
+            m[3] = m[7] = m[11] = 0
+            m[15] = 1                      # affine: vsg takes t_inverse_4x3
+        if rng.random() < 0.05:
+            m[4:8] = m[0:4]                # singular: NaN on the diagonal
+        out.append(m)
+    out += [np.zeros(16, np.float32), np.eye(4, dtype=np.float32).reshape(-1)]
+    return [np.ascontiguousarray(m, np.float32) for m in out]
+
+
+def _same_bits(a, b):
+    x, y = np.asarray(a, np.float32).view(np.uint32).copy(), np.asarray(b, np.float32).view(np.uint32).copy()
+    nan = np.isnan(a) & np.isnan(b)
+    x[nan] = 0
+    y[nan] = 0
+    return np.array_equal(x, y)
+
+
 def test_inverse_matches_the_oracle_bit_for_bit(oracle):
-    L = oracle.lib()
-    rng = np.random.default_rng(7)
-    for _ in range(50):
-        m = rng.standard_normal(16).astype(np.float32)
-        want = (C.c_float * 16)()
-        L.vkpbrt_oracle_mat_inverse((C.c_float * 16)(*[float(x) for x in m]), want)
-        np.testing.assert_array_equal(_inverse(m).view(np.uint32), np.array(list(want), np.float32).view(np.uint32))
+    """the library's vkpbrt_mat4_inverse (what matrix_io and include/vkpbrt/io.hpp call) against the oracle's restatement"""
+    for m in _matrices(300, 7):
+        assert _same_bits(_inverse(m), oracle.vsg_inverse(m))
+
+
+def _hostref():
+    from oracle import ref as R
+    if not R.build_host():
+        pytest.skip("oracle/_ref host library is not built and /root/reference is not mounted")
+    h = C.CDLL(str(R._HOST_LIB))
+    return h
+
+
+def test_vsg_inverse_equals_the_reference_source(oracle):
+    """pins vkpbrt_oracle_vsg_inverse: vsg's own t_inverse_4x3 / t_inverse_4x4 / inverse(mat4) text
+    (external/vsg/src/vsg/maths/maths_transform.cpp, compiled by oracle/host_shim) on affine, general and singular
+    matrices, bit for bit.  (Round 1 and most of round 2 restated the HOST inverse with the shader-side cofactor formula:
+    same value to the last bits or so, not the same bits.)"""
+    h = _hostref()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    for m in _matrices(2000, 1):
+        want = np.zeros(16, np.float32)
+        h.hostref_inverse(p(m), p(want))
+        assert _same_bits(oracle.vsg_inverse(m), want), m
+
+
+@pytest.mark.parametrize("separate", [True, False])
+def test_set_camera_matrices_equals_the_reference_source(oracle, separate):
+    """pins the oracle's Accumulator::set_camera_matrices against the reference's own text (Accumulator.cpp:85-117, compiled
+    by oracle/host_shim together with vsg's inverse): the 212-byte push-constant block frame by frame, both matrix modes;
+    `inverse(prev.view)[3]` and `prev_pos /= prev_pos.w` (a multiplication by the reciprocal in vsg) included"""
+    from vulkanpbrt_b200.pipeline import _combined
+    h = _hostref()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    W, H = 160, 128
+    chain = oracle.OracleChain(W, H, "bmfr", 32, separate_matrices=separate)
+    pc = np.zeros(53, np.float32)
+
+    def pack(cam):
+        if separate:
+            return np.concatenate([cam.view, cam.inv_view, cam.proj, cam.inv_proj]).astype(np.float32), 1
+        vp, ivp = _combined(cam)
+        return np.concatenate([vp, ivp, np.zeros(32, np.float32)]).astype(np.float32), 0
+
+    prev_cam = None
+    for f in range(6):
+        cam = synth.camera(W, H, f)
+        chain._set_camera_matrices(f, cam)
+        cur64, has = pack(cam)
+        if separate:
+            # VulkanPBRT.cpp:578-584: prev.view is the push constants' prev_view (identity before the first frame)
+            prev64 = np.concatenate([chain.prev_view, np.zeros(48, np.float32)]).astype(np.float32)
+        else:
+            prev64, _ = pack(prev_cam if prev_cam is not None else cam)
+        assert h.hostref_set_camera_matrices(1 if separate else 0, f, p(cur64), has, p(prev64), has if not separate else 0, p(pc)) == 0
+        got = np.concatenate([np.array(list(chain.pc.view), np.float32), np.array(list(chain.pc.inv_view), np.float32),
+                              np.array(list(chain.pc.prev_view), np.float32), np.array(list(chain.pc.prev_origin), np.float32)])
+        assert _same_bits(got, pc[:52]), f"frame {f}"
+        assert chain.pc.frame_number == int(pc[52:].view(np.int32)[0]) == f
+        chain.prev_view = np.asarray(cam.view, np.float32).copy()        # what run_frame does at the end of a frame
+        chain.prev_cam = prev_cam = cam
+    # the missing-matrices error of the separate mode (Accumulator.cpp:89-94)
+    if separate:
+        cur64, _ = pack(synth.camera(W, H, 0))
+        assert h.hostref_set_camera_matrices(1, 0, p(cur64), 0, p(cur64), 0, p(pc)) == 1
 
 
 def test_missing_file_returns_an_empty_list(tmp_path, capsys):

@@ -39,6 +39,7 @@
 #include <cstring>
 #include <fstream>
 #include <iostream>
+#include <limits>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -340,21 +341,70 @@ struct AccumulatorPush { float view[16], inv_view[16], prev_view[16], prev_pos[4
 struct RayTracingPush { float view_inverse[16], proj_inverse[16], prev_view[16]; uint32_t frame_number, sample_number; };
 static_assert(sizeof(AccumulatorPush) == 212 && sizeof(RayTracingPush) == 200, "push constant layouts");
 
-// translation column of inverse(m) for a column-major 4x4: vsg's inverse_4x4 (cofactors over one determinant, all in
-// float, products before sums), the terms inverse(prev.view)[3] needs (Accumulator.cpp:100)
-static void inverse_column3(const float* m, float out[3])
+// vsg::inverse(const mat4&) (external/vsg/src/vsg/maths/maths_transform.cpp:36-156), which Accumulator.cpp:100 calls for
+// inverse(prev.view)[3]: affine matrices take t_inverse_4x3, the rest t_inverse_4x4; expressions in the source's order
+#define M_(c, r) m[4 * (c) + (r)]
+static void vsg_inverse(const float* m, float* o)
 {
-    const float a00 = m[0], a01 = m[1], a02 = m[2], a03 = m[3], a10 = m[4], a11 = m[5], a12 = m[6], a13 = m[7];
-    const float a20 = m[8], a21 = m[9], a22 = m[10], a23 = m[11], a30 = m[12], a31 = m[13], a32 = m[14], a33 = m[15];
-    const float b00 = a00 * a11 - a01 * a10, b01 = a00 * a12 - a02 * a10, b02 = a00 * a13 - a03 * a10, b03 = a01 * a12 - a02 * a11;
-    const float b04 = a01 * a13 - a03 * a11, b05 = a02 * a13 - a03 * a12, b06 = a20 * a31 - a21 * a30, b07 = a20 * a32 - a22 * a30;
-    const float b08 = a20 * a33 - a23 * a30, b09 = a21 * a32 - a22 * a31, b10 = a21 * a33 - a23 * a31, b11 = a22 * a33 - a23 * a32;
-    const float det = ((((b00 * b11 - b01 * b10) + b02 * b09) + b03 * b08) - b04 * b07) + b05 * b06;
+    const float nan = std::numeric_limits<float>::quiet_NaN();
+    if (M_(0, 3) == 0.0f && M_(1, 3) == 0.0f && M_(2, 3) == 0.0f && M_(3, 3) == 1.0f) {
+        const float det = (M_(0, 0) * (M_(1, 1) * M_(2, 2) - M_(1, 2) * M_(2, 1)) - M_(0, 1) * (M_(1, 0) * M_(2, 2) - M_(1, 2) * M_(2, 0))) +
+                          M_(0, 2) * (M_(1, 0) * M_(2, 1) - M_(1, 1) * M_(2, 0));
+        if (det == 0.0f) { for (int i = 0; i < 16; ++i) o[i] = (i % 5 == 0) ? nan : 0.0f; return; }
+        const float A1223 = M_(2, 1) * M_(3, 2) - M_(2, 2) * M_(3, 1), A0223 = M_(2, 0) * M_(3, 2) - M_(2, 2) * M_(3, 0);
+        const float A0123 = M_(2, 0) * M_(3, 1) - M_(2, 1) * M_(3, 0), A1213 = M_(1, 1) * M_(3, 2) - M_(1, 2) * M_(3, 1);
+        const float A0213 = M_(1, 0) * M_(3, 2) - M_(1, 2) * M_(3, 0), A0113 = M_(1, 0) * M_(3, 1) - M_(1, 1) * M_(3, 0);
+        const float id = 1.0f / det;
+        o[0] = id * (M_(1, 1) * M_(2, 2) - M_(1, 2) * M_(2, 1));
+        o[1] = id * (M_(0, 2) * M_(2, 1) - M_(0, 1) * M_(2, 2));
+        o[2] = id * (M_(0, 1) * M_(1, 2) - M_(0, 2) * M_(1, 1));
+        o[3] = 0.0f;
+        o[4] = id * (M_(1, 2) * M_(2, 0) - M_(1, 0) * M_(2, 2));
+        o[5] = id * (M_(0, 0) * M_(2, 2) - M_(0, 2) * M_(2, 0));
+        o[6] = id * (M_(0, 2) * M_(1, 0) - M_(0, 0) * M_(1, 2));
+        o[7] = 0.0f;
+        o[8] = id * (M_(1, 0) * M_(2, 1) - M_(1, 1) * M_(2, 0));
+        o[9] = id * (M_(0, 1) * M_(2, 0) - M_(0, 0) * M_(2, 1));
+        o[10] = id * (M_(0, 0) * M_(1, 1) - M_(0, 1) * M_(1, 0));
+        o[11] = 0.0f;
+        o[12] = id * ((M_(1, 1) * A0223 - M_(1, 2) * A0123) - M_(1, 0) * A1223);
+        o[13] = id * ((M_(0, 0) * A1223 - M_(0, 1) * A0223) + M_(0, 2) * A0123);
+        o[14] = id * ((M_(0, 1) * A0213 - M_(0, 2) * A0113) - M_(0, 0) * A1213);
+        o[15] = 1.0f;
+        return;
+    }
+    const float A2323 = M_(2, 2) * M_(3, 3) - M_(2, 3) * M_(3, 2), A1323 = M_(2, 1) * M_(3, 3) - M_(2, 3) * M_(3, 1);
+    const float A1223 = M_(2, 1) * M_(3, 2) - M_(2, 2) * M_(3, 1), A0323 = M_(2, 0) * M_(3, 3) - M_(2, 3) * M_(3, 0);
+    const float A0223 = M_(2, 0) * M_(3, 2) - M_(2, 2) * M_(3, 0), A0123 = M_(2, 0) * M_(3, 1) - M_(2, 1) * M_(3, 0);
+    const float A2313 = M_(1, 2) * M_(3, 3) - M_(1, 3) * M_(3, 2), A1313 = M_(1, 1) * M_(3, 3) - M_(1, 3) * M_(3, 1);
+    const float A1213 = M_(1, 1) * M_(3, 2) - M_(1, 2) * M_(3, 1), A2312 = M_(1, 2) * M_(2, 3) - M_(1, 3) * M_(2, 2);
+    const float A1312 = M_(1, 1) * M_(2, 3) - M_(1, 3) * M_(2, 1), A1212 = M_(1, 1) * M_(2, 2) - M_(1, 2) * M_(2, 1);
+    const float A0313 = M_(1, 0) * M_(3, 3) - M_(1, 3) * M_(3, 0), A0213 = M_(1, 0) * M_(3, 2) - M_(1, 2) * M_(3, 0);
+    const float A0312 = M_(1, 0) * M_(2, 3) - M_(1, 3) * M_(2, 0), A0212 = M_(1, 0) * M_(2, 2) - M_(1, 2) * M_(2, 0);
+    const float A0113 = M_(1, 0) * M_(3, 1) - M_(1, 1) * M_(3, 0), A0112 = M_(1, 0) * M_(2, 1) - M_(1, 1) * M_(2, 0);
+    const float det = ((M_(0, 0) * ((M_(1, 1) * A2323 - M_(1, 2) * A1323) + M_(1, 3) * A1223) - M_(0, 1) * ((M_(1, 0) * A2323 - M_(1, 2) * A0323) + M_(1, 3) * A0223)) +
+                       M_(0, 2) * ((M_(1, 0) * A1323 - M_(1, 1) * A0323) + M_(1, 3) * A0123)) -
+                      M_(0, 3) * ((M_(1, 0) * A1223 - M_(1, 1) * A0223) + M_(1, 2) * A0123);
+    if (det == 0.0f) { for (int i = 0; i < 16; ++i) o[i] = (i % 5 == 0) ? nan : 0.0f; return; }
     const float id = 1.0f / det;
-    out[0] = ((a11 * b07 - a10 * b09) - a12 * b06) * id;
-    out[1] = ((a00 * b09 - a01 * b07) + a02 * b06) * id;
-    out[2] = ((a31 * b01 - a30 * b03) - a32 * b00) * id;
+    o[0] = id * ((M_(1, 1) * A2323 - M_(1, 2) * A1323) + M_(1, 3) * A1223);
+    o[1] = id * -((M_(0, 1) * A2323 - M_(0, 2) * A1323) + M_(0, 3) * A1223);
+    o[2] = id * ((M_(0, 1) * A2313 - M_(0, 2) * A1313) + M_(0, 3) * A1213);
+    o[3] = id * -((M_(0, 1) * A2312 - M_(0, 2) * A1312) + M_(0, 3) * A1212);
+    o[4] = id * -((M_(1, 0) * A2323 - M_(1, 2) * A0323) + M_(1, 3) * A0223);
+    o[5] = id * ((M_(0, 0) * A2323 - M_(0, 2) * A0323) + M_(0, 3) * A0223);
+    o[6] = id * -((M_(0, 0) * A2313 - M_(0, 2) * A0313) + M_(0, 3) * A0213);
+    o[7] = id * ((M_(0, 0) * A2312 - M_(0, 2) * A0312) + M_(0, 3) * A0212);
+    o[8] = id * ((M_(1, 0) * A1323 - M_(1, 1) * A0323) + M_(1, 3) * A0123);
+    o[9] = id * -((M_(0, 0) * A1323 - M_(0, 1) * A0323) + M_(0, 3) * A0123);
+    o[10] = id * ((M_(0, 0) * A1313 - M_(0, 1) * A0313) + M_(0, 3) * A0113);
+    o[11] = id * -((M_(0, 0) * A1312 - M_(0, 1) * A0312) + M_(0, 3) * A0112);
+    o[12] = id * -((M_(1, 0) * A1223 - M_(1, 1) * A0223) + M_(1, 2) * A0123);
+    o[13] = id * ((M_(0, 0) * A1223 - M_(0, 1) * A0223) + M_(0, 2) * A0123);
+    o[14] = id * -((M_(0, 0) * A1213 - M_(0, 1) * A0213) + M_(0, 2) * A0113);
+    o[15] = id * ((M_(0, 0) * A1212 - M_(0, 1) * A0212) + M_(0, 2) * A0112);
 }
+#undef M_
 
 static void barrier(const Vk& vk, VkCommandBuffer cb, VkPipelineStageFlags src, VkPipelineStageFlags dst)
 {
@@ -553,7 +603,9 @@ int main(int argc, char** argv)
             memcpy(apc.inv_view, inv_view, 64);
             if (f != 0) {
                 memcpy(apc.prev_view, rpc.prev_view, 64);                // b.view = pc.prev_view (VulkanPBRT.cpp:578-584)
-                inverse_column3(rpc.prev_view, apc.prev_pos);
+                float inv[16];
+                vsg_inverse(rpc.prev_view, inv);
+                apc.prev_pos[0] = inv[12]; apc.prev_pos[1] = inv[13]; apc.prev_pos[2] = inv[14];
                 apc.prev_pos[3] = 1.f;
             }
             apc.frame_number = f;

@@ -97,6 +97,7 @@ _PROTOS = {
     "vkpbrt_image_download": [H, C.c_void_p, u64],
     "vkpbrt_image_clear": [H],
     "vkpbrt_image_copy_record": [H, H],
+    "vkpbrt_mat4_inverse": [C.c_void_p, C.c_void_p],
     "vkpbrt_device_count": [C.POINTER(i32)],
     "vkpbrt_device_uuid": [i32, C.c_void_p],
     "vkpbrt_image_retain": [H],

@@ -17,6 +17,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <new>
 #include <string>
 #include <vector>
@@ -89,6 +90,73 @@ void mat_inverse(const float* m, float* inv)
     inv[14] = ((a31 * b01 - a30 * b03) - a32 * b00) * id;
     inv[15] = ((a20 * b03 - a21 * b01) + a22 * b00) * id;
 }
+
+// vsg::inverse(const mat4&), what the reference's HOST code calls (Accumulator.cpp:100 `inverse(prev.view)[3]`, the
+// BMFR-dataset matrix import RenderIO.cpp:639-664): external/vsg/src/vsg/maths/maths_transform.cpp:36-156 -- affine
+// matrices take t_inverse_4x3, the rest t_inverse_4x4, a zero determinant yields NaN on the diagonal; expressions in the
+// source's order.  Not the shader's inverse() above.  The oracle's copy is pinned against that source (oracle/host_shim).
+#define M_(c, r) m[4 * (c) + (r)]
+void vsg_inverse(const float* m, float* o)
+{
+    const float nan = std::numeric_limits<float>::quiet_NaN();
+    if (M_(0, 3) == 0.0f && M_(1, 3) == 0.0f && M_(2, 3) == 0.0f && M_(3, 3) == 1.0f) {
+        const float det = (M_(0, 0) * (M_(1, 1) * M_(2, 2) - M_(1, 2) * M_(2, 1)) - M_(0, 1) * (M_(1, 0) * M_(2, 2) - M_(1, 2) * M_(2, 0))) +
+                          M_(0, 2) * (M_(1, 0) * M_(2, 1) - M_(1, 1) * M_(2, 0));
+        if (det == 0.0f) { for (int i = 0; i < 16; ++i) o[i] = (i % 5 == 0) ? nan : 0.0f; return; }
+        const float A1223 = M_(2, 1) * M_(3, 2) - M_(2, 2) * M_(3, 1), A0223 = M_(2, 0) * M_(3, 2) - M_(2, 2) * M_(3, 0);
+        const float A0123 = M_(2, 0) * M_(3, 1) - M_(2, 1) * M_(3, 0), A1213 = M_(1, 1) * M_(3, 2) - M_(1, 2) * M_(3, 1);
+        const float A0213 = M_(1, 0) * M_(3, 2) - M_(1, 2) * M_(3, 0), A0113 = M_(1, 0) * M_(3, 1) - M_(1, 1) * M_(3, 0);
+        const float id = 1.0f / det;
+        o[0] = id * (M_(1, 1) * M_(2, 2) - M_(1, 2) * M_(2, 1));
+        o[1] = id * (M_(0, 2) * M_(2, 1) - M_(0, 1) * M_(2, 2));
+        o[2] = id * (M_(0, 1) * M_(1, 2) - M_(0, 2) * M_(1, 1));
+        o[3] = 0.0f;
+        o[4] = id * (M_(1, 2) * M_(2, 0) - M_(1, 0) * M_(2, 2));
+        o[5] = id * (M_(0, 0) * M_(2, 2) - M_(0, 2) * M_(2, 0));
+        o[6] = id * (M_(0, 2) * M_(1, 0) - M_(0, 0) * M_(1, 2));
+        o[7] = 0.0f;
+        o[8] = id * (M_(1, 0) * M_(2, 1) - M_(1, 1) * M_(2, 0));
+        o[9] = id * (M_(0, 1) * M_(2, 0) - M_(0, 0) * M_(2, 1));
+        o[10] = id * (M_(0, 0) * M_(1, 1) - M_(0, 1) * M_(1, 0));
+        o[11] = 0.0f;
+        o[12] = id * ((M_(1, 1) * A0223 - M_(1, 2) * A0123) - M_(1, 0) * A1223);
+        o[13] = id * ((M_(0, 0) * A1223 - M_(0, 1) * A0223) + M_(0, 2) * A0123);
+        o[14] = id * ((M_(0, 1) * A0213 - M_(0, 2) * A0113) - M_(0, 0) * A1213);
+        o[15] = 1.0f;
+        return;
+    }
+    const float A2323 = M_(2, 2) * M_(3, 3) - M_(2, 3) * M_(3, 2), A1323 = M_(2, 1) * M_(3, 3) - M_(2, 3) * M_(3, 1);
+    const float A1223 = M_(2, 1) * M_(3, 2) - M_(2, 2) * M_(3, 1), A0323 = M_(2, 0) * M_(3, 3) - M_(2, 3) * M_(3, 0);
+    const float A0223 = M_(2, 0) * M_(3, 2) - M_(2, 2) * M_(3, 0), A0123 = M_(2, 0) * M_(3, 1) - M_(2, 1) * M_(3, 0);
+    const float A2313 = M_(1, 2) * M_(3, 3) - M_(1, 3) * M_(3, 2), A1313 = M_(1, 1) * M_(3, 3) - M_(1, 3) * M_(3, 1);
+    const float A1213 = M_(1, 1) * M_(3, 2) - M_(1, 2) * M_(3, 1), A2312 = M_(1, 2) * M_(2, 3) - M_(1, 3) * M_(2, 2);
+    const float A1312 = M_(1, 1) * M_(2, 3) - M_(1, 3) * M_(2, 1), A1212 = M_(1, 1) * M_(2, 2) - M_(1, 2) * M_(2, 1);
+    const float A0313 = M_(1, 0) * M_(3, 3) - M_(1, 3) * M_(3, 0), A0213 = M_(1, 0) * M_(3, 2) - M_(1, 2) * M_(3, 0);
+    const float A0312 = M_(1, 0) * M_(2, 3) - M_(1, 3) * M_(2, 0), A0212 = M_(1, 0) * M_(2, 2) - M_(1, 2) * M_(2, 0);
+    const float A0113 = M_(1, 0) * M_(3, 1) - M_(1, 1) * M_(3, 0), A0112 = M_(1, 0) * M_(2, 1) - M_(1, 1) * M_(2, 0);
+    const float det = ((M_(0, 0) * ((M_(1, 1) * A2323 - M_(1, 2) * A1323) + M_(1, 3) * A1223) - M_(0, 1) * ((M_(1, 0) * A2323 - M_(1, 2) * A0323) + M_(1, 3) * A0223)) +
+                       M_(0, 2) * ((M_(1, 0) * A1323 - M_(1, 1) * A0323) + M_(1, 3) * A0123)) -
+                      M_(0, 3) * ((M_(1, 0) * A1223 - M_(1, 1) * A0223) + M_(1, 2) * A0123);
+    if (det == 0.0f) { for (int i = 0; i < 16; ++i) o[i] = (i % 5 == 0) ? nan : 0.0f; return; }
+    const float id = 1.0f / det;
+    o[0] = id * ((M_(1, 1) * A2323 - M_(1, 2) * A1323) + M_(1, 3) * A1223);
+    o[1] = id * -((M_(0, 1) * A2323 - M_(0, 2) * A1323) + M_(0, 3) * A1223);
+    o[2] = id * ((M_(0, 1) * A2313 - M_(0, 2) * A1313) + M_(0, 3) * A1213);
+    o[3] = id * -((M_(0, 1) * A2312 - M_(0, 2) * A1312) + M_(0, 3) * A1212);
+    o[4] = id * -((M_(1, 0) * A2323 - M_(1, 2) * A0323) + M_(1, 3) * A0223);
+    o[5] = id * ((M_(0, 0) * A2323 - M_(0, 2) * A0323) + M_(0, 3) * A0223);
+    o[6] = id * -((M_(0, 0) * A2313 - M_(0, 2) * A0313) + M_(0, 3) * A0213);
+    o[7] = id * ((M_(0, 0) * A2312 - M_(0, 2) * A0312) + M_(0, 3) * A0212);
+    o[8] = id * ((M_(1, 0) * A1323 - M_(1, 1) * A0323) + M_(1, 3) * A0123);
+    o[9] = id * -((M_(0, 0) * A1323 - M_(0, 1) * A0323) + M_(0, 3) * A0123);
+    o[10] = id * ((M_(0, 0) * A1313 - M_(0, 1) * A0313) + M_(0, 3) * A0113);
+    o[11] = id * -((M_(0, 0) * A1312 - M_(0, 1) * A0312) + M_(0, 3) * A0112);
+    o[12] = id * -((M_(1, 0) * A1223 - M_(1, 1) * A0223) + M_(1, 2) * A0123);
+    o[13] = id * ((M_(0, 0) * A1223 - M_(0, 1) * A0223) + M_(0, 2) * A0123);
+    o[14] = id * -((M_(0, 0) * A1213 - M_(0, 1) * A0213) + M_(0, 2) * A0113);
+    o[15] = id * ((M_(0, 0) * A1212 - M_(0, 1) * A0212) + M_(0, 2) * A0112);
+}
+#undef M_
 
 }  // namespace
 
@@ -358,6 +426,15 @@ int vkpbrt_context_launch_count(vkpbrt_context_t ctx, uint64_t* out)
 {
     VK_REQUIRE(ctx && out, "null argument");
     *out = ctx->launches.load();
+    return VKPBRT_OK;
+}
+
+int vkpbrt_mat4_inverse(const float* m, float* inverse)
+{
+    VK_REQUIRE(m && inverse, "vkpbrt_mat4_inverse: null argument");
+    float tmp[16];
+    vsg_inverse(m, tmp);
+    std::memcpy(inverse, tmp, sizeof tmp);
     return VKPBRT_OK;
 }
 
@@ -811,7 +888,7 @@ int vkpbrt_accumulator_set_camera_matrices(vkpbrt_accumulator_t a, int frame_ind
         if (frame_index != 0) {
             std::memcpy(a->pc_prev_view, prev->view, 64);
             float inv[16];
-            mat_inverse(prev->view, inv);
+            vsg_inverse(prev->view, inv);                // Accumulator.cpp:100: vsg's host-side inverse, not the shader's
             a->pc_prev_pos[0] = inv[12]; a->pc_prev_pos[1] = inv[13]; a->pc_prev_pos[2] = inv[14]; a->pc_prev_pos[3] = 1.0f;
         }
     } else {
@@ -819,8 +896,10 @@ int vkpbrt_accumulator_set_camera_matrices(vkpbrt_accumulator_t a, int frame_ind
         std::memcpy(a->pc_inv_view, cur->inv_view, 64);
         if (frame_index != 0) {
             std::memcpy(a->pc_prev_view, prev->view, 64);
-            const float w = prev->inv_view[11];
-            for (int i = 0; i < 4; ++i) a->pc_prev_pos[i] = prev->inv_view[8 + i] / w;
+            // Accumulator.cpp:110-111 `prev_pos = prev.inv_view[2]; prev_pos /= prev_pos.w`: vsg's vec4 /= multiplies by the
+            // reciprocal (vsg/maths/vec4.h:131-140)
+            const float inv_w = 1.0f / prev->inv_view[11];
+            for (int i = 0; i < 4; ++i) a->pc_prev_pos[i] = prev->inv_view[8 + i] * inv_w;
         }
     }
     a->pc_frame_number = frame_index;

@@ -22,25 +22,14 @@ from .modules import CameraMatrices
 
 
 def _inverse(m: np.ndarray) -> np.ndarray:
-    """4x4 inverse by cofactors in binary32, column-major in and out: the same evaluation order as the library's
-    (and the oracle's) mat_inverse, so a matrix loaded from a text file gets the inverse the accumulator would get"""
-    f = np.float32
-    a = [f(x) for x in m]
-    a00, a01, a02, a03, a10, a11, a12, a13, a20, a21, a22, a23, a30, a31, a32, a33 = a
-    b00, b01, b02 = a00 * a11 - a01 * a10, a00 * a12 - a02 * a10, a00 * a13 - a03 * a10
-    b03, b04, b05 = a01 * a12 - a02 * a11, a01 * a13 - a03 * a11, a02 * a13 - a03 * a12
-    b06, b07, b08 = a20 * a31 - a21 * a30, a20 * a32 - a22 * a30, a20 * a33 - a23 * a30
-    b09, b10, b11 = a21 * a32 - a22 * a31, a21 * a33 - a23 * a31, a22 * a33 - a23 * a32
-    det = ((((b00 * b11 - b01 * b10) + b02 * b09) + b03 * b08) - b04 * b07) + b05 * b06
-    with np.errstate(divide="ignore", invalid="ignore"):
-        inv_det = f(1.0) / det
-    out = [((a11 * b11 - a12 * b10) + a13 * b09), ((a02 * b10 - a01 * b11) - a03 * b09), ((a31 * b05 - a32 * b04) + a33 * b03),
-           ((a22 * b04 - a21 * b05) - a23 * b03), ((a12 * b08 - a10 * b11) - a13 * b07), ((a00 * b11 - a02 * b08) + a03 * b07),
-           ((a32 * b02 - a30 * b05) - a33 * b01), ((a20 * b05 - a22 * b02) + a23 * b01), ((a10 * b10 - a11 * b08) + a13 * b06),
-           ((a01 * b08 - a00 * b10) - a03 * b06), ((a30 * b04 - a31 * b02) + a33 * b00), ((a21 * b02 - a20 * b04) - a23 * b00),
-           ((a11 * b07 - a10 * b09) - a12 * b06), ((a00 * b09 - a01 * b07) + a02 * b06), ((a31 * b01 - a30 * b03) - a32 * b00),
-           ((a20 * b03 - a21 * b01) + a22 * b00)]
-    return np.array([x * inv_det for x in out], dtype=np.float32)
+    """vsg::inverse(mat4), the routine the reference's matrix import calls (RenderIO.cpp:659): the library's restatement
+    (vkpbrt_mat4_inverse -- host code, no device needed), so a matrix loaded from a text file gets the inverse bits the
+    reference would compute"""
+    from . import _capi as capi
+    a = np.ascontiguousarray(m, dtype=np.float32).reshape(16)
+    out = np.empty(16, np.float32)
+    capi.call("vkpbrt_mat4_inverse", a.ctypes.data, out.ctypes.data)
+    return out
 
 
 def _mat(values) -> np.ndarray:
