@@ -211,12 +211,18 @@ private:
     }
     static std::string arr(const mat4& m)
     {
-        std::ostringstream o;
-        o.precision(9);                      // round-trips binary32
-        o << "[";
-        for (int i = 0; i < 16; ++i) o << (i ? ", " : "") << m.m[i];
-        o << "]";
-        return o.str();
+        std::string out = "[";
+        for (int i = 0; i < 16; ++i) {
+            std::ostringstream o;
+            o.precision(9);                  // round-trips binary32
+            o << m.m[i];
+            std::string t = o.str();
+            // keep it a JSON *number with a fraction* (nlohmann writes floats that way): "-0" would be read back as the
+            // integer 0 and lose its sign
+            if (t.find_first_of(".en") == std::string::npos) t += ".0";
+            out += (i ? ", " : "") + t;
+        }
+        return out + "]";
     }
 };
 

@@ -184,3 +184,54 @@ def test_offline_mode_driven_from_a_matrix_file_equals_the_oracle(tmp_path, back
         pipe.ctx.synchronize()
         orc.run_frame(f, fr)
         assert_frame_equal(pipe, orc, f)
+
+
+TEXT_FILES = {
+    # the BMFR dataset's layout: braces, commas, several matrices, a trailing "};"
+    "dataset": lambda cams: "const float camera_matrices[2][4][4] = {\n" + "\n".join(
+        "{" + ", ".join(f"{float(x):.9g}" for x in c[:8]) + ",\n " + ", ".join(f"{float(x):.9g}" for x in c[8:]) + "}," for c in cams) + "\n};\n",
+    # bare numbers, one per line, no trailing newline after the last one
+    "bare": lambda cams: "\n".join(f"{float(x):.9g}" for c in cams for x in c),
+    # numbers glued to braces, exponents, a negative zero, a comment word that starts with a digit ("4x4")
+    "glued": lambda cams: "matrix 4x4 float\n" + " ".join("{%s}" % f"{float(x):.6e}" for c in cams for x in c) + " -0.0",
+}
+
+
+@pytest.mark.parametrize("name", sorted(TEXT_FILES))
+def test_text_matrix_files_import_like_the_reference(tmp_path, name):
+    """the BMFR-dataset text branch of MatrixIO::import_matrices (RenderIO.cpp:637-664) as the reference's own text
+    (oracle/host_shim) against the Python importer and the C++ one (include/vkpbrt/io.hpp): the same matrices, and the
+    same inverses (vsg's), bit for bit"""
+    import subprocess
+    from pathlib import Path
+    h = _hostref()
+    cams = [synth.camera(160, 128, f) for f in range(2)]
+    mats = []
+    for c in cams:
+        v = np.asarray(c.view, np.float64).reshape(4, 4).T
+        p = np.asarray(c.proj, np.float64).reshape(4, 4).T
+        mats.append((p @ v).T.astype(np.float32).reshape(-1))
+    path = tmp_path / f"{name}.txt"
+    path.write_text(TEXT_FILES[name](mats))
+    buf = np.zeros(32 * 8, np.float32)
+    n = h.hostref_import_matrices_text(str(path).encode(), buf.ctypes.data_as(C.c_void_p), 8)
+    got = import_matrices(path)
+    assert len(got) == n and n >= 2
+    for i, m in enumerate(got):
+        assert _same_bits(np.asarray(m.view, np.float32), buf[32 * i:32 * i + 16]), f"view {i}"
+        assert _same_bits(np.asarray(m.inv_view, np.float32), buf[32 * i + 16:32 * i + 32]), f"inverse {i}"
+    # the C++ layer: import, then export to JSON, which the Python reader takes back
+    root = Path(__file__).resolve().parents[1]
+    src = tmp_path / "conv.cpp"
+    src.write_text('#include <vkpbrt/io.hpp>\nint main(int, char** a) { auto m = vkpbrt::MatrixIO::import_matrices(a[1]); return vkpbrt::MatrixIO::export_matrices(a[2], m) ? 0 : 1; }\n')
+    libdir = root / "tests" / "hostsim"
+    subprocess.run(["make", "-C", str(libdir)], check=True, capture_output=True)
+    exe = tmp_path / "conv"
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-I", str(root / "include"), str(src), "-o", str(exe), f"-L{libdir}", "-lvkpbrt_hostsim", f"-Wl,-rpath,{libdir}", "-lz"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert subprocess.run([str(exe), str(path), str(tmp_path / "back.json")]).returncode == 0
+    back = import_matrices(tmp_path / "back.json")
+    assert len(back) == n
+    for i, m in enumerate(back):
+        assert _same_bits(np.asarray(m.view, np.float32), buf[32 * i:32 * i + 16]) and _same_bits(np.asarray(m.inv_view, np.float32), buf[32 * i + 16:32 * i + 32])
