@@ -2,8 +2,13 @@
 // written against include/vkpbrt/vkpbrt.hpp.  Reads a raw synthetic sequence (tests/test_cpp_layer.py writes it),
 // replays the recorded command list once per frame and writes the final BGRA8 image of every frame.
 //
-//   cpp_frame_loop <dir> <width> <height> <frames> <bmfr|bfr> <taa 0|1>
+//   cpp_frame_loop <dir> <width> <height> <frames> <bmfr|bfr> <taa 0|1> [block 8|16|32]
 //   <dir>/frame_%d.{depth,normal,albedo,illum,cam}  ->  <dir>/final_%d.bgra
+//
+// -DVKPBRT_REFERENCE_WIRING=<file>: instead of this repository's add_denoiser_to_commands, <file> -- the reference's OWN
+// source/util/DenoiserUtils.cpp, its #include lines removed (tests/test_cpp_layer.py generates it from the reference tree) --
+// is compiled in, behind the three substitutions vkpbrt.hpp documents (vsg::ref_ptr, vsg::Context / CompileTraversal,
+// vsg::Commands / PushConstants / DescriptorImage), and called with the reference's signature.
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -11,6 +16,19 @@
 #include <vector>
 
 #include "vkpbrt/vkpbrt.hpp"
+
+#ifdef VKPBRT_REFERENCE_WIRING
+namespace vsg {
+template <class T> using ref_ptr = vkpbrt::ref_ptr<T>;
+using Commands = vkpbrt::Commands;
+using PushConstants = vkpbrt::PushConstants;
+using DescriptorImage = vkpbrt::DescriptorImage;
+struct CompileTraversal { vkpbrt::Context& context; };      // the reference reaches the context through compile.context
+}
+#define VKPBRT_STRINGIFY_(x) #x
+#define VKPBRT_STRINGIFY(x) VKPBRT_STRINGIFY_(x)
+#include VKPBRT_STRINGIFY(VKPBRT_REFERENCE_WIRING)
+#endif
 
 using namespace vkpbrt;
 
@@ -28,6 +46,8 @@ int main(int argc, char** argv)
     const int width = atoi(argv[2]), height = atoi(argv[3]), num_frames = atoi(argv[4]);
     const DenoisingType denoising_type = std::string(argv[5]) == "bfr" ? DenoisingType::BFR : DenoisingType::BMFR;
     const bool use_taa = atoi(argv[6]) != 0;
+    const int block = argc > 7 ? atoi(argv[7]) : 32;
+    const DenoisingBlockSize denoising_size = block == 8 ? DenoisingBlockSize::X8 : block == 16 ? DenoisingBlockSize::X16 : DenoisingBlockSize::X32;
     try {
         Context context(0);
         make_current(context);
@@ -48,8 +68,14 @@ int main(int argc, char** argv)
         auto accumulation_buffer = accumulator->accumulation_buffer;
         // :443
         ref_ptr<DescriptorImage> final_descriptor_image;
-        add_denoiser_to_commands(denoising_type, DenoisingBlockSize::X32, commands, context, width, height, ray_tracing_push_constants,
+#ifdef VKPBRT_REFERENCE_WIRING
+        vsg::CompileTraversal compile{context};
+        add_denoiser_to_commands(denoising_type, denoising_size, commands, compile, width, height, ray_tracing_push_constants,
                                  g_buffer, illumination_buffer, accumulation_buffer, final_descriptor_image);
+#else
+        add_denoiser_to_commands(denoising_type, denoising_size, commands, context, width, height, ray_tracing_push_constants,
+                                 g_buffer, illumination_buffer, accumulation_buffer, final_descriptor_image);
+#endif
         // :448-456 -- a block-local ref_ptr, exactly as in the reference: the command graph keeps the module alive
         if (use_taa) {
             auto taa = Taa::create(width, height, 16, 16, g_buffer, accumulation_buffer, final_descriptor_image);

@@ -12,13 +12,13 @@ from vulkanpbrt_b200 import synth
 ROOT = Path(__file__).resolve().parents[1]
 
 
-def _run(tmp_path, oracle, libdir, libname, denoiser, taa, W=160, H=128, frames=3):
+def _run(tmp_path, oracle, libdir, libname, denoiser, taa, W=160, H=128, frames=3, block=32, extra_flags=()):
     exe = tmp_path / "cpp_frame_loop"
-    cmd = ["g++", "-std=c++17", "-O1", "-I", str(ROOT / "include"), str(ROOT / "examples" / "cpp_frame_loop.cpp"), "-o", str(exe),
+    cmd = ["g++", "-std=c++17", "-O1", "-I", str(ROOT / "include"), *extra_flags, str(ROOT / "examples" / "cpp_frame_loop.cpp"), "-o", str(exe),
            f"-L{libdir}", f"-l{libname}", f"-Wl,-rpath,{libdir}"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
-    orc = oracle.OracleChain(W, H, denoiser, 32, use_taa=taa)
+    orc = oracle.OracleChain(W, H, denoiser, block, use_taa=taa)
     want = []
     for f in range(frames):
         fr = synth.render_frame(W, H, f)
@@ -28,11 +28,27 @@ def _run(tmp_path, oracle, libdir, libname, denoiser, taa, W=160, H=128, frames=
         np.concatenate([fr.camera.view, fr.camera.inv_view, fr.camera.proj, fr.camera.inv_proj]).astype(np.float32).tofile(str(base) + ".cam")
         orc.run_frame(f, fr)
         want.append(orc.final().copy())
-    r = subprocess.run([str(exe), str(tmp_path), str(W), str(H), str(frames), denoiser, "1" if taa else "0"], capture_output=True, text=True)
+    r = subprocess.run([str(exe), str(tmp_path), str(W), str(H), str(frames), denoiser, "1" if taa else "0", str(block)], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     for f in range(frames):
         got = np.fromfile(tmp_path / f"final_{f}.bgra", dtype=np.uint8).reshape(H, W, 4)
         np.testing.assert_array_equal(got, want[f], err_msg=f"frame {f}")
+
+
+@pytest.mark.parametrize("denoiser,taa,block", [("bmfr", True, 32), ("bfr", False, 16), ("bmfr", False, 8), ("bfr", True, 32)])
+def test_the_references_own_wiring_source_compiles_against_the_cpp_layer(tmp_path, oracle, denoiser, taa, block):
+    """the drop-in claim, literally: source/util/DenoiserUtils.cpp -- the reference's text, only its #include lines removed --
+    is compiled against include/vkpbrt/vkpbrt.hpp behind the three documented substitutions (examples/cpp_frame_loop.cpp
+    with -DVKPBRT_REFERENCE_WIRING) and drives the modules; the frames equal the oracle bit for bit.  (The BMFR X8X16X32 case
+    of that file indexes illumination_images[2] of a two-image buffer and is not exercised.)"""
+    import re
+    ref_src = Path("/root/reference/source/util/DenoiserUtils.cpp")
+    if not ref_src.exists():
+        pytest.skip("/root/reference is not mounted")
+    wiring = tmp_path / "reference_wiring.inc"             # derived from the reference: lives in the test's temporary directory only
+    wiring.write_text(re.sub(r'^\s*#include[^\n]*$', '', ref_src.read_text(), flags=re.M))
+    subprocess.run(["make", "-C", str(ROOT / "tests" / "hostsim")], check=True, capture_output=True)
+    _run(tmp_path, oracle, ROOT / "tests" / "hostsim", "vkpbrt_hostsim", denoiser, taa, block=block, extra_flags=(f"-DVKPBRT_REFERENCE_WIRING={wiring}",))
 
 
 @pytest.mark.parametrize("denoiser,taa", [("bmfr", True), ("bfr", False)])
