@@ -32,10 +32,15 @@ class _RtPush(C.Structure):    # RayTracingPushConstants, source/renderModules/P
 
 def build(reference: str = "/root/reference") -> bool:
     """compiles oracle/_ref from the reference tree when it is mounted; returns availability"""
-    if Path(reference, "shaders").exists():
-        r = subprocess.run(["make", "-C", str(_DIR / "glsl_shim"), f"REF={reference}"], capture_output=True, text=True)
-        if r.returncode != 0:
-            raise RuntimeError("oracle/_ref build failed:\n" + r.stdout[-3000:] + r.stderr[-3000:])
+    shaders = Path(reference, "shaders")
+    if shaders.exists():
+        # the Makefile deletes its intermediates (text derived from the reference is never kept), so make itself would
+        # rebuild everything on every call: decide here whether the library is older than anything it is made from
+        deps = [p for p in (_DIR / "glsl_shim").iterdir() if p.is_file()] + [p for p in shaders.iterdir() if p.is_file()]
+        if not _LIB.exists() or any(p.stat().st_mtime > _LIB.stat().st_mtime for p in deps):
+            r = subprocess.run(["make", "-C", str(_DIR / "glsl_shim"), f"REF={reference}"], capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError("oracle/_ref build failed:\n" + r.stdout[-3000:] + r.stderr[-3000:])
     return _LIB.exists()
 
 
