@@ -442,7 +442,9 @@ inline void add_denoiser_to_commands(DenoisingType denoising_type, DenoisingBloc
         const bool bmfr = denoising_type == DenoisingType::BMFR;
         if (denoising_size == DenoisingBlockSize::X8X16X32) {
             // DenoiserUtils.cpp:48-70 / :106-124.  The three block sizes are independent: b = 16 and b = 32 run on side
-            // lanes, concurrently with b = 8; the blender (context stream) waits for all three.
+            // lanes, concurrently with b = 8; the blender (context stream) waits for all three.  The blender reads
+            // illumination_images[0] / [1] in both cases: the reference's BMFR case passes [1] / [2] (:109-110), and [2]
+            // does not exist on the two-image accumulated buffer (a defect there; its BFR case, :53-54, passes [0] / [1]).
             std::vector<ref_ptr<DescriptorImage>> finals;
             int lane = 0;
             for (uint32_t b : {8u, 16u, 32u}) {
