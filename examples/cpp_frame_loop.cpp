@@ -2,7 +2,7 @@
 // written against include/vkpbrt/vkpbrt.hpp.  Reads a raw synthetic sequence (tests/test_cpp_layer.py writes it),
 // replays the recorded command list once per frame and writes the final BGRA8 image of every frame.
 //
-//   cpp_frame_loop <dir> <width> <height> <frames> <bmfr|bfr> <taa 0|1> [block 8|16|32]
+//   cpp_frame_loop <dir> <width> <height> <frames> <bmfr|bfr> <taa 0|1> [block 8|16|32, or 0 = X8X16X32 + blender]
 //   <dir>/frame_%d.{depth,normal,albedo,illum,cam}  ->  <dir>/final_%d.bgra
 //
 // -DVKPBRT_REFERENCE_WIRING=<file>: instead of this repository's add_denoiser_to_commands, <file> -- the reference's OWN
@@ -47,7 +47,7 @@ int main(int argc, char** argv)
     const DenoisingType denoising_type = std::string(argv[5]) == "bfr" ? DenoisingType::BFR : DenoisingType::BMFR;
     const bool use_taa = atoi(argv[6]) != 0;
     const int block = argc > 7 ? atoi(argv[7]) : 32;
-    const DenoisingBlockSize denoising_size = block == 8 ? DenoisingBlockSize::X8 : block == 16 ? DenoisingBlockSize::X16 : DenoisingBlockSize::X32;
+    const DenoisingBlockSize denoising_size = block == 0 ? DenoisingBlockSize::X8X16X32 : block == 8 ? DenoisingBlockSize::X8 : block == 16 ? DenoisingBlockSize::X16 : DenoisingBlockSize::X32;
     try {
         Context context(0);
         make_current(context);
