@@ -62,11 +62,13 @@ struct VkShaderModule_T { std::string name; };
 struct VkDescriptorSetLayout_T { std::map<uint32_t, VkDescriptorType> bindings; };
 struct VkPipelineLayout_T { std::vector<VkDescriptorSetLayout_T*> sets; uint32_t push_size; };
 struct VkPipeline_T { std::string shader; std::map<uint32_t, int32_t> spec; VkPipelineLayout_T* layout; };
-struct VkDescriptorPool_T { int dummy; };
+struct VkDescriptorSet_T;
+struct VkDescriptorPool_T { std::vector<VkDescriptorSet_T*> sets; };      // sets die with their pool
 struct Descriptor { VkDescriptorType type; VkImageView_T* view; VkSampler_T* sampler; VkImageLayout layout; };
 struct VkDescriptorSet_T { VkDescriptorSetLayout_T* layout; std::map<uint32_t, Descriptor> bound; };
 struct VkSemaphore_T { bool timeline; bool exportable; int fd; SemaphorePage* page; };
-struct VkCommandPool_T { int dummy; };
+struct VkCommandBuffer_T;
+struct VkCommandPool_T { std::vector<VkCommandBuffer_T*> buffers; };      // command buffers that were not freed die with their pool
 struct VkCommandBuffer_T {
     std::vector<std::function<void()>> cmds; bool recording = false;
     VkPipeline_T* pipeline = nullptr; VkDescriptorSet_T* set = nullptr; std::vector<unsigned char> push;     // state while recording
@@ -371,14 +373,26 @@ static VKAPI_ATTR VkResult VKAPI_CALL mock_GetSemaphoreCounterValue(VkDevice, Vk
 }
 
 // ---- command buffers: closures, executed at submit ------------------------------------------------------------------
-static VKAPI_ATTR VkResult VKAPI_CALL mock_CreateCommandPool(VkDevice, const VkCommandPoolCreateInfo*, const VkAllocationCallbacks*, VkCommandPool* out) { *out = new VkCommandPool_T{0}; return VK_SUCCESS; }
-static VKAPI_ATTR void VKAPI_CALL mock_DestroyCommandPool(VkDevice, VkCommandPool p, const VkAllocationCallbacks*) { delete p; }
+static VKAPI_ATTR VkResult VKAPI_CALL mock_CreateCommandPool(VkDevice, const VkCommandPoolCreateInfo*, const VkAllocationCallbacks*, VkCommandPool* out) { *out = new VkCommandPool_T(); return VK_SUCCESS; }
+static VKAPI_ATTR void VKAPI_CALL mock_DestroyCommandPool(VkDevice, VkCommandPool p, const VkAllocationCallbacks*)
+{
+    if (!p) return;
+    for (VkCommandBuffer_T* cb : p->buffers) delete cb;
+    delete p;
+}
 static VKAPI_ATTR VkResult VKAPI_CALL mock_AllocateCommandBuffers(VkDevice, const VkCommandBufferAllocateInfo* ai, VkCommandBuffer* out)
 {
-    for (uint32_t i = 0; i < ai->commandBufferCount; ++i) out[i] = new VkCommandBuffer_T();
+    for (uint32_t i = 0; i < ai->commandBufferCount; ++i) { out[i] = new VkCommandBuffer_T(); ai->commandPool->buffers.push_back(out[i]); }
     return VK_SUCCESS;
 }
-static VKAPI_ATTR void VKAPI_CALL mock_FreeCommandBuffers(VkDevice, VkCommandPool, uint32_t n, const VkCommandBuffer* cbs) { for (uint32_t i = 0; i < n; ++i) delete cbs[i]; }
+static VKAPI_ATTR void VKAPI_CALL mock_FreeCommandBuffers(VkDevice, VkCommandPool pool, uint32_t n, const VkCommandBuffer* cbs)
+{
+    for (uint32_t i = 0; i < n; ++i) {
+        for (size_t k = 0; k < pool->buffers.size(); ++k)
+            if (pool->buffers[k] == cbs[i]) { pool->buffers.erase(pool->buffers.begin() + k); break; }
+        delete cbs[i];
+    }
+}
 static VKAPI_ATTR VkResult VKAPI_CALL mock_BeginCommandBuffer(VkCommandBuffer cb, const VkCommandBufferBeginInfo*) { cb->cmds.clear(); cb->recording = true; return VK_SUCCESS; }
 static VKAPI_ATTR VkResult VKAPI_CALL mock_EndCommandBuffer(VkCommandBuffer cb) { if (!cb->recording) MOCK_FAIL("vkEndCommandBuffer: not recording"); cb->recording = false; return VK_SUCCESS; }
 static VKAPI_ATTR void VKAPI_CALL mock_CmdPipelineBarrier(VkCommandBuffer cb, VkPipelineStageFlags, VkPipelineStageFlags, VkDependencyFlags, uint32_t, const VkMemoryBarrier*,
@@ -572,12 +586,18 @@ static VKAPI_ATTR VkResult VKAPI_CALL mock_CreateComputePipelines(VkDevice, VkPi
     return VK_SUCCESS;
 }
 static VKAPI_ATTR void VKAPI_CALL mock_DestroyPipeline(VkDevice, VkPipeline p, const VkAllocationCallbacks*) { delete p; }
-static VKAPI_ATTR VkResult VKAPI_CALL mock_CreateDescriptorPool(VkDevice, const VkDescriptorPoolCreateInfo*, const VkAllocationCallbacks*, VkDescriptorPool* out) { *out = new VkDescriptorPool_T{0}; return VK_SUCCESS; }
-static VKAPI_ATTR void VKAPI_CALL mock_DestroyDescriptorPool(VkDevice, VkDescriptorPool p, const VkAllocationCallbacks*) { delete p; }
+static VKAPI_ATTR VkResult VKAPI_CALL mock_CreateDescriptorPool(VkDevice, const VkDescriptorPoolCreateInfo*, const VkAllocationCallbacks*, VkDescriptorPool* out) { *out = new VkDescriptorPool_T(); return VK_SUCCESS; }
+static VKAPI_ATTR void VKAPI_CALL mock_DestroyDescriptorPool(VkDevice, VkDescriptorPool p, const VkAllocationCallbacks*);
 static VKAPI_ATTR VkResult VKAPI_CALL mock_AllocateDescriptorSets(VkDevice, const VkDescriptorSetAllocateInfo* ai, VkDescriptorSet* out)
 {
-    for (uint32_t i = 0; i < ai->descriptorSetCount; ++i) out[i] = new VkDescriptorSet_T{ai->pSetLayouts[i], {}};     // (leaked with the pool: test process)
+    for (uint32_t i = 0; i < ai->descriptorSetCount; ++i) { out[i] = new VkDescriptorSet_T{ai->pSetLayouts[i], {}}; ai->descriptorPool->sets.push_back(out[i]); }
     return VK_SUCCESS;
+}
+static VKAPI_ATTR void VKAPI_CALL mock_DestroyDescriptorPool(VkDevice, VkDescriptorPool p, const VkAllocationCallbacks*)
+{
+    if (!p) return;
+    for (VkDescriptorSet_T* s : p->sets) delete s;
+    delete p;
 }
 static VKAPI_ATTR void VKAPI_CALL mock_UpdateDescriptorSets(VkDevice, uint32_t n, const VkWriteDescriptorSet* writes, uint32_t ncopies, const VkCopyDescriptorSet*)
 {
