@@ -5,8 +5,11 @@
 //   MatrixIO::import_matrices / export_matrices        RenderIO.cpp:593-711  (JSON layout of the reference, BMFR-dataset text)
 //   GBufferIO::import_g_buffer_depth / _position       RenderIO.cpp:6-158    (printf-style per-frame EXR file names)
 //   IlluminationBufferIO::import_illumination          RenderIO.cpp:501-548
-//   OfflineGBuffer::upload_to_g_buffer                 RenderIO.cpp:400-440  (upload_to_g_buffer_command)
-//   OfflineIllumination::upload_to_illumination_buffer RenderIO.cpp:713-740
+//   OfflineGBuffer::upload_to_g_buffer                 RenderIO.cpp:718-746  (upload_to_g_buffer_command)
+//   OfflineIllumination::upload_to_illumination_buffer RenderIO.cpp:384-399
+//   GBufferIO::export_g_buffer + its conversions       RenderIO.cpp:213-382  (host loops, as in the reference)
+//   OfflineGBuffer::download_from_g_buffer             RenderIO.cpp:748-928  (download command + transfer_staging_data_to)
+//   OfflineIllumination::download_from_illumination_buffer RenderIO.cpp:401-467
 //
 // What differs from the reference: the conversions between what the files hold and what the G-buffer holds --
 // world position -> Euclidean depth (:101-120), cartesian -> spherical normals (:160-178), float albedo -> rgba8
@@ -468,7 +471,7 @@ public:
     std::optional<mat4> inv_view;                   // of the frame's (combined) matrices: the eye point for position -> depth
     bool valid() const { return width && !normal.empty() && !albedo.empty() && (!depth.empty() || !position.empty()); }
 
-    // upload_to_g_buffer_command (RenderIO.cpp:400-440) + the import conversions, enqueued on the context's stream
+    // upload_to_g_buffer_command (RenderIO.cpp:718-746) + the import conversions, enqueued on the context's stream
     void upload_to_g_buffer(ref_ptr<GBuffer>& g_buffer, Context& context)
     {
         if (!valid()) throw std::runtime_error("OfflineGBuffer: frame was not loaded");
@@ -483,6 +486,21 @@ public:
         if (!depth.empty()) check(vkpbrt_image_upload(g_buffer->depth->handle, depth.data(), depth.size() * sizeof(float)));
         if (p && !inv_view) throw std::runtime_error("OfflineGBuffer: positions need the frame's camera matrices");
         g_buffer->import_planes(p, p ? &*inv_view : nullptr, n, a);
+    }
+    // the export side (download_from_g_buffer_command + transfer_staging_data_to, RenderIO.cpp:748-928): the GBuffer's own
+    // planes -- depth above, normals as (theta, phi), material / albedo as rgba8 -- read back once the frame's work is done
+    std::vector<float> normal_spherical;            // [H][W][2]
+    std::vector<uint8_t> material_unorm, albedo_unorm;   // [H][W][4]
+    void download_from_g_buffer(ref_ptr<GBuffer>& g_buffer, Context& context)
+    {
+        width = g_buffer->width; height = g_buffer->height;
+        const size_t n = (size_t)width * height;
+        depth.resize(n); normal_spherical.resize(n * 2); albedo_unorm.resize(n * 4);
+        check(vkpbrt_image_download(g_buffer->depth->handle, depth.data(), n * sizeof(float)));
+        check(vkpbrt_image_download(g_buffer->normal->handle, normal_spherical.data(), n * 2 * sizeof(float)));
+        check(vkpbrt_image_download(g_buffer->albedo->handle, albedo_unorm.data(), n * 4));
+        if (g_buffer->material) { material_unorm.resize(n * 4); check(vkpbrt_image_download(g_buffer->material->handle, material_unorm.data(), n * 4)); }
+        context.waitForCompletion();
     }
 private:
     ref_ptr<DescriptorImage> _position, _normal, _albedo;      // staging images, reused from frame to frame
@@ -533,6 +551,90 @@ public:
         if (verbosity > 0) std::cout << "Done loading GBuffer" << std::endl;
         return out;
     }
+    // ---- the export side, RenderIO.cpp:213-382: host loops like the reference's (an offline tool, not on the frame path) ----
+    // :312-329.  cos / sin are called unqualified on floats there: with <cmath> alone in scope those are the C library's double
+    // routines and each product is rounded once -- written out here so that it does not depend on the headers in scope
+    static std::vector<float> spherical_to_cartesian(const std::vector<float>& normals)
+    {
+        std::vector<float> out(normals.size() * 2);
+        for (size_t i = 0; i < normals.size() / 2; ++i) {
+            const double theta = normals[2 * i], phi = normals[2 * i + 1];
+            out[4 * i] = (float)(std::cos(phi) * std::sin(theta));
+            out[4 * i + 1] = (float)(std::sin(phi) * std::sin(theta));
+            out[4 * i + 2] = (float)std::cos(theta);
+            out[4 * i + 3] = 1.0f;
+        }
+        return out;
+    }
+    // :331-346
+    static std::vector<float> unorm_to_float(const std::vector<uint8_t>& array)
+    {
+        std::vector<float> out(array.size());
+        for (size_t i = 0; i < array.size(); ++i) out[i] = (float)array[i] / 255.0f;
+        return out;
+    }
+    // :348-382: world position = inv_view[3] + depth * (inv_view * normalize((inv_proj * (clip, 1, 1)) with w = 0)); empty
+    // without a separate projection matrix.  mat4 * vec4 and normalize as vsg writes them (sums left to right, v * (1 / length))
+    static std::vector<float> depth_to_position(const std::vector<float>& depths, uint32_t w, uint32_t h, const CameraMatrices& matrix)
+    {
+        if (depths.empty()) return {};
+        if (!matrix.proj || !matrix.inv_proj) {
+            std::cout << "GBufferIO::depthToPosition: Camera matrix in wrong layout. Expected camera matrix with separate projection matrix" << std::endl;
+            return {};
+        }
+        auto mat_vec = [](const float* m, const float* v, float* o) {
+            for (int r = 0; r < 4; ++r) {
+                volatile float s = m[r] * v[0];         // one rounding per operation whatever the compiler's contraction mode
+                s = s + m[4 + r] * v[1]; s = s + m[8 + r] * v[2]; s = s + m[12 + r] * v[3];
+                o[r] = s;
+            }
+        };
+        const float* ip = matrix.inv_proj->m; const float* iv = matrix.inv_view.m;
+        std::vector<float> out((size_t)w * h * 4);
+        for (uint32_t i = 0; i < w * h; ++i) {
+            const uint32_t x = i % w, y = i / w;
+            const float clip[4] = {((float)x + .5f) / (float)w * 2.0f - 1.0f, ((float)y + .5f) / (float)h * 2.0f - 1.0f, 1.0f, 1.0f};
+            float dir[4], world[4];
+            mat_vec(ip, clip, dir);
+            dir[3] = 0.0f;
+            volatile float l2 = dir[0] * dir[0];
+            l2 = l2 + dir[1] * dir[1]; l2 = l2 + dir[2] * dir[2]; l2 = l2 + dir[3] * dir[3];
+            const float inv_len = 1.0f / std::sqrt((float)l2);
+            for (float& c : dir) c *= inv_len;
+            mat_vec(iv, dir, world);
+            for (int c = 0; c < 3; ++c) { volatile float t = world[c] * depths[i]; out[4 * (size_t)i + c] = iv[12 + c] + t; }
+            out[4 * (size_t)i + 3] = 1.0f;
+        }
+        return out;
+    }
+    // :213-310: empty format strings skip a plane; g_buffers hold what download_from_g_buffer read back
+    static bool export_g_buffer(const std::string& position_format, const std::string& depth_format, const std::string& normal_format,
+                                const std::string& material_format, const std::string& albedo_format, int num_frames, const OfflineGBuffers& g_buffers,
+                                const std::vector<CameraMatrices>& matrices, int verbosity = 1)
+    {
+        if (verbosity > 0) std::cout << "Start exporting GBuffer" << std::endl;
+        bool fine = true;
+        for (int f = 0; f < num_frames; ++f) {
+            const OfflineGBuffer* g = (size_t)f < g_buffers.size() ? g_buffers[f].get() : nullptr;
+            auto store = [&](const std::string& format, const std::vector<float>& plane, int channels) {
+                if (format.empty()) return true;
+                const std::string name = detail::frame_name(format, f);
+                if (g && !plane.empty() && plane.size() == (size_t)g->width * g->height * channels &&
+                    exr::write(name, plane.data(), (int)g->width, (int)g->height, channels)) return true;
+                std::cerr << "Failed to store image: " << name << std::endl;
+                return false;
+            };
+            static const std::vector<float> none;
+            const bool ok = store(depth_format, g ? g->depth : none, 1) &&
+                            store(position_format, g && !position_format.empty() && (size_t)f < matrices.size() ? depth_to_position(g->depth, g->width, g->height, matrices[f]) : none, 4) &&
+                            store(normal_format, g && !normal_format.empty() ? spherical_to_cartesian(g->normal_spherical) : none, 4) &&
+                            store(material_format, g && !material_format.empty() ? unorm_to_float(g->material_unorm) : none, 4) &&
+                            store(albedo_format, g && !albedo_format.empty() ? unorm_to_float(g->albedo_unorm) : none, 4);
+            fine = fine && ok;       // like the reference, a frame stops at its first failed plane and the other frames go on
+        }
+        if (verbosity > 0) std::cout << "Done exporting GBuffer" << std::endl;
+        return fine;
+    }
 private:
     static bool load_normal_albedo(OfflineGBuffer& g, const std::string& normal_path, const std::string& albedo_path)
     {
@@ -554,7 +656,7 @@ class OfflineIllumination : public Inherit<OfflineIllumination> {   // source/io
 public:
     uint32_t width = 0, height = 0;
     std::vector<float> noisy;                       // [H][W][4]
-    // upload_to_illumination_buffer_command (RenderIO.cpp:713-740): image 0 of an IlluminationBufferDemodulatedFloat
+    // upload_to_illumination_buffer_command (RenderIO.cpp:384-399): image 0 of an IlluminationBufferDemodulatedFloat
     void upload_to_illumination_buffer(ref_ptr<IlluminationBuffer>& illu_buffer, Context&)
     {
         if (noisy.empty()) throw std::runtime_error("OfflineIllumination: frame was not loaded");
@@ -563,12 +665,22 @@ public:
             throw std::runtime_error("OfflineIllumination: the illumination buffer must be rgba32f of the sequence's extent");
         check(vkpbrt_image_upload(illu_buffer->illumination_images[0]->handle, noisy.data(), noisy.size() * sizeof(float)));
     }
+    // download_from_illumination_buffer_command + transfer_staging_data_to (RenderIO.cpp:401-467): image 0, rgba32f
+    void download_from_illumination_buffer(ref_ptr<IlluminationBuffer>& illu_buffer, Context& context)
+    {
+        const vkpbrt_image_info i = illu_buffer->illumination_images.at(0)->info();
+        if (i.format != VKPBRT_FORMAT_R32G32B32A32_SFLOAT) throw std::runtime_error("OfflineIllumination: the illumination buffer must be rgba32f");
+        width = i.width; height = i.height;
+        noisy.resize((size_t)width * height * 4);
+        check(vkpbrt_image_download(illu_buffer->illumination_images[0]->handle, noisy.data(), noisy.size() * sizeof(float)));
+        context.waitForCompletion();
+    }
 };
 using OfflineIlluminations = std::vector<ref_ptr<OfflineIllumination>>;
 
 class IlluminationBufferIO {   // source/io/RenderIO.hpp:111-118
 public:
-    // RenderIO.cpp:501-548
+    // RenderIO.cpp:502-547
     static OfflineIlluminations import_illumination(const std::string& illumination_format, int num_frames, int verbosity = 1)
     {
         if (verbosity > 0) std::cout << "Start loading Illumination" << std::endl;
@@ -584,7 +696,7 @@ public:
         if (verbosity > 0) std::cout << "Done loading Illumination" << std::endl;
         return out;
     }
-    // RenderIO.cpp:550-591
+    // RenderIO.cpp:549-591
     static bool export_illumination(const std::string& illumination_format, int num_frames, const OfflineIlluminations& illus, int verbosity = 1)
     {
         (void)verbosity;

@@ -19,7 +19,7 @@
 #include <vsg/maths/vec3.h>
 #include <vsg/maths/vec4.h>
 
-enum { VK_FORMAT_R32_SFLOAT = 100, VK_FORMAT_R32G32_SFLOAT = 103, VK_FORMAT_R8G8B8A8_UNORM = 37 };
+enum { VK_FORMAT_R32_SFLOAT = 100, VK_FORMAT_R32G32_SFLOAT = 103, VK_FORMAT_R32G32B32A32_SFLOAT = 109, VK_FORMAT_R8G8B8A8_UNORM = 37 };
 
 namespace vsg {
 

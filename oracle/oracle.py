@@ -68,6 +68,7 @@ def lib():
         l.vkpbrt_oracle_taa.argtypes = [i32, i32, u32, i32] + [vp] * 4; l.vkpbrt_oracle_taa.restype = None
         l.vkpbrt_oracle_format_converter.argtypes = [i32, i32, i32, vp, vp]; l.vkpbrt_oracle_format_converter.restype = None
         l.vkpbrt_oracle_gbuffer_import.argtypes = [i32, i32] + [vp] * 7; l.vkpbrt_oracle_gbuffer_import.restype = None
+        l.vkpbrt_oracle_gbuffer_export.argtypes = [i32, i32] + [vp] * 8; l.vkpbrt_oracle_gbuffer_export.restype = None
         l.vkpbrt_oracle_demodulate.argtypes = [i32, i32, vp, vp, vp, vp]; l.vkpbrt_oracle_demodulate.restype = None
         l.vkpbrt_oracle_num_threads.argtypes = []; l.vkpbrt_oracle_num_threads.restype = i32
         l.vkpbrt_oracle_set_num_threads.argtypes = [i32]; l.vkpbrt_oracle_set_num_threads.restype = None
@@ -265,3 +266,19 @@ def gbuffer_import(inv_view, position=None, normal=None, albedo=None):
     q = lambda x: None if x is None else _p(x)
     lib().vkpbrt_oracle_gbuffer_import(W, H, q(iv), q(position), q(normal), q(albedo), q(d), q(n), q(a))
     return d, n, a
+
+
+def gbuffer_export(inv_view=None, inv_proj=None, depth=None, normal=None, unorm=None):
+    """GBufferIO::export_g_buffer's conversions (RenderIO.cpp:312-382); returns (position, cartesian normal, float rgba), each
+    rgba32f, None where there is no input (or, for positions, no separate projection matrix)"""
+    ref = next(a for a in (depth, normal, unorm) if a is not None)
+    H, W = ref.shape[:2]
+    f = lambda a: None if a is None else np.ascontiguousarray(a, np.float32)
+    depth, normal, inv_view, inv_proj = f(depth), f(normal), f(inv_view), f(inv_proj)
+    unorm = None if unorm is None else np.ascontiguousarray(unorm, np.uint8)
+    p = np.zeros((H, W, 4), np.float32) if depth is not None and inv_proj is not None and inv_view is not None else None
+    n = np.zeros((H, W, 4), np.float32) if normal is not None else None
+    u = np.zeros((H, W, 4), np.float32) if unorm is not None else None
+    q = lambda x: None if x is None else _p(x)
+    lib().vkpbrt_oracle_gbuffer_export(W, H, q(inv_view), q(inv_proj), q(depth), q(normal), q(unorm), q(p), q(n), q(u))
+    return p, n, u

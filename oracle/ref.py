@@ -220,3 +220,32 @@ def gbuffer_import(inv_view, position=None, normal=None, albedo=None):
         a = np.zeros((H, W, 4), np.uint8)
         assert _host.hostref_albedo(p(albedo), W, H, p(a)) == 0
     return d, n, a
+
+
+def gbuffer_export(matrices64=None, has_proj=True, depth=None, normal=None, unorm=None):
+    """GBufferIO::depth_to_position, spherical_to_cartesian and unorm_to_float (RenderIO.cpp:312-382) as the reference's own
+    C++ text.  matrices64 = view, inv_view, proj, inv_proj (16 floats each, column-major).  Returns (position, cartesian
+    normal, float rgba); position is None when the reference returns no data (no separate projection matrix)"""
+    global _host
+    if _host is None:
+        _host = C.CDLL(str(_HOST_LIB))
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    pos = n = u = None
+    if depth is not None:
+        depth = np.ascontiguousarray(depth, np.float32)
+        H, W = depth.shape
+        pos = np.zeros((H, W, 4), np.float32)
+        m = np.ascontiguousarray(matrices64, np.float32)
+        if _host.hostref_depth_to_position(p(depth), W, H, p(m), 1 if has_proj else 0, p(pos)) != 0:
+            pos = None
+    if normal is not None:
+        normal = np.ascontiguousarray(normal, np.float32)
+        H, W = normal.shape[:2]
+        n = np.zeros((H, W, 4), np.float32)
+        assert _host.hostref_spherical_to_cartesian(p(normal), W, H, p(n)) == 0
+    if unorm is not None:
+        unorm = np.ascontiguousarray(unorm, np.uint8)
+        H, W = unorm.shape[:2]
+        u = np.zeros((H, W, 4), np.float32)
+        assert _host.hostref_unorm_to_float(p(unorm), W, H, p(u)) == 0
+    return pos, n, u

@@ -1250,3 +1250,52 @@ ORACLE_API void vkpbrt_oracle_gbuffer_import(int W, int H, const float* inv_view
             }
     }
 }
+
+/* ------------------------------------------------------------------------------------ */
+/* GBufferIO::export_g_buffer's conversions (source/io/RenderIO.cpp:213-310): the planes  */
+/* of a GBuffer back to what the sequence files hold.  depth [H][W], normal (theta, phi)  */
+/* [H][W][2], unorm rgba8 [H][W][4]; outputs rgba32f [H][W][4].  Any input may be NULL.    */
+/*   depth_to_position       :348-382  needs separate matrices (inv_proj), else no output */
+/*   spherical_to_cartesian  :312-329                                                     */
+/*   unorm_to_float          :331-346                                                     */
+/* mat4 * vec4, normalize(vec4) = v * (1 / length(v)) and vec3 *= as vsg's headers write  */
+/* them (vsg/maths/mat4.h:159-165, vec4.h:225-254, vec3.h:107-113).  Pinned against that  */
+/* C++ text itself (oracle/host_shim, tests/test_render_io.py).                            */
+/* ------------------------------------------------------------------------------------ */
+static void oracle_mat_vec(const float* m, const float* v, float* o)      /* column-major m[4 * col + row] */
+{
+    for (int r = 0; r < 4; ++r) o[r] = ((m[r] * v[0] + m[4 + r] * v[1]) + m[8 + r] * v[2]) + m[12 + r] * v[3];
+}
+
+ORACLE_API void vkpbrt_oracle_gbuffer_export(int W, int H, const float* inv_view, const float* inv_proj, const float* depth, const float* normal,
+                                             const uint8_t* unorm, float* position_out, float* normal_out, float* unorm_out)
+{
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < W * H; ++i) {
+        if (depth && inv_proj && inv_view && position_out) {
+            const unsigned x = (unsigned)i % (unsigned)W, y = (unsigned)i / (unsigned)W;                  /* :367-368 */
+            const float clip[4] = {((float)x + .5f) / (float)W * 2.0f - 1.0f, ((float)y + .5f) / (float)H * 2.0f - 1.0f, 1.0f, 1.0f};   /* :369 */
+            float dir[4], world[4];
+            oracle_mat_vec(inv_proj, clip, dir);                                                          /* :370 */
+            dir[3] = 0.0f;                                                                                /* :371 */
+            const float inv_len = 1.0f / sqrtf(((dir[0] * dir[0] + dir[1] * dir[1]) + dir[2] * dir[2]) + dir[3] * dir[3]);
+            for (int c = 0; c < 4; ++c) dir[c] *= inv_len;                                                /* :372 normalize */
+            oracle_mat_vec(inv_view, dir, world);
+            for (int c = 0; c < 3; ++c) position_out[4 * i + c] = inv_view[12 + c] + world[c] * depth[i];  /* :372-374, camera_pos = inv_view[3] */
+            position_out[4 * i + 3] = 1.0f;
+        }
+        if (normal && normal_out) {
+            /* :322-324 call cos / sin unqualified on floats: with <cmath> alone in scope (vsg's headers, libstdc++) those are the
+             * C library's DOUBLE routines, the products are formed in double and rounded once by the store -- which is what the
+             * reference's text compiles to here, bit for bit (a translation unit that also sees <math.h>'s float overloads would
+             * round each factor to float first: at most 1 ulp away) */
+            const double theta = normal[2 * i], phi = normal[2 * i + 1];
+            normal_out[4 * i] = (float)(cos(phi) * sin(theta));
+            normal_out[4 * i + 1] = (float)(sin(phi) * sin(theta));
+            normal_out[4 * i + 2] = (float)cos(theta);
+            normal_out[4 * i + 3] = 1.0f;
+        }
+        if (unorm && unorm_out)
+            for (int c = 0; c < 4; ++c) unorm_out[4 * i + c] = (float)unorm[4 * i + c] / 255.0f;          /* :341-342 */
+    }
+}

@@ -291,3 +291,146 @@ def test_import_oracle_equals_the_reference_host_code(oracle):
             np.testing.assert_array_equal(a[0].view(np.uint32), b[0].view(np.uint32), err_msg="depth")
             np.testing.assert_array_equal(a[2], b[2], err_msg="albedo")
             np.testing.assert_array_max_ulp(a[1], b[1], maxulp=1)
+
+
+def _export_inputs(rng, H, W):
+    depth = rng.uniform(0.05, 200, (H, W)).astype(np.float32)
+    depth.reshape(-1)[:3] = np.float32([0.0, 1e10, np.inf])[:min(3, H * W)]             # a hit at the eye, the miss distance, an overflowed one
+    sph = np.stack([rng.uniform(0, np.pi, (H, W)), rng.uniform(-np.pi, np.pi, (H, W))], -1).astype(np.float32)
+    special = np.float32([[0, 0], [np.pi, 0], [np.pi / 2, np.pi], [0, np.pi / 4], [1e-30, -np.pi / 2], [3.0, 100.0]])    # poles, the miss normal, a denormal-ish angle, phi beyond pi
+    sph.reshape(-1, 2)[:min(len(special), H * W)] = special[:H * W]
+    unorm = rng.integers(0, 256, (H, W, 4), dtype=np.uint8)
+    unorm.reshape(-1)[:min(4, unorm.size)] = np.uint8([0, 1, 254, 255])[:unorm.size]
+    return depth, sph, unorm
+
+
+def test_export_oracle_equals_the_reference_host_code(oracle):
+    """pins vkpbrt_oracle_gbuffer_export: GBufferIO::depth_to_position, spherical_to_cartesian and unorm_to_float, cut whole out
+    of source/io/RenderIO.cpp (:312-382) by oracle/host_shim/extract_host.py and compiled against vsg's maths headers, against
+    the oracle -- every plane bit for bit (this is what showed that the unqualified cos / sin of :322-324 are the double
+    routines, and that normalize() multiplies by the reciprocal of the length), and no position plane without a separate
+    projection matrix"""
+    from oracle import ref as R
+    if not R.build_host():
+        pytest.skip("oracle/_ref host library is not built and /root/reference is not mounted")
+    rng = np.random.default_rng(17)
+    for (H, W) in ((37, 50), (1, 1), (16, 129), (3, 2)):
+        depth, sph, unorm = _export_inputs(rng, H, W)
+        for trial in range(3):
+            m = rng.uniform(-2, 2, 64).astype(np.float32)
+            if trial == 2:                                                                # a real camera
+                c = synth.render_frame(32, 32, 5).camera
+                m = np.concatenate([np.asarray(x, np.float32).reshape(-1) for x in (c.view, c.inv_view, c.proj, c.inv_proj)])
+            a = oracle.gbuffer_export(m[16:32], m[48:64], depth, sph, unorm)
+            b = R.gbuffer_export(m, True, depth, sph, unorm)
+            for got, want, name in zip(a, b, ("position", "normal", "unorm")):
+                np.testing.assert_array_equal(got.view(np.uint32), want.view(np.uint32), err_msg=f"{name} {H}x{W} trial {trial}")
+    assert R.gbuffer_export(m, False, depth)[0] is None and oracle.gbuffer_export(m[16:32], None, depth)[0] is None
+
+
+def test_export_conversions_equal_the_oracle(oracle):
+    """the Python layer's export conversions against the oracle: positions and unorm -> float bit for bit, cartesian normals
+    within one ulp (numpy's double cos / sin are not the C library's)"""
+    rng = np.random.default_rng(23)
+    H, W = 41, 67
+    depth, sph, unorm = _export_inputs(rng, H, W)
+    c = synth.render_frame(W, H, 3).camera
+    cm = CameraMatrices(view=c.view, inv_view=c.inv_view, proj=c.proj, inv_proj=c.inv_proj)
+    want_p, want_n, want_u = oracle.gbuffer_export(np.asarray(c.inv_view, np.float32), np.asarray(c.inv_proj, np.float32), depth, sph, unorm)
+    np.testing.assert_array_equal(GBufferIO.depth_to_position(depth, cm).view(np.uint32), want_p.view(np.uint32))
+    np.testing.assert_array_equal(GBufferIO.unorm_to_float(unorm).view(np.uint32), want_u.view(np.uint32))
+    np.testing.assert_array_max_ulp(GBufferIO.spherical_to_cartesian(sph), want_n, maxulp=1)
+
+
+def test_cxx_g_buffer_export(tmp_path, oracle):
+    """include/vkpbrt/io.hpp's export side on the emulator (memory copies only: nothing here computes on the device): planes
+    uploaded into a GBuffer / an illumination buffer are read back by OfflineGBuffer::download_from_g_buffer and
+    OfflineIllumination::download_from_illumination_buffer, written by GBufferIO::export_g_buffer /
+    IlluminationBufferIO::export_illumination, and the files -- decoded by OpenCV -- hold the oracle's conversions bit for
+    bit; a skipped plane (empty format) writes nothing, an unwritable path and a missing projection matrix fail the call"""
+    import subprocess
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    src = tmp_path / "export_probe.cpp"
+    src.write_text(r'''
+#include <vkpbrt/io.hpp>
+using namespace vkpbrt;
+template <class T> static std::vector<T> slurp(const std::string& path)
+{
+    std::ifstream f(path, std::ios::binary);
+    std::vector<char> b((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    std::vector<T> out(b.size() / sizeof(T));
+    std::memcpy(out.data(), b.data(), out.size() * sizeof(T));
+    return out;
+}
+int main(int argc, char** argv) {
+    const std::string dir = argv[1];
+    const uint32_t W = std::stoul(argv[2]), H = std::stoul(argv[3]);
+    const int frames = std::stoi(argv[4]);
+    auto ctx = Context::create(0);
+    auto matrices = MatrixIO::import_matrices(dir + "/matrices.json");
+    auto g_buffer = GBuffer::create(*ctx, W, H);
+    g_buffer->compile(*ctx);
+    ref_ptr<IlluminationBuffer> illu = IlluminationBufferDemodulatedFloat::create(*ctx, W, H);
+    illu->compile(*ctx);
+    OfflineGBuffers g(frames);
+    OfflineIlluminations il(frames);
+    for (int f = 0; f < frames; ++f) {
+        const std::string n = std::to_string(f);
+        auto d = slurp<float>(dir + "/in_depth_" + n), nr = slurp<float>(dir + "/in_normal_" + n), no = slurp<float>(dir + "/in_illu_" + n);
+        auto al = slurp<uint8_t>(dir + "/in_albedo_" + n), ma = slurp<uint8_t>(dir + "/in_material_" + n);
+        check(vkpbrt_image_upload(g_buffer->depth->handle, d.data(), d.size() * 4));
+        check(vkpbrt_image_upload(g_buffer->normal->handle, nr.data(), nr.size() * 4));
+        check(vkpbrt_image_upload(g_buffer->albedo->handle, al.data(), al.size()));
+        check(vkpbrt_image_upload(g_buffer->material->handle, ma.data(), ma.size()));
+        check(vkpbrt_image_upload(illu->illumination_images[0]->handle, no.data(), no.size() * 4));
+        g[f] = OfflineGBuffer::create();
+        g[f]->download_from_g_buffer(g_buffer, *ctx);
+        il[f] = OfflineIllumination::create();
+        il[f]->download_from_illumination_buffer(illu, *ctx);
+    }
+    if (!GBufferIO::export_g_buffer(dir + "/pos_%d.exr", dir + "/depth_%d.exr", dir + "/normal_%d.exr", dir + "/material_%d.exr", dir + "/albedo_%d.exr", frames, g, matrices, 0)) return 1;
+    if (!IlluminationBufferIO::export_illumination(dir + "/illu_%d.exr", frames, il, 0)) return 2;
+    if (!GBufferIO::export_g_buffer("", dir + "/only_depth_%d.exr", "", "", "", frames, g, matrices, 0)) return 3;
+    if (GBufferIO::export_g_buffer("", dir + "/no/such/dir/depth_%d.exr", "", "", "", frames, g, matrices, 0)) return 4;
+    std::vector<CameraMatrices> combined(matrices);
+    for (auto& m : combined) { m.proj.reset(); m.inv_proj.reset(); }
+    if (GBufferIO::export_g_buffer(dir + "/nopos_%d.exr", "", "", "", "", frames, g, combined, 0)) return 5;
+    return 0;
+}
+''')
+    from vulkanpbrt_b200.matrix_io import export_matrices
+    libdir = root / "tests" / "hostsim"
+    subprocess.run(["make", "-C", str(libdir)], check=True, capture_output=True)
+    exe = tmp_path / "export_probe"
+    r = subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-I", str(root / "include"), str(src), "-o", str(exe), f"-L{libdir}", "-lvkpbrt_hostsim",
+                        f"-Wl,-rpath,{libdir}", "-lz"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    W, H, frames = 80, 48, 2
+    seq = _sequence(W, H, frames)
+    mats = [CameraMatrices(view=fr.camera.view, inv_view=fr.camera.inv_view, proj=fr.camera.proj, inv_proj=fr.camera.inv_proj) for fr in seq]
+    assert export_matrices(tmp_path / "matrices.json", mats)
+    rng = np.random.default_rng(4)
+    material = [rng.integers(0, 256, (H, W, 4), dtype=np.uint8) for _ in seq]
+    for f, fr in enumerate(seq):
+        for name, a in (("depth", fr.depth), ("normal", fr.normal), ("illu", fr.illumination), ("albedo", fr.albedo), ("material", material[f])):
+            np.ascontiguousarray(a).tofile(tmp_path / f"in_{name}_{f}")
+    r = subprocess.run([str(exe), str(tmp_path), str(W), str(H), str(frames)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert "no/such/dir" in r.stderr and "depthToPosition" in r.stdout
+    assert not list(tmp_path.glob("nopos_*")) and len(list(tmp_path.glob("only_depth_*.exr"))) == frames
+    for f, fr in enumerate(seq):
+        c = fr.camera
+        want_p, want_n, want_a = oracle.gbuffer_export(np.asarray(c.inv_view, np.float32), np.asarray(c.inv_proj, np.float32), fr.depth, fr.normal, fr.albedo)
+        want_m = oracle.gbuffer_export(unorm=material[f])[2]
+        for name, want in (("pos", want_p), ("normal", want_n), ("albedo", want_a), ("material", want_m), ("illu", np.ascontiguousarray(fr.illumination, np.float32)),
+                           ("depth", fr.depth), ("only_depth", fr.depth)):
+            got = read_exr(tmp_path / f"{name}_{f}.exr")
+            np.testing.assert_array_equal(got.reshape(want.shape).view(np.uint32), want.view(np.uint32), err_msg=f"{name} {f}")
+        # and the Python layer's export of the same frame holds the same planes
+    g = [OfflineGBuffer(depth=fr.depth, normal=fr.normal, material=material[f], albedo=fr.albedo) for f, fr in enumerate(seq)]
+    d = str(tmp_path)
+    assert GBufferIO.export_g_buffer(d + "/py_pos_%d.exr", "", "", d + "/py_material_%d.exr", d + "/py_albedo_%d.exr", frames, g, mats, verbosity=0)
+    for f in range(frames):
+        for name in ("pos", "material", "albedo"):
+            np.testing.assert_array_equal(read_exr(tmp_path / f"py_{name}_{f}.exr").view(np.uint32), read_exr(tmp_path / f"{name}_{f}.exr").view(np.uint32), err_msg=f"py {name} {f}")

@@ -1,7 +1,7 @@
 """Offline sequence I/O: the reference's way of feeding pre-rendered sequences.
 
-Host-side mirror of `GBufferIO` and `IlluminationBufferIO` (source/io/RenderIO.cpp:6-158 import, :212-327 export,
-:329-398 conversions, :501-591 illumination): printf-style per-frame file names, OpenEXR planes, and the conversions
+Host-side mirror of `GBufferIO` and `IlluminationBufferIO` (source/io/RenderIO.cpp:6-158 import, :213-310 export,
+:312-382 conversions, :501-591 illumination): printf-style per-frame file names, OpenEXR planes, and the conversions
 between what is stored (world position / cartesian normal / float albedo, all rgba32f) and what the G-buffer holds
 (Euclidean depth r32f, spherical normal rg32f, albedo rgba8).  The EXR codec is OpenCV's bundled OpenEXR (the
 reference uses vsgXchange::openexr); planes come back in R, G, B, A channel order, row 0 at the top.
@@ -76,7 +76,7 @@ def _rgba(img: np.ndarray) -> np.ndarray:
     return out
 
 
-# ---- conversions (RenderIO.cpp:160-211, :329-398) -------------------------------------------------------------------
+# ---- conversions (RenderIO.cpp:160-211, :312-382) -------------------------------------------------------------------
 class GBufferIO:
     @staticmethod
     def convert_normal_to_spherical(normals: np.ndarray) -> np.ndarray:
@@ -87,8 +87,10 @@ class GBufferIO:
 
     @staticmethod
     def spherical_to_cartesian(normals: np.ndarray) -> np.ndarray:
-        """:329-346"""
-        t, p = normals[..., 0].astype(np.float32), normals[..., 1].astype(np.float32)
+        """:312-329"""
+        # cos / sin are the C library's double routines in the reference's translation unit (unqualified calls on floats with
+        # only <cmath> in scope); the products are rounded once
+        t, p = normals[..., 0].astype(np.float64), normals[..., 1].astype(np.float64)
         out = np.empty(normals.shape[:2] + (4,), np.float32)
         out[..., 0] = np.cos(p) * np.sin(t)
         out[..., 1] = np.sin(p) * np.sin(t)
@@ -108,7 +110,7 @@ class GBufferIO:
 
     @staticmethod
     def unorm_to_float(array: np.ndarray) -> np.ndarray:
-        """:348-363"""
+        """:331-346"""
         return (array.astype(np.float32) / np.float32(255.0)).astype(np.float32)
 
     @staticmethod
@@ -123,7 +125,7 @@ class GBufferIO:
 
     @staticmethod
     def depth_to_position(depth: np.ndarray, matrices: CameraMatrices) -> Optional[np.ndarray]:
-        """:365-398  needs separate view / projection matrices"""
+        """:348-382  needs separate view / projection matrices"""
         if matrices.proj is None or matrices.inv_proj is None:
             print("GBufferIO::depthToPosition: Camera matrix in wrong layout. Expected camera matrix with separate projection matrix")
             return None
@@ -131,15 +133,21 @@ class GBufferIO:
         H, W = depth.shape
         ip = np.asarray(matrices.inv_proj, dtype=f).reshape(4, 4)       # [col][row]
         iv = np.asarray(matrices.inv_view, dtype=f).reshape(4, 4)
-        x = ((np.arange(W, dtype=f) + f(.5)) / f(W) * f(2) - f(1))[None, :].repeat(H, 0)
-        y = ((np.arange(H, dtype=f) + f(.5)) / f(H) * f(2) - f(1))[:, None].repeat(W, 1)
-        clip = np.stack([x, y, np.ones_like(x), np.ones_like(x)], axis=-1)
-        d = np.einsum("cr,hwc->hwr", ip, clip).astype(f)                # m * v = sum_c col[c] * v[c]
-        d[..., 3] = 0
-        d = d / np.sqrt((d * d).sum(axis=-1, keepdims=True, dtype=f))
-        direction = np.einsum("cr,hwc->hwr", iv, d).astype(f)[..., :3] * depth[..., None].astype(f)
-        out = np.ones((H, W, 4), f)
-        out[..., :3] = iv[3][:3][None, None, :] + direction
+
+        def mat_vec(m, v):      # vsg/maths/mat4.h:159-165, the sums in the source's order (binary32 throughout)
+            return [((m[0][r] * v[0] + m[1][r] * v[1]) + m[2][r] * v[2]) + m[3][r] * v[3] for r in range(4)]
+
+        x = np.broadcast_to(((np.arange(W, dtype=f) + f(.5)) / f(W) * f(2) - f(1))[None, :], (H, W))
+        y = np.broadcast_to(((np.arange(H, dtype=f) + f(.5)) / f(H) * f(2) - f(1))[:, None], (H, W))
+        one = np.ones((H, W), f)
+        d = mat_vec(ip, [x, y, one, one])
+        d[3] = np.zeros((H, W), f)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            inv_len = f(1.0) / np.sqrt(((d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]) + d[3] * d[3])      # normalize = v * (1 / length), vec4.h:225-254
+            world = mat_vec(iv, [c * inv_len for c in d])
+            out = np.ones((H, W, 4), f)
+            for c in range(3):
+                out[..., c] = iv[3][c] + world[c] * depth.astype(f)
         return out
 
     # ---- on the device ---------------------------------------------------------------------------------------------
@@ -224,7 +232,7 @@ class GBufferIO:
     @staticmethod
     def export_g_buffer(position_format: str, depth_format: str, normal_format: str, material_format: str, albedo_format: str,
                         num_frames: int, g_buffers: List[OfflineGBuffer], matrices: List[CameraMatrices], verbosity: int = 1) -> bool:
-        """:212-327  empty format strings skip a plane"""
+        """:213-310  empty format strings skip a plane"""
         fine = True
         for f in range(num_frames):
             g = g_buffers[f]
