@@ -1240,8 +1240,10 @@ ORACLE_API void vkpbrt_oracle_gbuffer_import(int W, int H, const float* inv_view
             depth_out[i] = sqrtf((dx * dx + dy * dy) + dz * dz);                             /* :116 length() */
         }
         if (normal) {
-            normal_out[2 * i] = acosf(normal[4 * i + 2]);                                    /* :174 */
-            normal_out[2 * i + 1] = atan2f(normal[4 * i + 1], normal[4 * i]);                /* :175 */
+            /* :174-175 call acos / atan2 unqualified on floats: the C library's DOUBLE routines with <cmath> alone in scope
+             * (vsg's headers, libstdc++), rounded by the store -- what the reference's text compiles to here, bit for bit */
+            normal_out[2 * i] = (float)acos((double)normal[4 * i + 2]);
+            normal_out[2 * i + 1] = (float)atan2((double)normal[4 * i + 1], (double)normal[4 * i]);
         }
         if (albedo)
             for (int c = 0; c < 4; ++c) {
