@@ -2,9 +2,11 @@
 // against include/vkpbrt/io.hpp + vkpbrt.hpp: a pre-rendered sequence (EXR planes + the matrix JSON the reference writes)
 // is imported with MatrixIO / GBufferIO / IlluminationBufferIO, staged frame by frame and denoised.
 //
-//   cpp_offline_sequence <dir> <frames> <position|depth>
+//   cpp_offline_sequence <dir> <frames> <position|depth> [export-dir]
 //   <dir>/matrices.json, <dir>/{pos|depth}_%d.exr, normal_%d.exr, albedo_%d.exr, illu_%d.exr
 //     -> <dir>/final_%d.bgra and the imported G-buffer as <dir>/gbuffer_%d.{depth,normal,albedo}
+//   with an export directory, the reference's export flags too (VulkanPBRT.cpp:595-630): every frame's G-buffer and raw
+//   illumination are read back after the frame and written as <export-dir>/{pos,depth,normal,albedo,illu}_%d.exr + matrices.json
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -29,6 +31,7 @@ int main(int argc, char** argv)
     const std::string dir = argv[1];
     const int num_frames = atoi(argv[2]);
     const bool from_position = std::string(argv[3]) == "position";
+    const std::string export_dir = argc > 4 ? argv[4] : "";
     try {
         // VulkanPBRT.cpp:340-372: matrices first (positions need them), then the G-buffer and illumination sequences
         const std::vector<CameraMatrices> camera_matrices = MatrixIO::import_matrices(dir + "/matrices.json");
@@ -64,6 +67,8 @@ int main(int argc, char** argv)
         final_descriptor_image = taa->get_final_descriptor_image();
         accumulation_buffer->copy_to_back_images(commands, g_buffer, illumination_buffer);
 
+        OfflineGBuffers exported_g_buffers(num_frames);
+        OfflineIlluminations exported_illuminations(num_frames);
         for (int frame_index = 0; frame_index < num_frames; ++frame_index) {
             // :566-573: stage the frame, hand the accumulator this frame's and the previous frame's matrices
             offline_g_buffers.at(frame_index)->upload_to_g_buffer(g_buffer, context);
@@ -83,6 +88,21 @@ int main(int argc, char** argv)
             commands->record();
             pc.prev_view = cur.view;
             dump(dir + "/final_" + n + ".bgra", final_descriptor_image, context);
+            if (!export_dir.empty()) {
+                // :595-607: wait for the frame, then copy the staged planes into this frame's offline buffers
+                exported_g_buffers[frame_index] = OfflineGBuffer::create();
+                exported_g_buffers[frame_index]->download_from_g_buffer(g_buffer, context);
+                exported_illuminations[frame_index] = OfflineIllumination::create();
+                exported_illuminations[frame_index]->download_from_illumination_buffer(raw_illumination, context);
+            }
+        }
+        if (!export_dir.empty()) {
+            // :620-634: exporting all images
+            const bool fine = GBufferIO::export_g_buffer(separate_matrices ? export_dir + "/pos_%d.exr" : "", export_dir + "/depth_%d.exr", export_dir + "/normal_%d.exr", "",
+                                                         export_dir + "/albedo_%d.exr", num_frames, exported_g_buffers, camera_matrices, 0) &&
+                              IlluminationBufferIO::export_illumination(export_dir + "/illu_%d.exr", num_frames, exported_illuminations, 0) &&
+                              MatrixIO::export_matrices(export_dir + "/matrices.json", camera_matrices);
+            if (!fine) throw std::runtime_error("export failed");
         }
     } catch (const std::exception& e) {
         std::cerr << "error: " << e.what() << std::endl;

@@ -163,8 +163,23 @@ def test_cxx_offline_sequence_import(tmp_path, backend, source):
     assert IlluminationBufferIO.export_illumination(d + "/illu_%d.exr", frames, [OfflineIllumination(noisy=fr.illumination) for fr in seq])
     assert export_matrices(d + "/matrices.json", mats)
     exe = _cxx_offline(tmp_path, backend)
-    r = subprocess.run([str(exe), d, str(frames), source], capture_output=True, text=True, timeout=600)
+    out = tmp_path / "exported"
+    out.mkdir()
+    # the export flags of the reference's loop as well -- on the emulator only (memory copies + host loops, nothing of it computes on the device)
+    r = subprocess.run([str(exe), d, str(frames), source] + ([str(out)] if backend == "hostsim" else []), capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
+    if backend == "hostsim":
+        # what the C++ layer exported is the imported G-buffer run through the oracle's export conversions, and imports again
+        from oracle import oracle as orc        # the checker
+        back = import_matrices(out / "matrices.json")
+        for f in range(frames):
+            dep = np.fromfile(tmp_path / f"gbuffer_{f}.depth", np.float32).reshape(H, W)
+            nrm = np.fromfile(tmp_path / f"gbuffer_{f}.normal", np.float32).reshape(H, W, 2)
+            alb = np.fromfile(tmp_path / f"gbuffer_{f}.albedo", np.uint8).reshape(H, W, 4)
+            want_p, want_n, want_a = orc.gbuffer_export(np.asarray(mats[f].inv_view, np.float32), np.asarray(mats[f].inv_proj, np.float32), dep, nrm, alb)
+            for name, want in (("pos", want_p), ("normal", want_n), ("albedo", want_a), ("depth", dep), ("illu", np.ascontiguousarray(seq[f].illumination, np.float32))):
+                np.testing.assert_array_equal(read_exr(out / f"{name}_{f}.exr").reshape(want.shape).view(np.uint32), want.view(np.uint32), err_msg=f"exported {name} {f}")
+            np.testing.assert_array_equal(np.asarray(back[f].view, np.float32), np.asarray(mats[f].view, np.float32))
     # the same import through the Python layer
     loaded = import_matrices(d + "/matrices.json")
     pipe = DenoisePipeline(W, H, use_taa=True, separate_matrices=True)
