@@ -31,6 +31,21 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "slow: longer CPU test")
 
 
+# GPU variants added after the round's last visit to a GPU (commit 61a08ea): they have run on the emulator only.  The GPU
+# suite runs them LAST, so that under `-x` a surprise in one of them cannot hide the result of a test that has a GPU record
+# (profiles/r02_pytest_gpu_*.log).  Order only: nothing is skipped or deselected.
+_GPU_UNCONFIRMED = ("test_copy_final_image_and_device_uuid[cuda]", "test_images_smaller_than_one_block_are_rejected[cuda]",
+                    "test_reprojection_beyond_the_halo_is_counted[cuda]", "test_bmfr_image_narrower_than_two_blocks[cuda]",
+                    "test_caller_supplied_motion_outside_the_unit_square[", "test_bfr_descent_with_a_non_finite_gradient[",
+                    "test_cxx_offline_sequence_import[")
+
+
+def pytest_collection_modifyitems(config, items):
+    def late(item):
+        return "cuda" in item.nodeid and any(name in item.nodeid for name in _GPU_UNCONFIRMED)
+    items[:] = [i for i in items if not late(i)] + [i for i in items if late(i)]
+
+
 def _build_native():
     from vulkanpbrt_b200 import build
     build.build_all()
