@@ -1,8 +1,18 @@
-"""Generates the committed golden hashes under tests/golden/.
+"""Generates the committed golden vectors under tests/golden/.
 
-The reference cannot be executed in this environment (GLSL; no glslc / Vulkan ICD) and ships no test
-vectors, so these goldens come from the oracle (oracle/vkpbrt_oracle.c) on the deterministic synthetic
-sequence.  They pin the oracle bit for bit; the CUDA path is compared with the oracle directly.
+The reference cannot be executed as it ships (GLSL; no glslc / Vulkan ICD here) and holds no test vectors, so the
+goldens are OUTPUTS OF THE REFERENCE'S OWN TEXT compiled for the CPU in this container (oracle/_ref: the shaders through
+oracle/glsl_shim, the host conversion code of source/io/RenderIO.cpp through oracle/host_shim) on deterministic inputs:
+
+  <case>.json               per-frame SHA-256 of every plane of the chain.  Produced by the oracle AND by the reference's
+                            shader source; the script refuses to write a file on which the two differ, and records which
+                            produced it ("verified_against").  Without /root/reference it can only re-derive them from the
+                            oracle and says so.
+  host_conversions.json     inputs and outputs (bit patterns) of GBufferIO's import / export conversions as computed by
+                            the reference's C++ (oracle/_ref/libhostref.so).  Not regenerated without the reference.
+
+tests/test_oracle_kat.py compares the oracle with both on every machine, including those where /root/reference and
+oracle/_ref do not exist.
 
     python -m tests.golden.make_golden        # rewrites tests/golden/*.json
 """
@@ -48,9 +58,70 @@ def run_case(oracle, c):
     return {"case": c, "frames": frames}
 
 
+def _hex(a):
+    a = np.ascontiguousarray(a)
+    return {"dtype": str(a.dtype), "shape": list(a.shape), "hex": a.tobytes().hex()}
+
+
+def from_hex(d):
+    return np.frombuffer(bytes.fromhex(d["hex"]), dtype=d["dtype"]).reshape(d["shape"]).copy()
+
+
+def host_conversion_inputs():
+    """small planes with the special values of each conversion (poles, the miss normal, truncation edges, the miss distance)"""
+    rng = np.random.default_rng(2026)
+    H, W = 6, 9
+    cam = synth.render_frame(32, 32, 3).camera
+    m64 = np.concatenate([np.asarray(x, np.float32).reshape(-1) for x in (cam.view, cam.inv_view, cam.proj, cam.inv_proj)])
+    position = rng.uniform(-30, 30, (H, W, 4)).astype(np.float32)
+    v = rng.standard_normal((H, W, 3))
+    v /= np.linalg.norm(v, axis=-1, keepdims=True)
+    cart = np.concatenate([v, np.ones((H, W, 1))], -1).astype(np.float32)
+    cart.reshape(-1, 4)[:6] = np.float32([[0, 0, 1, 1], [0, 0, -1, 1], [1, 0, 0, 1], [0, -1, 0, 1], [-1, 0, 0, 1], [0.6, 0.8, 0, 1]])
+    albedo = rng.uniform(0, 1, (H, W, 4)).astype(np.float32)
+    albedo.reshape(-1)[:8] = np.float32([0, 0.5, 1.0, 0.999, 0.0039, 0.25, 1 / 255, 254.5 / 255])
+    depth = rng.uniform(0.05, 200, (H, W)).astype(np.float32)
+    depth.reshape(-1)[:2] = np.float32([0.0, 1e10])
+    sph = np.stack([rng.uniform(0, np.pi, (H, W)), rng.uniform(-np.pi, np.pi, (H, W))], -1).astype(np.float32)
+    sph.reshape(-1, 2)[:4] = np.float32([[0, 0], [np.pi, 0], [np.pi / 2, np.pi], [0, np.pi / 4]])
+    unorm = rng.integers(0, 256, (H, W, 4), dtype=np.uint8)
+    unorm.reshape(-1)[:4] = np.uint8([0, 1, 254, 255])
+    return dict(matrices64=m64, position=position, cartesian=cart, albedo=albedo, depth=depth, spherical=sph, unorm=unorm)
+
+
+def host_conversions(R):
+    i = host_conversion_inputs()
+    d, n, a = R.gbuffer_import(i["matrices64"][16:32], i["position"], i["cartesian"], i["albedo"])
+    p, c, u = R.gbuffer_export(i["matrices64"], True, i["depth"], i["spherical"], i["unorm"])
+    return {"produced_by": "GBufferIO's conversions as the reference's own C++ text (source/io/RenderIO.cpp:101-120, :160-211, :312-382) "
+                           "compiled by oracle/host_shim against vsg's maths headers",
+            "inputs": {k: _hex(x) for k, x in i.items()},
+            "outputs": {"import_depth": _hex(d), "import_normal": _hex(n), "import_albedo": _hex(a),
+                        "export_position": _hex(p), "export_normal": _hex(c), "export_unorm": _hex(u)}}
+
+
+class _RefAsOracle:
+    """the reference's shader source behind the oracle's chain interface"""
+    def __init__(self, O, R):
+        self.OracleChain, self.f16_bits_to_f32 = R.RefChain, O.f16_bits_to_f32
+
+
 if __name__ == "__main__":
     from oracle import oracle as O
+    from oracle import ref as R
     out = Path(__file__).resolve().parent
+    have_ref = R.build() and R.build_host()
     for name, c in CASES.items():
-        (out / f"{name}.json").write_text(json.dumps(run_case(O, c), indent=1))
-        print("wrote", name)
+        got = run_case(O, c)
+        if have_ref:
+            ref = run_case(_RefAsOracle(O, R), c)
+            if ref["frames"] != got["frames"]:
+                raise SystemExit(f"{name}: the oracle differs from the reference's shader source -- nothing written")
+            got["verified_against"] = "the reference's shader source (shaders/*.comp via oracle/glsl_shim -> oracle/_ref/libref.so): identical hashes"
+        else:
+            got["verified_against"] = "nothing (no /root/reference here): derived from the oracle alone"
+        (out / f"{name}.json").write_text(json.dumps(got, indent=1))
+        print("wrote", name, "--", got["verified_against"])
+    if have_ref:
+        (out / "host_conversions.json").write_text(json.dumps(host_conversions(R), indent=1))
+        print("wrote host_conversions")

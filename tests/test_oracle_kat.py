@@ -212,6 +212,29 @@ def test_oracle_matches_committed_golden_hashes(oracle, name):
     assert got["frames"] == spec["frames"]
 
 
+def test_committed_goldens_are_outputs_of_the_reference():
+    """the hash files say what produced them: make_golden.py writes them only when the reference's shader source yields the
+    same hashes as the oracle"""
+    for name in ("bmfr32_taa_256x256_8f", "bfrx3_taa_160x128_3f"):
+        assert "reference's shader source" in json.loads((GOLDEN / f"{name}.json").read_text())["verified_against"]
+
+
+def test_oracle_matches_the_reference_host_code_vectors(oracle):
+    """tests/golden/host_conversions.json holds inputs and outputs of GBufferIO's import / export conversions computed by
+    the reference's own C++ (source/io/RenderIO.cpp through oracle/host_shim, written by make_golden.py where the
+    reference is mounted): the oracle reproduces every output bit for bit -- on machines without /root/reference too"""
+    from tests.golden.make_golden import from_hex, host_conversion_inputs
+    spec = json.loads((GOLDEN / "host_conversions.json").read_text())
+    i = {k: from_hex(v) for k, v in spec["inputs"].items()}
+    for k, v in host_conversion_inputs().items():                      # the committed inputs are the generator's
+        np.testing.assert_array_equal(i[k].view(np.uint8), np.ascontiguousarray(v).view(np.uint8), err_msg=k)
+    want = {k: from_hex(v) for k, v in spec["outputs"].items()}
+    d, n, a = oracle.gbuffer_import(i["matrices64"][16:32], i["position"], i["cartesian"], i["albedo"])
+    p, c, u = oracle.gbuffer_export(i["matrices64"][16:32], i["matrices64"][48:64], i["depth"], i["spherical"], i["unorm"])
+    for name, got in (("import_depth", d), ("import_normal", n), ("import_albedo", a), ("export_position", p), ("export_normal", c), ("export_unorm", u)):
+        np.testing.assert_array_equal(np.ascontiguousarray(got).view(np.uint8), want[name].view(np.uint8), err_msg=name)
+
+
 # ---- the transposing shuffle networks of bmfr.cu / bfr.cu, restated symbolically ----------------------
 def _network(n_values, lanes=32, plain_tail=False):
     """ReduceN<N, 16> of bfr.cu, or with plain_tail MultiReduce<N, 16> of bmfr.cu (N a power of two; once one value
