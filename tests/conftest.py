@@ -37,7 +37,7 @@ def pytest_configure(config):
 _GPU_UNCONFIRMED = ("test_copy_final_image_and_device_uuid[cuda]", "test_images_smaller_than_one_block_are_rejected[cuda]",
                     "test_reprojection_beyond_the_halo_is_counted[cuda]", "test_bmfr_image_narrower_than_two_blocks[cuda]",
                     "test_caller_supplied_motion_outside_the_unit_square[", "test_bfr_descent_with_a_non_finite_gradient[",
-                    "test_cxx_offline_sequence_import[")
+                    "test_cxx_offline_sequence_import[", "test_kernels_reproduce_the_committed_reference_hashes[")
 
 
 def pytest_collection_modifyitems(config, items):

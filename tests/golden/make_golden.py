@@ -32,6 +32,15 @@ from vulkanpbrt_b200 import synth  # noqa: E402
 CASES = {
     "bmfr32_taa_256x256_8f": dict(W=256, H=256, denoiser="bmfr", block=32, taa=True, frames=8),
     "bfrx3_taa_160x128_3f": dict(W=160, H=128, denoiser="bfrx3", block=32, taa=True, frames=3),
+    # the other block sizes, the single-scale BFR, the WORLD feature modes, the offline (combined-matrix) accumulator with an
+    # rgba16f raw input, the BMFR X8X16X32 wiring; frames 7.. so that the negative-jitter frames 8 / 9 are inside
+    "bmfr16_taa_208x144_4f": dict(W=208, H=144, denoiser="bmfr", block=16, taa=True, frames=4, first=7),
+    "bmfr8_200x136_3f": dict(W=200, H=136, denoiser="bmfr", block=8, taa=False, frames=3, first=7),
+    "bfr16_taa_168x104_4f": dict(W=168, H=104, denoiser="bfr", block=16, taa=True, frames=4, first=7),
+    "bmfr32_world1_160x128_3f": dict(W=160, H=128, denoiser="bmfr", block=32, taa=False, frames=3, first=7, position_type=1),
+    "bmfr32_world2_160x128_3f": dict(W=160, H=128, denoiser="bmfr", block=32, taa=False, frames=3, first=7, position_type=2),
+    "bmfr32_combined_f16_192x128_4f": dict(W=192, H=128, denoiser="bmfr", block=32, taa=True, frames=4, separate=False, raw_f16=True),
+    "bmfrx3_taa_160x128_3f": dict(W=160, H=128, denoiser="bmfrx3", block=32, taa=True, frames=3),
 }
 
 
@@ -40,9 +49,10 @@ def _sha(a):
 
 
 def run_case(oracle, c):
-    orc = oracle.OracleChain(c["W"], c["H"], c["denoiser"], c["block"], use_taa=c["taa"])
+    orc = oracle.OracleChain(c["W"], c["H"], c["denoiser"], c["block"], use_taa=c["taa"], separate_matrices=c.get("separate", True),
+                             raw_f16=c.get("raw_f16", False), position_type=c.get("position_type", 0))
     frames = []
-    for f in range(c["frames"]):
+    for f in range(c.get("first", 0), c.get("first", 0) + c["frames"]):
         fr = synth.render_frame(c["W"], c["H"], f)
         if c["denoiser"].endswith("x3"):
             av = oracle.f16_bits_to_f32(orc.prev_illu)

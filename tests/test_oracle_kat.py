@@ -202,7 +202,12 @@ def _sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
-@pytest.mark.parametrize("name", ["bmfr32_taa_256x256_8f", "bfrx3_taa_160x128_3f"])
+def _golden_cases():
+    from tests.golden.make_golden import CASES
+    return sorted(CASES)
+
+
+@pytest.mark.parametrize("name", _golden_cases())
 def test_oracle_matches_committed_golden_hashes(oracle, name):
     """tests/golden/*.json were produced by tests/golden/make_golden.py from this oracle; they pin its
     outputs bit for bit (any change to the restatement, the compiler flags or the host libm shows up here)."""
@@ -215,7 +220,7 @@ def test_oracle_matches_committed_golden_hashes(oracle, name):
 def test_committed_goldens_are_outputs_of_the_reference():
     """the hash files say what produced them: make_golden.py writes them only when the reference's shader source yields the
     same hashes as the oracle"""
-    for name in ("bmfr32_taa_256x256_8f", "bfrx3_taa_160x128_3f"):
+    for name in _golden_cases():
         assert "reference's shader source" in json.loads((GOLDEN / f"{name}.json").read_text())["verified_against"]
 
 
