@@ -10,12 +10,15 @@ oracle/glsl_shim, the host conversion code of source/io/RenderIO.cpp through ora
                             oracle and says so.
   host_conversions.json     inputs and outputs (bit patterns) of GBufferIO's import / export conversions as computed by
                             the reference's C++ (oracle/_ref/libhostref.so).  Not regenerated without the reference.
+  reference_vectors.json    the same for vsg's matrix inverse, Accumulator::set_camera_matrices (the push-constant block of six
+                            frames, both matrix modes), formatConverter.comp and the demodulation statements of ptRaygen.rgen.
 
 tests/test_oracle_kat.py compares the oracle with both on every machine, including those where /root/reference and
 oracle/_ref do not exist.
 
     python -m tests.golden.make_golden        # rewrites tests/golden/*.json
 """
+import ctypes
 import hashlib
 import json
 import sys
@@ -110,6 +113,98 @@ def host_conversions(R):
                         "export_position": _hex(p), "export_normal": _hex(c), "export_unorm": _hex(u)}}
 
 
+def more_inputs():
+    """inputs of the other reference-pinned functions: matrices for vsg's inverse (affine -> t_inverse_4x3, general,
+    singular -> NaN diagonal), an image with the format converter's rounding boundaries, radiance / albedo / position.x
+    planes with the demodulation's clamps"""
+    rng = np.random.default_rng(77)
+    mats = []
+    for f in (0, 5):
+        cam = synth.camera(160, 128, f)
+        mats += [cam.view, cam.proj, cam.inv_view, cam.inv_proj]
+    for k in range(16):
+        m = rng.uniform(-3, 3, 16).astype(np.float32)
+        if k % 2 == 0:
+            m[3] = m[7] = m[11] = 0
+            m[15] = 1
+        if k % 7 == 6:
+            m[4:8] = m[0:4]
+        mats.append(m)
+    mats += [np.zeros(16, np.float32), np.eye(4, dtype=np.float32).reshape(-1)]
+    H, W = 5, 12
+    img = rng.uniform(-0.25, 1.25, (H, W, 4)).astype(np.float32)
+    img[0, 0] = [np.nan, np.inf, -np.inf, 0.5]
+    img[0, 1] = [0.0, 1.0, 0.5 / 255.0, 254.5 / 255.0]
+    img[1] = (np.arange(W)[:, None] / 255.0 + np.array([0, 1e-4, -1e-4, 0.5 / 255.0])[None, :]).astype(np.float32)
+    L = rng.uniform(-1, 14, (H, W, 4)).astype(np.float32)
+    L.reshape(-1)[:10] = np.float32([0.0, -0.0, 1e-40, 1e-6, 9.999999, 10.0, 10.000001, 3e38, np.inf, -np.inf])
+    alb = rng.uniform(0, 1, (H, W, 4)).astype(np.float32)
+    alb[2, :4, :3] = 0.0
+    alb.reshape(-1)[40:46] = np.float32([0.0, 1e-7, 1e-6, 1e-3, 0.01, 1.0])
+    px = rng.uniform(-50, 50, (H, W)).astype(np.float32)
+    px[3, 2:6] = np.inf
+    px[4, 3] = -np.inf
+    return dict(matrices=np.stack([np.ascontiguousarray(m, np.float32) for m in mats]), image=img,
+                image_f16=img.astype(np.float16).view(np.uint16), image_u8=(np.clip(np.nan_to_num(img), 0, 1) * 255).astype(np.uint8),
+                radiance=L, albedo=alb, position_x=px)
+
+
+def push_constant_blocks(O, set_camera_matrices=None):
+    """Accumulator::set_camera_matrices over six frames of the synthetic camera, both matrix modes: the oracle's 212-byte
+    block (and, given the reference's function, the reference's) per frame"""
+    from vulkanpbrt_b200.pipeline import _combined
+    W, H = 160, 128
+    out = {}
+    for separate in (True, False):
+        chain = O.OracleChain(W, H, "bmfr", 32, separate_matrices=separate)
+        pc = np.zeros(53, np.float32)
+        blocks, prev_cam = [], None
+
+        def pack(cam):
+            if separate:
+                return np.concatenate([cam.view, cam.inv_view, cam.proj, cam.inv_proj]).astype(np.float32), 1
+            vp, ivp = _combined(cam)
+            return np.concatenate([vp, ivp, np.zeros(32, np.float32)]).astype(np.float32), 0
+
+        for f in range(6):
+            cam = synth.camera(W, H, f)
+            chain._set_camera_matrices(f, cam)
+            got = np.concatenate([np.array(list(chain.pc.view), np.float32), np.array(list(chain.pc.inv_view), np.float32),
+                                  np.array(list(chain.pc.prev_view), np.float32), np.array(list(chain.pc.prev_origin), np.float32),
+                                  np.array([chain.pc.frame_number], np.int32).view(np.float32)])
+            if set_camera_matrices is not None:
+                cur64, has = pack(cam)
+                prev64 = (np.concatenate([chain.prev_view, np.zeros(48, np.float32)]).astype(np.float32) if separate
+                          else pack(prev_cam if prev_cam is not None else cam)[0])
+                p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+                assert set_camera_matrices(1 if separate else 0, f, p(cur64), has, p(prev64), has if not separate else 0, p(pc)) == 0
+                got = pc.copy()
+            blocks.append(got)
+            chain.prev_view = np.asarray(cam.view, np.float32).copy()
+            chain.prev_cam = prev_cam = cam
+        out["separate" if separate else "combined"] = np.stack(blocks)
+    return out
+
+
+def reference_vectors(O, R):
+    import ctypes as C
+    i = more_inputs()
+    h = C.CDLL(str(R._HOST_LIB))
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    inv = np.zeros_like(i["matrices"])
+    for k, m in enumerate(i["matrices"]):
+        h.hostref_inverse(p(np.ascontiguousarray(m)), p(inv[k]))
+    pcs = push_constant_blocks(O, h.hostref_set_camera_matrices)
+    return {"produced_by": "the reference's own text compiled for the CPU (oracle/_ref): vsg::inverse(mat4) (maths_transform.cpp:36-156) and "
+                           "Accumulator::set_camera_matrices (Accumulator.cpp:85-117) through oracle/host_shim; formatConverter.comp and the "
+                           "demodulation statements of ptRaygen.rgen:81-88 through oracle/glsl_shim",
+            "inputs": {k: _hex(x) for k, x in i.items()},
+            "outputs": {"inverse": _hex(inv), "format_converter_f32": _hex(R.format_converter(i["image"])),
+                        "format_converter_f16": _hex(R.format_converter(i["image_f16"])), "format_converter_u8": _hex(R.format_converter(i["image_u8"])),
+                        "demodulate": _hex(R.demodulate(i["radiance"], i["albedo"], i["position_x"])),
+                        "push_constants_separate": _hex(pcs["separate"]), "push_constants_combined": _hex(pcs["combined"])}}
+
+
 class _RefAsOracle:
     """the reference's shader source behind the oracle's chain interface"""
     def __init__(self, O, R):
@@ -134,4 +229,5 @@ if __name__ == "__main__":
         print("wrote", name, "--", got["verified_against"])
     if have_ref:
         (out / "host_conversions.json").write_text(json.dumps(host_conversions(R), indent=1))
-        print("wrote host_conversions")
+        (out / "reference_vectors.json").write_text(json.dumps(reference_vectors(O, R), indent=1))
+        print("wrote host_conversions, reference_vectors")

@@ -240,6 +240,37 @@ def test_oracle_matches_the_reference_host_code_vectors(oracle):
         np.testing.assert_array_equal(np.ascontiguousarray(got).view(np.uint8), want[name].view(np.uint8), err_msg=name)
 
 
+def test_oracle_matches_the_reference_vectors(oracle):
+    """tests/golden/reference_vectors.json: vsg's matrix inverse, Accumulator::set_camera_matrices (push-constant blocks of
+    six frames, both matrix modes), formatConverter.comp and the demodulation statements of ptRaygen.rgen as computed by
+    the reference's own text (oracle/_ref, written by make_golden.py) -- the oracle reproduces every output bit for bit
+    (NaNs compared as NaNs), with no reference tree on the machine"""
+    from tests.golden.make_golden import from_hex, more_inputs, push_constant_blocks
+    spec = json.loads((GOLDEN / "reference_vectors.json").read_text())
+    i = {k: from_hex(v) for k, v in spec["inputs"].items()}
+    for k, v in more_inputs().items():
+        np.testing.assert_array_equal(i[k].view(np.uint8), np.ascontiguousarray(v).view(np.uint8), err_msg=k)
+    want = {k: from_hex(v) for k, v in spec["outputs"].items()}
+
+    def same(got, name):
+        got, w = np.ascontiguousarray(got), want[name]
+        assert got.shape == w.shape and got.dtype == w.dtype, name
+        if got.dtype == np.float32:
+            nan = np.isnan(got) & np.isnan(w)
+            np.testing.assert_array_equal(np.where(nan, 0, got.view(np.uint32)), np.where(nan, 0, w.view(np.uint32)), err_msg=name)
+        else:
+            np.testing.assert_array_equal(got, w, err_msg=name)
+
+    same(np.stack([np.asarray(oracle.vsg_inverse(m), np.float32) for m in i["matrices"]]), "inverse")
+    same(oracle.format_converter(i["image"]), "format_converter_f32")
+    same(oracle.format_converter(i["image_f16"]), "format_converter_f16")
+    same(oracle.format_converter(i["image_u8"]), "format_converter_u8")
+    same(oracle.demodulate(i["radiance"], i["albedo"], i["position_x"]), "demodulate")
+    pcs = push_constant_blocks(oracle)
+    same(pcs["separate"], "push_constants_separate")
+    same(pcs["combined"], "push_constants_combined")
+
+
 # ---- the transposing shuffle networks of bmfr.cu / bfr.cu, restated symbolically ----------------------
 def _network(n_values, lanes=32, plain_tail=False):
     """ReduceN<N, 16> of bfr.cu, or with plain_tail MultiReduce<N, 16> of bmfr.cu (N a power of two; once one value
