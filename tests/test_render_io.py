@@ -449,3 +449,46 @@ int main(int argc, char** argv) {
     for f in range(frames):
         for name in ("pos", "material", "albedo"):
             np.testing.assert_array_equal(read_exr(tmp_path / f"py_{name}_{f}.exr").view(np.uint32), read_exr(tmp_path / f"{name}_{f}.exr").view(np.uint32), err_msg=f"py {name} {f}")
+
+
+def test_seeded_fuzz_of_the_host_conversions_against_the_reference(oracle):
+    """oracle against the reference's host code on extreme data: magnitudes over 18 decades, zeros, denormals, infinities and
+    NaNs sprinkled over positions / normals / depths / angles / matrices (300 draws of this ran clean by hand); every plane
+    bit for bit with NaNs compared as NaNs.  Albedo stays in [0, 1]: the reference's float -> byte conversion of anything else
+    is undefined behaviour"""
+    from oracle import ref as R
+    if not R.build_host():
+        pytest.skip("oracle/_ref host library is not built and /root/reference is not mounted")
+    rng = np.random.default_rng(99)
+    spec = np.float32([0, -0.0, 1e-45, 1e-38, 1e-20, 1e20, 3e38, np.inf, -np.inf, np.nan, -1, 1, np.pi, -np.pi, np.pi / 2])
+
+    def same(a, b, what):
+        a, b = a.view(np.uint32).copy(), b.view(np.uint32).copy()
+        na, nb = (a & 0x7FFFFFFF) > 0x7F800000, (b & 0x7FFFFFFF) > 0x7F800000
+        np.testing.assert_array_equal(na, nb, err_msg=what + " (NaN positions)")
+        a[na] = 0
+        b[nb] = 0
+        np.testing.assert_array_equal(a, b, err_msg=what)
+
+    def sprinkle(arr, p):
+        k = rng.random(arr.shape) < p
+        arr[k] = rng.choice(spec, size=int(k.sum()))
+
+    for it in range(40):
+        H, W = int(rng.integers(1, 40)), int(rng.integers(1, 40))
+        depth = (10.0 ** rng.uniform(-6, 12, (H, W))).astype(np.float32)
+        sph = rng.uniform(-10, 10, (H, W, 2)).astype(np.float32)
+        m = (rng.uniform(-2, 2, 64) * 10.0 ** rng.uniform(-3, 3)).astype(np.float32)
+        pos = (rng.uniform(-50, 50, (H, W, 4)) * 10.0 ** rng.uniform(-3, 6)).astype(np.float32)
+        nrm = rng.uniform(-1.2, 1.2, (H, W, 4)).astype(np.float32)                    # |n.z| > 1: acos -> NaN on both sides
+        alb = rng.uniform(0, 1, (H, W, 4)).astype(np.float32)
+        for arr, p in ((depth, 0.08), (sph, 0.08), (m, 0.08), (pos, 0.05), (nrm, 0.05)):
+            sprinkle(arr, p)
+        unorm = rng.integers(0, 256, (H, W, 4), dtype=np.uint8)
+        a, b = oracle.gbuffer_export(m[16:32], m[48:64], depth, sph, unorm), R.gbuffer_export(m, True, depth, sph, unorm)
+        for x, y, name in zip(a, b, ("position", "cartesian normal", "unorm")):
+            same(x, y, f"export {name}, draw {it}")
+        c, d = oracle.gbuffer_import(m[16:32], pos, nrm, alb), R.gbuffer_import(m[16:32], pos, nrm, alb)
+        same(c[0], d[0], f"import depth, draw {it}")
+        same(c[1], d[1], f"import normal, draw {it}")
+        np.testing.assert_array_equal(c[2], d[2], err_msg=f"import albedo, draw {it}")
