@@ -81,7 +81,7 @@ class GBufferIO:
     @staticmethod
     def convert_normal_to_spherical(normals: np.ndarray) -> np.ndarray:
         """:160-178  (theta, phi) = (acos(n.z), atan2(n.y, n.x))"""
-        n = _rgba(normals).astype(np.float32)
+        n = _rgba(normals).astype(np.float32).astype(np.float64)      # the reference's unqualified acos / atan2 are the double routines
         with np.errstate(invalid="ignore"):
             return np.stack([np.arccos(n[..., 2]), np.arctan2(n[..., 1], n[..., 0])], axis=-1).astype(np.float32)
 
