@@ -263,7 +263,7 @@ struct Reader {
     size_t i = 0;
     template <typename T> T get()
     {
-        if (i + sizeof(T) > b.size()) throw std::runtime_error("truncated file");
+        if (sizeof(T) > b.size() || i > b.size() - sizeof(T)) throw std::runtime_error("truncated file");      // (i may come from the file: no i + n that can wrap)
         T v;
         std::memcpy(&v, b.data() + i, sizeof(T));
         i += sizeof(T);
@@ -331,7 +331,14 @@ inline bool read(const std::string& path, Image& out)
         if (channels.empty() || x1 < x0 || y1 < y0) throw std::runtime_error("incomplete header");
         if (compression < 0 || compression > 3) throw std::runtime_error("compression " + std::to_string(compression) + " is not supported (NONE, RLE, ZIPS, ZIP are)");
         (void)line_order;                                       // every block carries its y: any order is fine
-        const int W = x1 - x0 + 1, H = y1 - y0 + 1, lines_per_block = compression == 3 ? 16 : 1, nblocks = (H + lines_per_block - 1) / lines_per_block;
+        // a corrupt data window must not turn into a giant allocation: every scan line block takes 8 bytes of the offset table
+        // and 8 of its own header, and no codec here expands more than deflate's 1032 : 1
+        const int64_t W64 = (int64_t)x1 - x0 + 1, H64 = (int64_t)y1 - y0 + 1;
+        const int lines_per_block = compression == 3 ? 16 : 1;
+        if (W64 > (1 << 24) || H64 > (1 << 24) || (H64 + lines_per_block - 1) / lines_per_block * 16 > (int64_t)bytes.size() ||
+            W64 * H64 * (int64_t)channels.size() * 2 > (int64_t)bytes.size() * 1100 + (1 << 20))
+            throw std::runtime_error("data window does not fit the file");
+        const int W = (int)W64, H = (int)H64, nblocks = (H + lines_per_block - 1) / lines_per_block;
         // where each file channel goes: R, G, B, A -> 0..3; a lone Y (or any single channel) -> 0
         std::vector<int> slot(channels.size(), -1);
         int nout = 0;

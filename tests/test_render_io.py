@@ -206,6 +206,16 @@ def test_cxx_offline_sequence_import(tmp_path, backend, source):
     assert np.abs(pipe.g_buffer.albedo.download().astype(int) - seq[-1].albedo.astype(int)).max() <= 1
 
 
+def _exr_offset_table(b: bytes) -> int:
+    """byte position of the scan line offset table: right after the header's empty attribute name"""
+    i = 8                                             # magic + version
+    while b[i] != 0:
+        i = b.index(b"\0", i) + 1                     # attribute name
+        i = b.index(b"\0", i) + 1                     # type name
+        i += 4 + int.from_bytes(b[i:i + 4], "little")
+    return i + 1
+
+
 def test_cxx_exr_reader_and_matrix_files(tmp_path):
     """io.hpp on its own (no device): EXR files written by OpenCV in float / half, 1 / 3 / 4 channels, ZIP (default), and its
     own uncompressed files read back by OpenCV; the matrix JSON and the BMFR-dataset text layout against the Python reader"""
@@ -228,6 +238,7 @@ int main(int argc, char** argv) {
     }
     exr::Image none;
     if (exr::read(dir + "/missing.exr", none) || exr::read(dir + "/garbage.exr", none)) return 3;
+    if (exr::read(dir + "/huge_window.exr", none) || exr::read(dir + "/wild_offset.exr", none)) return 7;
     auto m = MatrixIO::import_matrices(dir + "/m.json");
     if (!MatrixIO::export_matrices(dir + "/m_back.json", m)) return 4;
     auto t = MatrixIO::import_matrices(dir + "/cams.txt");
@@ -252,6 +263,17 @@ int main(int argc, char** argv) {
     assert cv2.imwrite(str(tmp_path / "rgba_f16.exr"), b, [cv2.IMWRITE_EXR_TYPE, cv2.IMWRITE_EXR_TYPE_HALF])
     planes["rgba_f16"] = half.astype(np.float32)
     (tmp_path / "garbage.exr").write_bytes(b"not an exr file at all")
+    # corrupt sizes must be refused, not allocated or dereferenced (found by mutating files under ASan): a data window of 2^31
+    # columns, and a scan line offset near 2^64
+    good = bytearray((tmp_path / "rgba_f32.exr").read_bytes())
+    at = good.index(b"dataWindow\0box2i\0") + len(b"dataWindow\0box2i\0") + 4
+    huge = bytearray(good)
+    huge[at + 8:at + 12] = (0x7FFFFFFF).to_bytes(4, "little")
+    (tmp_path / "huge_window.exr").write_bytes(huge)
+    wild = bytearray(good)
+    table = _exr_offset_table(good)
+    wild[table:table + 8] = (0xFFFFFFFFFFFFFFFC).to_bytes(8, "little")
+    (tmp_path / "wild_offset.exr").write_bytes(wild)
     seq = _sequence(32, 32, 2)
     mats = [CameraMatrices(view=fr.camera.view, inv_view=fr.camera.inv_view, proj=fr.camera.proj, inv_proj=fr.camera.inv_proj) for fr in seq]
     mats.append(CameraMatrices(view=seq[0].camera.view, inv_view=seq[0].camera.inv_view))           # one combined-matrix entry
@@ -259,7 +281,7 @@ int main(int argc, char** argv) {
     (tmp_path / "cams.txt").write_text("{" + ", ".join(f"{v:.9g}" for v in seq[0].camera.view) + "},\n{" + " ".join(f"{v:.9g}," for v in seq[1].camera.proj) + "}\n")
     r = subprocess.run([str(exe), str(tmp_path)], capture_output=True, text=True)
     assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
-    assert "missing.exr" not in r.stderr and "garbage.exr" in r.stderr
+    assert "missing.exr" not in r.stderr and "garbage.exr" in r.stderr and "huge_window.exr" in r.stderr and "wild_offset.exr" in r.stderr
     for name, a in planes.items():
         w, h, c = map(int, (tmp_path / f"{name}.dims").read_text().split())
         assert (h, w) == a.shape[:2] and c == (a.shape[2] if a.ndim == 3 else 1)
