@@ -514,3 +514,31 @@ def test_seeded_fuzz_of_the_host_conversions_against_the_reference(oracle):
         same(c[0], d[0], f"import depth, draw {it}")
         same(c[1], d[1], f"import normal, draw {it}")
         np.testing.assert_array_equal(c[2], d[2], err_msg=f"import albedo, draw {it}")
+
+
+@pytest.mark.parametrize("backend", [backend_params()[0]], indirect=True)
+def test_download_helpers_feed_the_export(tmp_path, backend, oracle):
+    """OfflineGBuffer.download_from_g_buffer / OfflineIllumination.download_from_illumination_buffer (the reference's export
+    staging, RenderIO.cpp:401-467, :748-928) -> export_g_buffer / export_illumination -> the files hold the oracle's
+    conversions of what was uploaded.  Emulator only: uploads, downloads and host code"""
+    from vulkanpbrt_b200 import DenoisePipeline
+    W, H = 64, 48
+    fr = _sequence(W, H, 2)[1]
+    pipe = DenoisePipeline(W, H, use_taa=False)
+    pipe.upload_frame(fr)
+    g = OfflineGBuffer().download_from_g_buffer(pipe.g_buffer)
+    il = OfflineIllumination().download_from_illumination_buffer(pipe.raw_illumination)
+    np.testing.assert_array_equal(g.depth, fr.depth)
+    np.testing.assert_array_equal(g.normal, fr.normal)
+    np.testing.assert_array_equal(g.albedo, fr.albedo)
+    np.testing.assert_array_equal(il.noisy.view(np.uint32), np.ascontiguousarray(fr.illumination, np.float32).view(np.uint32))
+    c = fr.camera
+    cm = CameraMatrices(view=c.view, inv_view=c.inv_view, proj=c.proj, inv_proj=c.inv_proj)
+    d = str(tmp_path)
+    assert GBufferIO.export_g_buffer(d + "/pos_%d.exr", d + "/depth_%d.exr", d + "/normal_%d.exr", "", d + "/albedo_%d.exr", 1, [g], [cm], verbosity=0)
+    assert IlluminationBufferIO.export_illumination(d + "/illu_%d.exr", 1, [il], verbosity=0)
+    want_p, want_n, want_a = oracle.gbuffer_export(np.asarray(c.inv_view, np.float32), np.asarray(c.inv_proj, np.float32), fr.depth, fr.normal, fr.albedo)
+    np.testing.assert_array_equal(read_exr(d + "/pos_0.exr").view(np.uint32), want_p.view(np.uint32))
+    np.testing.assert_array_max_ulp(read_exr(d + "/normal_0.exr"), want_n, maxulp=1)
+    np.testing.assert_array_equal(read_exr(d + "/albedo_0.exr").view(np.uint32), want_a.view(np.uint32))
+    np.testing.assert_array_equal(read_exr(d + "/illu_0.exr").view(np.uint32), il.noisy.view(np.uint32))

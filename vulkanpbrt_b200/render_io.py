@@ -36,10 +36,22 @@ class OfflineGBuffer:           # source/io/RenderIO.hpp: depth / normal / mater
     material: Optional[np.ndarray] = None       # uint8   [H][W][4]
     albedo: Optional[np.ndarray] = None         # uint8   [H][W][4]
 
+    def download_from_g_buffer(self, g_buffer) -> "OfflineGBuffer":
+        """download_from_g_buffer_command + transfer_staging_data_to (RenderIO.cpp:748-928): the GBuffer's own planes, read back
+        once the frame's work on the context's stream is done (Image.download synchronises)"""
+        self.depth, self.normal, self.albedo = g_buffer.depth.download(), g_buffer.normal.download(), g_buffer.albedo.download()
+        self.material = g_buffer.material.download() if getattr(g_buffer, "material", None) is not None else None
+        return self
+
 
 @dataclass
 class OfflineIllumination:
     noisy: Optional[np.ndarray] = None          # float32 [H][W][4]
+
+    def download_from_illumination_buffer(self, illu_buffer) -> "OfflineIllumination":
+        """download_from_illumination_buffer_command + transfer_staging_data_to (RenderIO.cpp:401-467): image 0"""
+        self.noisy = illu_buffer.illumination_images[0].download()
+        return self
 
 
 # ---- EXR planes --------------------------------------------------------------------------------------------------
