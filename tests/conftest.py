@@ -31,9 +31,9 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "slow: longer CPU test")
 
 
-# GPU variants added after the round's last visit to a GPU (commit 61a08ea): they have run on the emulator only.  The GPU
-# suite runs them LAST, so that under `-x` a surprise in one of them cannot hide the result of a test that has a GPU record
-# (profiles/r02_pytest_gpu_*.log).  Order only: nothing is skipped or deselected.
+# GPU variants added after the round's main evidence visit (commit 61a08ea).  They ran on a B200 in the round's last session
+# (profiles/r02_pytest_gpu_late_tests.log: 20 passed); the GPU suite still runs them after the older tests -- order only,
+# nothing is skipped or deselected.
 _GPU_UNCONFIRMED = ("test_copy_final_image_and_device_uuid[cuda]", "test_images_smaller_than_one_block_are_rejected[cuda]",
                     "test_reprojection_beyond_the_halo_is_counted[cuda]", "test_bmfr_image_narrower_than_two_blocks[cuda]",
                     "test_caller_supplied_motion_outside_the_unit_square[", "test_bfr_descent_with_a_non_finite_gradient[",
